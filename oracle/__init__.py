@@ -202,6 +202,13 @@ def real_text(n: int) -> np.ndarray:
     return np.frombuffer(data[:n], np.uint8).copy()
 
 
+def gen_small_alphabet(n: int, nsym: int = 9, seed: int = 3) -> np.ndarray:
+    """Skewed symbols 0..nsym-1: libzstd emits Huffman literals whose tree uses DIRECT 4-bit weights."""
+    rng = np.random.default_rng(seed)
+    p = np.array([2.0 ** -(i + 1) for i in range(nsym - 1)] + [2.0 ** -(nsym - 1)])
+    return rng.choice(np.arange(nsym), n, p=p).astype(np.uint8)
+
+
 def gen_rle_literals(n_matches: int = 3000, seed: int = 0) -> np.ndarray:
     """128 KiB of noise followed by (run of 'a', slice copied from the noise) pairs: at zstd level 19 the second
     and later blocks carry RLE literals sections plus repeat-mode tables (a path the README corpora never hit)."""

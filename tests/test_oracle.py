@@ -133,6 +133,7 @@ def test_zstd_path_coverage_union(oracle):
         (rt[:300], 3), (rt[:2000], 19),
         (np.frombuffer(bytes(np.random.default_rng(3).choice([97, 98, 99, 100], 50000).astype(np.uint8)), np.uint8), 3),
         (np.tile(rt[:50], 40), 1), (O.gen_rle_literals(), 19),
+        (O.gen_small_alphabet(300), 1), (O.gen_small_alphabet(3000), 1),
     ]
     tot = {}
     for data, lvl in corpora:
