@@ -209,6 +209,17 @@ def gen_small_alphabet(n: int, nsym: int = 9, seed: int = 3) -> np.ndarray:
     return rng.choice(np.arange(nsym), n, p=p).astype(np.uint8)
 
 
+def gen_periodic_noise(n: int, dist: int, period: int, seed: int = 3) -> np.ndarray:
+    """out[i] = out[i-dist] except every `period`-th byte is fresh noise: many near-identical sequences, which makes
+    libzstd choose RLE mode for a sequence table (dist=200, period=12, n=2000 at level 3)."""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 256, n, dtype=np.uint8)
+    for i in range(dist, n):
+        if i % period:
+            d[i] = d[i - dist]
+    return d
+
+
 def gen_rle_literals(n_matches: int = 3000, seed: int = 0) -> np.ndarray:
     """128 KiB of noise followed by (run of 'a', slice copied from the noise) pairs: at zstd level 19 the second
     and later blocks carry RLE literals sections plus repeat-mode tables (a path the README corpora never hit)."""

@@ -134,6 +134,7 @@ def test_zstd_path_coverage_union(oracle):
         (np.frombuffer(bytes(np.random.default_rng(3).choice([97, 98, 99, 100], 50000).astype(np.uint8)), np.uint8), 3),
         (np.tile(rt[:50], 40), 1), (O.gen_rle_literals(), 19),
         (O.gen_small_alphabet(300), 1), (O.gen_small_alphabet(3000), 1),
+        (O.gen_periodic_noise(2000, 200, 12), 3), (O.gen_periodic_noise(20000, 64, 8), 19),
     ]
     tot = {}
     for data, lvl in corpora:
