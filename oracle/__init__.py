@@ -209,7 +209,7 @@ def gen_small_alphabet(n: int, nsym: int = 9, seed: int = 3) -> np.ndarray:
     return rng.choice(np.arange(nsym), n, p=p).astype(np.uint8)
 
 
-def gen_periodic_noise(n: int, dist: int, period: int, seed: int = 3) -> np.ndarray:
+def gen_periodic_noise(n: int, dist: int, period: int, seed: int = 1) -> np.ndarray:
     """out[i] = out[i-dist] except every `period`-th byte is fresh noise: many near-identical sequences, which makes
     libzstd choose RLE mode for a sequence table (dist=200, period=12, n=2000 at level 3)."""
     rng = np.random.default_rng(seed)
