@@ -1,0 +1,148 @@
+/*
+ * znippy_cuda.h — C ABI of libznippy_cuda.so, the B200 (sm_100a) back-end for znippy's per-chunk codec +
+ * integrity hot path.  Plain pointers and sizes only; no CUDA/torch types in any signature (streams are
+ * passed as opaque `void*` = cudaStream_t).
+ *
+ * What each entry point replaces in the reference (paths relative to the znippy repository root):
+ *
+ *   zn_decode_verify_batch / zn_plan_*      the body of the read worker loop, znippy-common/src/decompress.rs:148-184
+ *                                           (codec::decompress_into, codec.rs:67-78, then blake3::hash + 32-byte
+ *                                           compare, decompress.rs:172-184), and the per-chunk decode of
+ *                                           ZnippyArchive::extract_file, znippy-common/src/archive.rs:154-165
+ *   zn_hash_batch                           blake3::hash(&[u8]) at decompress.rs:172, stream_packer.rs:219,
+ *                                           slot_packer.rs:553 (store-as-is rows: decompress.rs:164-166)
+ *   zn_compress_batch                       CompressCtx::compress_into (codec.rs:43-55) + blake3::hash of the source
+ *                                           slice, i.e. the barrel body stream_packer.rs:217-232 and the worker body
+ *                                           slot_packer.rs:551-572
+ *   zn_compress_bound                       openzl zl_compress_bound as used at codec.rs:32,45
+ *   zn_frame_content_size                   zl_get_decompressed_size as used at codec.rs:69
+ *   zn_ctx_create / zn_ctx_destroy          CompressCtx::new (codec.rs:16-28) — one long-lived context per worker,
+ *                                           Send but not Sync (codec.rs:13): a zn_ctx is likewise single-threaded
+ *   zn_ctx_pinned                           a Magazine slot (znippy-common/src/slotpool.rs:93-130) as a pinned
+ *                                           host staging buffer
+ *
+ * Error model: the int return value reports whole-call failures (bad arguments, CUDA errors);
+ * data errors are reported per blob in status[] so that one corrupt blob never fails the batch — the
+ * reference's read loop logs and `continue`s on a codec error (decompress.rs:159-162) and counts a digest
+ * mismatch (decompress.rs:175-184).  Nothing aborts or throws across this boundary.  There is no CPU fallback:
+ * every entry point that computes runs CUDA kernels, and fails with ZN_E_CUDA when no device is usable.
+ *
+ * Blob wire formats accepted by the decoder (self-identifying by magic): Zstandard frames (RFC 8878, magic
+ * 28 B5 2F FD; several concatenated frames and skippable frames allowed) and LZ4 frames (magic 04 22 4D 18,
+ * independent blocks).  The OpenZL envelope the reference writes around those payloads is NOT parsed (its layout
+ * is unpinned in this environment); such blobs get ZN_S_UNSUPPORTED.
+ */
+#ifndef ZNIPPY_CUDA_H
+#define ZNIPPY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZN_ABI_VERSION 1
+
+/* ---- whole-call return codes ---- */
+enum {
+  ZN_OK = 0,
+  ZN_E_ARG = -1,     /* null pointer / inconsistent sizes */
+  ZN_E_CUDA = -2,    /* CUDA runtime error; see zn_last_error() */
+  ZN_E_NOMEM = -3,   /* device or pinned allocation failed */
+  ZN_E_STATE = -4    /* call out of order (e.g. results before run) */
+};
+
+/* ---- per-blob status[] values ---- */
+enum {
+  ZN_S_OK = 0,
+  ZN_S_DECODE_ERROR = 1,     /* corrupt / truncated compressed data (reference: codec Err -> row skipped) */
+  ZN_S_DIGEST_MISMATCH = 2,  /* decoded fine, blake3 != expected (reference: corrupt_bytes / corrupt_rows) */
+  ZN_S_DST_TOO_SMALL = 3,    /* decoded size exceeds the capacity given in out_len[] */
+  ZN_S_UNSUPPORTED = 4,      /* unknown magic, dictionary id, linked LZ4 blocks, reserved bits */
+  ZN_S_SIZE_MISMATCH = 5     /* decoded size != out_len[] (index uncompressed_size) or != frame content size */
+};
+
+/* ---- codecs for zn_compress_batch ---- */
+enum {
+  ZN_CODEC_ZSTD = 1, /* one Zstandard frame per slice */
+  ZN_CODEC_LZ4 = 2   /* one LZ4 frame (independent 64 KiB blocks, content size in header) per slice */
+};
+
+typedef struct zn_ctx zn_ctx;   /* one CUDA device + streams + scratch + pinned staging; not thread-safe */
+typedef struct zn_plan zn_plan; /* device-resident descriptors of one decode/verify batch, reusable */
+
+/* ---- library / context ---- */
+int zn_abi_version(void);
+int zn_device_count(void);
+const char* zn_strerror(int code);            /* whole-call codes */
+const char* zn_status_name(uint32_t status);  /* per-blob codes */
+zn_ctx* zn_ctx_create(int device, size_t staging_bytes); /* NULL on failure */
+void zn_ctx_destroy(zn_ctx* ctx);
+const char* zn_last_error(const zn_ctx* ctx);
+/* pinned host staging buffer owned by the ctx (the Magazine-slot analogue); *bytes receives its size */
+void* zn_ctx_pinned(zn_ctx* ctx, size_t* bytes);
+/* number of kernels this ctx has launched since creation (bench.py reports it as gpu_launches) */
+uint64_t zn_ctx_kernel_launches(const zn_ctx* ctx);
+
+/* ---- host-buffer API: H2D, kernels, D2H all inside the call; synchronous on return ---- */
+
+/* digests[i] = BLAKE3(base[off[i] .. off[i]+len[i]))  */
+int zn_hash_batch(zn_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t n,
+                  uint8_t* digests /* n*32 */);
+
+/*
+ * For each blob i: if compressed[i], decode blobs_base[blob_off[i] .. +blob_len[i]) (capacity out_len[i]);
+ * else the blob bytes are the content.  Then BLAKE3 the content, compare with expect_digest[i] when given,
+ * and copy the content to out_base[out_off[i] ..] when out_base is given.
+ *   expect_digest  nullable (n*32)  -> no compare (extract_file semantics, archive.rs:144-168)
+ *   out_base       nullable         -> verify-only (decompress_archive with save_data=false)
+ *   digest_out     nullable (n*32)
+ *   status         required (n)
+ */
+int zn_decode_verify_batch(zn_ctx* ctx, const uint8_t* blobs_base, const uint64_t* blob_off,
+                           const uint64_t* blob_len, const uint8_t* compressed, const uint64_t* out_len,
+                           const uint8_t* expect_digest, uint8_t* out_base, const uint64_t* out_off, uint32_t n,
+                           uint32_t* status, uint8_t* digest_out);
+
+/*
+ * For each slice i: digest_out[i] = BLAKE3(src), dst_base[dst_off[i] ..] = one frame of `codec` holding src.
+ * dst_off has n+1 entries; capacity of slice i is dst_off[i+1]-dst_off[i] and must be >= zn_compress_bound().
+ * `level` selects the match-finder effort (1 = fastest .. 3); the frame is always decodable by stock
+ * libzstd / liblz4.
+ */
+int zn_compress_batch(zn_ctx* ctx, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                      uint32_t n, int level, int codec, uint8_t* dst_base, const uint64_t* dst_off,
+                      uint64_t* dst_len_out, uint8_t* digest_out /* nullable */, uint32_t* status);
+
+size_t zn_compress_bound(size_t src_len, int codec);
+
+/* decoded size announced by the frame header. returns ZN_OK, 1 when the frame carries no size, <0 on error */
+int zn_frame_content_size(const uint8_t* blob, size_t len, uint64_t* size_out);
+
+/* ---- device-resident API (inputs and outputs already in HBM; used for the device GB/s metric and by
+ *      callers that keep a batch resident).  d_* are device pointers; h_* host pointers. ---- */
+
+/* Builds the device-side descriptor tables for a decode+verify batch (uploads them, sizes scratch). */
+zn_plan* zn_plan_decode_verify(zn_ctx* ctx, uint32_t n, const uint64_t* h_blob_off, const uint64_t* h_blob_len,
+                               const uint8_t* h_compressed, const uint64_t* h_out_off, const uint64_t* h_out_len,
+                               const uint8_t* h_expect_digest /* nullable */);
+/* Hash-only plan over resident bytes (store-as-is verify / write-side hashing). */
+zn_plan* zn_plan_hash(zn_ctx* ctx, uint32_t n, const uint64_t* h_off, const uint64_t* h_len,
+                      const uint8_t* h_expect_digest /* nullable */);
+void zn_plan_destroy(zn_plan* plan);
+/* Enqueues the batch on `stream` (cudaStream_t; NULL = the ctx's own stream). Asynchronous.
+ * d_out may be NULL only for hash-only plans. */
+int zn_plan_run(zn_plan* plan, const uint8_t* d_blobs, uint8_t* d_out, void* stream);
+/* Waits for the last run and copies results back. status / digests nullable. */
+int zn_plan_results(zn_plan* plan, uint32_t* h_status, uint8_t* h_digests);
+/* kernels launched by one zn_plan_run of this plan */
+uint32_t zn_plan_launches(const zn_plan* plan);
+/* device time of the most recent completed run, per stage, in ms (CUDA events on the run's stream):
+ * [0] total, [1] decode stage, [2] hash stage (chunks), [3] tree+compare stage.  Synchronises. */
+int zn_plan_last_ms(zn_plan* plan, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZNIPPY_CUDA_H */

@@ -1,0 +1,101 @@
+// Bit-stream readers and byte-granular global-memory helpers shared by the codec kernels.
+// Everything here is warp-uniform scalar code unless it takes a `lane` argument.  It also compiles for the
+// host (tests/host_decode_check drives the same parsing logic on the CPU).
+#pragma once
+#include "common.cuh"
+
+namespace zn {
+
+#if defined(__CUDA_ARCH__)
+ZN_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+ZN_D int hibit32(uint32_t v) { return 31 - __clz((int)v); }
+#else
+inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+  sh &= 31;
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+inline int hibit32(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
+#endif
+
+ZN_HD uint32_t ld8(const uint8_t* p) { return *p; }
+ZN_HD uint32_t ld16le(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+ZN_HD uint32_t ld24le(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+ZN_HD uint32_t ld32le(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// Aligned 32-bit word that contains byte address `a` is always safe to read when byte `a` itself is valid.
+ZN_HD uint32_t ld_word_aligned(const uint8_t* a) {
+  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward bit reader (RFC 8878 §4.1 / §4.2.2): the stream occupies bytes [p, p+len); its last byte holds the
+// end marker (highest set bit).  Bits are consumed from the top down.  A 64-bit window is refilled with ALIGNED
+// 32-bit words; bytes below the stream start are masked to zero, so over-reads see zeros and are detected by
+// bits_left going negative (never by a fault).
+// ---------------------------------------------------------------------------------------------------------
+struct BackBits {
+  const uint32_t* wbase;  // aligned word holding the first stream byte
+  uint32_t lowmask;       // clears the bytes of word 0 that precede the stream
+  int32_t widx;           // next word to load (descending); < 0 -> zeros
+  uint64_t win;           // unread bits, MSB-aligned
+  int32_t navail;         // valid bits in win
+  int32_t bits_left;      // unread bits in the stream; < 0 == over-read
+
+  ZN_HD bool init(const uint8_t* p, uint32_t len) {
+    if (len == 0) return false;
+    const uint32_t last = p[len - 1];
+    if (last == 0) return false;
+    const int hb = hibit32(last);
+    bits_left = (int32_t)(len - 1) * 8 + hb;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), s_al = a & ~(uintptr_t)3, e = a + len;
+    wbase = reinterpret_cast<const uint32_t*>(s_al);
+    lowmask = 0xFFFFFFFFu << ((a & 3) * 8);
+    const int32_t t = (int32_t)((((e - 1) & ~(uintptr_t)3) - s_al) >> 2);
+    const int nb_top = (int)(e - (s_al + 4 * (uintptr_t)t));  // 1..4 bytes of the top word belong to the stream
+    uint32_t w = wbase[t];
+    if (t == 0) w &= lowmask;
+    const int nvalid = (nb_top - 1) * 8 + hb;  // bits below the end marker
+    win = nvalid ? ((uint64_t)w << (64 - nvalid)) : 0;
+    navail = nvalid;
+    widx = t - 1;
+    return true;
+  }
+  ZN_HD void refill() {  // afterwards navail > 32, so any read of <= 32 bits is served from the window
+    while (navail <= 32) {
+      uint32_t w = 0;
+      if (widx >= 0) {
+        w = wbase[widx];
+        if (widx == 0) w &= lowmask;
+      }
+      win |= (uint64_t)w << (32 - navail);
+      navail += 32;
+      widx--;
+    }
+  }
+  ZN_HD uint32_t peek(uint32_t n) const { return n ? (uint32_t)(win >> (64 - n)) : 0u; }  // n <= 32
+  ZN_HD void skip(uint32_t n) { win <<= n; navail -= (int32_t)n; bits_left -= (int32_t)n; }
+  ZN_HD uint32_t read(uint32_t n) {  // n <= 32; caller guarantees a refill() since the last 32 bits consumed
+    const uint32_t v = peek(n);
+    skip(n);
+    return v;
+  }
+};
+
+// Forward little-endian bit reader over a byte range (FSE table descriptions; tiny, byte loads are fine).
+struct FwdBits {
+  const uint8_t* p;
+  uint32_t len;
+  uint32_t bitpos;
+  ZN_HD uint32_t peek(uint32_t n) const {  // n <= 16
+    const uint32_t byte = bitpos >> 3;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (byte + i < len) v |= (uint32_t)p[byte + i] << (8 * i);
+    return (v >> (bitpos & 7)) & ((1u << n) - 1u);
+  }
+};
+
+}  // namespace zn
