@@ -1,0 +1,35 @@
+// TEST INFRASTRUCTURE ONLY — compiles the team-uniform codec logic of znippy_b200/csrc (the very code the CUDA
+// kernels run, with a team of one and plain-loop copies) for the host, so that frame/block/entropy parsing can be
+// checked against the oracle without a GPU.  Never linked into libznippy_cuda.so.
+#include <cstdlib>
+#include <cstring>
+
+#include "../../znippy_b200/csrc/lz4_decode.cuh"
+
+extern "C" int zn_hostemu_decode(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap,
+                                 uint32_t* produced) {
+  zn::DecShared* sh = (zn::DecShared*)calloc(1, sizeof(zn::DecShared));
+  uint8_t* lit = (uint8_t*)malloc(zn::kZstdBlockMax + 64);
+  zn::Team t{0, 1};
+  // the device code may read the aligned 32-bit word around any valid byte: give the input 4-byte alignment + slack
+  uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 16);
+  memcpy(in + 4, src, src_len);
+  uint32_t st = zn::decode_blob(t, sh, in + 4, src_len, out, cap, lit, produced);
+  free(in);
+  free(lit);
+  free(sh);
+  return (int)st;
+}
+extern "C" int zn_hostemu_decode_at(const uint8_t* src, uint32_t src_len, uint32_t misalign, uint8_t* out,
+                                    uint32_t cap, uint32_t* produced) {
+  zn::DecShared* sh = (zn::DecShared*)calloc(1, sizeof(zn::DecShared));
+  uint8_t* lit = (uint8_t*)malloc(zn::kZstdBlockMax + 64);
+  zn::Team t{0, 1};
+  uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 32);
+  memcpy(in + 8 + (misalign & 7), src, src_len);
+  uint32_t st = zn::decode_blob(t, sh, in + 8 + (misalign & 7), src_len, out, cap, lit, produced);
+  free(in);
+  free(lit);
+  free(sh);
+  return (int)st;
+}

@@ -1,0 +1,511 @@
+"""`.znippy` v0.7 container (unchanged) and the three host loops that sit on the GPU codec boundary.
+
+Mirrors, with the same names and semantics:
+
+    read_znippy_index / interpret_footer / manifest      znippy-common/src/index.rs:245-468
+    ArrowIpcSink.push_subindex / finish                  znippy-common/src/meta_sink.rs:71-118
+    decompress_archive -> VerifyReport                   znippy-common/src/decompress.rs:39-222
+    ZnippyArchive.open / extract_file / extract_files    znippy-common/src/archive.rs:20-168
+    compress_stream -> StreamCompressor                  znippy-compress/src/stream_packer.rs:58-372
+    should_skip_compression                              znippy-common/src/index.rs:470-488
+
+The loop shells (row cursor, pread, pwrite, counters) stay on the host; the loop BODIES (decode / blake3 / compare /
+compress) are one `zn_*_batch` call per batch of rows.  Index I/O uses pyarrow (the container is metadata, not the
+hot path).  Archives written here hold standard Zstandard / LZ4 frames as blobs (OpenZL envelope unpinned).
+"""
+from __future__ import annotations
+
+import io
+import os
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+import pyarrow as pa
+
+from . import codec
+from ._native import Ctx, default_ctx
+
+MULTI_INDEX_MAGIC = b"ZNPYMIDX"  # index.rs:245
+SLICE_SIZE = 8 * 1024 * 1024     # stream_packer.rs:31
+COMPRESSION_LEVEL = 19           # common_config.rs:37 (echoed into the schema metadata)
+
+_SKIP_EXT = {  # index.rs:470-484
+    "zip", "gz", "bz2", "xz", "lz", "lzma", "7z", "rar", "cab", "jar", "war", "ear", "zst", "sz", "lz4", "tgz", "txz",
+    "tbz", "apk", "dmg", "deb", "rpm", "arrow", "mpeg", "mpg", "jpeg", "jpg", "gif", "bmp", "png", "crate", "znippy",
+    "zdata", "parquet", "webp", "webm"}
+
+
+def should_skip_compression(path: str) -> bool:
+    """Case-insensitive test of the LAST extension only (`deps.tar.gz` -> `gz`)."""
+    base = os.path.basename(path)
+    if "." not in base:
+        return False
+    return base.rsplit(".", 1)[1].lower() in _SKIP_EXT
+
+
+INDEX_SCHEMA = pa.schema([  # index.rs:43-54, all non-nullable
+    pa.field("relative_path", pa.utf8(), False), pa.field("chunk_seq", pa.uint32(), False),
+    pa.field("fdata_offset", pa.uint64(), False), pa.field("compressed", pa.bool_(), False),
+    pa.field("uncompressed_size", pa.uint64(), False), pa.field("blob_offset", pa.uint64(), False),
+    pa.field("blob_size", pa.uint64(), False), pa.field("checksum", pa.binary(32), False)])
+
+MANIFEST_SCHEMA = pa.schema([  # index.rs:279-288
+    pa.field("pkg_type", pa.int8(), False), pa.field("repo", pa.utf8(), False),
+    pa.field("module_name", pa.utf8(), False), pa.field("index_offset", pa.uint64(), False),
+    pa.field("index_len", pa.uint64(), False), pa.field("row_count", pa.uint64(), False)])
+
+
+def config_metadata(level: int = COMPRESSION_LEVEL) -> dict:
+    """index.rs:73-85: config echoed as decimal strings into the schema metadata."""
+    cores = os.cpu_count() or 1
+    return {"znippy_format_version": "3", "max_core_in_flight": str(max(1, -(-cores * 9 // 10))),
+            "max_core_in_compress": str(cores), "max_mem_allowed": "0", "min_free_memory_ratio": "0.1",
+            "file_split_block_size": str(10 * 1024 * 1024), "max_chunks": "128", "compression_level": str(level),
+            "zstd_output_buffer_size": str(1 << 20)}
+
+
+@dataclass
+class VerifyReport:  # index.rs:490-499
+    total_files: int = 0
+    verified_files: int = 0
+    corrupt_files: int = 0
+    total_bytes: int = 0
+    verified_bytes: int = 0
+    corrupt_bytes: int = 0
+    chunks: int = 0
+
+
+@dataclass
+class CompressionReport:  # znippy-common/src/lib.rs:39-51
+    total_files: int = 0
+    compressed_files: int = 0
+    uncompressed_files: int = 0
+    chunks: int = 0
+    total_bytes_in: int = 0
+    total_bytes_out: int = 0
+    compressed_bytes: int = 0
+    uncompressed_bytes: int = 0
+
+
+# --------------------------------------------------------------------------------------------- container
+
+def interpret_footer(tail: bytes):
+    """index.rs:269-277 -> ("multi", manifest_offset) | ("single", index_offset)."""
+    off = struct.unpack("<Q", tail[-8:])[0]
+    if len(tail) >= 16 and tail[-16:-8] == MULTI_INDEX_MAGIC:
+        return "multi", off
+    return "single", off
+
+
+def write_manifest_bytes(entries) -> bytes:
+    cols = list(zip(*entries)) if entries else [[] for _ in range(6)]
+    batch = pa.record_batch([pa.array(cols[i], type=MANIFEST_SCHEMA.field(i).type) for i in range(6)],
+                            schema=MANIFEST_SCHEMA)
+    sink = io.BytesIO()
+    with pa.ipc.new_stream(sink, MANIFEST_SCHEMA) as w:
+        w.write_batch(batch)
+    return sink.getvalue()
+
+
+def read_manifest_bytes(b: bytes):
+    t = pa.ipc.open_stream(b).read_all()
+    return [tuple(t.column(i)[r].as_py() for i in range(6)) for r in range(t.num_rows)]
+
+
+def read_znippy_manifest(path: str):
+    with open(path, "rb") as f:
+        f.seek(0, 2)
+        flen = f.tell()
+        if flen < 16:
+            raise ValueError("not a znippy archive (too small)")
+        f.seek(flen - 16)
+        kind, off = interpret_footer(f.read(16))
+        if kind != "multi":
+            raise ValueError("v0.6 archives are not supported")  # index.rs:387-389
+        f.seek(off)
+        return read_manifest_bytes(f.read(flen - 16 - off))
+
+
+def read_znippy_index(path: str) -> pa.Table:
+    """index.rs:374-441: footer -> manifest -> every sub-index, concatenated with the first sub-index's schema."""
+    entries = read_znippy_manifest(path)
+    tables = []
+    with open(path, "rb") as f:
+        for (_pt, _repo, _mod, ioff, ilen, _rows) in entries:
+            f.seek(ioff)
+            tables.append(pa.ipc.open_stream(f.read(ilen)).read_all())
+    if not tables:
+        return INDEX_SCHEMA.empty_table()
+    first = tables[0].schema
+    return pa.concat_tables([t.cast(first) if t.schema != first else t for t in tables])
+
+
+class ArrowIpcSink:
+    """meta_sink.rs:52-118: sub-index(es) -> manifest -> magic + LE offset, appended after the blob region."""
+
+    def __init__(self, f, cursor: int):
+        self.f, self.cursor, self.entries = f, cursor, []
+
+    def push_subindex(self, key, schema: pa.Schema, batches):
+        sink = io.BytesIO()
+        with pa.ipc.new_stream(sink, schema) as w:
+            for b in batches:
+                w.write_batch(b)
+        data = sink.getvalue()
+        self.f.seek(self.cursor)
+        self.f.write(data)
+        pkg_type, repo = key
+        self.entries.append((pkg_type, repo, "", self.cursor, len(data), sum(b.num_rows for b in batches)))
+        self.cursor += len(data)
+
+    def finish(self):
+        m = write_manifest_bytes(self.entries)
+        self.f.seek(self.cursor)
+        self.f.write(m)
+        self.f.write(MULTI_INDEX_MAGIC + struct.pack("<Q", self.cursor))
+        self.f.flush()
+        os.fsync(self.f.fileno())
+
+
+def build_metadata_batch(rows, schema: pa.Schema) -> pa.RecordBatch:
+    """index.rs:131-191.  rows: (path, chunk_seq, fdata_offset, compressed, uncompressed_size, blob_offset, blob_size, checksum)."""
+    cols = list(zip(*rows)) if rows else [[] for _ in range(8)]
+    arrays = [pa.array(cols[i], type=INDEX_SCHEMA.field(i).type) for i in range(8)]
+    return pa.record_batch(arrays, schema=schema)
+
+
+# --------------------------------------------------------------------------------------------- read side
+
+def _columns(table: pa.Table):
+    g = lambda name, dt: np.asarray(table.column(name).combine_chunks().to_numpy(zero_copy_only=False), dtype=dt)
+    checks = table.column("checksum").combine_chunks()
+    n = table.num_rows
+    ck = (np.frombuffer(checks.buffers()[1], np.uint8, count=32 * n, offset=32 * checks.offset).reshape(n, 32)
+          if n else np.zeros((0, 32), np.uint8))
+    return (g("blob_offset", np.uint64), g("blob_size", np.uint64), g("fdata_offset", np.uint64),
+            g("compressed", np.uint8), g("uncompressed_size", np.uint64), ck)
+
+
+def plan_row_batches(blob_size, uncompressed_size, lo: int, hi: int, budget: int):
+    """Cuts the row range [lo, hi) into consecutive batches whose blobs + outputs fit `budget` bytes: the GPU
+    analogue of `cursor.fetch_add(1)` (decompress.rs:136) is `cursor.fetch_add(B)` over these ranges."""
+    out, start, acc = [], lo, 0
+    for r in range(lo, hi):
+        need = int(blob_size[r]) + int(uncompressed_size[r])
+        if r > start and acc + need > budget:
+            out.append((start, r))
+            start, acc = r, 0
+        acc += need
+    if hi > start:
+        out.append((start, hi))
+    return out
+
+
+def shard_rows(uncompressed_size, world: int):
+    """contiguous row ranges balanced on the prefix sum of uncompressed_size; no exchange."""
+    n = len(uncompressed_size)
+    pre = np.concatenate([[0], np.cumsum(np.asarray(uncompressed_size, dtype=np.float64) + 1.0)])
+    cuts = [int(np.searchsorted(pre, pre[-1] * k / world, side="left")) for k in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    for k in range(1, world + 1):
+        cuts[k] = max(cuts[k], cuts[k - 1])
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
+def decompress_rows(archive_fd: int, cols, lo: int, hi: int, save_files=None, ctx: Ctx | None = None,
+                    budget: int = 1 << 30):
+    """The worker of decompress.rs:113-192 over rows [lo, hi): returns WorkerStats as a dict.
+
+    Per batch: pread blobs -> zn_decode_verify_batch -> fold status[] with the reference's rules
+    (decompress.rs:140,156-184) -> pwrite at fdata_offset."""
+    blob_off, blob_size, fdata_off, compressed, usize, checks = cols
+    st = dict(total_chunks=0, total_written_bytes=0, verified_bytes=0, corrupt_bytes=0, corrupt_rows=[])
+    for (a, b) in plan_row_batches(blob_size, usize, lo, hi, budget):
+        n = b - a
+        order = np.argsort(blob_off[a:b], kind="stable")  # sequential reads inside the batch
+        lens = blob_size[a:b]
+        offs = np.zeros(n, np.uint64)
+        cur = 0
+        for i in order:
+            offs[i] = cur
+            cur += (int(lens[i]) + 15) & ~15
+        buf = np.zeros(max(cur, 1), np.uint8)
+        for i in order:
+            ln = int(lens[i])
+            if ln:
+                got = os.preadv(archive_fd, [memoryview(buf)[int(offs[i]): int(offs[i]) + ln]], int(blob_off[a + i]))
+                if got != ln:
+                    raise IOError("failed to read blob from archive")
+        ooffs = np.zeros(n, np.uint64)
+        cur = 0
+        for i in range(n):
+            ooffs[i] = cur
+            cur += (int(usize[a + i]) + 15) & ~15
+        want_out = save_files is not None
+        out = np.zeros(max(cur, 1), np.uint8) if want_out else None
+        status, _ = codec.decode_verify_batch(buf, offs, lens, compressed[a:b], usize[a:b], checks[a:b], out,
+                                              ooffs if want_out else None, ctx)
+        for i in range(n):
+            row = a + i
+            st["total_chunks"] += 1
+            s = int(status[i])
+            if s not in (codec.S_OK, codec.S_DIGEST_MISMATCH):
+                continue  # codec error: logged and skipped (decompress.rs:159-162)
+            ln = int(usize[row])
+            st["total_written_bytes"] += ln
+            if s == codec.S_OK:
+                st["verified_bytes"] += ln
+            else:
+                st["corrupt_bytes"] += ln
+                st["corrupt_rows"].append(row)
+            if want_out and save_files[row] is not None:
+                os.pwrite(save_files[row], memoryview(out)[int(ooffs[i]): int(ooffs[i]) + ln], int(fdata_off[row]))
+    return st
+
+
+def decompress_archive(index_path: str, save_data: bool, out_dir: str, ctx: Ctx | None = None,
+                       row_range=None) -> VerifyReport:
+    """decompress.rs:39-222.  `row_range` restricts the call to one shard (multi-GPU: one process per GPU)."""
+    table = read_znippy_index(index_path)
+    cols = _columns(table)
+    paths = table.column("relative_path").to_pylist()
+    total_rows = table.num_rows
+    lo, hi = row_range if row_range is not None else (0, total_rows)
+    total_files = len(set(paths[lo:hi]))
+    files, opened = None, {}
+    if save_data:
+        files = [None] * total_rows
+        for r in range(lo, hi):
+            p = paths[r]
+            if p not in opened:
+                full = os.path.join(out_dir, p)
+                os.makedirs(os.path.dirname(full) or ".", exist_ok=True)
+                opened[p] = os.open(full, os.O_CREAT | os.O_WRONLY | os.O_TRUNC, 0o644)
+            files[r] = opened[p]
+    fd = os.open(index_path, os.O_RDONLY)
+    try:
+        st = decompress_rows(fd, cols, lo, hi, files, ctx)
+    finally:
+        os.close(fd)
+        for f in opened.values():
+            os.close(f)
+    corrupt_files = len(set(st["corrupt_rows"]))  # the reference counts corrupt ROWS here (decompress.rs:210)
+    return VerifyReport(total_files=total_files, verified_files=max(0, total_files - corrupt_files),
+                        corrupt_files=corrupt_files, total_bytes=st["total_written_bytes"],
+                        verified_bytes=st["verified_bytes"], corrupt_bytes=st["corrupt_bytes"],
+                        chunks=st["total_chunks"])
+
+
+def verify_archive_integrity(path: str, ctx: Ctx | None = None) -> VerifyReport:
+    return decompress_archive(path, False, "/dev/null", ctx)  # index.rs:550-553
+
+
+class ZnippyArchive:
+    """archive.rs:46-168: random-access reader; `extract_files` is one GPU batch over all requested chunks."""
+
+    def __init__(self, path: str, ctx: Ctx | None = None):
+        self.path, self.ctx = path, ctx
+        table = read_znippy_index(path)
+        bo, bs, fo, comp, us, _ = _columns(table)
+        self.file_index: dict[str, dict] = {}
+        for r, p in enumerate(table.column("relative_path").to_pylist()):
+            e = self.file_index.setdefault(p, {"uncompressed_size": 0, "chunks": []})
+            e["uncompressed_size"] += int(us[r])
+            e["chunks"].append((int(fo[r]), int(bo[r]), int(bs[r]), bool(comp[r]), int(us[r])))
+        for e in self.file_index.values():
+            e["chunks"].sort(key=lambda c: c[0])  # archive.rs:131-133
+        self._fd = os.open(path, os.O_RDONLY)
+
+    @classmethod
+    def open(cls, path: str, ctx: Ctx | None = None) -> "ZnippyArchive":
+        return cls(path, ctx)
+
+    def close(self):
+        if self._fd is not None:
+            os.close(self._fd)
+            self._fd = None
+
+    def list_files(self):
+        return list(self.file_index.keys())
+
+    def contains(self, relative_path: str) -> bool:
+        return relative_path in self.file_index
+
+    def file_size(self, relative_path: str):
+        e = self.file_index.get(relative_path)
+        return None if e is None else e["uncompressed_size"]
+
+    def extract_file(self, relative_path: str) -> bytes:
+        r = self.extract_files([relative_path])[0]
+        if isinstance(r, Exception):
+            raise r
+        return r
+
+    def extract_files(self, paths):
+        """archive.rs:27-29, batched: every chunk of every requested file in one zn_decode_verify_batch
+        (expect_digest = NULL: extract_file does not verify, archive.rs:144-168)."""
+        results: list = [None] * len(paths)
+        bo, bl, cf, ol, oo, owner = [], [], [], [], [], []
+        out_cur = in_cur = 0
+        reads = []
+        for k, p in enumerate(paths):
+            e = self.file_index.get(p)
+            if e is None:
+                results[k] = KeyError(f"file not found in archive: {p}")
+                continue
+            for (_fo, boff, bsz, comp, usz) in e["chunks"]:
+                reads.append((boff, bsz, in_cur))
+                bo.append(in_cur); bl.append(bsz); cf.append(1 if comp else 0); ol.append(usz); oo.append(out_cur)
+                owner.append(k)
+                in_cur += (bsz + 15) & ~15
+                out_cur += usz  # chunks of one file are concatenated in fdata_offset order
+        if not bo:
+            return results
+        buf = np.zeros(max(in_cur, 1), np.uint8)
+        for (boff, bsz, at) in reads:
+            if bsz and os.preadv(self._fd, [memoryview(buf)[at: at + bsz]], boff) != bsz:
+                raise IOError("short read from archive")
+        out = np.zeros(max(out_cur, 1), np.uint8)
+        status, _ = codec.decode_verify_batch(buf, bo, bl, cf, ol, None, out, oo, self.ctx)
+        bad = {}
+        for i, k in enumerate(owner):
+            if status[i] != codec.S_OK and k not in bad:
+                bad[k] = codec.CodecError(int(status[i]), f"decompress chunk of {paths[k]}")
+        pos = 0
+        for k, p in enumerate(paths):
+            if results[k] is not None:
+                continue
+            size = self.file_index[p]["uncompressed_size"]
+            results[k] = bad.get(k, None) or out[pos: pos + size].tobytes()
+            pos += size
+        return results
+
+
+# --------------------------------------------------------------------------------------------- write side
+
+@dataclass
+class ArchiveEntry:  # stream_packer.rs:34-43
+    relative_path: str
+    data: bytes
+    pkg_type: int | None = None
+    repo: str | None = None
+
+
+@dataclass
+class _Round:  # slotpool.rs:39-63
+    file_index: int
+    chunk_seq: int
+    fdata_offset: int
+    start: int
+    length: int
+    skip: bool
+
+
+class StreamCompressor:
+    """stream_packer.rs:58-372.  `send()` queues entries; `finish()` runs reader -> GPU barrels -> writer -> sink.
+    One `zn_compress_batch` (blake3 + frame per slice) per batch of rounds replaces the N barrel threads; skip
+    rounds go through `zn_hash_batch` only (stream_packer.rs:222-227)."""
+
+    def __init__(self, output: str, no_skip: bool, level: int = 3, codec_id: int = codec.CODEC_ZSTD,
+                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20):
+        self.output = os.path.splitext(output)[0] + ".znippy"  # stream_packer.rs:132
+        self.no_skip, self.level, self.codec_id, self.ctx, self.batch_bytes = no_skip, level, codec_id, ctx, batch_bytes
+        self.entries: list[ArchiveEntry] = []
+
+    def send(self, entry: ArchiveEntry):
+        self.entries.append(entry)
+
+    def sender(self):
+        return self
+
+    def _rounds(self):
+        for fi, e in enumerate(self.entries):
+            skip = (not self.no_skip) and should_skip_compression(e.relative_path)
+            n = len(e.data)
+            if n <= SLICE_SIZE:  # whole entry (also the empty entry: one len-0 round), stream_packer.rs:169-183
+                yield _Round(fi, 0, 0, 0, n, skip)
+            else:
+                for seq, start in enumerate(range(0, n, SLICE_SIZE)):
+                    yield _Round(fi, seq, start, start, min(SLICE_SIZE, n - start), skip)
+
+    def finish(self) -> CompressionReport:
+        rep = CompressionReport(total_files=len(self.entries))
+        blobs_meta = []  # (file_index, chunk_seq, fdata_offset, compressed, usize, blob_offset, blob_size, checksum)
+        out_cursor = 0
+        with open(self.output, "wb") as f:
+            batch, acc = [], 0
+
+            def flush():
+                nonlocal out_cursor, batch, acc
+                if not batch:
+                    return
+                parts, offs, lens, cur = [], [], [], 0
+                for r in batch:
+                    d = self.entries[r.file_index].data
+                    parts.append(np.frombuffer(d, np.uint8, r.length, r.start) if r.length else np.zeros(0, np.uint8))
+                    offs.append(cur); lens.append(r.length)
+                    cur += (r.length + 15) & ~15
+                src = np.zeros(max(cur, 1), np.uint8)
+                for p, o in zip(parts, offs):
+                    src[o: o + p.size] = p
+                ci = [i for i, r in enumerate(batch) if not r.skip]
+                si = [i for i, r in enumerate(batch) if r.skip]
+                payload, digest = [None] * len(batch), [None] * len(batch)
+                if ci:
+                    bl, dg, st = codec.compress_batch(src, [offs[i] for i in ci], [lens[i] for i in ci], self.level,
+                                                      self.codec_id, self.ctx)
+                    for k, i in enumerate(ci):
+                        if st[k] != codec.S_OK:
+                            raise codec.CodecError(int(st[k]), "compress")  # `?` propagates, stream_packer.rs:230
+                        payload[i], digest[i] = bl[k], dg[k].tobytes()
+                if si:
+                    dg = codec.hash_batch(src, [offs[i] for i in si], [lens[i] for i in si], self.ctx)
+                    for k, i in enumerate(si):
+                        payload[i] = src[offs[i]: offs[i] + lens[i]].tobytes()
+                        digest[i] = dg[k].tobytes()
+                for i, r in enumerate(batch):  # writer, stream_packer.rs:252-285
+                    f.seek(out_cursor)
+                    f.write(payload[i])
+                    blobs_meta.append((r.file_index, r.chunk_seq, r.fdata_offset, not r.skip, r.length, out_cursor,
+                                       len(payload[i]), digest[i]))
+                    out_cursor += len(payload[i])
+                    rep.chunks += 1
+                    rep.total_bytes_in += r.length
+                    rep.total_bytes_out += len(payload[i])
+                    if r.skip:
+                        rep.uncompressed_bytes += r.length
+                    else:
+                        rep.compressed_bytes += r.length
+                batch, acc = [], 0
+
+            for r in self._rounds():
+                if batch and acc + r.length > self.batch_bytes:
+                    flush()
+                batch.append(r)
+                acc += r.length
+            flush()
+            for fi, e in enumerate(self.entries):
+                if (not self.no_skip) and should_skip_compression(e.relative_path):
+                    rep.uncompressed_files += 1
+                else:
+                    rep.compressed_files += 1
+            # finalizer, stream_packer.rs:293-346: sort by (file_index, chunk_seq), group by (pkg_type, repo)
+            blobs_meta.sort(key=lambda b: (b[0], b[1]))
+            groups: dict = {}
+            for b in blobs_meta:
+                e = self.entries[b[0]]
+                key = (e.pkg_type if e.pkg_type is not None else 0, e.repo or "")
+                groups.setdefault(key, []).append((e.relative_path,) + b[1:])
+            if not groups:
+                groups[(0, "")] = []
+            schema = INDEX_SCHEMA.with_metadata(config_metadata())
+            sink = ArrowIpcSink(f, out_cursor)
+            for key in sorted(groups):
+                sink.push_subindex(key, schema, [build_metadata_batch(groups[key], schema)])
+            sink.finish()
+        return rep
+
+
+def compress_stream(output: str, no_skip: bool, **kw) -> StreamCompressor:
+    return StreamCompressor(output, no_skip, **kw)

@@ -144,11 +144,11 @@ ZN_D void parent(const uint32_t (&l)[8], const uint32_t (&r)[8], bool root, uint
   compress(out, m, 0, 0, 64, PARENT | (root ? ROOT : 0u));
 }
 
-ZN_D void load_cv(const uint32_t* __restrict__ p, uint32_t (&cv)[8]) {
+ZN_D void load_cv(const uint32_t* p, uint32_t (&cv)[8]) {
   const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
   cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w; cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
 }
-ZN_D void store_cv(uint32_t* __restrict__ p, const uint32_t (&cv)[8]) {
+ZN_D void store_cv(uint32_t* p, const uint32_t (&cv)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
   *reinterpret_cast<uint4*>(p + 4) = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }

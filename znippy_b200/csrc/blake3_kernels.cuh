@@ -1,4 +1,12 @@
-// BLAKE3 batch kernels: chunk chaining values (flat over every chunk of every blob) and tree merge + compare.
+// BLAKE3 batch kernels: chunk chaining values (flat over every 1 KiB chunk of every blob in the batch) and the
+// tree merge + digest compare.  Replaces blake3::hash + the 32-byte compare of the reference's read loop
+// (znippy-common/src/decompress.rs:172-184) and the write-side hash (stream_packer.rs:219, slot_packer.rs:553).
+//
+// Roofline note: BLAKE3 is bound by the integer ALU pipe, not by HBM — 7 rounds x 8 G x 12 ops per
+// 64-byte block ~ 10.5 ops/byte.  The chunk kernel therefore keeps the ALU pipe fed: one lane per chunk, message
+// words staged through shared memory by coalesced 16-byte cp.async copies (double buffered per warp, no CTA
+// barriers), conflict-free 128-bit shared loads (odd row stride), and a full 32-lane tile even when a batch is
+// 100 000 ten-chunk blobs, because lanes are assigned over the flat (blob, chunk) index space.
 #pragma once
 #include "blake3.cuh"
 
@@ -9,29 +17,123 @@ ZN_D const uint8_t* content_ptr(const BlobDesc& d, const uint8_t* blobs_base, co
   return (d.flags & F_COMPRESSED) ? out_base + d.dst_off : blobs_base + d.src_off;
 }
 
-// K3a: one lane per 1 KiB chunk, flat over the whole batch (so 100k x 10 KiB files fill warps as well as
-// 256 x 8 MiB slices do).  chunk_prefix[b] = first flat chunk index of blob b (n_blobs+1 entries).
-__global__ void __launch_bounds__(256) k_b3_chunks(const BlobDesc* __restrict__ blobs,
-                                                   const uint32_t* __restrict__ chunk_prefix, uint32_t n_blobs,
-                                                   uint32_t total_chunks, const uint8_t* __restrict__ blobs_base,
-                                                   const uint8_t* __restrict__ out_base,
-                                                   uint32_t* __restrict__ cvs) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total_chunks) return;
-  // binary search: largest b with chunk_prefix[b] <= g
-  uint32_t lo = 0, hi = n_blobs;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(chunk_prefix + mid) <= g) lo = mid; else hi = mid;
+constexpr int kB3Warps = 8;                      // warps per CTA
+constexpr int kB3RowBytes = 128;                 // bytes of each chunk staged per pipeline stage (2 blocks)
+constexpr int kB3RowStride = kB3RowBytes + 16;   // 9 quads: odd -> conflict-free LDS.128 across lanes
+constexpr int kB3Stages = 2;
+constexpr int kB3StageBytes = 32 * kB3RowStride;
+constexpr int kB3SmemPerWarp = kB3Stages * kB3StageBytes;
+constexpr int kB3RowsPerIssue = 32 / (kB3RowBytes / 16);  // rows covered by one warp-wide 16-byte copy (4)
+
+ZN_D void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+ZN_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+ZN_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Stage `stage_idx` (bytes [stage_idx*128, +128) of each of the warp's 32 chunks) -> shared memory.
+// ptr/len are this lane's chunk; rows are other lanes' chunks, fetched by shuffle.
+ZN_D void b3_issue_stage(uint8_t* buf, const uint8_t* ptr, uint32_t len, uint32_t stage_idx, uint32_t lane) {
+  const uint32_t q = lane & 7u;          // quad inside the row
+  const uint32_t sub = lane >> 3;        // row inside the issue group
+  const uint32_t ptr_lo = (uint32_t)reinterpret_cast<uintptr_t>(ptr);
+  const uint32_t ptr_hi = (uint32_t)(reinterpret_cast<uintptr_t>(ptr) >> 32);
+  const uint32_t base = stage_idx * kB3RowBytes + q * 16u;
+#pragma unroll
+  for (int it = 0; it < 32 / kB3RowsPerIssue; it++) {
+    const uint32_t row = it * kB3RowsPerIssue + sub;
+    const uint32_t rlo = __shfl_sync(0xFFFFFFFFu, ptr_lo, row);
+    const uint32_t rhi = __shfl_sync(0xFFFFFFFFu, ptr_hi, row);
+    const uint32_t rlen = __shfl_sync(0xFFFFFFFFu, len, row);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(((uintptr_t)rhi << 32) | rlo) + base;
+    uint8_t* dst = buf + row * kB3RowStride + q * 16u;
+    if (base + 16u <= rlen && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      cp_async16(dst, src);
+    } else if (base < rlen) {  // unaligned source or the blob's last, partial quad: assemble from byte loads
+      uint32_t w[4] = {0, 0, 0, 0};
+      const uint32_t nb = min(16u, rlen - base);
+      for (uint32_t j = 0; j < nb; j++) w[j >> 2] |= (uint32_t)__ldg(src + j) << (8 * (j & 3));
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
-  const BlobDesc d = blobs[lo];
-  const uint32_t c = g - __ldg(chunk_prefix + lo);
-  const uint8_t* p = content_ptr(d, blobs_base, out_base) + (uint64_t)c * kChunk;
-  const uint64_t remain = d.dst_cap - (uint64_t)c * kChunk;
-  const uint32_t len = remain < kChunk ? (uint32_t)remain : kChunk;
-  uint32_t cv[8];
-  b3::hash_chunk(p, len, c, d.n_chunks == 1, cv);
-  b3::store_cv(cvs + (uint64_t)g * 8, cv);
+}
+
+// K3a: chunk chaining values.  chunk_prefix[b] = first flat chunk index of blob b (n_blobs+1 entries).
+__global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __restrict__ blobs,
+                                                              const uint32_t* __restrict__ chunk_prefix,
+                                                              uint32_t n_blobs, uint32_t total_chunks,
+                                                              const uint8_t* __restrict__ blobs_base,
+                                                              const uint8_t* __restrict__ out_base,
+                                                              uint32_t* cvs) {
+  extern __shared__ __align__(16) uint8_t b3_smem[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* wbuf = b3_smem + warp * kB3SmemPerWarp;
+  const uint32_t n_tiles = (total_chunks + 31u) >> 5;
+  const uint32_t warps_total = gridDim.x * kB3Warps;
+  for (uint32_t tile = blockIdx.x * kB3Warps + warp; tile < n_tiles; tile += warps_total) {
+    const uint32_t g = tile * 32u + lane;
+    const bool act = g < total_chunks;
+    // ---- which chunk of which blob is mine
+    const uint8_t* ptr = nullptr;
+    uint32_t len = 0, ctr = 0;
+    bool root = false;
+    if (act) {
+      uint32_t lo = 0, hi = n_blobs;
+      while (hi - lo > 1) {  // largest b with chunk_prefix[b] <= g
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(chunk_prefix + mid) <= g) lo = mid; else hi = mid;
+      }
+      const BlobDesc d = blobs[lo];
+      ctr = g - __ldg(chunk_prefix + lo);
+      ptr = content_ptr(d, blobs_base, out_base) + (uint64_t)ctr * kChunk;
+      const uint64_t remain = d.dst_cap - (uint64_t)ctr * kChunk;
+      len = remain < kChunk ? (uint32_t)remain : kChunk;
+      root = d.n_chunks == 1;
+    }
+    const uint32_t nblocks = act ? (len == 0 ? 1u : (len + 63u) >> 6) : 0u;
+    uint32_t cv[8];
+    b3::set_iv(cv);
+    // ---- software pipeline over the 8 stages of a chunk
+    __syncwarp();
+    b3_issue_stage(wbuf, ptr, len, 0, lane);
+    cp_async_commit();
+#pragma unroll 1
+    for (uint32_t s = 0; s < kChunk / kB3RowBytes; s++) {
+      uint8_t* cur = wbuf + (s & 1u) * kB3StageBytes;
+      if (s + 1 < kChunk / kB3RowBytes) b3_issue_stage(wbuf + ((s + 1) & 1u) * kB3StageBytes, ptr, len, s + 1, lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const uint4* row = reinterpret_cast<const uint4*>(cur + lane * kB3RowStride);
+#pragma unroll
+      for (uint32_t j = 0; j < kB3RowBytes / 64; j++) {
+        const uint32_t b = s * (kB3RowBytes / 64) + j;
+        if (b < nblocks) {
+          uint32_t m[16];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint4 v = row[j * 4 + k];
+            m[4 * k] = v.x; m[4 * k + 1] = v.y; m[4 * k + 2] = v.z; m[4 * k + 3] = v.w;
+          }
+          const uint32_t n = min(64u, len - b * 64u);
+          if (n < 64u) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              const int vb = (int)n - 4 * k;  // valid bytes in word k
+              m[k] = vb >= 4 ? m[k] : (vb <= 0 ? 0u : (m[k] & (0xFFFFFFFFu >> (8 * (4 - vb)))));
+            }
+          }
+          uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
+          if (b + 1 == nblocks) flags |= b3::CHUNK_END | (root ? b3::ROOT : 0u);
+          b3::compress(cv, m, ctr, 0u, n, flags);
+        }
+      }
+      __syncwarp();  // everyone is done with `cur` before the next iteration's copies land in it
+    }
+    if (act) b3::store_cv(cvs + (uint64_t)g * 8, cv);
+  }
 }
 
 // digest = cv words little-endian; compare with expect and fold into status (decode errors win).
@@ -49,7 +151,7 @@ ZN_D void finish_blob(const BlobDesc& d, uint32_t blob, const uint32_t (&cv)[8],
 // K3b: small blobs (<= kTreeSmallMax chunks): one lane walks the levels of its own blob in place.
 __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restrict__ blobs,
                                                        const uint32_t* __restrict__ list, uint32_t n_list,
-                                                       uint32_t* __restrict__ cvs, uint32_t* __restrict__ digests,
+                                                       uint32_t* cvs, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
                                                        uint32_t* __restrict__ status) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -80,7 +182,7 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
 // K3c: large blobs: one CTA per blob, every level spread over the CTA, in place (read -> barrier -> write).
 __global__ void __launch_bounds__(256) k_b3_tree_large(const BlobDesc* __restrict__ blobs,
                                                        const uint32_t* __restrict__ list,
-                                                       uint32_t* __restrict__ cvs, uint32_t* __restrict__ digests,
+                                                       uint32_t* cvs, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
                                                        uint32_t* __restrict__ status) {
   const uint32_t blob = list[blockIdx.x];
@@ -103,7 +205,7 @@ __global__ void __launch_bounds__(256) k_b3_tree_large(const BlobDesc* __restric
           for (int i = 0; i < 8; i++) o[i] = l[i];
         }
       }
-      __syncthreads();  // all reads of slots [2*j0, 2*j0+2*blockDim) done before slots [j0, j0+blockDim) are overwritten
+      __syncthreads();  // reads of slots [2*j0, 2*j0+2*blockDim) are done before slots [j0, j0+blockDim) are overwritten
       if (act) b3::store_cv(base + (uint64_t)j * 8, o);
     }
     __syncthreads();

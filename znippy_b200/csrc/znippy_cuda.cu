@@ -1,0 +1,558 @@
+// libznippy_cuda.so — host side of the C ABI declared in include/znippy_cuda.h (sm_100a only, no CPU fallback).
+//
+// A zn_ctx owns one device, one stream, device staging buffers and the decode scratch; a zn_plan owns the device
+// descriptor tables of one batch (the index rows blob_offset/blob_size/compressed/uncompressed_size/checksum of
+// znippy-common/src/index.rs:45-52) and can be run any number of times on resident data.  The host-buffer entry
+// points are the plan API wrapped in one H2D copy before and one D2H copy after.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/znippy_cuda.h"
+#include "blake3_kernels.cuh"
+#include "compress_kernels.cuh"
+#include "decode_kernels.cuh"
+
+using namespace zn;
+
+// --------------------------------------------------------------------------------------------- ctx / plan
+struct zn_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  uint8_t* d_lit = nullptr;  // Huffman literal scratch, one slot per decode CTA
+  uint32_t dec_grid = 0;
+  uint8_t* d_in = nullptr;   // staging for the host-buffer API
+  size_t d_in_cap = 0;
+  uint8_t* d_out = nullptr;
+  size_t d_out_cap = 0;
+  CompressScratch cs;        // compressor work space (grown on demand)
+  uint64_t launches = 0;
+  std::string err;
+};
+
+enum PlanKind { PLAN_DECODE_VERIFY = 1, PLAN_HASH = 2 };
+
+struct zn_plan {
+  zn_ctx* ctx = nullptr;
+  int kind = 0;
+  uint32_t n = 0;
+  uint32_t total_chunks = 0;
+  uint32_t n_dec = 0, n_small = 0, n_large = 0, n_pieces = 0;
+  BlobDesc* d_blobs = nullptr;
+  uint32_t* d_chunk_prefix = nullptr;
+  uint32_t *d_list_dec = nullptr, *d_list_small = nullptr, *d_list_large = nullptr;
+  uint32_t *d_piece_blob = nullptr, *d_piece_idx = nullptr;
+  uint32_t *d_cvs = nullptr, *d_digests = nullptr, *d_expect = nullptr, *d_status = nullptr, *d_produced = nullptr,
+           *d_counter = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t last_stream = nullptr;
+  bool ran = false;
+  uint32_t launches_per_run = 0;
+};
+
+static const int kDecodeThreads = 128;
+static const int kDecodeCtasPerSm = 8;
+
+#define ZN_CUDA(ctx, call)                                                              \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      return ZN_E_CUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+extern "C" int zn_abi_version(void) { return ZN_ABI_VERSION; }
+
+extern "C" int zn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" const char* zn_strerror(int code) {
+  switch (code) {
+    case ZN_OK: return "ok";
+    case ZN_E_ARG: return "invalid argument";
+    case ZN_E_CUDA: return "CUDA error";
+    case ZN_E_NOMEM: return "out of memory";
+    case ZN_E_STATE: return "call out of order";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* zn_status_name(uint32_t s) {
+  switch (s) {
+    case ZN_S_OK: return "OK";
+    case ZN_S_DECODE_ERROR: return "DECODE_ERROR";
+    case ZN_S_DIGEST_MISMATCH: return "DIGEST_MISMATCH";
+    case ZN_S_DST_TOO_SMALL: return "DST_TOO_SMALL";
+    case ZN_S_UNSUPPORTED: return "UNSUPPORTED";
+    case ZN_S_SIZE_MISMATCH: return "SIZE_MISMATCH";
+    default: return "?";
+  }
+}
+
+static void build_predef(PredefTables* p) {
+  static zs::FseTable t;
+  uint16_t next[64];
+  zs::fse_build(&t, zs::kLLDefault, 36, 6, next);
+  for (int i = 0; i < 64; i++) p->ll[i] = t.e[i];
+  zs::fse_build(&t, zs::kOFDefault, 29, 5, next);
+  for (int i = 0; i < 32; i++) p->of[i] = t.e[i];
+  zs::fse_build(&t, zs::kMLDefault, 53, 6, next);
+  for (int i = 0; i < 64; i++) p->ml[i] = t.e[i];
+}
+
+extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  zn_ctx* c = new zn_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return nullptr; }
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  c->dec_grid = (uint32_t)(c->sm_count * kDecodeCtasPerSm);
+  if (cudaMalloc(&c->d_lit, (size_t)c->dec_grid * kLitStride) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
+  if (staging_bytes) {
+    if (cudaHostAlloc(&c->pinned, staging_bytes, cudaHostAllocDefault) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
+    c->pinned_bytes = staging_bytes;
+  }
+  PredefTables pd;
+  build_predef(&pd);
+  if (cudaMemcpyToSymbol(g_predef, &pd, sizeof pd) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
+  cudaFuncSetAttribute(k_b3_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Warps * kB3SmemPerWarp);
+  compress_init_attrs();
+  return c;
+}
+
+extern "C" void zn_ctx_destroy(zn_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->d_lit) cudaFree(c->d_lit);
+  if (c->d_in) cudaFree(c->d_in);
+  if (c->d_out) cudaFree(c->d_out);
+  c->cs.release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* zn_last_error(const zn_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+
+extern "C" void* zn_ctx_pinned(zn_ctx* c, size_t* bytes) {
+  if (!c) return nullptr;
+  if (bytes) *bytes = c->pinned_bytes;
+  return c->pinned;
+}
+
+extern "C" uint64_t zn_ctx_kernel_launches(const zn_ctx* c) { return c ? c->launches : 0; }
+
+// --------------------------------------------------------------------------------------------- plans
+template <typename T>
+static bool upload(zn_ctx* c, T** dptr, const T* h, size_t count) {
+  *dptr = nullptr;
+  if (cudaMalloc((void**)dptr, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return false;
+  if (count && h && cudaMemcpyAsync(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+    return false;
+  return true;
+}
+
+static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_off, const uint64_t* src_len,
+                           const uint8_t* compressed, const uint64_t* out_off, const uint64_t* out_len,
+                           const uint8_t* expect, bool gather_raw) {
+  if (!c || (n && (!src_off || !src_len))) return nullptr;
+  cudaSetDevice(c->device);
+  zn_plan* p = new zn_plan();
+  p->ctx = c;
+  p->kind = kind;
+  p->n = n;
+  std::vector<BlobDesc> descs(n);
+  std::vector<uint32_t> prefix(n + 1, 0), ldec, lsmall, llarge, pblob, pidx;
+  uint64_t chunks = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    BlobDesc& d = descs[i];
+    const bool comp = kind == PLAN_DECODE_VERIFY && compressed && compressed[i];
+    d.src_off = src_off[i];
+    d.src_len = src_len[i];
+    d.dst_off = out_off ? out_off[i] : 0;
+    d.dst_cap = kind == PLAN_DECODE_VERIFY ? (out_len ? out_len[i] : 0) : src_len[i];
+    if (!comp && kind == PLAN_DECODE_VERIFY && d.dst_cap != d.src_len) d.dst_cap = d.src_len;  // index invariant
+    const uint64_t nc = std::max<uint64_t>(1, (d.dst_cap + kChunk - 1) / kChunk);
+    d.n_chunks = (uint32_t)nc;
+    d.cv_base = chunks;
+    d.flags = (comp ? F_COMPRESSED : 0u) | (expect ? F_HAS_EXPECT : 0u);
+    prefix[i] = (uint32_t)chunks;
+    chunks += nc;
+    if (chunks > 0xFFFFFFF0ull) { delete p; c->err = "batch too large (chunk count)"; return nullptr; }
+    if (comp) ldec.push_back(i);
+    else if (gather_raw && kind == PLAN_DECODE_VERIFY)
+      for (uint64_t o = 0, k = 0; o < d.dst_cap; o += kGatherPiece, k++) { pblob.push_back(i); pidx.push_back((uint32_t)k); }
+    (nc <= kTreeSmallMax ? lsmall : llarge).push_back(i);
+  }
+  prefix[n] = (uint32_t)chunks;
+  p->total_chunks = (uint32_t)chunks;
+  std::stable_sort(ldec.begin(), ldec.end(), [&](uint32_t a, uint32_t b) { return descs[a].dst_cap > descs[b].dst_cap; });
+  p->n_dec = (uint32_t)ldec.size();
+  p->n_small = (uint32_t)lsmall.size();
+  p->n_large = (uint32_t)llarge.size();
+  p->n_pieces = (uint32_t)pblob.size();
+  bool ok = upload(c, &p->d_blobs, descs.data(), n) && upload(c, &p->d_chunk_prefix, prefix.data(), n + 1) &&
+            upload(c, &p->d_list_dec, ldec.data(), ldec.size()) && upload(c, &p->d_list_small, lsmall.data(), lsmall.size()) &&
+            upload(c, &p->d_list_large, llarge.data(), llarge.size()) &&
+            upload(c, &p->d_piece_blob, pblob.data(), pblob.size()) && upload(c, &p->d_piece_idx, pidx.data(), pidx.size()) &&
+            upload(c, &p->d_expect, (const uint32_t*)expect, expect ? (size_t)n * 8 : 0) &&
+            upload(c, &p->d_cvs, (const uint32_t*)nullptr, (size_t)chunks * 8) &&
+            upload(c, &p->d_digests, (const uint32_t*)nullptr, (size_t)n * 8) &&
+            upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
+            upload(c, &p->d_counter, (const uint32_t*)nullptr, 1);
+  for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
+  if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // host vectors go out of scope
+  if (!ok) {
+    c->err = std::string("plan allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    zn_plan_destroy(p);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" zn_plan* zn_plan_decode_verify(zn_ctx* ctx, uint32_t n, const uint64_t* h_blob_off, const uint64_t* h_blob_len,
+                                          const uint8_t* h_compressed, const uint64_t* h_out_off,
+                                          const uint64_t* h_out_len, const uint8_t* h_expect_digest) {
+  if (n && (!h_out_len || !h_compressed)) return nullptr;
+  return plan_build(ctx, PLAN_DECODE_VERIFY, n, h_blob_off, h_blob_len, h_compressed, h_out_off, h_out_len,
+                    h_expect_digest, h_out_off != nullptr);
+}
+
+extern "C" zn_plan* zn_plan_hash(zn_ctx* ctx, uint32_t n, const uint64_t* h_off, const uint64_t* h_len,
+                                 const uint8_t* h_expect_digest) {
+  return plan_build(ctx, PLAN_HASH, n, h_off, h_len, nullptr, nullptr, nullptr, h_expect_digest, false);
+}
+
+extern "C" void zn_plan_destroy(zn_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  if (p->ran) cudaStreamSynchronize(p->last_stream);
+  void* ptrs[] = {p->d_blobs, p->d_chunk_prefix, p->d_list_dec, p->d_list_small, p->d_list_large, p->d_piece_blob,
+                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  for (auto& e : p->ev)
+    if (e) cudaEventDestroy(e);
+  delete p;
+}
+
+extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, void* stream_v) {
+  if (!p) return ZN_E_ARG;
+  zn_ctx* c = p->ctx;
+  cudaSetDevice(c->device);
+  cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+  if (p->n && !d_blobs) return ZN_E_ARG;
+  if (p->n_dec && !d_out) return ZN_E_ARG;
+  uint32_t launches = 0;
+  ZN_CUDA(c, cudaEventRecord(p->ev[0], st));
+  if (p->n) {
+    ZN_CUDA(c, cudaMemsetAsync(p->d_status, 0, (size_t)p->n * 4, st));
+    ZN_CUDA(c, cudaMemsetAsync(p->d_counter, 0, 4, st));
+  }
+  if (p->n_dec) {
+    const uint32_t grid = std::min<uint32_t>(p->n_dec, c->dec_grid);
+    k_decode<kDecodeThreads><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, p->d_list_dec, p->n_dec, d_blobs, d_out, c->d_lit,
+                                                              p->d_status, p->d_produced, p->d_counter);
+    launches++;
+  }
+  if (p->n_pieces && d_out) {
+    const uint32_t grid = std::min<uint32_t>(p->n_pieces, (uint32_t)c->sm_count * 16u);
+    k_gather_raw<<<grid, 256, 0, st>>>(p->d_blobs, p->d_piece_blob, p->d_piece_idx, p->n_pieces, d_blobs, d_out);
+    launches++;
+  }
+  ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
+  if (p->total_chunks) {
+    const uint32_t tiles = (p->total_chunks + 31u) / 32u;
+    const uint32_t ctas = (tiles + kB3Warps - 1) / kB3Warps;
+    const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * 3u);
+    k_b3_chunks<<<grid, kB3Warps * 32, kB3Warps * kB3SmemPerWarp, st>>>(p->d_blobs, p->d_chunk_prefix, p->n, p->total_chunks,
+                                                                       d_blobs, d_out, p->d_cvs);
+    launches++;
+  }
+  ZN_CUDA(c, cudaEventRecord(p->ev[2], st));
+  if (p->n_small) {
+    k_b3_tree_small<<<(p->n_small + 127) / 128, 128, 0, st>>>(p->d_blobs, p->d_list_small, p->n_small, p->d_cvs, p->d_digests,
+                                                              p->d_expect, p->d_status);
+    launches++;
+  }
+  if (p->n_large) {
+    k_b3_tree_large<<<p->n_large, 256, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_digests, p->d_expect, p->d_status);
+    launches++;
+  }
+  ZN_CUDA(c, cudaEventRecord(p->ev[3], st));
+  ZN_CUDA(c, cudaGetLastError());
+  p->launches_per_run = launches;
+  c->launches += launches;
+  p->last_stream = st;
+  p->ran = true;
+  return ZN_OK;
+}
+
+extern "C" int zn_plan_results(zn_plan* p, uint32_t* h_status, uint8_t* h_digests) {
+  if (!p) return ZN_E_ARG;
+  if (!p->ran) return ZN_E_STATE;
+  zn_ctx* c = p->ctx;
+  cudaSetDevice(c->device);
+  if (h_status && p->n) ZN_CUDA(c, cudaMemcpyAsync(h_status, p->d_status, (size_t)p->n * 4, cudaMemcpyDeviceToHost, p->last_stream));
+  if (h_digests && p->n) ZN_CUDA(c, cudaMemcpyAsync(h_digests, p->d_digests, (size_t)p->n * 32, cudaMemcpyDeviceToHost, p->last_stream));
+  ZN_CUDA(c, cudaStreamSynchronize(p->last_stream));
+  return ZN_OK;
+}
+
+extern "C" uint32_t zn_plan_launches(const zn_plan* p) { return p ? p->launches_per_run : 0; }
+
+extern "C" int zn_plan_last_ms(zn_plan* p, float ms[4]) {
+  if (!p || !ms) return ZN_E_ARG;
+  if (!p->ran) return ZN_E_STATE;
+  zn_ctx* c = p->ctx;
+  cudaSetDevice(c->device);
+  ZN_CUDA(c, cudaEventSynchronize(p->ev[3]));
+  ZN_CUDA(c, cudaEventElapsedTime(&ms[0], p->ev[0], p->ev[3]));
+  ZN_CUDA(c, cudaEventElapsedTime(&ms[1], p->ev[0], p->ev[1]));
+  ZN_CUDA(c, cudaEventElapsedTime(&ms[2], p->ev[1], p->ev[2]));
+  ZN_CUDA(c, cudaEventElapsedTime(&ms[3], p->ev[2], p->ev[3]));
+  return ZN_OK;
+}
+
+// --------------------------------------------------------------------------------------------- host-buffer API
+static int ensure(zn_ctx* c, uint8_t** buf, size_t* cap, size_t need) {
+  need += 256;  // slack for the aligned-word over-reads of the byte movers
+  if (*cap >= need) return ZN_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  const size_t want = need + need / 8;
+  if (cudaMalloc((void**)buf, want) != cudaSuccess) {
+    c->err = "device staging allocation failed";
+    cudaGetLastError();
+    return ZN_E_NOMEM;
+  }
+  *cap = want;
+  return ZN_OK;
+}
+
+// Device layout of a set of host ranges: when the ranges sit compactly inside one span (an archive's blob region,
+// a Magazine slot) the device copy mirrors it and moves with ONE memcpy; otherwise ranges are packed 16-byte aligned.
+struct Layout {
+  bool span = false;
+  uint64_t span_lo = 0, span_bytes = 0;  // host span [span_lo, span_lo + span_bytes)
+  uint64_t total = 0;                    // device bytes
+  std::vector<uint64_t> dev_off;
+};
+
+static Layout make_layout(const uint64_t* off, const uint64_t* len, uint32_t n) {
+  Layout L;
+  L.dev_off.resize(n);
+  uint64_t lo = ~0ull, hi = 0, sum = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    lo = std::min(lo, off[i]);
+    hi = std::max(hi, off[i] + len[i]);
+    sum += len[i];
+  }
+  if (n == 0) return L;
+  bool disjoint = true;
+  if ((hi - lo) <= sum + sum / 4 + 4096) {
+    std::vector<uint32_t> ord(n);
+    std::iota(ord.begin(), ord.end(), 0u);
+    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return off[a] < off[b]; });
+    for (uint32_t k = 1; k < n && disjoint; k++)
+      if (off[ord[k]] < off[ord[k - 1]] + len[ord[k - 1]]) disjoint = false;
+    if (disjoint) {
+      L.span = true;
+      L.span_lo = lo;
+      L.span_bytes = hi - lo;
+      L.total = hi - lo;
+      for (uint32_t i = 0; i < n; i++) L.dev_off[i] = off[i] - lo;
+      return L;
+    }
+  }
+  uint64_t cur = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    L.dev_off[i] = cur;
+    cur += (len[i] + 15) & ~15ull;
+  }
+  L.total = cur;
+  return L;
+}
+
+static int copy_in(zn_ctx* c, uint8_t* d, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t n,
+                   const Layout& L) {
+  if (L.span) {
+    if (L.span_bytes) ZN_CUDA(c, cudaMemcpyAsync(d, base + L.span_lo, L.span_bytes, cudaMemcpyHostToDevice, c->stream));
+    return ZN_OK;
+  }
+  for (uint32_t i = 0; i < n; i++)
+    if (len[i]) ZN_CUDA(c, cudaMemcpyAsync(d + L.dev_off[i], base + off[i], len[i], cudaMemcpyHostToDevice, c->stream));
+  return ZN_OK;
+}
+
+extern "C" int zn_hash_batch(zn_ctx* c, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t n,
+                             uint8_t* digests) {
+  if (!c || (n && (!base || !off || !len || !digests))) return ZN_E_ARG;
+  if (n == 0) return ZN_OK;
+  cudaSetDevice(c->device);
+  Layout L = make_layout(off, len, n);
+  int rc = ensure(c, &c->d_in, &c->d_in_cap, L.total);
+  if (rc) return rc;
+  rc = copy_in(c, c->d_in, base, off, len, n, L);
+  if (rc) return rc;
+  zn_plan* p = zn_plan_hash(c, n, L.dev_off.data(), len, nullptr);
+  if (!p) return ZN_E_NOMEM;
+  rc = zn_plan_run(p, c->d_in, nullptr, nullptr);
+  if (rc == ZN_OK) rc = zn_plan_results(p, nullptr, digests);
+  zn_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int zn_decode_verify_batch(zn_ctx* c, const uint8_t* blobs_base, const uint64_t* blob_off,
+                                      const uint64_t* blob_len, const uint8_t* compressed, const uint64_t* out_len,
+                                      const uint8_t* expect_digest, uint8_t* out_base, const uint64_t* out_off, uint32_t n,
+                                      uint32_t* status, uint8_t* digest_out) {
+  if (!c || (n && (!blobs_base || !blob_off || !blob_len || !compressed || !out_len || !status))) return ZN_E_ARG;
+  if (out_base && n && !out_off) return ZN_E_ARG;
+  if (n == 0) return ZN_OK;
+  cudaSetDevice(c->device);
+  Layout Li = make_layout(blob_off, blob_len, n);
+  // output layout: mirror the caller's when it is compact, so that one D2H copy returns everything
+  Layout Lo;
+  std::vector<uint64_t> zero_off;
+  if (out_base) {
+    Lo = make_layout(out_off, out_len, n);
+  } else {  // verify-only: decoded rows still need device space; store-as-is rows need none
+    std::vector<uint64_t> need(n);
+    for (uint32_t i = 0; i < n; i++) need[i] = compressed[i] ? out_len[i] : 0;
+    Lo.dev_off.resize(n);
+    uint64_t cur = 0;
+    for (uint32_t i = 0; i < n; i++) { Lo.dev_off[i] = cur; cur += (need[i] + 15) & ~15ull; }
+    Lo.total = cur;
+  }
+  int rc = ensure(c, &c->d_in, &c->d_in_cap, Li.total);
+  if (rc) return rc;
+  rc = ensure(c, &c->d_out, &c->d_out_cap, Lo.total);
+  if (rc) return rc;
+  rc = copy_in(c, c->d_in, blobs_base, blob_off, blob_len, n, Li);
+  if (rc) return rc;
+  zn_plan* p = plan_build(c, PLAN_DECODE_VERIFY, n, Li.dev_off.data(), blob_len, compressed, Lo.dev_off.data(), out_len,
+                          expect_digest, out_base != nullptr);
+  if (!p) return ZN_E_NOMEM;
+  rc = zn_plan_run(p, c->d_in, c->d_out, nullptr);
+  if (rc == ZN_OK && out_base) {
+    if (Lo.span) {
+      if (Lo.span_bytes)
+        rc = cudaMemcpyAsync(out_base + Lo.span_lo, c->d_out, Lo.span_bytes, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess
+                 ? ZN_OK : ZN_E_CUDA;
+    } else {
+      for (uint32_t i = 0; i < n && rc == ZN_OK; i++)
+        if (out_len[i] &&
+            cudaMemcpyAsync(out_base + out_off[i], c->d_out + Lo.dev_off[i], out_len[i], cudaMemcpyDeviceToHost, c->stream) !=
+                cudaSuccess)
+          rc = ZN_E_CUDA;
+    }
+    if (rc != ZN_OK) c->err = std::string("D2H: ") + cudaGetErrorString(cudaGetLastError());
+  }
+  if (rc == ZN_OK) rc = zn_plan_results(p, status, digest_out);
+  zn_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int zn_frame_content_size(const uint8_t* blob, size_t len, uint64_t* size_out) {
+  if (!blob || !size_out) return ZN_E_ARG;
+  *size_out = 0;
+  if (len >= 4 && ld32le(blob) == 0x184D2204u) {  // LZ4 frame
+    if (len < 7) return ZN_E_ARG;
+    const uint32_t flg = blob[4];
+    if (!((flg >> 3) & 1)) return 1;
+    if (len < 14) return ZN_E_ARG;
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v |= (uint64_t)blob[6 + i] << (8 * i);
+    *size_out = v;
+    return ZN_OK;
+  }
+  if (len < 5 || ld32le(blob) != 0xFD2FB528u) return ZN_E_ARG;
+  const uint32_t fhd = blob[4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did_flag = fhd & 3;
+  size_t pos = 5 + (single ? 0 : 1) + (did_flag == 3 ? 4 : did_flag);
+  const uint32_t fb = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2u : (fcs_flag == 2 ? 4u : 8u));
+  if (fb == 0) return 1;
+  if (len < pos + fb) return ZN_E_ARG;
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < fb; i++) v |= (uint64_t)blob[pos + i] << (8 * i);
+  if (fb == 2) v += 256;
+  *size_out = v;
+  return ZN_OK;
+}
+
+// --------------------------------------------------------------------------------------------- compression
+extern "C" size_t zn_compress_bound(size_t src_len, int codec) { return compress_bound(src_len, codec); }
+
+extern "C" int zn_compress_batch(zn_ctx* c, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                                 uint32_t n, int level, int codec, uint8_t* dst_base, const uint64_t* dst_off,
+                                 uint64_t* dst_len_out, uint8_t* digest_out, uint32_t* status) {
+  if (!c || (n && (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_len_out || !status))) return ZN_E_ARG;
+  if (codec != ZN_CODEC_ZSTD && codec != ZN_CODEC_LZ4) return ZN_E_ARG;
+  if (n == 0) return ZN_OK;
+  cudaSetDevice(c->device);
+  for (uint32_t i = 0; i < n; i++)
+    if (dst_off[i + 1] < dst_off[i] || dst_off[i + 1] - dst_off[i] < compress_bound(src_len[i], codec)) {
+      c->err = "zn_compress_batch: destination capacity below zn_compress_bound";
+      return ZN_E_ARG;
+    }
+  Layout Li = make_layout(src_off, src_len, n);
+  std::vector<uint64_t> cap(n), doff(n);
+  uint64_t cur = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    cap[i] = compress_bound(src_len[i], codec);
+    doff[i] = cur;
+    cur += (cap[i] + 15) & ~15ull;
+  }
+  int rc = ensure(c, &c->d_in, &c->d_in_cap, Li.total);
+  if (rc) return rc;
+  rc = ensure(c, &c->d_out, &c->d_out_cap, cur);
+  if (rc) return rc;
+  rc = copy_in(c, c->d_in, src_base, src_off, src_len, n, Li);
+  if (rc) return rc;
+  // digest of the ORIGINAL bytes (stream_packer.rs:219) — same kernels as the read side
+  zn_plan* hp = nullptr;
+  if (digest_out) {
+    hp = zn_plan_hash(c, n, Li.dev_off.data(), src_len, nullptr);
+    if (!hp) return ZN_E_NOMEM;
+    rc = zn_plan_run(hp, c->d_in, nullptr, nullptr);
+    if (rc) { zn_plan_destroy(hp); return rc; }
+  }
+  std::vector<uint64_t> out_len(n, 0);
+  uint32_t launches = 0;
+  rc = compress_run(&c->cs, c->stream, c->sm_count, c->d_in, Li.dev_off.data(), src_len, n, level, codec, c->d_out, doff.data(),
+                    cap.data(), out_len.data(), status, &launches, &c->err);
+  c->launches += launches;
+  if (rc == ZN_OK) {
+    for (uint32_t i = 0; i < n && rc == ZN_OK; i++) {
+      dst_len_out[i] = out_len[i];
+      if (status[i] == ZN_S_OK && out_len[i] &&
+          cudaMemcpyAsync(dst_base + dst_off[i], c->d_out + doff[i], out_len[i], cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = ZN_E_CUDA;
+    }
+    if (rc == ZN_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = ZN_E_CUDA;
+    if (rc != ZN_OK) c->err = std::string("compress D2H: ") + cudaGetErrorString(cudaGetLastError());
+  }
+  if (hp) {
+    if (rc == ZN_OK) rc = zn_plan_results(hp, nullptr, digest_out);
+    zn_plan_destroy(hp);
+  }
+  return rc;
+}
