@@ -105,7 +105,28 @@ class Clocks:
     def __init__(self, index: int):
         self.index, self.samples, self.stop, self.t = index, [], False, None
 
+    def _loop_nvml(self, pynvml):
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        R = pynvml
+        bits = [("hw_slowdown", getattr(R, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(R, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = get_reasons(h)
+            self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            time.sleep(0.002)
+
     def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return self._loop_nvml(pynvml)
+        except Exception:
+            pass
         while not self.stop:
             try:
                 r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -145,7 +166,7 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------- reference / cpu baseline arm
-def cpu_pipeline(blobs, lens, digs, min_seconds: float, passes_cap: int = 64):
+def cpu_pipeline(blobs, lens, digs, min_seconds: float, passes_cap: int = 100000):
     """The reference's read worker loop on host cores (oracle/cpu_pipeline.c: libzstd + SIMD blake3, atomic row
     cursor, N = ceil(0.9*cores) threads as common_config.rs:34).  Returns (GB/s, threads, sample description)."""
     import oracle as O
@@ -221,10 +242,12 @@ def run_ours(args):
     comp = np.ones(n, np.uint8)
 
     ctx = Ctx(local, staging_bytes=out_bytes + in_buf.size + (1 << 20))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-default) stream: kernels and the timing events share it
+    torch.cuda.set_stream(stream)
     d_in = torch.from_numpy(in_buf).cuda()
     d_out = torch.empty(out_bytes + 256, dtype=torch.uint8, device="cuda")
     plan = Plan.decode_verify(ctx, in_off, in_len, comp, out_off, out_len, digs)
+    plan.set_overlap(args.groups)  # decode of row range g+1 overlaps blake3 of range g (znippy_cuda.h)
 
     def step():
         plan.run(d_in.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
@@ -253,7 +276,9 @@ def run_ours(args):
         e1.record(stream)
         sync_all()
         dev_ms = e0.elapsed_time(e1)
-        # per-stage times of single steps (each plan run brackets its stages with events on the same stream)
+        # per-kernel times: the same step with the stages back to back on one stream (no overlap), each bracketed by
+        # CUDA events on that stream inside zn_plan_run
+        plan.set_overlap(1)
         for _ in range(args.steps):
             step()
             stage_ms += np.array(plan.last_ms())
@@ -261,6 +286,10 @@ def run_ours(args):
     clocks = clk.summary()
     st, _ = plan.results()
     assert not st.any()
+    serial_launches = plan.launches()
+    plan.set_overlap(args.groups)
+    step()
+    torch.cuda.synchronize()
     launches = plan.launches() * args.steps
 
     # ---- end to end: host buffers in pinned memory, H2D + kernels + D2H inside the timed region
@@ -323,7 +352,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
         "config": {"workload": f"configs[1]: single {args.gib:g} GiB text-pattern file per GPU = {n} rows x 8 MiB slices, "
                                "zstd L19 frames (libzstd 1.5.5), decode + blake3 + 32-byte compare, output materialised in HBM",
-                   "rows_per_gpu": n, "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"},
+                   "rows_per_gpu": n, "schedule": f"{args.groups} row groups, decode(g+1) overlaps blake3(g) on 2 streams",
+                   "serial_ms_per_step": round(float(stage_ms[0]), 4), "serial_launches_per_step": serial_launches,
+                   "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": blob_bytes + 32 * n,
                 "d2h_bytes_per_step": out_bytes + 36 * n, "steps": e2e_steps,
@@ -336,10 +367,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=2.0, help="uncompressed GiB per GPU (2 = BASELINE configs[1])")
+    ap.add_argument("--groups", type=int, default=4, help="row groups of the overlapped decode/hash schedule (1 = serial)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()

@@ -28,9 +28,11 @@
  * every entry point that computes runs CUDA kernels, and fails with ZN_E_CUDA when no device is usable.
  *
  * Blob wire formats accepted by the decoder (self-identifying by magic): Zstandard frames (RFC 8878, magic
- * 28 B5 2F FD; several concatenated frames and skippable frames allowed) and LZ4 frames (magic 04 22 4D 18,
- * independent blocks).  The OpenZL envelope the reference writes around those payloads is NOT parsed (its layout
- * is unpinned in this environment); such blobs get ZN_S_UNSUPPORTED.
+ * 28 B5 2F FD; several concatenated frames and skippable frames allowed; no dictionaries) and LZ4 frames (magic
+ * 04 22 4D 18, independent or linked blocks).  The optional XXH64 / XXH32 content and block checksums of those frames
+ * are skipped, not verified: integrity on this path is the blake3 digest.  The OpenZL envelope the reference writes
+ * around those payloads is NOT parsed (its layout is unpinned in this environment); such blobs get
+ * ZN_S_UNSUPPORTED.
  */
 #ifndef ZNIPPY_CUDA_H
 #define ZNIPPY_CUDA_H
@@ -59,7 +61,7 @@ enum {
   ZN_S_DECODE_ERROR = 1,     /* corrupt / truncated compressed data (reference: codec Err -> row skipped) */
   ZN_S_DIGEST_MISMATCH = 2,  /* decoded fine, blake3 != expected (reference: corrupt_bytes / corrupt_rows) */
   ZN_S_DST_TOO_SMALL = 3,    /* decoded size exceeds the capacity given in out_len[] */
-  ZN_S_UNSUPPORTED = 4,      /* unknown magic, dictionary id, linked LZ4 blocks, reserved bits */
+  ZN_S_UNSUPPORTED = 4,      /* unknown magic, dictionary id, reserved bits, blob >= 4 GiB */
   ZN_S_SIZE_MISMATCH = 5     /* decoded size != out_len[] (index uncompressed_size) or != frame content size */
 };
 
@@ -136,6 +138,11 @@ void zn_plan_destroy(zn_plan* plan);
 int zn_plan_run(zn_plan* plan, const uint8_t* d_blobs, uint8_t* d_out, void* stream);
 /* Waits for the last run and copies results back. status / digests nullable. */
 int zn_plan_results(zn_plan* plan, uint32_t* h_status, uint8_t* h_digests);
+/* Schedule of a decode+verify plan.  groups <= 1: decode, then hash, then tree, back to back on one stream (per-stage
+ * times of zn_plan_last_ms are then exact).  groups > 1 (default 4 for batches >= 256 MiB; env ZN_OVERLAP_GROUPS):
+ * rows are cut into `groups` contiguous ranges and the HBM-bound decode of range g+1 overlaps the ALU-bound blake3 of
+ * range g on a second stream of the context. */
+int zn_plan_set_overlap(zn_plan* plan, int groups);
 /* kernels launched by one zn_plan_run of this plan */
 uint32_t zn_plan_launches(const zn_plan* plan);
 /* device time of the most recent completed run, per stage, in ms (CUDA events on the run's stream):

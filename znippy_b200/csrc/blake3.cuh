@@ -30,14 +30,23 @@ ZN_D uint32_t rotr8(uint32_t x) { return __byte_perm(x, x, 0x0321); }
 ZN_D uint32_t rotr12(uint32_t x) { return __funnelshift_r(x, x, 12); }
 ZN_D uint32_t rotr7(uint32_t x) { return __funnelshift_r(x, x, 7); }
 
-#define ZN_G(a, b, c, d, mx, my) \
-  a = a + b + (mx);              \
-  d = rotr16(d ^ a);             \
-  c = c + d;                     \
-  b = rotr12(b ^ c);             \
-  a = a + b + (my);              \
-  d = rotr8(d ^ a);              \
-  c = c + d;                     \
+// Pipe balance (measured with tools/ubench_b3.cu on B200): xor / rotate can only issue on the ALU pipe, which is the
+// binding limit of this function; the message add is therefore written as a multiply-add by an opaque 1 so that it
+// goes to the otherwise idle FMA pipe (IMAD) instead of becoming a 3-input IADD3 on the ALU pipe.  +19 % throughput.
+ZN_D uint32_t add_fma(uint32_t x, uint32_t one, uint32_t acc) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(acc));
+  return d;
+}
+
+#define ZN_G(a, b, c, d, mx, my)   \
+  a = add_fma((mx), one, a + b);   \
+  d = rotr16(d ^ a);               \
+  c = c + d;                       \
+  b = rotr12(b ^ c);               \
+  a = add_fma((my), one, a + b);   \
+  d = rotr8(d ^ a);                \
+  c = c + d;                       \
   b = rotr7(b ^ c);
 
 #define ZN_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
@@ -50,9 +59,10 @@ ZN_D uint32_t rotr7(uint32_t x) { return __funnelshift_r(x, x, 7); }
   ZN_G(v2, v7, v8, v13, m[s12], m[s13])                                                \
   ZN_G(v3, v4, v9, v14, m[s14], m[s15])
 
-// cv <- compress(cv, m, counter, block_len, flags)[0..8]
+// cv <- compress(cv, m, counter, block_len, flags)[0..8].  `one` must be the value 1 held in a register the compiler
+// cannot see through (a kernel argument).
 ZN_D void compress(uint32_t (&cv)[8], const uint32_t (&m)[16], uint32_t ctr_lo, uint32_t ctr_hi,
-                   uint32_t block_len, uint32_t flags) {
+                   uint32_t block_len, uint32_t flags, uint32_t one) {
   uint32_t v0 = cv[0], v1 = cv[1], v2 = cv[2], v3 = cv[3], v4 = cv[4], v5 = cv[5], v6 = cv[6], v7 = cv[7];
   uint32_t v8 = ZN_IV0, v9 = ZN_IV1, v10 = ZN_IV2, v11 = ZN_IV3;
   uint32_t v12 = ctr_lo, v13 = ctr_hi, v14 = block_len, v15 = flags;
@@ -119,7 +129,7 @@ ZN_D void load_block_partial(const uint8_t* __restrict__ p, uint32_t n, uint32_t
 }
 
 // Chaining value of one chunk: `len` in 0..1024 bytes at p, chunk counter `ctr`; `root` marks a single-chunk input.
-ZN_D void hash_chunk(const uint8_t* __restrict__ p, uint32_t len, uint64_t ctr, bool root, uint32_t (&cv)[8]) {
+ZN_D void hash_chunk(const uint8_t* __restrict__ p, uint32_t len, uint64_t ctr, bool root, uint32_t (&cv)[8], uint32_t one) {
   set_iv(cv);
   const uint32_t nblocks = len == 0 ? 1u : (len + 63u) >> 6;
   const uint32_t clo = (uint32_t)ctr, chi = (uint32_t)(ctr >> 32);
@@ -131,17 +141,17 @@ ZN_D void hash_chunk(const uint8_t* __restrict__ p, uint32_t len, uint64_t ctr, 
     if (b + 1 == nblocks) flags |= CHUNK_END | (root ? ROOT : 0u);
     if (n == 64) load_block_full(p + b * 64u, m);
     else load_block_partial(p + b * 64u, n, m);
-    compress(cv, m, clo, chi, n, flags);
+    compress(cv, m, clo, chi, n, flags, one);
   }
 }
 
 // parent node: cv_out = compress(IV, left || right, 0, 64, PARENT [| ROOT])
-ZN_D void parent(const uint32_t (&l)[8], const uint32_t (&r)[8], bool root, uint32_t (&out)[8]) {
+ZN_D void parent(const uint32_t (&l)[8], const uint32_t (&r)[8], bool root, uint32_t (&out)[8], uint32_t one) {
   uint32_t m[16];
 #pragma unroll
   for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = r[i]; }
   set_iv(out);
-  compress(out, m, 0, 0, 64, PARENT | (root ? ROOT : 0u));
+  compress(out, m, 0, 0, 64, PARENT | (root ? ROOT : 0u), one);
 }
 
 ZN_D void load_cv(const uint32_t* p, uint32_t (&cv)[8]) {

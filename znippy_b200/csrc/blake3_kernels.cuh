@@ -34,13 +34,24 @@ template <int N>
 ZN_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Stage `stage_idx` (bytes [stage_idx*128, +128) of each of the warp's 32 chunks) -> shared memory.
-// ptr/len are this lane's chunk; rows are other lanes' chunks, fetched by shuffle.
-ZN_D void b3_issue_stage(uint8_t* buf, const uint8_t* ptr, uint32_t len, uint32_t stage_idx, uint32_t lane) {
+// ptr/len are this lane's chunk; rows are other lanes' chunks, fetched by shuffle.  `regular` (warp-uniform) = the 32
+// chunks are full, 16-byte aligned and contiguous in memory (the common case inside a large blob): rows are then
+// addressed from lane 0's pointer without any shuffle.
+ZN_D void b3_issue_stage(uint8_t* buf, const uint8_t* ptr, uint32_t len, uint32_t stage_idx, uint32_t lane, bool regular,
+                         const uint8_t* base0) {
   const uint32_t q = lane & 7u;          // quad inside the row
   const uint32_t sub = lane >> 3;        // row inside the issue group
+  const uint32_t base = stage_idx * kB3RowBytes + q * 16u;
+  if (regular) {
+#pragma unroll
+    for (int it = 0; it < 32 / kB3RowsPerIssue; it++) {
+      const uint32_t row = it * kB3RowsPerIssue + sub;
+      cp_async16(buf + row * kB3RowStride + q * 16u, base0 + (size_t)row * kChunk + base);
+    }
+    return;
+  }
   const uint32_t ptr_lo = (uint32_t)reinterpret_cast<uintptr_t>(ptr);
   const uint32_t ptr_hi = (uint32_t)(reinterpret_cast<uintptr_t>(ptr) >> 32);
-  const uint32_t base = stage_idx * kB3RowBytes + q * 16u;
 #pragma unroll
   for (int it = 0; it < 32 / kB3RowsPerIssue; it++) {
     const uint32_t row = it * kB3RowsPerIssue + sub;
@@ -52,29 +63,36 @@ ZN_D void b3_issue_stage(uint8_t* buf, const uint8_t* ptr, uint32_t len, uint32_
     if (base + 16u <= rlen && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
       cp_async16(dst, src);
     } else if (base < rlen) {  // unaligned source or the blob's last, partial quad: assemble from byte loads
-      uint32_t w[4] = {0, 0, 0, 0};
       const uint32_t nb = min(16u, rlen - base);
-      for (uint32_t j = 0; j < nb; j++) w[j >> 2] |= (uint32_t)__ldg(src + j) << (8 * (j & 3));
-      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < 4; j++) {
+        if (j < nb) w0 |= (uint32_t)__ldg(src + j) << (8 * j);
+        if (j + 4 < nb) w1 |= (uint32_t)__ldg(src + j + 4) << (8 * j);
+        if (j + 8 < nb) w2 |= (uint32_t)__ldg(src + j + 8) << (8 * j);
+        if (j + 12 < nb) w3 |= (uint32_t)__ldg(src + j + 12) << (8 * j);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
     }
   }
 }
 
-// K3a: chunk chaining values.  chunk_prefix[b] = first flat chunk index of blob b (n_blobs+1 entries).
+// K3a: chunk chaining values of the flat chunks [chunk_lo, chunk_hi).  chunk_prefix[b] = first flat chunk index of
+// blob b (n_blobs+1 entries).
 __global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __restrict__ blobs,
                                                               const uint32_t* __restrict__ chunk_prefix,
-                                                              uint32_t n_blobs, uint32_t total_chunks,
+                                                              uint32_t n_blobs, uint32_t chunk_lo, uint32_t chunk_hi,
                                                               const uint8_t* __restrict__ blobs_base,
                                                               const uint8_t* __restrict__ out_base,
-                                                              uint32_t* cvs) {
+                                                              uint32_t* cvs, uint32_t one) {
   extern __shared__ __align__(16) uint8_t b3_smem[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint8_t* wbuf = b3_smem + warp * kB3SmemPerWarp;
-  const uint32_t n_tiles = (total_chunks + 31u) >> 5;
+  const uint32_t n_tiles = (chunk_hi - chunk_lo + 31u) >> 5;
   const uint32_t warps_total = gridDim.x * kB3Warps;
   for (uint32_t tile = blockIdx.x * kB3Warps + warp; tile < n_tiles; tile += warps_total) {
-    const uint32_t g = tile * 32u + lane;
-    const bool act = g < total_chunks;
+    const uint32_t g = chunk_lo + tile * 32u + lane;
+    const bool act = g < chunk_hi;
     // ---- which chunk of which blob is mine
     const uint8_t* ptr = nullptr;
     uint32_t len = 0, ctr = 0;
@@ -96,13 +114,18 @@ __global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __r
     uint32_t cv[8];
     b3::set_iv(cv);
     // ---- software pipeline over the 8 stages of a chunk
+    const uint8_t* base0 = reinterpret_cast<const uint8_t*>(
+        ((uintptr_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(reinterpret_cast<uintptr_t>(ptr) >> 32), 0) << 32) |
+        __shfl_sync(0xFFFFFFFFu, (uint32_t)reinterpret_cast<uintptr_t>(ptr), 0));
+    const bool regular = __all_sync(0xFFFFFFFFu, act && len == kChunk && ptr == base0 + (size_t)lane * kChunk) &&
+                         (reinterpret_cast<uintptr_t>(base0) & 15) == 0;
     __syncwarp();
-    b3_issue_stage(wbuf, ptr, len, 0, lane);
+    b3_issue_stage(wbuf, ptr, len, 0, lane, regular, base0);
     cp_async_commit();
 #pragma unroll 1
     for (uint32_t s = 0; s < kChunk / kB3RowBytes; s++) {
       uint8_t* cur = wbuf + (s & 1u) * kB3StageBytes;
-      if (s + 1 < kChunk / kB3RowBytes) b3_issue_stage(wbuf + ((s + 1) & 1u) * kB3StageBytes, ptr, len, s + 1, lane);
+      if (s + 1 < kChunk / kB3RowBytes) b3_issue_stage(wbuf + ((s + 1) & 1u) * kB3StageBytes, ptr, len, s + 1, lane, regular, base0);
       cp_async_commit();
       cp_async_wait<1>();
       __syncwarp();
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __r
           }
           uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
           if (b + 1 == nblocks) flags |= b3::CHUNK_END | (root ? b3::ROOT : 0u);
-          b3::compress(cv, m, ctr, 0u, n, flags);
+          b3::compress(cv, m, ctr, 0u, n, flags, one);
         }
       }
       __syncwarp();  // everyone is done with `cur` before the next iteration's copies land in it
@@ -153,7 +176,7 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
                                                        const uint32_t* __restrict__ list, uint32_t n_list,
                                                        uint32_t* cvs, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
-                                                       uint32_t* __restrict__ status) {
+                                                       uint32_t* __restrict__ status, uint32_t one) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_list) return;
   const uint32_t blob = list[t];
@@ -166,7 +189,7 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
     for (uint32_t j = 0; j < pairs; j++) {
       b3::load_cv(base + (uint64_t)(2 * j) * 8, l);
       b3::load_cv(base + (uint64_t)(2 * j + 1) * 8, r);
-      b3::parent(l, r, n == 2, o);
+      b3::parent(l, r, n == 2, o, one);
       b3::store_cv(base + (uint64_t)j * 8, o);
     }
     if (n & 1) {
@@ -184,7 +207,7 @@ __global__ void __launch_bounds__(256) k_b3_tree_large(const BlobDesc* __restric
                                                        const uint32_t* __restrict__ list,
                                                        uint32_t* cvs, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
-                                                       uint32_t* __restrict__ status) {
+                                                       uint32_t* __restrict__ status, uint32_t one) {
   const uint32_t blob = list[blockIdx.x];
   const BlobDesc d = blobs[blob];
   uint32_t* base = cvs + d.cv_base * 8;
@@ -199,7 +222,7 @@ __global__ void __launch_bounds__(256) k_b3_tree_large(const BlobDesc* __restric
         b3::load_cv(base + (uint64_t)(2 * j) * 8, l);
         if (j < pairs) {
           b3::load_cv(base + (uint64_t)(2 * j + 1) * 8, r);
-          b3::parent(l, r, n == 2, o);
+          b3::parent(l, r, n == 2, o, one);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; i++) o[i] = l[i];

@@ -99,16 +99,18 @@ ZN_HD uint32_t lz4_compress_block(const Warp& w, const uint8_t* in, uint32_t n, 
       const uint32_t v = valid ? ld32le(in + p) : 0u;
       const uint32_t h = hash4(v, kLz4HashLog);
       const uint32_t cand = valid ? tab[h] : 0u;
-      w_sync(w);
-      if (valid) tab[h] = (uint16_t)p;
-      w_sync(w);
       const bool ok = valid && cand < p && ld32le(in + cand) == v;
       const uint32_t m = w_ballot(w, ok);
+      const uint32_t f = m ? ffs32(m) - 1u : w.n;
+      // insert only the positions up to the match: later lanes are looked up again next step (or lie inside the
+      // match) and must not find themselves in the table instead of their real candidate
+      w_sync(w);
+      if (valid && w.lane <= f) tab[h] = (uint16_t)p;
+      w_sync(w);
       if (!m) {
         pos += w.n;
         continue;
       }
-      const uint32_t f = ffs32(m) - 1u;
       const uint32_t mp = pos + f, mc = w_shfl(w, cand, f);
       const uint32_t ml = 4u + match_extend(w, in + mp + 4, in + mc + 4, matchlimit - (mp + 4));
       // ---- emit: token, literal length, literals, offset, match length
@@ -245,8 +247,6 @@ struct BitWriter {
   }
 };
 
-ZN_HD uint32_t ll_code(uint32_t ll) { return ll < 16 ? ll : (ll < 64 ? 0 : 0) + 0; }  // placeholder, see below
-
 // code of a literal length / match length: the code c with base[c] <= v < base[c] + 2^bits[c]
 ZN_HD uint32_t len_code(uint32_t v, const uint32_t* base, const uint8_t* bits, uint32_t direct, uint32_t ncodes) {
   if (v < direct + base[0]) return v - base[0];
@@ -275,8 +275,9 @@ struct FseCState {
 // packed sequence: ll | ml << 20 | off << 40 (each < 2^20)
 ZN_HD uint64_t seq_pack(uint32_t ll, uint32_t ml, uint32_t off) { return (uint64_t)ll | ((uint64_t)ml << 20) | ((uint64_t)off << 40); }
 
-// Sequences section with predefined tables.  One thread.  Returns bytes written.
-ZN_HD uint32_t zstd_encode_sequences(uint8_t* dst, const uint64_t* seqs, uint32_t nseq) {
+// Sequences section with predefined tables.  One thread.  Returns bytes written, or 0 as soon as the section
+// would exceed `limit` bytes (the block is then stored raw); the writer overshoots `limit` by < 16 bytes.
+ZN_HD uint32_t zstd_encode_sequences(uint8_t* dst, const uint64_t* seqs, uint32_t nseq, uint32_t limit) {
   uint8_t* p = dst;
   if (nseq < 128) *p++ = (uint8_t)nseq;
   else if (nseq < 0x7F00) { *p++ = (uint8_t)((nseq >> 8) + 128); *p++ = (uint8_t)nseq; }
@@ -308,6 +309,7 @@ ZN_HD uint32_t zstd_encode_sequences(uint8_t* dst, const uint64_t* seqs, uint32_
     bw.flush();
     bw.add(ofb - (1u << oc), oc);
     bw.flush();
+    if ((uint32_t)(bw.p - dst) > limit) return 0;
   }
   sm.flush(bw, &ct->ml);
   bw.flush();
@@ -344,16 +346,16 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       const uint32_t v = valid ? ld32le(in + p) : 0u;
       const uint32_t h = hash4(v, kZstdHashLog);
       const uint32_t cand = valid ? tab[h] : 0xFFFFFFFFu;
-      w_sync(w);
-      if (valid) tab[h] = p;
-      w_sync(w);
       const bool ok = valid && cand < p && ld32le(in + cand) == v;
       const uint32_t m = w_ballot(w, ok);
+      const uint32_t f = m ? ffs32(m) - 1u : w.n;
+      w_sync(w);
+      if (valid && w.lane <= f) tab[h] = p;  // see lz4_compress_block
+      w_sync(w);
       if (!m) {
         pos += w.n;
         continue;
       }
-      const uint32_t f = ffs32(m) - 1u;
       const uint32_t mp = pos + f, mc = w_shfl(w, cand, f);
       const uint32_t ml = 4u + match_extend(w, in + mp + 4, in + mc + 4, end - (mp + 4));
       const uint32_t ll = mp - anchor;
@@ -377,14 +379,16 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
     if (hs == 1) hp[0] = (uint8_t)(nlit << 3);
     else if (hs == 2) { hp[0] = (uint8_t)(0x04 | ((nlit & 0xF) << 4)); hp[1] = (uint8_t)(nlit >> 4); }
     else { hp[0] = (uint8_t)(0x0C | ((nlit & 0xF) << 4)); hp[1] = (uint8_t)(nlit >> 4); hp[2] = (uint8_t)(nlit >> 12); }
-    // worst case of the sequences section: 4 header bytes + ~7 bytes per sequence; must fit the slot and beat raw
-    if ((uint64_t)hs + nlit + 4u + 8ull * nseq + 8u < (uint64_t)n)
-      total = hs + nlit + zstd_encode_sequences(lit + nlit, seqs, nseq);
+    // the block must beat its raw form, which also keeps the section inside the slot
+    if (hs + nlit + 16u < n) {
+      const uint32_t ss = zstd_encode_sequences(lit + nlit, seqs, nseq, n - (hs + nlit) - 16u);
+      if (ss) total = hs + nlit + ss;
+    }
   }
   total = w_shfl(w, total, 0);
   w_sync(w);
   *payload_off = 3 - hs;
-  return total < n ? total : 0u;
+  return (total && total < n) ? total : 0u;
 }
 
 // Zstandard frame header: single segment, 8-byte content size (13 bytes); empty content uses the 1-byte form.

@@ -25,6 +25,7 @@ struct zn_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // hash stream of the overlapped schedule
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   uint8_t* d_lit = nullptr;  // Huffman literal scratch, one slot per decode CTA
@@ -55,6 +56,18 @@ struct zn_plan {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool ran = false;
+  bool big_blobs = false;
+  // overlapped schedule: blobs are cut into `groups` contiguous index ranges; group g+1 decodes (HBM-bound) on the
+  // caller's stream while group g is hashed (int-ALU-bound) on the context's second stream
+  static const int kMaxGroups = 16;
+  int groups = 1;
+  uint32_t grp_dec_off[kMaxGroups + 1] = {0};
+  uint32_t grp_chunk_lo[kMaxGroups + 1] = {0};
+  cudaEvent_t evg[kMaxGroups] = {nullptr};
+  cudaEvent_t ev_join = nullptr;
+  std::vector<uint64_t> h_cap;
+  std::vector<uint8_t> h_comp;
+  std::vector<uint32_t> h_prefix;
   uint32_t launches_per_run = 0;
 };
 
@@ -121,7 +134,8 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return nullptr; }
   c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->dec_grid = (uint32_t)(c->sm_count * kDecodeCtasPerSm);
   if (cudaMalloc(&c->d_lit, (size_t)c->dec_grid * kLitStride) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
   if (staging_bytes) {
@@ -146,6 +160,7 @@ extern "C" void zn_ctx_destroy(zn_ctx* c) {
   c->cs.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
 }
 
@@ -167,6 +182,49 @@ static bool upload(zn_ctx* c, T** dptr, const T* h, size_t count) {
   if (count && h && cudaMemcpyAsync(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
     return false;
   return true;
+}
+
+// (Re)builds the decode work list for `groups` contiguous blob-index ranges of equal decoded bytes: within a group
+// blobs are ordered largest first (dynamic work counter), groups are laid out back to back.
+static int plan_set_groups(zn_plan* p, int groups) {
+  zn_ctx* c = p->ctx;
+  const uint32_t n = p->n;
+  if (groups < 1) groups = 1;
+  if (groups > zn_plan::kMaxGroups) groups = zn_plan::kMaxGroups;
+  if (p->n_dec < 8u * (uint32_t)groups) groups = 1;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; i++) total += p->h_cap[i];
+  std::vector<uint32_t> ldec;
+  ldec.reserve(p->n_dec);
+  uint32_t b0 = 0;
+  uint64_t acc = 0;
+  p->grp_dec_off[0] = 0;
+  p->grp_chunk_lo[0] = 0;
+  for (int g = 0; g < groups; g++) {
+    uint32_t b1 = b0;
+    const uint64_t target = total * (uint64_t)(g + 1) / (uint64_t)groups;
+    while (b1 < n && (g + 1 == groups || acc + p->h_cap[b1] <= target || b1 == b0)) acc += p->h_cap[b1++];
+    const size_t first = ldec.size();
+    for (uint32_t i = b0; i < b1; i++)
+      if (p->h_comp[i]) ldec.push_back(i);
+    std::stable_sort(ldec.begin() + first, ldec.end(), [&](uint32_t a, uint32_t b) { return p->h_cap[a] > p->h_cap[b]; });
+    p->grp_dec_off[g + 1] = (uint32_t)ldec.size();
+    p->grp_chunk_lo[g + 1] = p->h_prefix[b1];
+    b0 = b1;
+  }
+  p->groups = groups;
+  if (!ldec.empty()) {
+    ZN_CUDA(c, cudaMemcpyAsync(p->d_list_dec, ldec.data(), ldec.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    ZN_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return ZN_OK;
+}
+
+extern "C" int zn_plan_set_overlap(zn_plan* p, int groups) {
+  if (!p) return ZN_E_ARG;
+  cudaSetDevice(p->ctx->device);
+  if (p->ran) cudaStreamSynchronize(p->last_stream);
+  return plan_set_groups(p, groups);
 }
 
 static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_off, const uint64_t* src_len,
@@ -200,11 +258,19 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     else if (gather_raw && kind == PLAN_DECODE_VERIFY)
       for (uint64_t o = 0, k = 0; o < d.dst_cap; o += kGatherPiece, k++) { pblob.push_back(i); pidx.push_back((uint32_t)k); }
     (nc <= kTreeSmallMax ? lsmall : llarge).push_back(i);
+    p->h_cap.push_back(d.dst_cap);
+    p->h_comp.push_back(comp ? 1 : 0);
   }
   prefix[n] = (uint32_t)chunks;
+  p->h_prefix = prefix;
   p->total_chunks = (uint32_t)chunks;
   std::stable_sort(ldec.begin(), ldec.end(), [&](uint32_t a, uint32_t b) { return descs[a].dst_cap > descs[b].dst_cap; });
   p->n_dec = (uint32_t)ldec.size();
+  {
+    uint64_t dec_bytes = 0;
+    for (uint32_t i : ldec) dec_bytes += descs[i].dst_cap;
+    p->big_blobs = !ldec.empty() && dec_bytes / ldec.size() >= (512u << 10);
+  }
   p->n_small = (uint32_t)lsmall.size();
   p->n_large = (uint32_t)llarge.size();
   p->n_pieces = (uint32_t)pblob.size();
@@ -216,9 +282,22 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_cvs, (const uint32_t*)nullptr, (size_t)chunks * 8) &&
             upload(c, &p->d_digests, (const uint32_t*)nullptr, (size_t)n * 8) &&
             upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
-            upload(c, &p->d_counter, (const uint32_t*)nullptr, 1);
+            upload(c, &p->d_counter, (const uint32_t*)nullptr, zn_plan::kMaxGroups);
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < zn_plan::kMaxGroups; i++) ok = cudaEventCreateWithFlags(&p->evg[i], cudaEventDisableTiming) == cudaSuccess;
+  if (ok) ok = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) == cudaSuccess;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // host vectors go out of scope
+  if (ok) {
+    // default schedule: overlap decode and hash when the batch is large enough to pipeline
+    uint64_t dec_bytes = 0;
+    for (uint32_t i = 0; i < n; i++) dec_bytes += p->h_comp[i] ? p->h_cap[i] : 0;
+    int g = 1;
+    if (dec_bytes >= (256ull << 20)) {
+      const char* e = getenv("ZN_OVERLAP_GROUPS");
+      g = e ? atoi(e) : 4;
+    }
+    ok = plan_set_groups(p, g) == ZN_OK;
+  }
   if (!ok) {
     c->err = std::string("plan allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     zn_plan_destroy(p);
@@ -250,6 +329,9 @@ extern "C" void zn_plan_destroy(zn_plan* p) {
     if (q) cudaFree(q);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : p->evg)
+    if (e) cudaEventDestroy(e);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
 }
 
@@ -264,36 +346,58 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
   ZN_CUDA(c, cudaEventRecord(p->ev[0], st));
   if (p->n) {
     ZN_CUDA(c, cudaMemsetAsync(p->d_status, 0, (size_t)p->n * 4, st));
-    ZN_CUDA(c, cudaMemsetAsync(p->d_counter, 0, 4, st));
-  }
-  if (p->n_dec) {
-    const uint32_t grid = std::min<uint32_t>(p->n_dec, c->dec_grid);
-    k_decode<kDecodeThreads><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, p->d_list_dec, p->n_dec, d_blobs, d_out, c->d_lit,
-                                                              p->d_status, p->d_produced, p->d_counter);
-    launches++;
+    ZN_CUDA(c, cudaMemsetAsync(p->d_counter, 0, 4 * zn_plan::kMaxGroups, st));
   }
   if (p->n_pieces && d_out) {
     const uint32_t grid = std::min<uint32_t>(p->n_pieces, (uint32_t)c->sm_count * 16u);
     k_gather_raw<<<grid, 256, 0, st>>>(p->d_blobs, p->d_piece_blob, p->d_piece_idx, p->n_pieces, d_blobs, d_out);
     launches++;
   }
-  ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
-  if (p->total_chunks) {
-    const uint32_t tiles = (p->total_chunks + 31u) / 32u;
-    const uint32_t ctas = (tiles + kB3Warps - 1) / kB3Warps;
-    const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * 3u);
-    k_b3_chunks<<<grid, kB3Warps * 32, kB3Warps * kB3SmemPerWarp, st>>>(p->d_blobs, p->d_chunk_prefix, p->n, p->total_chunks,
-                                                                       d_blobs, d_out, p->d_cvs);
-    launches++;
+  const bool overlap = p->groups > 1;
+  for (int g = 0; g < p->groups; g++) {
+    const uint32_t nd = p->grp_dec_off[g + 1] - p->grp_dec_off[g];
+    if (nd) {
+      const uint32_t* list = p->d_list_dec + p->grp_dec_off[g];
+      if (p->big_blobs) {  // few large blobs: wider teams (more bytes in flight per blob)
+        const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
+        k_decode<256><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+                                            p->d_counter + g);
+      } else {
+        const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid);
+        k_decode<kDecodeThreads><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                                  p->d_produced, p->d_counter + g);
+      }
+      launches++;
+    }
+    if (g + 1 == p->groups) ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
+    const uint32_t clo = p->grp_chunk_lo[g], chi = p->grp_chunk_lo[g + 1];
+    if (chi > clo) {
+      cudaStream_t hs = st;
+      if (overlap) {
+        ZN_CUDA(c, cudaEventRecord(p->evg[g], st));
+        ZN_CUDA(c, cudaStreamWaitEvent(c->stream2, p->evg[g], 0));
+        hs = c->stream2;
+      }
+      const uint32_t tiles = (chi - clo + 31u) / 32u;
+      const uint32_t ctas = (tiles + kB3Warps - 1) / kB3Warps;
+      const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * 3u);
+      k_b3_chunks<<<grid, kB3Warps * 32, kB3Warps * kB3SmemPerWarp, hs>>>(p->d_blobs, p->d_chunk_prefix, p->n, clo, chi, d_blobs,
+                                                                         d_out, p->d_cvs, 1u);
+      launches++;
+    }
+  }
+  if (overlap) {
+    ZN_CUDA(c, cudaEventRecord(p->ev_join, c->stream2));
+    ZN_CUDA(c, cudaStreamWaitEvent(st, p->ev_join, 0));
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[2], st));
   if (p->n_small) {
     k_b3_tree_small<<<(p->n_small + 127) / 128, 128, 0, st>>>(p->d_blobs, p->d_list_small, p->n_small, p->d_cvs, p->d_digests,
-                                                              p->d_expect, p->d_status);
+                                                              p->d_expect, p->d_status, 1u);
     launches++;
   }
   if (p->n_large) {
-    k_b3_tree_large<<<p->n_large, 256, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_digests, p->d_expect, p->d_status);
+    k_b3_tree_large<<<p->n_large, 256, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_digests, p->d_expect, p->d_status, 1u);
     launches++;
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[3], st));

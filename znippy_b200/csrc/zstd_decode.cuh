@@ -231,9 +231,8 @@ ZN_HD uint32_t decode_literals(const Team& t, DecShared* sh, const uint8_t* p, u
 // One of the three sequence tables (RFC 8878 §3.1.1.3.2.1).  Called by thread 0 only.  Returns false on error.
 ZN_HD bool setup_seq_table(FseTable* t, uint32_t mode, const uint8_t*& q, const uint8_t* end, int max_log, int max_sym,
                            const uint32_t* predef, int predef_log, DecShared* sh) {
-  if (mode == 0) {
-    const int n = 1 << predef_log;
-    for (int i = 0; i < n; i++) t->e[i] = predef[i];
+  if (mode == 0) {  // entries were copied by the whole team (decode_block)
+    (void)predef;
     t->log = (uint32_t)predef_log;
     t->valid = 1;
     return true;
@@ -319,6 +318,7 @@ ZN_HD uint32_t decode_seq_batch(DecShared* sh, SeqDecoder& d, uint32_t first, ui
 // rep[] = repeat-offset history carried across the blocks of a frame (team-uniform copy in every thread)
 struct FrameState {
   uint32_t rep0, rep1, rep2;
+  uint32_t predef;  // bit0/1/2: the LL/OF/ML table in shared memory currently holds the predefined distribution
 };
 
 // Compressed block.  Team-uniform.  Advances es.pos.
@@ -342,9 +342,19 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
     const uint32_t modes = *q++;
     if (modes & 3) return S_DECODE_ERROR;
     SeqDecoder d;
-    // -- tables + initial states (thread 0); outcome in sh->err_tab
+    const PredefTables* pd = predef_tables();
+    // -- predefined tables: copied by the whole team, and only when the table does not already hold them
+    {
+      const uint32_t mll = modes >> 6, mof = (modes >> 4) & 3, mml = (modes >> 2) & 3;
+      if (mll == 0 && !(fs.predef & 1u)) for (uint32_t i = t.tid; i < 64; i += t.n) sh->ll.e[i] = pd->ll[i];
+      if (mof == 0 && !(fs.predef & 2u)) for (uint32_t i = t.tid; i < 32; i += t.n) sh->of.e[i] = pd->of[i];
+      if (mml == 0 && !(fs.predef & 4u)) for (uint32_t i = t.tid; i < 64; i += t.n) sh->ml.e[i] = pd->ml[i];
+      if (mll != 3) fs.predef = (fs.predef & ~1u) | (mll == 0 ? 1u : 0u);
+      if (mof != 3) fs.predef = (fs.predef & ~2u) | (mof == 0 ? 2u : 0u);
+      if (mml != 3) fs.predef = (fs.predef & ~4u) | (mml == 0 ? 4u : 0u);
+    }
+    // -- other table modes + initial states (thread 0); outcome in sh->err_tab
     if (t.tid == 0) {
-      const PredefTables* pd = predef_tables();
       uint32_t e = S_OK;
       const uint8_t* qq = q;
       if (!setup_seq_table(&sh->ll, modes >> 6, qq, end, 9, 35, pd->ll, 6, sh) ||
@@ -450,6 +460,7 @@ ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, u
     const uint32_t block_max = window < kZstdBlockMax ? (uint32_t)window : kZstdBlockMax;
     FrameState fs;
     fs.rep0 = 1; fs.rep1 = 4; fs.rep2 = 8;
+    fs.predef = 0;
     team_sync(t);  // nobody may still be using the previous frame's tables
     if (t.tid == 0) sh->huf.valid = sh->ll.valid = sh->of.valid = sh->ml.valid = 0;
     team_sync(t);
