@@ -1,0 +1,124 @@
+"""The reference's integration tests (tests/tests/integration_test.rs, repro_crate.rs) restated against the GPU-backed
+host loops of znippy_b200.archive: compress_stream -> .znippy v0.7 -> decompress_archive / verify / extract_file."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A():
+    from znippy_b200 import archive, codec
+    codec.default_ctx()
+    return archive
+
+
+def _pack(A, tmp_path, entries, no_skip=False, **kw):
+    sc = A.compress_stream(str(tmp_path / "out.znippy"), no_skip, **kw)
+    for path, data in entries:
+        sc.sender().send(A.ArchiveEntry(path, data))
+    rep = sc.finish()
+    return sc.output, rep
+
+
+def test_single_small_file_roundtrip(A, tmp_path):  # integration_test.rs:38-67
+    content = b"Hello, znippy! This is a test of streaming compression.\n" * 4
+    path, rep = _pack(A, tmp_path, [("hello.txt", content)])
+    assert rep.total_files == 1 and rep.chunks == 1
+    out = tmp_path / "x"
+    vr = A.decompress_archive(path, True, str(out))
+    assert vr.total_files == 1 and vr.verified_files == 1 and vr.corrupt_files == 0 and vr.chunks == 1
+    assert (out / "hello.txt").read_bytes() == content
+
+
+def test_multiple_files_and_empty_file(A, tmp_path):  # :69-131
+    entries = [(f"dir/file_{i}.txt", (f"content of file {i}\n" * (i + 1)).encode()) for i in range(10)] + [("empty.txt", b"")]
+    path, rep = _pack(A, tmp_path, entries)
+    t = A.read_znippy_index(path)
+    assert t.num_rows == 11  # empty file -> exactly one row (stream_packer.rs:169-183)
+    vr = A.decompress_archive(path, True, str(tmp_path / "x"))
+    assert vr.total_files == 11 and vr.corrupt_files == 0
+    for p, d in entries:
+        assert (tmp_path / "x" / p).read_bytes() == d
+
+
+def test_large_file_is_cut_at_8mib_and_reassembles(A, tmp_path):  # :133-158 and :616-642
+    data = (np.arange(12 * 1024 * 1024, dtype=np.uint32) % 251).astype(np.uint8).tobytes()
+    path, rep = _pack(A, tmp_path, [("big.bin", data)])
+    t = A.read_znippy_index(path)
+    assert t.num_rows >= 2 and t.column("chunk_seq").to_pylist() == [0, 1]
+    assert t.column("fdata_offset").to_pylist() == [0, 8 << 20]
+    ar = A.ZnippyArchive.open(path)
+    assert ar.contains("big.bin") and ar.file_size("big.bin") == len(data)
+    assert ar.extract_file("big.bin") == data
+    with pytest.raises(KeyError):
+        ar.extract_file("nope")
+    vr = A.decompress_archive(path, True, str(tmp_path / "x"))
+    assert vr.chunks == 2 and (tmp_path / "x" / "big.bin").read_bytes() == data
+
+
+def test_skip_list_and_no_skip(A, tmp_path):  # :160-210
+    png = bytes(np.random.default_rng(0).integers(0, 256, 5000, dtype=np.uint8))
+    path, rep = _pack(A, tmp_path, [("image.png", png), ("a.txt", b"abc" * 100)])
+    t = A.read_znippy_index(path)
+    rows = dict(zip(t.column("relative_path").to_pylist(), t.column("compressed").to_pylist()))
+    assert rows == {"image.png": False, "a.txt": True}
+    sizes = dict(zip(t.column("relative_path").to_pylist(), t.column("blob_size").to_pylist()))
+    assert sizes["image.png"] == 5000
+    (tmp_path / "ns").mkdir()
+    path2, _ = _pack(A, tmp_path / "ns", [("image.png", png)], no_skip=True)
+    assert A.read_znippy_index(path2).column("compressed").to_pylist() == [True]
+    assert A.ZnippyArchive.open(path2).extract_file("image.png") == png
+
+
+def test_empty_archive(A, tmp_path):  # :212-223
+    path, rep = _pack(A, tmp_path, [])
+    assert rep.total_files == 0
+    vr = A.verify_archive_integrity(path)
+    assert vr.total_files == 0 and vr.chunks == 0
+
+
+def test_verify_detects_corruption(A, tmp_path, oracle):  # :414-443 + fault injection
+    text = oracle.real_text(300_000).tobytes()
+    jar = bytes(np.random.default_rng(1).integers(0, 256, 40_000, dtype=np.uint8))
+    path, _ = _pack(A, tmp_path, [("t.txt", text), ("lib.jar", jar), ("u.txt", text[:1000])])
+    assert A.verify_archive_integrity(path).verified_files == 3
+    t = A.read_znippy_index(path)
+    rows = {p: (o, s) for p, o, s in zip(t.column("relative_path").to_pylist(), t.column("blob_offset").to_pylist(),
+                                         t.column("blob_size").to_pylist())}
+    raw = bytearray(open(path, "rb").read())
+    raw[rows["lib.jar"][0] + 100] ^= 0x40        # store-as-is row: digest mismatch
+    open(path, "wb").write(raw)
+    vr = A.verify_archive_integrity(path)
+    assert vr.corrupt_files == 1 and vr.verified_files == 2 and vr.corrupt_bytes == 40_000 and vr.chunks == 3
+    raw[rows["t.txt"][0] + rows["t.txt"][1] // 2] ^= 0x01  # compressed row: decode error (row skipped) or mismatch
+    open(path, "wb").write(raw)
+    vr = A.verify_archive_integrity(path)
+    assert vr.chunks == 3 and vr.verified_bytes == 1000 and vr.total_bytes in (41_000, 341_000)
+
+
+def test_repro_incompressible_blobs(A, tmp_path, oracle):  # repro_crate.rs:19-66, scaled to 600 blobs
+    entries = []
+    for i in range(600):
+        n = 1000 + (i * 7919) % 99_000
+        entries.append((f"crates/c{i}.crate", oracle.gen_incompressible(n, i).tobytes()))
+    path, rep = _pack(A, tmp_path, entries, no_skip=True)
+    vr = A.decompress_archive(path, False, "/dev/null")
+    assert vr.corrupt_files == 0 and vr.chunks == 600
+    ar = A.ZnippyArchive.open(path)
+    some = [entries[i] for i in range(0, 600, 137)]
+    got = ar.extract_files([p for p, _ in some])
+    for (p, d), g in zip(some, got):
+        assert g == d
+
+
+def test_lz4_archive(A, tmp_path, oracle):
+    from znippy_b200 import codec
+    entries = [("a.txt", oracle.real_text(200_000).tobytes()), ("b.bin", oracle.gen_binary(9 << 20).tobytes())]
+    path, _ = _pack(A, tmp_path, entries, codec_id=codec.CODEC_LZ4)
+    vr = A.decompress_archive(path, True, str(tmp_path / "x"))
+    assert vr.corrupt_files == 0 and vr.chunks == 3
+    for p, d in entries:
+        assert (tmp_path / "x" / p).read_bytes() == d

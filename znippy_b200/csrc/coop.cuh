@@ -10,6 +10,8 @@ namespace zn {
 constexpr uint32_t kPatWords = 144;   // periodic-match pattern buffer: periods <= kPatMaxOff plus 20 bytes run-out
 constexpr uint32_t kPatMaxOff = 512;
 constexpr uint32_t kShortCopy = 48;   // below this a copy is one byte per thread
+constexpr uint32_t kTileBytes = 16384;  // shared-memory tile that long periodic matches are bulk-stored from
+constexpr uint32_t kBulkMin = 4096;     // shortest periodic match that takes the bulk-store path
 
 struct Team {
   uint32_t tid, n;
@@ -18,6 +20,17 @@ struct Team {
 #if defined(__CUDA_ARCH__)
 
 ZN_D void team_sync(const Team&) { __syncthreads(); }
+
+// ---- TMA bulk stores (cp.async.bulk shared -> global): one instruction moves up to a whole tile, so a 128 KiB
+// periodic match is ~8 instructions from one thread instead of 8192 STG.128 spread over the team.
+ZN_D void bulk_store(uint8_t* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(__cvta_generic_to_global(gdst)),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+ZN_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+ZN_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+ZN_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // 16 bytes from any alignment, assembled from aligned 32-bit words (the extra word always overlaps valid bytes)
 ZN_D uint4 load16_any(const uint8_t* s) {
@@ -68,14 +81,52 @@ ZN_D void team_fill(const Team& t, uint8_t* dst, uint32_t byte, uint32_t n) {
 // it started: no ordering between the team's stores is needed.  Precondition: the window is final and visible to
 // the team (the caller barriers when it was written since the last barrier).  `pat` = kPatWords of shared memory.
 // Contains team_sync() on the small-period path, so every thread of the team must call it with the same arguments.
-ZN_D void team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uint32_t* pat) {
+// `tile` = kTileBytes of 128-byte aligned shared memory.  Returns true when part of the match was issued as bulk
+// (async-proxy) stores that are still in flight: the caller must bulk_wait_all() + barrier before anyone reads those
+// bytes or before tile / pat are rewritten (zstd_decode.cuh: mem_sync).
+ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uint32_t* pat, uint8_t* tile) {
   if (off >= ml) {
     team_copy(t, dst, dst - off, ml);
-    return;
+    return false;
   }
   if (ml <= kShortCopy) {
     for (uint32_t i = t.tid; i < ml; i += t.n) dst[i] = dst[(int32_t)(i % off) - (int32_t)off];
-    return;
+    return false;
+  }
+  if (off <= kPatMaxOff && ml >= kBulkMin) {
+    // The aligned body of the match is periodic with period lcm(off, 16): build one tile holding a whole number of
+    // such periods in shared memory, then bulk-store the same tile back to back over the body.
+    uint8_t* pat8 = reinterpret_cast<uint8_t*>(pat);
+    for (uint32_t x = t.tid; x < off + 20; x += t.n) pat8[x] = dst[(int32_t)(x % off) - (int32_t)off];
+    __syncthreads();
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
+    const uint32_t body = (ml - head) & ~15u;
+    const uint32_t g = min(16u, off & (0u - off));      // gcd(off, 16)
+    const uint32_t period = off * (16u / g);             // lcm(off, 16) <= 8192
+    const uint32_t tlen = period * (kTileBytes / period);
+    const uint32_t fill = min(tlen, body);
+    {
+      uint32_t phase = (head + 16u * t.tid) % off;
+      const uint32_t step = (16u * t.n) % off;
+      uint4* tv = reinterpret_cast<uint4*>(tile);
+      for (uint32_t v = t.tid; v < (fill >> 4); v += t.n) {
+        const uint32_t sh = (phase & 3) * 8, wi = phase >> 2;
+        const uint32_t w0 = pat[wi], w1 = pat[wi + 1], w2 = pat[wi + 2], w3 = pat[wi + 3], w4 = pat[wi + 4];
+        tv[v] = make_uint4(funnel_r(w0, w1, sh), funnel_r(w1, w2, sh), funnel_r(w2, w3, sh), funnel_r(w3, w4, sh));
+        phase += step;
+        if (phase >= off) phase -= off;
+      }
+    }
+    if (t.tid < head) dst[t.tid] = pat8[t.tid % off];
+    const uint32_t k = head + body + t.tid;
+    if (k < ml) dst[k] = pat8[k % off];
+    fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      for (uint32_t o = 0; o < body; o += tlen) bulk_store(dst + head + o, tile, min(tlen, body - o));
+      bulk_commit();
+    }
+    return true;
   }
   const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
   const uint32_t nvec = (ml - head) >> 4;
@@ -99,7 +150,7 @@ ZN_D void team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     }
     const uint32_t k = head + (nvec << 4) + t.tid;
     if (k < ml) dst[k] = pat8[k % off];
-    return;
+    return false;
   }
   // long period: gather straight from the window in global memory
   const uint8_t* win = dst - off;
@@ -124,6 +175,7 @@ ZN_D void team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
   }
   const uint32_t k = head + (nvec << 4) + t.tid;
   if (k < ml) dst[k] = win[k % off];
+  return false;
 }
 
 #else  // ------------------------------------------------------------------ host emulation (team of one)
@@ -135,9 +187,11 @@ inline void team_copy(const Team&, uint8_t* dst, const uint8_t* src, uint32_t n)
 inline void team_fill(const Team&, uint8_t* dst, uint32_t byte, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) dst[i] = (uint8_t)byte;
 }
-inline void team_match(const Team&, uint8_t* dst, uint32_t off, uint32_t ml, uint32_t*) {
+inline bool team_match(const Team&, uint8_t* dst, uint32_t off, uint32_t ml, uint32_t*, uint8_t*) {
   for (uint32_t i = 0; i < ml; i++) dst[i] = dst[(int64_t)i - (int64_t)off];
+  return false;
 }
+inline void bulk_wait_all() {}
 
 #endif
 

@@ -11,7 +11,7 @@ constexpr uint32_t kLitStride = kZstdBlockMax + 256;  // per-CTA Huffman literal
 constexpr uint32_t kSrcStage = 8192;                  // blobs up to this size are parsed out of shared memory
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_decode(const BlobDesc* __restrict__ blobs, const uint32_t* __restrict__ list,
+__global__ void __launch_bounds__(NT, 512 / NT) k_decode(const BlobDesc* __restrict__ blobs, const uint32_t* __restrict__ list,
                                                uint32_t n_list, const uint8_t* blobs_base, uint8_t* out_base,
                                                uint8_t* lit_scratch, uint32_t* status, uint32_t* produced,
                                                uint32_t* work_counter) {
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(NT) k_decode(const BlobDesc* __restrict__ blob
       st = decode_blob(t, &sh, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, lit, &got);
       if (st == S_OK && got != (uint32_t)d.dst_cap) st = S_SIZE_MISMATCH;
     }
+    if (threadIdx.x == 0) bulk_wait_all();  // bulk stores read sh.tile: drain before the next blob (or exit) reuses it
     __syncthreads();  // every path out of decode_blob is team-uniform; this also fences the blob's last stores
     if (threadIdx.x == 0) {
       status[blob] = st;

@@ -108,7 +108,7 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
     const uint32_t n = sh->rep_pub[0], done = sh->rep_pub[1];
     zs::exec_batch(t, sh, n, out, p, -1, es);
     team_sync(t);
-    es.wm = es.pos;
+    if (!es.bulk) es.wm = es.pos;
     if (done) break;
   }
   return S_OK;
@@ -138,7 +138,7 @@ ZN_HD uint32_t decode_frame(const Team& t, DecShared* sh, const uint8_t* src, ui
   if ((uint8_t)(xxh32_short(src + 4, ip - 4) >> 8) != src[ip]) return S_DECODE_ERROR;
   ip += 1;
   zs::ExecState es;
-  es.pos = 0; es.wm = 0;
+  es.pos = 0; es.wm = 0; es.bulk = 0;
   for (;;) {
     if (src_len - ip < 4) return S_DECODE_ERROR;
     const uint32_t w = ld32le(src + ip);

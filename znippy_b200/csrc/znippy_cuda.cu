@@ -72,7 +72,7 @@ struct zn_plan {
 };
 
 static const int kDecodeThreads = 128;
-static const int kDecodeCtasPerSm = 8;
+static const int kDecodeCtasPerSm = 4;  // resident k_decode<128> CTAs per SM (128 regs, 42 KB smem); <256>: half
 
 #define ZN_CUDA(ctx, call)                                                              \
   do {                                                                                  \

@@ -34,6 +34,7 @@ struct DecShared {
   zs::HufTable huf;
   zs::FseTable ll, of, ml, wt;  // wt: scratch table for FSE-compressed Huffman weights
   SeqRec ring[kSeqBatch];
+  alignas(128) uint8_t tile[kTileBytes];  // bulk-store source of long periodic matches (coop.cuh)
   uint32_t pat[kPatWords];
   uint16_t next[256];
   int16_t norm[64];
@@ -81,9 +82,20 @@ namespace zs {
 
 // cursors of one frame that thread 0's sequence decoder and the executors both advance
 struct ExecState {
-  uint32_t pos;  // next output byte (relative to the blob's output start)
-  uint32_t wm;   // bytes below wm were written before the team's last barrier
+  uint32_t pos;   // next output byte (relative to the blob's output start)
+  uint32_t wm;    // bytes below wm were written, and are visible to the team, since its last memory barrier
+  uint32_t bulk;  // bulk (async-proxy) stores are in flight: they cover bytes at or above wm only
 };
+
+// Barrier after which every byte written so far is visible to the whole team (and tile / pat may be rewritten).
+ZN_HD void mem_sync(const Team& t, ExecState& es) {
+  if (es.bulk) {
+    if (t.tid == 0) bulk_wait_all();
+    es.bulk = 0;
+  }
+  team_sync(t);
+  es.wm = es.pos;
+}
 
 // Executes ring[0..n): literal copy then match copy per sequence.  Team-uniform.
 ZN_HD void exec_batch(const Team& t, DecShared* sh, uint32_t n, uint8_t* out, const uint8_t* lit_base, int lit_rle,
@@ -98,11 +110,8 @@ ZN_HD void exec_batch(const Team& t, DecShared* sh, uint32_t n, uint8_t* out, co
     if (s.ml) {
       const uint32_t src_lo = es.pos - s.off;
       const uint32_t src_hi = s.off >= s.ml ? src_lo + s.ml : es.pos;
-      if (src_hi > es.wm) {
-        team_sync(t);
-        es.wm = es.pos;
-      }
-      team_match(t, out + es.pos, s.off, s.ml, sh->pat);
+      if (src_hi > es.wm) mem_sync(t, es);
+      if (team_match(t, out + es.pos, s.off, s.ml, sh->pat, sh->tile)) es.bulk = 1;
       es.pos += s.ml;
     }
   }
@@ -390,8 +399,8 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
       team_sync(t);
       if (sh->err_seq != S_OK) return sh->err_seq;
       exec_batch(t, sh, count, out, li.base, li.rle, es);
-      team_sync(t);  // ring, err_seq and pat are rewritten by the next batch
-      es.wm = es.pos;
+      team_sync(t);  // ring and err_seq are rewritten by the next batch
+      if (!es.bulk) es.wm = es.pos;
     }
     fs.rep0 = sh->rep_pub[0]; fs.rep1 = sh->rep_pub[1]; fs.rep2 = sh->rep_pub[2];
     lit_pos = sh->lit_pub;
@@ -416,6 +425,7 @@ ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, u
   ExecState es;
   es.pos = 0;
   es.wm = 0;
+  es.bulk = 0;
   *produced = 0;
   if (src_len == 0) return S_DECODE_ERROR;
   while (ip < src_len) {
