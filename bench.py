@@ -292,28 +292,39 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = plan.launches() * args.steps
 
-    # ---- end to end: host buffers in pinned memory, H2D + kernels + D2H inside the timed region
+    # ---- end to end through the reference-facing call, HOST buffers in pinned memory (zn_ctx_pinned), every step:
+    #   verify  (the metric: `znippy verify` / decompress_archive(save_data=false), decompress.rs:135-184 without :186-189)
+    #           H2D blobs + expected digests, kernels, D2H statuses + digests
+    #   extract (save_data=true): additionally D2H of every decoded byte — PCIe-bound by construction
     pinned = ctx.pinned()
     h_in = pinned[: in_buf.size]
     h_in[:] = in_buf
     h_out = pinned[in_buf.size + 4096 - in_buf.size % 4096:][:out_bytes]
-    e2e_steps = max(1, min(args.steps, 5))
-    codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)  # warm (allocations)
+    e2e_steps = max(3, min(args.steps, 20))
+    codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)  # warm (allocations)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        est, edg = codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert not est.any() and (edg == digs).all()
+    x_steps = 3
+    codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(x_steps):
         est, _ = codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    x_s = (time.perf_counter() - t0) / x_steps
     assert not est.any()
-    # spot-check the bytes that came back
-    assert bytes(h_out[:45]) == text_slice((rank * total) % len(PHRASE), 45).tobytes()
+    assert bytes(h_out[:45]) == text_slice((rank * total) % len(PHRASE), 45).tobytes()  # spot-check returned bytes
 
     # ---- reduce: max time over ranks
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s * 1e3, x_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    dev_ms, e2e_ms, x_ms = float(times[0]), float(times[1]), float(times[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,7 +333,8 @@ def run_ours(args):
     peak, peak_src = peaks()
     ms_per_step = dev_ms / args.steps
     value = world * out_bytes / (ms_per_step * 1e-3) / 1e9
-    e2e_value = world * out_bytes / (e2e_ms * 1e-3 / e2e_steps) / 1e9
+    e2e_value = world * out_bytes / (e2e_ms * 1e-3) / 1e9
+    x_value = world * out_bytes / (x_ms * 1e-3) / 1e9
     blob_bytes = int(in_len.sum())
     # dominant kernel: the largest stage
     k_decode_bytes = blob_bytes + out_bytes            # blob read + uncompressed written
@@ -356,9 +368,12 @@ def run_ours(args):
                    "serial_ms_per_step": round(float(stage_ms[0]), 4), "serial_launches_per_step": serial_launches,
                    "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": blob_bytes + 32 * n,
-                "d2h_bytes_per_step": out_bytes + 36 * n, "steps": e2e_steps,
-                "api": "zn_decode_verify_batch (pinned host buffers from zn_ctx_pinned)"},
+        "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": blob_bytes + 32 * n + 33 * n,
+                "d2h_bytes_per_step": 36 * n, "steps": e2e_steps, "ms_per_step": round(e2e_ms, 4),
+                "api": "zn_decode_verify_batch, verify-only (out_base=NULL): pinned host blobs + digests in, statuses + "
+                       "digests out, timed with the host clock around the calls",
+                "extract": {"value": round(x_value, 3), "unit": "GB/s", "d2h_bytes_per_step": out_bytes + 36 * n,
+                            "steps": x_steps, "note": "save_data=true: every decoded byte returns over PCIe"}},
         "roofline": roofline, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

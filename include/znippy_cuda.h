@@ -139,7 +139,7 @@ int zn_plan_run(zn_plan* plan, const uint8_t* d_blobs, uint8_t* d_out, void* str
 /* Waits for the last run and copies results back. status / digests nullable. */
 int zn_plan_results(zn_plan* plan, uint32_t* h_status, uint8_t* h_digests);
 /* Schedule of a decode+verify plan.  groups <= 1: decode, then hash, then tree, back to back on one stream (per-stage
- * times of zn_plan_last_ms are then exact).  groups > 1 (default 4 for batches >= 256 MiB; env ZN_OVERLAP_GROUPS):
+ * times of zn_plan_last_ms are then exact).  groups > 1 (opt-in; env ZN_OVERLAP_GROUPS sets the default for batches >= 256 MiB):
  * rows are cut into `groups` contiguous ranges and the HBM-bound decode of range g+1 overlaps the ALU-bound blake3 of
  * range g on a second stream of the context. */
 int zn_plan_set_overlap(zn_plan* plan, int groups);

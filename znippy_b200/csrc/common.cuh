@@ -11,6 +11,10 @@
 #define ZN_D inline
 #endif
 
+#ifndef ZN_TP
+#define ZN_TP(id) do {} while (0)  // phase trace points, only live in tools/trace_decode.cu
+#endif
+
 namespace zn {
 
 // per-blob status values; must match include/znippy_cuda.h

@@ -12,6 +12,7 @@ constexpr uint32_t kPatMaxOff = 512;
 constexpr uint32_t kShortCopy = 48;   // below this a copy is one byte per thread
 constexpr uint32_t kTileBytes = 16384;  // shared-memory tile that long periodic matches are bulk-stored from
 constexpr uint32_t kBulkMin = 4096;     // shortest periodic match that takes the bulk-store path
+constexpr uint32_t kBulkIssuers = 32;   // threads that may issue (and must therefore wait for) bulk stores
 
 struct Team {
   uint32_t tid, n;
@@ -44,7 +45,16 @@ ZN_D uint4 load16_any(const uint8_t* s) {
   return make_uint4(funnel_r(w0, w1, sh), funnel_r(w1, w2, sh), funnel_r(w2, w3, sh), funnel_r(w3, w4, sh));
 }
 
+// 16 bytes at byte address (aligned word pointer q, bit shift sh = 8 * misalignment), sh != 0
+ZN_D uint4 load16_shift(const uint32_t* q, uint32_t sh) {
+  const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+  return make_uint4(funnel_r(w0, w1, sh), funnel_r(w1, w2, sh), funnel_r(w2, w3, sh), funnel_r(w3, w4, sh));
+}
+
 // dst[0..n) = src[0..n).  Every source byte is final and visible to the team; dst does not feed src.
+// The vector body keeps kCopyUnroll 16-byte loads in flight per thread before the first store: a lone CTA copying
+// 128 KiB would otherwise pay one full memory round trip per 4 KiB.
+constexpr int kCopyUnroll = 8;
 ZN_D void team_copy(const Team& t, uint8_t* dst, const uint8_t* src, uint32_t n) {
   if (n <= kShortCopy) {
     for (uint32_t i = t.tid; i < n; i += t.n) dst[i] = src[i];
@@ -55,8 +65,48 @@ ZN_D void team_copy(const Team& t, uint8_t* dst, const uint8_t* src, uint32_t n)
   const uint32_t nvec = (n - head) >> 4;
   const uint8_t* s = src + head;
   uint4* d = reinterpret_cast<uint4*>(dst + head);
-#pragma unroll 4
-  for (uint32_t v = t.tid; v < nvec; v += t.n) d[v] = load16_any(s + 16u * v);
+  const uintptr_t sa = reinterpret_cast<uintptr_t>(s);
+  uint32_t v = t.tid;
+  if ((sa & 3) == 0) {  // word-aligned source: 128-bit (or 4 x 32-bit) loads
+    if ((sa & 15) == 0) {
+      const uint4* q = reinterpret_cast<const uint4*>(s);
+      for (; v + (kCopyUnroll - 1) * t.n < nvec; v += kCopyUnroll * t.n) {
+        uint4 r[kCopyUnroll];
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) r[u] = q[v + u * t.n];
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) d[v + u * t.n] = r[u];
+      }
+      for (; v < nvec; v += t.n) d[v] = q[v];
+    } else {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(s);
+      for (; v + (kCopyUnroll - 1) * t.n < nvec; v += kCopyUnroll * t.n) {
+        uint4 r[kCopyUnroll];
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) {
+          const uint32_t* w = q + 4u * (v + u * t.n);
+          r[u] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) d[v + u * t.n] = r[u];
+      }
+      for (; v < nvec; v += t.n) {
+        const uint32_t* w = q + 4u * v;
+        d[v] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  } else {  // byte-misaligned source: aligned words + funnel shifts (the extra word always overlaps valid bytes)
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(sa & 3) * 8;
+    for (; v + (kCopyUnroll / 2 - 1) * t.n < nvec; v += (kCopyUnroll / 2) * t.n) {
+      uint4 r[kCopyUnroll / 2];
+#pragma unroll
+      for (int u = 0; u < kCopyUnroll / 2; u++) r[u] = load16_shift(q + 4u * (v + u * t.n), sh);
+#pragma unroll
+      for (int u = 0; u < kCopyUnroll / 2; u++) d[v + u * t.n] = r[u];
+    }
+    for (; v < nvec; v += t.n) d[v] = load16_shift(q + 4u * v, sh);
+  }
   const uint32_t k = head + (nvec << 4) + t.tid;
   if (k < n) dst[k] = src[k];
 }
@@ -99,6 +149,7 @@ ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     uint8_t* pat8 = reinterpret_cast<uint8_t*>(pat);
     for (uint32_t x = t.tid; x < off + 20; x += t.n) pat8[x] = dst[(int32_t)(x % off) - (int32_t)off];
     __syncthreads();
+    ZN_TP(10);
     const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
     const uint32_t body = (ml - head) & ~15u;
     const uint32_t g = min(16u, off & (0u - off));      // gcd(off, 16)
@@ -122,10 +173,15 @@ ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     if (k < ml) dst[k] = pat8[k % off];
     fence_async_smem();
     __syncthreads();
-    if (t.tid == 0) {
-      for (uint32_t o = 0; o < body; o += tlen) bulk_store(dst + head + o, tile, min(tlen, body - o));
-      bulk_commit();
+    ZN_TP(11);
+    // one bulk store per thread (bulk groups are per thread: mem_sync makes threads < kBulkIssuers wait)
+    for (uint32_t o = t.tid * tlen; o < body; o += kBulkIssuers * tlen) {
+      if (t.tid < kBulkIssuers) {
+        bulk_store(dst + head + o, tile, min(tlen, body - o));
+        bulk_commit();
+      }
     }
+    ZN_TP(12);
     return true;
   }
   const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
@@ -152,29 +208,9 @@ ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     if (k < ml) dst[k] = pat8[k % off];
     return false;
   }
-  // long period: gather straight from the window in global memory
-  const uint8_t* win = dst - off;
-  if (t.tid < head) dst[t.tid] = win[t.tid];  // head < 16 < off
-  uint32_t phase = (head + 16u * t.tid) % off;
-  uint4* dv = reinterpret_cast<uint4*>(dst + head);
-  for (uint32_t v = t.tid; v < nvec; v += t.n) {
-    if (phase + 16u <= off) {
-      dv[v] = load16_any(win + phase);
-    } else {
-      uint32_t w[4] = {0, 0, 0, 0};
-      uint32_t p = phase;
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        w[j >> 2] |= (uint32_t)win[p] << (8 * (j & 3));
-        if (++p == off) p = 0;
-      }
-      dv[v] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    phase += step;
-    if (phase >= off) phase -= off;
-  }
-  const uint32_t k = head + (nvec << 4) + t.tid;
-  if (k < ml) dst[k] = win[k % off];
+  // long period: every span of `off` bytes is a copy of the same window, which existed before the match started —
+  // so the spans are independent vectorised copies (no barrier between them)
+  for (uint32_t done = 0; done < ml; done += off) team_copy(t, dst + done, dst - off, min(off, ml - done));
   return false;
 }
 

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_decode(const BlobDesc* __restr
       st = decode_blob(t, &sh, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, lit, &got);
       if (st == S_OK && got != (uint32_t)d.dst_cap) st = S_SIZE_MISMATCH;
     }
-    if (threadIdx.x == 0) bulk_wait_all();  // bulk stores read sh.tile: drain before the next blob (or exit) reuses it
+    if (threadIdx.x < kBulkIssuers) bulk_wait_all();  // bulk stores read sh.tile: drain before the next blob (or exit) reuses it
     __syncthreads();  // every path out of decode_blob is team-uniform; this also fences the blob's last stores
     if (threadIdx.x == 0) {
       status[blob] = st;

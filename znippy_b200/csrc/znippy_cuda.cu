@@ -137,6 +137,13 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->dec_grid = (uint32_t)(c->sm_count * kDecodeCtasPerSm);
+  {  // keep freed plan memory cached in the device's default pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thresh = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+  }
   if (cudaMalloc(&c->d_lit, (size_t)c->dec_grid * kLitStride) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
   if (staging_bytes) {
     if (cudaHostAlloc(&c->pinned, staging_bytes, cudaHostAllocDefault) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
@@ -178,7 +185,8 @@ extern "C" uint64_t zn_ctx_kernel_launches(const zn_ctx* c) { return c ? c->laun
 template <typename T>
 static bool upload(zn_ctx* c, T** dptr, const T* h, size_t count) {
   *dptr = nullptr;
-  if (cudaMalloc((void**)dptr, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return false;
+  // stream-ordered pool allocation: plans are built per batch by the host-buffer API, so this must be cheap
+  if (cudaMallocAsync((void**)dptr, std::max<size_t>(count, 1) * sizeof(T), c->stream) != cudaSuccess) return false;
   if (count && h && cudaMemcpyAsync(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
     return false;
   return true;
@@ -291,10 +299,12 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     // default schedule: overlap decode and hash when the batch is large enough to pipeline
     uint64_t dec_bytes = 0;
     for (uint32_t i = 0; i < n; i++) dec_bytes += p->h_comp[i] ? p->h_cap[i] : 0;
+    // default: stages back to back.  The overlapped schedule only pays once a blob's decode latency is well below
+    // the hash time of its group ("overlap"); opt in with zn_plan_set_overlap or ZN_OVERLAP_GROUPS.
     int g = 1;
     if (dec_bytes >= (256ull << 20)) {
       const char* e = getenv("ZN_OVERLAP_GROUPS");
-      g = e ? atoi(e) : 4;
+      if (e) g = atoi(e);
     }
     ok = plan_set_groups(p, g) == ZN_OK;
   }
@@ -326,7 +336,7 @@ extern "C" void zn_plan_destroy(zn_plan* p) {
   void* ptrs[] = {p->d_blobs, p->d_chunk_prefix, p->d_list_dec, p->d_list_small, p->d_list_large, p->d_piece_blob,
                   p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter};
   for (void* q : ptrs)
-    if (q) cudaFree(q);
+    if (q) cudaFreeAsync(q, p->ctx->stream);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : p->evg)
@@ -380,7 +390,8 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
       }
       const uint32_t tiles = (chi - clo + 31u) / 32u;
       const uint32_t ctas = (tiles + kB3Warps - 1) / kB3Warps;
-      const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * 3u);
+      // 3 hash CTAs fill an SM's shared memory; when decode CTAs must co-reside (overlapped schedule) leave room
+      const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * (overlap ? 2u : 3u));
       k_b3_chunks<<<grid, kB3Warps * 32, kB3Warps * kB3SmemPerWarp, hs>>>(p->d_blobs, p->d_chunk_prefix, p->n, clo, chi, d_blobs,
                                                                          d_out, p->d_cvs, 1u);
       launches++;

@@ -90,7 +90,7 @@ struct ExecState {
 // Barrier after which every byte written so far is visible to the whole team (and tile / pat may be rewritten).
 ZN_HD void mem_sync(const Team& t, ExecState& es) {
   if (es.bulk) {
-    if (t.tid == 0) bulk_wait_all();
+    if (t.tid < kBulkIssuers) bulk_wait_all();
     es.bulk = 0;
   }
   team_sync(t);
@@ -110,7 +110,9 @@ ZN_HD void exec_batch(const Team& t, DecShared* sh, uint32_t n, uint8_t* out, co
     if (s.ml) {
       const uint32_t src_lo = es.pos - s.off;
       const uint32_t src_hi = s.off >= s.ml ? src_lo + s.ml : es.pos;
+      ZN_TP(6);
       if (src_hi > es.wm) mem_sync(t, es);
+      ZN_TP(7);
       if (team_match(t, out + es.pos, s.off, s.ml, sh->pat, sh->tile)) es.bulk = 1;
       es.pos += s.ml;
     }
@@ -333,6 +335,7 @@ struct FrameState {
 // Compressed block.  Team-uniform.  Advances es.pos.
 ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint32_t len, uint8_t* out, uint32_t cap,
                             uint32_t frame_start, FrameState& fs, ExecState& es, uint8_t* lit_scratch) {
+  ZN_TP(1);
   LitInfo li;
   uint32_t rc = decode_literals(t, sh, p, len, lit_scratch, li);
   if (rc != S_OK) return rc;
@@ -383,7 +386,9 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
       }
       sh->err_tab = e;
     }
+    ZN_TP(2);
     team_sync(t);
+    ZN_TP(3);
     if (sh->err_tab != S_OK) return sh->err_tab;
     for (uint32_t first = 0; first < nseq; first += kSeqBatch) {
       const uint32_t count = nseq - first < kSeqBatch ? nseq - first : kSeqBatch;
@@ -396,9 +401,12 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
           sh->lit_pub = d.lit_pos;
         }
       }
+      ZN_TP(4);
       team_sync(t);
+      ZN_TP(5);
       if (sh->err_seq != S_OK) return sh->err_seq;
       exec_batch(t, sh, count, out, li.base, li.rle, es);
+      ZN_TP(9);
       team_sync(t);  // ring and err_seq are rewritten by the next batch
       if (!es.bulk) es.wm = es.pos;
     }
