@@ -158,6 +158,15 @@ class Clocks:
                 "samples": len(self.samples)}
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full summary
+    of this same workload (profiles/r1_ncu_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -348,7 +357,7 @@ def run_ours(args):
     dom = "k_b3_chunks" if stage_ms[2] >= stage_ms[1] else "k_decode"
     achieved = kernels[dom]["gbs"]
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
                 "frac_of_nominal_8000": round(achieved / 8000.0, 4), "kernels": kernels,
                 "note": "blake3 is int-ALU bound (~10.5 int ops/byte), see DESIGN.md; hbm frac reported as asked"}
 
@@ -364,7 +373,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
         "config": {"workload": f"configs[1]: single {args.gib:g} GiB text-pattern file per GPU = {n} rows x 8 MiB slices, "
                                "zstd L19 frames (libzstd 1.5.5), decode + blake3 + 32-byte compare, output materialised in HBM",
-                   "rows_per_gpu": n, "schedule": f"{args.groups} row groups, decode(g+1) overlaps blake3(g) on 2 streams",
+                   "rows_per_gpu": n, "schedule": ("stages back to back on one stream" if args.groups <= 1 else
+                                f"{args.groups} row groups, decode(g+1) overlaps blake3(g) on 2 streams"),
                    "serial_ms_per_step": round(float(stage_ms[0]), 4), "serial_launches_per_step": serial_launches,
                    "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
@@ -386,7 +396,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=2.0, help="uncompressed GiB per GPU (2 = BASELINE configs[1])")
-    ap.add_argument("--groups", type=int, default=4, help="row groups of the overlapped decode/hash schedule (1 = serial)")
+    ap.add_argument("--groups", type=int, default=1, help="row groups of the overlapped decode/hash schedule (1 = serial)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
