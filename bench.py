@@ -86,6 +86,66 @@ def build_text_corpus(total_bytes: int, level: int = 19, first_byte: int = 0):
     return blobs, lens, np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy()
 
 
+def lcg_random(n: int) -> np.ndarray:
+    """perf_bench.rs:86-92 exactly (val = val*6364136223846793005 + 1 from 12345; byte = val >> 33), vectorised with
+    the closed form x_k = a^k x_0 + c (a^k - 1)/(a - 1) in wrapping uint64 arithmetic."""
+    a, x = np.uint64(6364136223846793005), np.uint64(12345)
+    out = np.empty(n, np.uint8)
+    blk = 1 << 22
+    with np.errstate(over="ignore"):
+        A = np.cumprod(np.full(blk, a, np.uint64))            # a^1 .. a^blk
+        S = np.concatenate([[np.uint64(1)], np.cumsum(A[:-1]) + np.uint64(1)])  # 1 + a + .. + a^(k-1), k = 1..blk
+        for o in range(0, n, blk):
+            m = min(blk, n - o)
+            xs = A[:m] * x + S[:m]
+            out[o:o + m] = (xs >> np.uint64(33)).astype(np.uint8)
+            x = xs[m - 1]
+    return out
+
+
+def build_rows(entries, level_for):
+    """entries: (path, data ndarray, skip) -> index rows cut at 8 MiB (stream_packer.rs:169-202)."""
+    z = _libzstd()
+    cache = {}
+    blobs, lens, digs, comp = [], [], [], []
+    for path, data, skip in entries:
+        for o in range(0, max(len(data), 1), SLICE):
+            sl = data[o:o + SLICE]
+            key = (hash(sl[:4096].tobytes()), hash(sl[-4096:].tobytes()), len(sl), skip)
+            if key not in cache:
+                cache[key] = (sl.tobytes() if skip else _zstd_compress(z, np.ascontiguousarray(sl), level_for(path)), _digest(sl))
+            b, d = cache[key]
+            blobs.append(b); lens.append(len(sl)); digs.append(d); comp.append(0 if skip else 1)
+    return blobs, lens, np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy(), np.array(comp, np.uint8)
+
+
+def build_workload(name: str, gib: float, rank: int):
+    """Returns (blobs, lens, digests, compressed flags, description)."""
+    if name == "text2g":
+        total = int(gib * (1 << 30))
+        blobs, lens, digs = build_text_corpus(total, first_byte=rank * total)
+        return blobs, lens, digs, np.ones(len(blobs), np.uint8), (
+            f"configs[1]: single {gib:g} GiB text-pattern file per GPU = {len(blobs)} rows x 8 MiB slices, zstd L19 frames "
+            "(libzstd 1.5.5), decode + blake3 + 32-byte compare, output materialised in HBM")
+    if name == "small100k":  # configs[0] shape: 100 000 x text(10 240) (perf_bench.rs:133-141), one row per file
+        s = text_slice(0, 10240)
+        b, d = _zstd_compress(_libzstd(), s, 19), _digest(s)
+        n = 100_000
+        return [b] * n, [10240] * n, np.tile(np.frombuffer(d, np.uint8), (n, 1)), np.ones(n, np.uint8), (
+            "configs[0] corpus on the GPU: 100 000 x 10 KiB text files (977 MiB), one zstd L19 frame per file")
+    if name == "mixed":  # configs[2]: 500 MiB incompressible + the mixed store-as-is set (perf_bench.rs:120-181)
+        rnd = lcg_random(500 << 20)
+        ents = [("random.bin", rnd, False), ("pom.xml", text_slice(0, 32 << 10), False),
+                ("app.jar", rnd[:200 << 20], True), ("sources.jar", text_slice(0, 100 << 20), True),
+                ("javadoc.jar", text_slice(0, 80 << 20), True), ("metadata.xml", text_slice(0, 16 << 10), False),
+                ("deps.tar.gz", rnd[:150 << 20], True)]
+        blobs, lens, digs, comp = build_rows(ents, lambda p: 1 if p == "random.bin" else 19)
+        return blobs, lens, digs, comp, (
+            f"configs[2]: 500 MiB incompressible (zstd frames of raw blocks) + mixed repo set, {len(blobs)} rows, "
+            f"{int((comp == 0).sum())} store-as-is; decode/gather + blake3 + compare, output materialised in HBM")
+    raise SystemExit(f"unknown workload {name}")
+
+
 def pack(blobs, align=16):
     offs, cur = [], 0
     for b in blobs:
@@ -175,7 +235,7 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------- reference / cpu baseline arm
-def cpu_pipeline(blobs, lens, digs, min_seconds: float, passes_cap: int = 100000):
+def cpu_pipeline(blobs, lens, digs, min_seconds: float, passes_cap: int = 100000, comp=None):
     """The reference's read worker loop on host cores (oracle/cpu_pipeline.c: libzstd + SIMD blake3, atomic row
     cursor, N = ceil(0.9*cores) threads as common_config.rs:34).  Returns (GB/s, threads, sample description)."""
     import oracle as O
@@ -185,17 +245,18 @@ def cpu_pipeline(blobs, lens, digs, min_seconds: float, passes_cap: int = 100000
     n = len(blobs)
     bs = np.array([len(b) for b in blobs], np.uint64)
     us = np.array(lens, np.uint64)
-    O.decompress_rows(buf, offs[:2], bs[:2], np.zeros(2, np.uint64), np.ones(2, np.uint8), us[:2], digs[:2], threads)  # warm
+    cf = np.ones(n, np.uint8) if comp is None else np.ascontiguousarray(comp, np.uint8)
+    O.decompress_rows(buf, offs[:2], bs[:2], np.zeros(2, np.uint64), cf[:2], us[:2], digs[:2], threads)  # warm
     t0, done, passes = time.perf_counter(), 0, 0
     while True:
-        st = O.decompress_rows(buf, offs, bs, np.zeros(n, np.uint64), np.ones(n, np.uint8), us, digs, threads)
+        st = O.decompress_rows(buf, offs, bs, np.zeros(n, np.uint64), cf, us, digs, threads)
         assert st.corrupt_rows == 0 and st.decode_errors == 0 and st.verified_bytes == int(us.sum())
         done += int(us.sum())
         passes += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds or passes >= passes_cap:
             break
-    return done / dt / 1e9, threads, f"{n} rows x 8 MiB text slices (zstd L19), {passes} passes, {dt:.1f} s", dt / passes
+    return done / dt / 1e9, threads, f"{n} rows ({int(us.sum()) >> 20} MiB) of the workload, {passes} passes, {dt:.1f} s", dt / passes
 
 
 def run_reference(args):
@@ -241,14 +302,13 @@ def run_ours(args):
 
     total = int(args.gib * (1 << 30))
     # weak scaling: rank r holds rows [r*256, (r+1)*256) of an N x 2 GiB multi-file archive, no exchange
-    blobs, lens, digs = build_text_corpus(total, first_byte=rank * total)
+    blobs, lens, digs, comp, wl_desc = build_workload(args.workload, args.gib, rank)
     n = len(blobs)
     in_buf, in_off = pack(blobs, 16)
     in_len = np.array([len(b) for b in blobs], np.uint64)
     out_len = np.array(lens, np.uint64)
     out_off = np.concatenate([[0], np.cumsum(out_len)])[:-1].astype(np.uint64)
     out_bytes = int(out_len.sum())
-    comp = np.ones(n, np.uint8)
 
     ctx = Ctx(local, staging_bytes=out_bytes + in_buf.size + (1 << 20))
     stream = torch.cuda.Stream()  # a real (non-default) stream: kernels and the timing events share it
@@ -327,7 +387,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     x_s = (time.perf_counter() - t0) / x_steps
     assert not est.any()
-    assert bytes(h_out[:45]) == text_slice((rank * total) % len(PHRASE), 45).tobytes()  # spot-check returned bytes
+    if args.workload == "text2g":  # spot-check returned bytes
+        assert bytes(h_out[:45]) == text_slice((rank * total) % len(PHRASE), 45).tobytes()
 
     # ---- reduce: max time over ranks
     times = torch.tensor([dev_ms, e2e_s * 1e3, x_s * 1e3], dtype=torch.float64, device="cuda")
@@ -346,7 +407,8 @@ def run_ours(args):
     x_value = world * out_bytes / (x_ms * 1e-3) / 1e9
     blob_bytes = int(in_len.sum())
     # dominant kernel: the largest stage
-    k_decode_bytes = blob_bytes + out_bytes            # blob read + uncompressed written
+    dec = comp.astype(bool)
+    k_decode_bytes = int(in_len[dec].sum() + out_len[dec].sum())  # blob read + uncompressed written
     k_hash_bytes = out_bytes + 32 * (out_bytes // 1024)  # content read + one 32 B chaining value per chunk written
     kernels = {
         "k_decode": {"ms": round(float(stage_ms[1]), 4), "alg_bytes": k_decode_bytes,
@@ -363,17 +425,15 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu:
-        k = min(n, 64)
-        gbs, threads, desc, _ = cpu_pipeline(blobs[:k], lens[:k], digs[:k], args.cpu_seconds)
+        k = min(n, 64 if args.workload != "small100k" else 20000)
+        gbs, threads, desc, _ = cpu_pipeline(blobs[:k], lens[:k], digs[:k], args.cpu_seconds, comp=comp[:k])
         cpu = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": desc}
 
     print(json.dumps({
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: single {args.gib:g} GiB text-pattern file per GPU = {n} rows x 8 MiB slices, "
-                               "zstd L19 frames (libzstd 1.5.5), decode + blake3 + 32-byte compare, output materialised in HBM",
-                   "rows_per_gpu": n, "schedule": ("stages back to back on one stream" if args.groups <= 1 else
+        "config": {"workload": wl_desc, "rows_per_gpu": n, "schedule": ("stages back to back on one stream" if args.groups <= 1 else
                                 f"{args.groups} row groups, decode(g+1) overlaps blake3(g) on 2 streams"),
                    "serial_ms_per_step": round(float(stage_ms[0]), 4), "serial_launches_per_step": serial_launches,
                    "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"},
@@ -395,6 +455,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed"],
+                    help="text2g = BASELINE configs[1] (the metric's config); the others are secondary report lines")
     ap.add_argument("--gib", type=float, default=2.0, help="uncompressed GiB per GPU (2 = BASELINE configs[1])")
     ap.add_argument("--groups", type=int, default=1, help="row groups of the overlapped decode/hash schedule (1 = serial)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -5,6 +5,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#ifndef TRACE_NT
+#define TRACE_NT 256
+#define TRACE_KB 1
+#endif
 __device__ unsigned long long g_trace[4096];
 __device__ unsigned int g_trace_n;
 #if defined(__CUDA_ARCH__)
@@ -55,7 +59,7 @@ int main(int argc, char** argv) {
     cudaMemset(d_ctr, 0, 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    k_decode<256><<<nb, 256>>>(d_desc, d_list, nb, d_in, d_out, d_lit, d_status, d_prod, d_ctr);
+    k_decode<TRACE_NT, TRACE_KB><<<(nb + TRACE_KB - 1) / TRACE_KB, TRACE_NT>>>(d_desc, d_list, nb, d_in, d_out, d_lit, d_status, d_prod, d_ctr);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -67,14 +71,15 @@ int main(int argc, char** argv) {
   cudaMemcpyFromSymbol(&tn, g_trace_n, 4);
   cudaMemcpyFromSymbol(tr, g_trace, sizeof tr);
   if (tn > 4096) tn = 4096;
-  // print phases of blocks 20..23 (steady state): id, delta cycles
+  const int first = argc > 4 ? atoi(argv[4]) : 20;
+  // print phases of blocks first..first+3 (steady state): id, delta cycles
   unsigned long long prev = 0;
   int blocks = 0;
   for (unsigned i = 0; i < tn; i++) {
     const unsigned id = (unsigned)(tr[i] >> 56);
     const unsigned long long c = tr[i] & 0xFFFFFFFFFFFFFFull;
     if (id == 1) blocks++;
-    if (blocks >= 20 && blocks < 24) printf("  blk %d  tp %2u  +%llu cyc\n", blocks, id, prev ? c - prev : 0ull);
+    if (blocks >= first && blocks < first + 4) printf("  blk %d  tp %2u  +%llu cyc\n", blocks, id, prev ? c - prev : 0ull);
     prev = c;
   }
   return 0;

@@ -10,8 +10,8 @@ namespace zn {
 constexpr uint32_t kPatWords = 144;   // periodic-match pattern buffer: periods <= kPatMaxOff plus 20 bytes run-out
 constexpr uint32_t kPatMaxOff = 512;
 constexpr uint32_t kShortCopy = 48;   // below this a copy is one byte per thread
-constexpr uint32_t kTileBytes = 16384;  // shared-memory tile that long periodic matches are bulk-stored from
-constexpr uint32_t kBulkMin = 4096;     // shortest periodic match that takes the bulk-store path
+constexpr uint32_t kTileBytes = 8192;   // shared-memory tile that long periodic matches are bulk-stored from
+constexpr uint32_t kBulkMin = 32768;    // shortest periodic match that takes the bulk-store path
 constexpr uint32_t kBulkIssuers = 32;   // threads that may issue (and must therefore wait for) bulk stores
 
 struct Team {
@@ -20,7 +20,10 @@ struct Team {
 
 #if defined(__CUDA_ARCH__)
 
-ZN_D void team_sync(const Team&) { __syncthreads(); }
+// A team is either a whole CTA or, for small blobs, a CTA of exactly one warp.
+ZN_D void team_sync(const Team& t) {
+  if (t.n == 32) __syncwarp(); else __syncthreads();
+}
 
 // ---- TMA bulk stores (cp.async.bulk shared -> global): one instruction moves up to a whole tile, so a 128 KiB
 // periodic match is ~8 instructions from one thread instead of 8192 STG.128 spread over the team.
@@ -143,12 +146,12 @@ ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     for (uint32_t i = t.tid; i < ml; i += t.n) dst[i] = dst[(int32_t)(i % off) - (int32_t)off];
     return false;
   }
-  if (off <= kPatMaxOff && ml >= kBulkMin) {
+  if (off <= kPatMaxOff && ml >= kBulkMin && tile != nullptr) {
     // The aligned body of the match is periodic with period lcm(off, 16): build one tile holding a whole number of
     // such periods in shared memory, then bulk-store the same tile back to back over the body.
     uint8_t* pat8 = reinterpret_cast<uint8_t*>(pat);
     for (uint32_t x = t.tid; x < off + 20; x += t.n) pat8[x] = dst[(int32_t)(x % off) - (int32_t)off];
-    __syncthreads();
+    team_sync(t);
     ZN_TP(10);
     const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
     const uint32_t body = (ml - head) & ~15u;
@@ -172,7 +175,7 @@ ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     const uint32_t k = head + body + t.tid;
     if (k < ml) dst[k] = pat8[k % off];
     fence_async_smem();
-    __syncthreads();
+    team_sync(t);
     ZN_TP(11);
     // one bulk store per thread (bulk groups are per thread: mem_sync makes threads < kBulkIssuers wait)
     for (uint32_t o = t.tid * tlen; o < body; o += kBulkIssuers * tlen) {
@@ -192,7 +195,7 @@ ZN_D bool team_match(const Team& t, uint8_t* dst, uint32_t off, uint32_t ml, uin
     // whose source is the pattern at its own phase.
     uint8_t* pat8 = reinterpret_cast<uint8_t*>(pat);
     for (uint32_t x = t.tid; x < off + 20; x += t.n) pat8[x] = dst[(int32_t)(x % off) - (int32_t)off];
-    __syncthreads();
+    team_sync(t);
     if (t.tid < head) dst[t.tid] = pat8[t.tid % off];
     uint32_t phase = (head + 16u * t.tid) % off;
     uint4* dv = reinterpret_cast<uint4*>(dst + head);

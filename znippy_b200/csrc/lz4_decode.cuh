@@ -175,11 +175,13 @@ ZN_HD uint32_t decode_frame(const Team& t, DecShared* sh, const uint8_t* src, ui
 }  // namespace lz
 
 // Entry point of the codec for one blob: picks the payload format by its magic number.
+// `predef` (team-uniform, owned by the caller across blobs) records which sequence tables in `sh` hold the
+// predefined distributions, so consecutive blobs do not copy them again.
 ZN_HD uint32_t decode_blob(const Team& t, DecShared* sh, const uint8_t* src, uint32_t src_len, uint8_t* out,
-                           uint32_t cap, uint8_t* lit_scratch, uint32_t* produced) {
+                           uint32_t cap, uint8_t* lit_scratch, uint32_t& predef, uint32_t* produced) {
   *produced = 0;
   if (src_len >= 4 && ld32le(src) == 0x184D2204u) return lz::decode_frame(t, sh, src, src_len, out, cap, produced);
-  return zs::decode_frames(t, sh, src, src_len, out, cap, lit_scratch, produced);
+  return zs::decode_frames(t, sh, src, src_len, out, cap, lit_scratch, predef, produced);
 }
 
 }  // namespace zn

@@ -30,6 +30,7 @@ struct zn_ctx {
   size_t pinned_bytes = 0;
   uint8_t* d_lit = nullptr;  // Huffman literal scratch, one slot per decode CTA
   uint32_t dec_grid = 0;
+  uint32_t dec_grid_small = 0;
   uint8_t* d_in = nullptr;   // staging for the host-buffer API
   size_t d_in_cap = 0;
   uint8_t* d_out = nullptr;
@@ -56,7 +57,8 @@ struct zn_plan {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool ran = false;
-  bool big_blobs = false;
+  bool big_blobs = false;    // mean decoded size >= 512 KiB: 256-thread teams
+  bool small_blobs = false;  // mean decoded size <= 64 KiB: one-warp teams
   // overlapped schedule: blobs are cut into `groups` contiguous index ranges; group g+1 decodes (HBM-bound) on the
   // caller's stream while group g is hashed (int-ALU-bound) on the context's second stream
   static const int kMaxGroups = 16;
@@ -144,7 +146,8 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
   }
-  if (cudaMalloc(&c->d_lit, (size_t)c->dec_grid * kLitStride) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
+  c->dec_grid_small = (uint32_t)(c->sm_count * 10);
+  if (cudaMalloc(&c->d_lit, (size_t)std::max(c->dec_grid, c->dec_grid_small) * kLitStride) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
   if (staging_bytes) {
     if (cudaHostAlloc(&c->pinned, staging_bytes, cudaHostAllocDefault) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
     c->pinned_bytes = staging_bytes;
@@ -215,7 +218,10 @@ static int plan_set_groups(zn_plan* p, int groups) {
     const size_t first = ldec.size();
     for (uint32_t i = b0; i < b1; i++)
       if (p->h_comp[i]) ldec.push_back(i);
-    std::stable_sort(ldec.begin() + first, ldec.end(), [&](uint32_t a, uint32_t b) { return p->h_cap[a] > p->h_cap[b]; });
+    bool sorted_desc = true;  // largest first for the dynamic work counter; uniform sizes need no sort
+    for (size_t k = first + 1; k < ldec.size() && sorted_desc; k++) sorted_desc = p->h_cap[ldec[k]] <= p->h_cap[ldec[k - 1]];
+    if (!sorted_desc)
+      std::stable_sort(ldec.begin() + first, ldec.end(), [&](uint32_t a, uint32_t b) { return p->h_cap[a] > p->h_cap[b]; });
     p->grp_dec_off[g + 1] = (uint32_t)ldec.size();
     p->grp_chunk_lo[g + 1] = p->h_prefix[b1];
     b0 = b1;
@@ -272,12 +278,12 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
   prefix[n] = (uint32_t)chunks;
   p->h_prefix = prefix;
   p->total_chunks = (uint32_t)chunks;
-  std::stable_sort(ldec.begin(), ldec.end(), [&](uint32_t a, uint32_t b) { return descs[a].dst_cap > descs[b].dst_cap; });
   p->n_dec = (uint32_t)ldec.size();
   {
     uint64_t dec_bytes = 0;
     for (uint32_t i : ldec) dec_bytes += descs[i].dst_cap;
     p->big_blobs = !ldec.empty() && dec_bytes / ldec.size() >= (512u << 10);
+    p->small_blobs = !ldec.empty() && dec_bytes / ldec.size() <= (64u << 10);
   }
   p->n_small = (uint32_t)lsmall.size();
   p->n_large = (uint32_t)llarge.size();
@@ -370,11 +376,15 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
       const uint32_t* list = p->d_list_dec + p->grp_dec_off[g];
       if (p->big_blobs) {  // few large blobs: wider teams (more bytes in flight per blob)
         const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
-        k_decode<256><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+        k_decode<256, 1><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
                                             p->d_counter + g);
+      } else if (p->small_blobs) {  // many small blobs: one warp per blob, ~10 blobs in flight per SM
+        const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
+        k_decode<32, 2><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+                                             p->d_counter + g);
       } else {
-        const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid);
-        k_decode<kDecodeThreads><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+        const uint32_t grid = std::min<uint32_t>((nd + 3) / 4, c->dec_grid);
+        k_decode<kDecodeThreads, 4><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
                                                                   p->d_produced, p->d_counter + g);
       }
       launches++;
@@ -484,11 +494,15 @@ static Layout make_layout(const uint64_t* off, const uint64_t* len, uint32_t n) 
   if (n == 0) return L;
   bool disjoint = true;
   if ((hi - lo) <= sum + sum / 4 + 4096) {
-    std::vector<uint32_t> ord(n);
-    std::iota(ord.begin(), ord.end(), 0u);
-    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return off[a] < off[b]; });
-    for (uint32_t k = 1; k < n && disjoint; k++)
-      if (off[ord[k]] < off[ord[k - 1]] + len[ord[k - 1]]) disjoint = false;
+    bool ascending = true;  // the common case (rows in blob order) needs no sort
+    for (uint32_t k = 1; k < n && ascending; k++) ascending = off[k] >= off[k - 1] + len[k - 1];
+    if (!ascending) {
+      std::vector<uint32_t> ord(n);
+      std::iota(ord.begin(), ord.end(), 0u);
+      std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return off[a] < off[b]; });
+      for (uint32_t k = 1; k < n && disjoint; k++)
+        if (off[ord[k]] < off[ord[k - 1]] + len[ord[k - 1]]) disjoint = false;
+    }
     if (disjoint) {
       L.span = true;
       L.span_lo = lo;

@@ -34,7 +34,7 @@ struct DecShared {
   zs::HufTable huf;
   zs::FseTable ll, of, ml, wt;  // wt: scratch table for FSE-compressed Huffman weights
   SeqRec ring[kSeqBatch];
-  alignas(128) uint8_t tile[kTileBytes];  // bulk-store source of long periodic matches (coop.cuh)
+  uint8_t* tile;  // kTileBytes of 128-byte aligned shared memory, bulk-store source of long periodic matches; may be null
   uint32_t pat[kPatWords];
   uint16_t next[256];
   int16_t norm[64];
@@ -428,7 +428,7 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
 // All concatenated frames of one blob (skippable frames are skipped).  Team-uniform.
 // Returns the blob's status; *produced = bytes written to out.
 ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, uint32_t src_len, uint8_t* out,
-                             uint32_t cap, uint8_t* lit_scratch, uint32_t* produced) {
+                             uint32_t cap, uint8_t* lit_scratch, uint32_t& predef, uint32_t* produced) {
   uint32_t ip = 0;
   ExecState es;
   es.pos = 0;
@@ -478,7 +478,7 @@ ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, u
     const uint32_t block_max = window < kZstdBlockMax ? (uint32_t)window : kZstdBlockMax;
     FrameState fs;
     fs.rep0 = 1; fs.rep1 = 4; fs.rep2 = 8;
-    fs.predef = 0;
+    fs.predef = predef;  // table CONTENT survives the per-frame validity reset below
     team_sync(t);  // nobody may still be using the previous frame's tables
     if (t.tid == 0) sh->huf.valid = sh->ll.valid = sh->of.valid = sh->ml.valid = 0;
     team_sync(t);
@@ -505,6 +505,7 @@ ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, u
         if (bsize > src_len - ip) return S_DECODE_ERROR;
         if (bsize > block_max || bsize < 2) return S_DECODE_ERROR;
         const uint32_t rc = decode_block(t, sh, src + ip, bsize, out, cap, frame_start, fs, es, lit_scratch);
+        predef = fs.predef;
         if (rc != S_OK) return rc;
         ip += bsize;
       }
