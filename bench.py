@@ -143,6 +143,25 @@ def build_workload(name: str, gib: float, rank: int):
         return blobs, lens, digs, comp, (
             f"configs[2]: 500 MiB incompressible (zstd frames of raw blocks) + mixed repo set, {len(blobs)} rows, "
             f"{int((comp == 0).sum())} store-as-is; decode/gather + blake3 + compare, output materialised in HBM")
+    if name == "realtext":  # entropy-coded corpus: python stdlib sources, 8 MiB slices, zstd level 3
+        import sysconfig
+        root = sysconfig.get_paths()["stdlib"]
+        parts, tot = [], 0
+        want = int(gib * (1 << 30))
+        for fn in sorted(os.listdir(root)):
+            if fn.endswith(".py"):
+                b = open(os.path.join(root, fn), "rb").read()
+                parts.append(b); tot += len(b)
+        data = np.frombuffer(b"".join(parts), np.uint8)
+        data = np.resize(data, want)
+        z = _libzstd()
+        blobs, lens, digs = [], [], []
+        for o in range(0, want, SLICE):
+            sl = np.ascontiguousarray(data[o:o + SLICE])
+            blobs.append(_zstd_compress(z, sl, 3)); lens.append(len(sl)); digs.append(_digest(sl))
+        return blobs, lens, np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy(), np.ones(len(blobs), np.uint8), (
+            f"real text (python stdlib sources, {tot >> 20} MiB cycled to {gib:g} GiB), {len(blobs)} rows x 8 MiB, zstd level 3 "
+            "frames: Huffman literals + FSE-described sequence tables")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -455,7 +474,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed"],
+    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed", "realtext"],
                     help="text2g = BASELINE configs[1] (the metric's config); the others are secondary report lines")
     ap.add_argument("--gib", type=float, default=2.0, help="uncompressed GiB per GPU (2 = BASELINE configs[1])")
     ap.add_argument("--groups", type=int, default=1, help="row groups of the overlapped decode/hash schedule (1 = serial)")

@@ -118,6 +118,8 @@ int zn_compress_batch(zn_ctx* ctx, const uint8_t* src_base, const uint64_t* src_
                       uint64_t* dst_len_out, uint8_t* digest_out /* nullable */, uint32_t* status);
 
 size_t zn_compress_bound(size_t src_len, int codec);
+/* device time (ms, CUDA events) of the compression kernels of the most recent zn_compress_batch on this ctx */
+float zn_ctx_last_compress_ms(const zn_ctx* ctx);
 
 /* decoded size announced by the frame header. returns ZN_OK, 1 when the frame carries no size, <0 on error */
 int zn_frame_content_size(const uint8_t* blob, size_t len, uint64_t* size_out);

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "../../znippy_b200/csrc/lz4_decode.cuh"
+#include "../../znippy_b200/csrc/zstd_par.cuh"
 
 extern "C" int zn_hostemu_decode(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap,
                                  uint32_t* produced) {
@@ -33,5 +34,14 @@ extern "C" int zn_hostemu_decode_at(const uint8_t* src, uint32_t src_len, uint32
   free(in);
   free(lit);
   free(sh);
+  return (int)st;
+}
+
+// block-parallel pipeline (walker, symbolic repeat offsets, table provenance, chaining), serial emulation
+extern "C" int zn_hostemu_decode_par(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap, uint32_t* produced) {
+  uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 32);
+  memcpy(in + 8, src, src_len);
+  uint32_t st = zn::par::host_decode_frames_par(in + 8, src_len, out, cap, produced);
+  free(in);
   return (int)st;
 }

@@ -22,12 +22,12 @@ __device__ unsigned int g_trace_n;
 #else
 #define ZN_TP(id) do {} while (0)
 #endif
-#include "../znippy_b200/csrc/decode_kernels.cuh"
+#include "../znippy_b200/csrc/par_kernel.cuh"
 using namespace zn;
 
 int main(int argc, char** argv) {
   FILE* f = fopen(argv[1], "rb");
-  std::vector<uint8_t> blob(1 << 20);
+  std::vector<uint8_t> blob(16 << 20);
   size_t n = fread(blob.data(), 1, blob.size(), f);
   fclose(f);
   const uint64_t out_len = strtoull(argv[2], 0, 10);
@@ -53,13 +53,22 @@ int main(int argc, char** argv) {
     zs::fse_build(&t, zs::kOFDefault, 29, 5, next); for (int i = 0; i < 32; i++) pd.of[i] = t.e[i];
     zs::fse_build(&t, zs::kMLDefault, 53, 6, next); for (int i = 0; i < 64; i++) pd.ml[i] = t.e[i]; }
   cudaMemcpyToSymbol(g_predef, &pd, sizeof pd);
+  uint8_t* d_par = nullptr;
+#ifdef TRACE_PAR
+  cudaMalloc(&d_par, par::kParScratchPerCta * nb);
+  cudaFuncSetAttribute(par::k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(par::ParShared));
+#endif
   for (int rep = 0; rep < 2; rep++) {
     unsigned int zero = 0;
     cudaMemcpyToSymbol(g_trace_n, &zero, 4);
     cudaMemset(d_ctr, 0, 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
+#ifdef TRACE_PAR
+    par::k_decode_par<<<nb, par::kParThreads, sizeof(par::ParShared)>>>(d_desc, d_list, nb, d_in, d_out, d_par, d_status, d_prod, d_ctr);
+#else
     k_decode<TRACE_NT, TRACE_KB><<<(nb + TRACE_KB - 1) / TRACE_KB, TRACE_NT>>>(d_desc, d_list, nb, d_in, d_out, d_lit, d_status, d_prod, d_ctr);
+#endif
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -78,7 +87,7 @@ int main(int argc, char** argv) {
   for (unsigned i = 0; i < tn; i++) {
     const unsigned id = (unsigned)(tr[i] >> 56);
     const unsigned long long c = tr[i] & 0xFFFFFFFFFFFFFFull;
-    if (id == 1) blocks++;
+    if (id == 1 || id == 30) blocks++;
     if (blocks >= first && blocks < first + 4) printf("  blk %d  tp %2u  +%llu cyc\n", blocks, id, prev ? c - prev : 0ull);
     prev = c;
   }

@@ -144,10 +144,15 @@ struct CompressScratch {
   size_t seqs_cap = 0;
   void* small = nullptr;  // slices + meta + dst_len
   size_t small_cap = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  float last_ms = 0.f;  // device time of the kernels of the last compress_run
   void release() {
     if (tmp) cudaFree(tmp);
     if (seqs) cudaFree(seqs);
     if (small) cudaFree(small);
+    if (ev[0]) cudaEventDestroy(ev[0]);
+    if (ev[1]) cudaEventDestroy(ev[1]);
+    ev[0] = ev[1] = nullptr;
     tmp = nullptr; seqs = nullptr; small = nullptr;
     tmp_cap = seqs_cap = small_cap = 0;
   }
@@ -215,7 +220,9 @@ inline int compress_run(CompressScratch* cs, cudaStream_t st, int sm_count, cons
     *err = "compress H2D failed";
     return -2;
   }
+  if (!cs->ev[0]) { cudaEventCreate(&cs->ev[0]); cudaEventCreate(&cs->ev[1]); }
   *launches = 0;
+  cudaEventRecord(cs->ev[0], st);
   if (nb) {
     if (lz4) k_lz4_blocks<<<grid, kLz4WarpsPerCta * 32, 0, st>>>(d_sl, n, nb, d_src, cs->tmp, d_meta);
     else k_zstd_blocks<<<grid, kZstdWarpsPerCta * 32, 0, st>>>(d_sl, n, nb, d_src, cs->tmp, cs->seqs, d_meta);
@@ -224,11 +231,13 @@ inline int compress_run(CompressScratch* cs, cudaStream_t st, int sm_count, cons
   if (lz4) k_lz4_assemble<<<n, 256, 0, st>>>(d_sl, d_src, cs->tmp, d_meta, d_dst, d_len);
   else k_zstd_assemble<<<n, 256, 0, st>>>(d_sl, d_src, cs->tmp, d_meta, d_dst, d_len);
   (*launches)++;
+  cudaEventRecord(cs->ev[1], st);
   if (cudaMemcpyAsync(out_len, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess) {
     *err = std::string("compress kernels: ") + cudaGetErrorString(cudaGetLastError());
     return -2;
   }
+  cudaEventElapsedTime(&cs->last_ms, cs->ev[0], cs->ev[1]);
   return 0;
 }
 

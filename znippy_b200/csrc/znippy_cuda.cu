@@ -17,6 +17,7 @@
 #include "blake3_kernels.cuh"
 #include "compress_kernels.cuh"
 #include "decode_kernels.cuh"
+#include "par_kernel.cuh"
 
 using namespace zn;
 
@@ -29,6 +30,7 @@ struct zn_ctx {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   uint8_t* d_lit = nullptr;  // Huffman literal scratch, one slot per decode CTA
+  uint8_t* d_par = nullptr;  // scratch of the block-parallel decoder (sequence records + literals), allocated on first use
   uint32_t dec_grid = 0;
   uint32_t dec_grid_small = 0;
   uint8_t* d_in = nullptr;   // staging for the host-buffer API
@@ -58,6 +60,7 @@ struct zn_plan {
   cudaStream_t last_stream = nullptr;
   bool ran = false;
   bool big_blobs = false;    // mean decoded size >= 512 KiB: 256-thread teams
+  bool entropy_heavy = false;  // compressed size > 1/64 of decoded size: many sequences per block -> block-parallel decode
   bool small_blobs = false;  // mean decoded size <= 64 KiB: one-warp teams
   // overlapped schedule: blobs are cut into `groups` contiguous index ranges; group g+1 decodes (HBM-bound) on the
   // caller's stream while group g is hashed (int-ALU-bound) on the context's second stream
@@ -156,6 +159,7 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   build_predef(&pd);
   if (cudaMemcpyToSymbol(g_predef, &pd, sizeof pd) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
   cudaFuncSetAttribute(k_b3_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Warps * kB3SmemPerWarp);
+  cudaFuncSetAttribute(par::k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(par::ParShared));
   compress_init_attrs();
   return c;
 }
@@ -165,6 +169,7 @@ extern "C" void zn_ctx_destroy(zn_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->d_lit) cudaFree(c->d_lit);
+  if (c->d_par) cudaFree(c->d_par);
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   c->cs.release();
@@ -283,6 +288,9 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     uint64_t dec_bytes = 0;
     for (uint32_t i : ldec) dec_bytes += descs[i].dst_cap;
     p->big_blobs = !ldec.empty() && dec_bytes / ldec.size() >= (512u << 10);
+    uint64_t src_bytes = 0;
+    for (uint32_t i : ldec) src_bytes += descs[i].src_len;
+    p->entropy_heavy = src_bytes * 64 > dec_bytes;
     p->small_blobs = !ldec.empty() && dec_bytes / ldec.size() <= (64u << 10);
   }
   p->n_small = (uint32_t)lsmall.size();
@@ -374,7 +382,17 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
     const uint32_t nd = p->grp_dec_off[g + 1] - p->grp_dec_off[g];
     if (nd) {
       const uint32_t* list = p->d_list_dec + p->grp_dec_off[g];
-      if (p->big_blobs) {  // few large blobs: wider teams (more bytes in flight per blob)
+      if (p->big_blobs && p->entropy_heavy && !getenv("ZN_NO_PAR")) {  // large blobs: block-parallel decode, one CTA per SM
+        const uint32_t max_grid = (uint32_t)c->sm_count;
+        if (!c->d_par && cudaMalloc(&c->d_par, (size_t)max_grid * par::kParScratchPerCta) != cudaSuccess) {
+          c->err = "block-parallel decode scratch allocation failed";
+          cudaGetLastError();
+          return ZN_E_NOMEM;
+        }
+        const uint32_t grid = std::min<uint32_t>(nd, max_grid);
+        par::k_decode_par<<<grid, par::kParThreads, sizeof(par::ParShared), st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_par,
+                                                                                 p->d_status, p->d_produced, p->d_counter + g);
+      } else if (p->big_blobs) {  // highly compressible large blobs (few, long sequences): one 256-thread team per blob
         const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
         k_decode<256, 1><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
                                             p->d_counter + g);
@@ -629,6 +647,8 @@ extern "C" int zn_frame_content_size(const uint8_t* blob, size_t len, uint64_t* 
 
 // --------------------------------------------------------------------------------------------- compression
 extern "C" size_t zn_compress_bound(size_t src_len, int codec) { return compress_bound(src_len, codec); }
+
+extern "C" float zn_ctx_last_compress_ms(const zn_ctx* c) { return c ? c->cs.last_ms : 0.f; }
 
 extern "C" int zn_compress_batch(zn_ctx* c, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
                                  uint32_t n, int level, int codec, uint8_t* dst_base, const uint64_t* dst_off,

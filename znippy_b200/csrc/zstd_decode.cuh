@@ -36,7 +36,8 @@ struct DecShared {
   SeqRec ring[kSeqBatch];
   uint8_t* tile;  // kTileBytes of 128-byte aligned shared memory, bulk-store source of long periodic matches; may be null
   uint32_t pat[kPatWords];
-  uint16_t next[256];
+  uint16_t next[256];    // scratch of the Huffman-weights FSE table build (literal decoder)
+  uint16_t next_seq[64]; // scratch of the sequence-table builds (sequence decoder; the two may run concurrently)
   int16_t norm[64];
   uint8_t weights[256];
   // single-writer mailboxes (thread 0 -> team); each has its own slot so that a fast thread 0 can never overwrite
@@ -259,7 +260,7 @@ ZN_HD bool setup_seq_table(FseTable* t, uint32_t mode, const uint8_t*& q, const 
     int log, nsym;
     const int used = fse_read_ncount(q, (uint32_t)(end - q), max_log, max_sym, sh->norm, &log, &nsym);
     if (used < 0) return false;
-    fse_build(t, sh->norm, nsym, log, sh->next);
+    fse_build(t, sh->norm, nsym, log, sh->next_seq);
     q += used;
     return true;
   }
