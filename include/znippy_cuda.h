@@ -124,6 +124,19 @@ float zn_ctx_last_compress_ms(const zn_ctx* ctx);
 /* decoded size announced by the frame header. returns ZN_OK, 1 when the frame carries no size, <0 on error */
 int zn_frame_content_size(const uint8_t* blob, size_t len, uint64_t* size_out);
 
+/* ---- native read worker: the loop shell of decompress_archive (znippy-common/src/decompress.rs:105-192) over rows
+ * [row_lo, row_hi) of the merged index.  Per batch of rows: pread blobs into pinned staging (io_threads threads),
+ * one zn_decode_verify_batch, pwrite of the decoded bytes at fdata_offset to out_fd[row] (out_fd NULL = verify only,
+ * out_fd[row] < 0 = skip), and the reference's counter rules.  corrupt_rows_out (nullable) receives the indices of
+ * digest-mismatch rows (capacity row_hi - row_lo). ---- */
+typedef struct {
+  uint64_t total_chunks, total_written_bytes, verified_bytes, corrupt_bytes, corrupt_rows, decode_errors;
+} zn_verify_stats;
+int zn_decompress_rows(zn_ctx* ctx, int archive_fd, uint64_t row_lo, uint64_t row_hi, const uint64_t* blob_offset,
+                       const uint64_t* blob_size, const uint64_t* fdata_offset, const uint8_t* compressed,
+                       const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd, size_t batch_bytes,
+                       int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats);
+
 /* ---- device-resident API (inputs and outputs already in HBM; used for the device GB/s metric and by
  *      callers that keep a batch resident).  d_* are device pointers; h_* host pointers. ---- */
 

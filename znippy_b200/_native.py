@@ -18,7 +18,7 @@ EXPORTS = [
     "zn_abi_version", "zn_device_count", "zn_strerror", "zn_status_name", "zn_ctx_create", "zn_ctx_destroy",
     "zn_last_error", "zn_ctx_pinned", "zn_ctx_kernel_launches", "zn_hash_batch", "zn_decode_verify_batch",
     "zn_compress_batch", "zn_compress_bound", "zn_frame_content_size", "zn_plan_decode_verify", "zn_plan_hash",
-    "zn_plan_destroy", "zn_plan_run", "zn_plan_results", "zn_plan_launches", "zn_plan_last_ms", "zn_plan_set_overlap", "zn_ctx_last_compress_ms",
+    "zn_plan_destroy", "zn_plan_run", "zn_plan_results", "zn_plan_launches", "zn_plan_last_ms", "zn_plan_set_overlap", "zn_ctx_last_compress_ms", "zn_decompress_rows",
 ]
 
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.zn_plan_launches.restype = u32
     L.zn_plan_last_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     L.zn_plan_set_overlap.argtypes = [vp, C.c_int]
+    L.zn_decompress_rows.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int, vp, vp]
     L.zn_ctx_last_compress_ms.argtypes = [vp]
     L.zn_ctx_last_compress_ms.restype = C.c_float
     if L.zn_abi_version() != 1:

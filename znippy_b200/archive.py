@@ -214,54 +214,29 @@ def shard_rows(uncompressed_size, world: int):
 
 
 def decompress_rows(archive_fd: int, cols, lo: int, hi: int, save_files=None, ctx: Ctx | None = None,
-                    budget: int = 1 << 30):
+                    budget: int = 1 << 30, io_threads: int = 8):
     """The worker of decompress.rs:113-192 over rows [lo, hi): returns WorkerStats as a dict.
 
-    Per batch: pread blobs -> zn_decode_verify_batch -> fold status[] with the reference's rules
-    (decompress.rs:140,156-184) -> pwrite at fdata_offset."""
-    blob_off, blob_size, fdata_off, compressed, usize, checks = cols
-    st = dict(total_chunks=0, total_written_bytes=0, verified_bytes=0, corrupt_bytes=0, corrupt_rows=[])
-    for (a, b) in plan_row_batches(blob_size, usize, lo, hi, budget):
-        n = b - a
-        order = np.argsort(blob_off[a:b], kind="stable")  # sequential reads inside the batch
-        lens = blob_size[a:b]
-        offs = np.zeros(n, np.uint64)
-        cur = 0
-        for i in order:
-            offs[i] = cur
-            cur += (int(lens[i]) + 15) & ~15
-        buf = np.zeros(max(cur, 1), np.uint8)
-        for i in order:
-            ln = int(lens[i])
-            if ln:
-                got = os.preadv(archive_fd, [memoryview(buf)[int(offs[i]): int(offs[i]) + ln]], int(blob_off[a + i]))
-                if got != ln:
-                    raise IOError("failed to read blob from archive")
-        ooffs = np.zeros(n, np.uint64)
-        cur = 0
-        for i in range(n):
-            ooffs[i] = cur
-            cur += (int(usize[a + i]) + 15) & ~15
-        want_out = save_files is not None
-        out = np.zeros(max(cur, 1), np.uint8) if want_out else None
-        status, _ = codec.decode_verify_batch(buf, offs, lens, compressed[a:b], usize[a:b], checks[a:b], out,
-                                              ooffs if want_out else None, ctx)
-        for i in range(n):
-            row = a + i
-            st["total_chunks"] += 1
-            s = int(status[i])
-            if s not in (codec.S_OK, codec.S_DIGEST_MISMATCH):
-                continue  # codec error: logged and skipped (decompress.rs:159-162)
-            ln = int(usize[row])
-            st["total_written_bytes"] += ln
-            if s == codec.S_OK:
-                st["verified_bytes"] += ln
-            else:
-                st["corrupt_bytes"] += ln
-                st["corrupt_rows"].append(row)
-            if want_out and save_files[row] is not None:
-                os.pwrite(save_files[row], memoryview(out)[int(ooffs[i]): int(ooffs[i]) + ln], int(fdata_off[row]))
-    return st
+    The loop itself is native (zn_decompress_rows in libznippy_cuda.so): per batch pread blobs into pinned staging ->
+    zn_decode_verify_batch -> fold status[] with the reference's rules (decompress.rs:140,156-184) -> pwrite at
+    fdata_offset.  Python only hands over the Arrow columns and the per-row output descriptors."""
+    import ctypes as C
+
+    from . import _native as N
+    ctx = ctx or default_ctx()
+    blob_off, blob_size, fdata_off, compressed, usize, checks = (np.ascontiguousarray(c) for c in cols)
+    n = len(blob_off)
+    fds = None
+    if save_files is not None:
+        fds = np.array([-1 if f is None else int(f) for f in save_files], dtype=np.int32)
+    st = np.zeros(6, np.uint64)
+    corrupt = np.zeros(max(hi - lo, 1), np.uint64)
+    rc = N.lib().zn_decompress_rows(ctx.handle, archive_fd, lo, hi, N.ptr(blob_off), N.ptr(blob_size), N.ptr(fdata_off),
+                                    N.ptr(compressed), N.ptr(usize), N.ptr(checks.reshape(-1)) if n else None,
+                                    None if fds is None else N.ptr(fds), budget, io_threads, N.ptr(corrupt), N.ptr(st))
+    ctx.check(rc, "zn_decompress_rows")
+    return dict(total_chunks=int(st[0]), total_written_bytes=int(st[1]), verified_bytes=int(st[2]), corrupt_bytes=int(st[3]),
+                corrupt_rows=[int(x) for x in corrupt[: int(st[4])]], decode_errors=int(st[5]))
 
 
 def decompress_archive(index_path: str, save_data: bool, out_dir: str, ctx: Ctx | None = None,

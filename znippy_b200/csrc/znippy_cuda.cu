@@ -705,3 +705,126 @@ extern "C" int zn_compress_batch(zn_ctx* c, const uint8_t* src_base, const uint6
   }
   return rc;
 }
+
+// --------------------------------------------------------------------------------------------- native read worker
+// The shell of the reference's read pipeline (znippy-common/src/decompress.rs:105-192) in C++: the row cursor advances
+// one BATCH at a time instead of one row at a time (fetch_add(B), §8b of SURVEY.md), blobs are pread into a pinned
+// staging slot by a few I/O threads, ONE zn_decode_verify_batch replaces the per-row decode + blake3 + compare, the
+// decoded bytes are pwritten at fdata_offset from the pinned output region, and status[] is folded into the
+// counters with the reference's rules (decompress.rs:140,156-184).
+#include <unistd.h>
+
+#include <atomic>
+#include <thread>
+
+namespace {
+struct Pinned {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t need) {
+    if (cap >= need) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaHostAlloc((void**)&p, need + 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = need + 4096;
+    return true;
+  }
+  ~Pinned() { if (p) cudaFreeHost(p); }
+};
+
+template <typename F>
+void parallel_rows(uint32_t n, int threads, F f) {
+  std::atomic<uint32_t> cur{0};
+  auto body = [&] {
+    for (;;) {
+      const uint32_t i = cur.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n) break;
+      f(i);
+    }
+  };
+  if (threads <= 1 || n < 8) { body(); return; }
+  std::vector<std::thread> ts;
+  for (int t = 0; t < threads; t++) ts.emplace_back(body);
+  for (auto& t : ts) t.join();
+}
+}  // namespace
+
+extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, uint64_t row_hi, const uint64_t* blob_offset,
+                                  const uint64_t* blob_size, const uint64_t* fdata_offset, const uint8_t* compressed,
+                                  const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd,
+                                  size_t batch_bytes, int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats) {
+  if (!c || !stats || row_hi < row_lo) return ZN_E_ARG;
+  if (row_hi > row_lo && (!blob_offset || !blob_size || !compressed || !uncompressed_size || !checksums)) return ZN_E_ARG;
+  if (out_fd && !fdata_offset) return ZN_E_ARG;
+  memset(stats, 0, sizeof *stats);
+  if (batch_bytes < (64u << 20)) batch_bytes = 64u << 20;
+  if (io_threads < 1) io_threads = 1;
+  Pinned pin_in, pin_out;
+  std::vector<uint64_t> in_off, out_off;
+  std::vector<uint32_t> status;
+  std::atomic<int> io_err{0};
+  uint64_t a = row_lo;
+  while (a < row_hi) {
+    uint64_t b = a, need = 0, in_bytes = 0, out_bytes = 0;
+    while (b < row_hi) {  // claim the next row range whose blobs + outputs fit the staging budget
+      const uint64_t r = blob_size[b] + uncompressed_size[b] + 32;
+      if (b > a && need + r > batch_bytes) break;
+      need += r;
+      in_bytes += (blob_size[b] + 15) & ~15ull;
+      out_bytes += (uncompressed_size[b] + 15) & ~15ull;
+      b++;
+    }
+    const uint32_t n = (uint32_t)(b - a);
+    if (!pin_in.ensure(in_bytes + 16) || (out_fd && !pin_out.ensure(out_bytes + 16))) { c->err = "pinned staging allocation failed"; return ZN_E_NOMEM; }
+    in_off.resize(n);
+    out_off.resize(n);
+    status.assign(n, 0);
+    uint64_t ci = 0, co = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      in_off[i] = ci; ci += (blob_size[a + i] + 15) & ~15ull;
+      out_off[i] = co; co += (uncompressed_size[a + i] + 15) & ~15ull;
+    }
+    parallel_rows(n, io_threads, [&](uint32_t i) {  // pread (decompress.rs:148-153)
+      uint64_t done = 0, len = blob_size[a + i];
+      while (done < len) {
+        const ssize_t r = pread(archive_fd, pin_in.p + in_off[i] + done, len - done, (off_t)(blob_offset[a + i] + done));
+        if (r <= 0) { io_err = 1; return; }
+        done += (uint64_t)r;
+      }
+    });
+    if (io_err) { c->err = "failed to read blob from archive"; return ZN_E_ARG; }
+    const int rc = zn_decode_verify_batch(c, pin_in.p, in_off.data(), blob_size + a, compressed + a, uncompressed_size + a,
+                                          checksums + 32 * a, out_fd ? pin_out.p : nullptr, out_fd ? out_off.data() : nullptr, n,
+                                          status.data(), nullptr);
+    if (rc != ZN_OK) return rc;
+    for (uint32_t i = 0; i < n; i++) {  // fold, decompress.rs:140,156-184
+      stats->total_chunks++;
+      const uint32_t s = status[i];
+      if (s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) { stats->decode_errors++; continue; }
+      const uint64_t len = uncompressed_size[a + i];
+      stats->total_written_bytes += len;
+      if (s == ZN_S_OK) stats->verified_bytes += len;
+      else {
+        stats->corrupt_bytes += len;
+        if (corrupt_rows_out) corrupt_rows_out[stats->corrupt_rows] = a + i;
+        stats->corrupt_rows++;
+      }
+    }
+    if (out_fd) {
+      parallel_rows(n, io_threads, [&](uint32_t i) {  // pwrite at fdata_offset (decompress.rs:186-189)
+        const uint32_t s = status[i];
+        if ((s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) || out_fd[a + i] < 0) return;
+        uint64_t done = 0, len = uncompressed_size[a + i];
+        while (done < len) {
+          const ssize_t r = pwrite(out_fd[a + i], pin_out.p + out_off[i] + done, len - done, (off_t)(fdata_offset[a + i] + done));
+          if (r <= 0) { io_err = 1; return; }
+          done += (uint64_t)r;
+        }
+      });
+      if (io_err) { c->err = "pwrite to output file failed"; return ZN_E_ARG; }
+    }
+    a = b;
+  }
+  return ZN_OK;
+}
