@@ -13,6 +13,7 @@ extern "C" int zn_hostemu_decode(const uint8_t* src, uint32_t src_len, uint8_t* 
   uint8_t* lit = (uint8_t*)malloc(zn::kZstdBlockMax + 64);
   zn::Team t{0, 1};
   uint32_t predef = 0;
+  zn::zs::init_luts(t, sh);
   // the device code may read the aligned 32-bit word around any valid byte: give the input 4-byte alignment + slack
   uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 16);
   memcpy(in + 4, src, src_len);
@@ -28,6 +29,7 @@ extern "C" int zn_hostemu_decode_at(const uint8_t* src, uint32_t src_len, uint32
   uint8_t* lit = (uint8_t*)malloc(zn::kZstdBlockMax + 64);
   zn::Team t{0, 1};
   uint32_t predef = 0;
+  zn::zs::init_luts(t, sh);
   uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 32);
   memcpy(in + 8 + (misalign & 7), src, src_len);
   uint32_t st = zn::decode_blob(t, sh, in + 8 + (misalign & 7), src_len, out, cap, lit, predef, produced);

@@ -228,3 +228,43 @@ def test_codec_rs_unit_tests(codec, oracle):
         out = bytearray()
         assert codec.decompress_into(z.compress(d, 3), out) == 4096 and bytes(out) == d
     assert codec.blake3_hash(b"").hex() == "af1349b9f5f9a1a6a0404dea36dcc9499bcb25c9adc112b7cc9a93cae41f3262"
+
+
+def test_block_parallel_path_levels_and_fuzz(codec, oracle):
+    """Large entropy-coded blobs take the block-parallel kernel (walker, symbolic repeat offsets, lane-parallel
+    executor).  All levels (treeless literals / repeat-mode tables appear at >= 7), multi-frame blobs, and injected
+    corruption: the verdict must match the oracle's and nothing may hang."""
+    O = oracle
+    z = O.libzstd()
+    rt = O.real_text(3_000_000)
+    contents, blobs = [], []
+    for lvl in (-5, 1, 3, 7, 12, 19):
+        contents.append(rt.tobytes()); blobs.append(z.compress(rt, lvl))
+    contents.append(O.gen_rle_literals().tobytes() * 4); blobs.append(z.compress(contents[-1], 19))
+    two = rt[:1_200_000].tobytes()
+    contents.append(two + two[:700_000]); blobs.append(z.compress(two, 3) + z.compress(two[:700_000], 19))
+    st, dg, out, out_off = _run(codec, blobs, [1] * len(blobs), contents)
+    assert st.tolist() == [0] * len(blobs)
+    for i, c in enumerate(contents):
+        assert out[out_off[i]:out_off[i] + len(c)].tobytes() == c, i
+        assert dg[i].tobytes() == O.blake3(c)
+    # corruption
+    base = z.compress(rt[:1_500_000], 3)
+    rnd = random.Random(11)
+    bad = []
+    for _ in range(48):
+        c = bytearray(base)
+        for _ in range(rnd.choice([1, 2, 3])):
+            c[rnd.randrange(len(c))] ^= 1 << rnd.randrange(8)
+        bad.append(bytes(c))
+    cap = 1_500_000
+    buf, offs = _pack(bad)
+    outb = np.zeros(len(bad) * (cap + 16), np.uint8)
+    ooff = [i * (cap + 16) for i in range(len(bad))]
+    st, _ = codec.decode_verify_batch(buf, offs, [len(b) for b in bad], [1] * len(bad), [cap] * len(bad), None, outb, ooff)
+    for i, b in enumerate(bad):
+        rc, o = O.zstd_decompress(b, cap)
+        ok_ref = rc == 0 and len(o) == cap
+        assert (st[i] == 0) == ok_ref, (i, st[i], rc, len(o))
+        if ok_ref:
+            assert outb[ooff[i]:ooff[i] + cap].tobytes() == o

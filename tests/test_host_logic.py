@@ -69,6 +69,7 @@ def emu():
     L.zn_hostemu_decode_at.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.zn_hostemu_compress.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
     L.zn_hostemu_compress.restype = C.c_long
+    L.zn_hostemu_decode_par.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
 
     class E:
         @staticmethod
@@ -77,6 +78,14 @@ def emu():
             out = np.zeros(max(cap, 1) + 64, np.uint8)
             n = C.c_uint32(0)
             st = L.zn_hostemu_decode_at(a.ctypes.data, a.size, mis, out.ctypes.data, cap, C.byref(n))
+            return st, out[:n.value].tobytes()
+
+        @staticmethod
+        def decode_par(blob, cap):
+            a = np.frombuffer(blob, np.uint8)
+            out = np.zeros(max(cap, 1) + 64, np.uint8)
+            n = C.c_uint32(0)
+            st = L.zn_hostemu_decode_par(a.ctypes.data, a.size, out.ctypes.data, cap, C.byref(n))
             return st, out[:n.value].tobytes()
 
         @staticmethod
@@ -128,6 +137,43 @@ def test_hostemu_bitflips_agree_with_oracle(emu, oracle):
         c[rnd.randrange(len(c))] ^= 1 << rnd.randrange(8)
         st, out = emu.decode(bytes(c), 50_000)
         rc, oo = O.zstd_decompress(bytes(c), 50_000)
+        assert (st == 0) == (rc == 0)
+        if st == 0:
+            assert out == oo
+
+
+def test_hostemu_block_parallel_pipeline(emu, oracle):
+    """zstd_par.cuh (walker, table provenance for treeless / repeat modes, symbolic repeat offsets, chaining) on the
+    CPU: every format path of the coverage corpus, all levels, multi-frame blobs and bit-flips vs the oracle."""
+    import random
+    O, z = oracle, oracle.libzstd()
+    rt = O.real_text(600_000)
+    corpora = [
+        (O.gen_text(300_000), 19), (O.gen_random(300_000), 3), (O.real_text(3 << 20), 19), (rt, 1), (rt, 7), (rt, -5),
+        (np.concatenate([np.full(200_000, 65, np.uint8), rt[:5000], np.full(150_000, 66, np.uint8)]), 3),
+        (rt[:300], 3), (rt[:2000], 19), (np.zeros(0, np.uint8), 3),
+        (np.frombuffer(bytes(np.random.default_rng(3).choice([97, 98, 99, 100], 50000).astype(np.uint8)), np.uint8), 3),
+        (np.tile(rt[:50], 40), 1), (O.gen_rle_literals(), 19), (O.gen_small_alphabet(300), 1), (O.gen_small_alphabet(3000), 1),
+        (O.gen_periodic_noise(2000, 200, 12), 3), (O.gen_periodic_noise(20000, 64, 8), 19)]
+    seen = {}
+    for d, lvl in corpora:
+        blob = z.compress(d, lvl)
+        st, out = emu.decode_par(blob, len(d))
+        assert st == 0 and out == d.tobytes(), lvl
+        _, _, s = O.zstd_decompress(blob, len(d), want_stats=True)
+        for k in ("lit_treeless", "mode_repeat", "mode_rle", "repcode_uses", "lit_rle", "blocks_rle", "blocks_raw"):
+            seen[k] = seen.get(k, 0) + s[k]
+    assert all(seen[k] > 0 for k in seen), seen  # the paths this pipeline treats specially are all exercised
+    b = z.compress(rt[:50000], 3, checksum=True) + b"\x50\x2a\x4d\x18\x03\x00\x00\x00abc" + z.compress(rt[50000:90000], 19)
+    st, out = emu.decode_par(b, 90000)
+    assert st == 0 and out == rt[:90000].tobytes()
+    base = z.compress(rt[:300_000], 3)
+    rnd = random.Random(2)
+    for _ in range(150):
+        c = bytearray(base)
+        c[rnd.randrange(len(c))] ^= 1 << rnd.randrange(8)
+        st, out = emu.decode_par(bytes(c), 300_000)
+        rc, oo = O.zstd_decompress(bytes(c), 300_000)
         assert (st == 0) == (rc == 0)
         if st == 0:
             assert out == oo

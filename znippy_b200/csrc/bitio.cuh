@@ -38,11 +38,17 @@ ZN_HD uint32_t ld_word_aligned(const uint8_t* a) {
 struct BackBits {
   const uint32_t* wbase;  // aligned word holding the first stream byte
   uint32_t lowmask;       // clears the bytes of word 0 that precede the stream
-  int32_t widx;           // next word to load (descending); < 0 -> zeros
+  int32_t widx;           // index of the word held in `pre` (descending); < 0 -> zeros
+  uint32_t pre;           // word widx, loaded one refill ahead so its memory latency is off the critical path
   uint64_t win;           // unread bits, MSB-aligned
   int32_t navail;         // valid bits in win
   int32_t bits_left;      // unread bits in the stream; < 0 == over-read
 
+  ZN_HD uint32_t fetch(int32_t i) const {
+    if (i < 0) return 0u;
+    const uint32_t w = wbase[i];
+    return i == 0 ? (w & lowmask) : w;
+  }
   ZN_HD bool init(const uint8_t* p, uint32_t len) {
     if (len == 0) return false;
     const uint32_t last = p[len - 1];
@@ -54,24 +60,20 @@ struct BackBits {
     lowmask = 0xFFFFFFFFu << ((a & 3) * 8);
     const int32_t t = (int32_t)((((e - 1) & ~(uintptr_t)3) - s_al) >> 2);
     const int nb_top = (int)(e - (s_al + 4 * (uintptr_t)t));  // 1..4 bytes of the top word belong to the stream
-    uint32_t w = wbase[t];
-    if (t == 0) w &= lowmask;
+    const uint32_t w = fetch(t);
     const int nvalid = (nb_top - 1) * 8 + hb;  // bits below the end marker
     win = nvalid ? ((uint64_t)w << (64 - nvalid)) : 0;
     navail = nvalid;
     widx = t - 1;
+    pre = fetch(widx);
     return true;
   }
   ZN_HD void refill() {  // afterwards navail > 32, so any read of <= 32 bits is served from the window
     while (navail <= 32) {
-      uint32_t w = 0;
-      if (widx >= 0) {
-        w = wbase[widx];
-        if (widx == 0) w &= lowmask;
-      }
-      win |= (uint64_t)w << (32 - navail);
+      win |= (uint64_t)pre << (32 - navail);
       navail += 32;
       widx--;
+      pre = fetch(widx);
     }
   }
   ZN_HD uint32_t peek(uint32_t n) const { return n ? (uint32_t)(win >> (64 - n)) : 0u; }  // n <= 32

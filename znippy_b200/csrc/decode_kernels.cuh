@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 16 : 512 / NT) k_decode(const B
   __shared__ __align__(16) uint8_t s_small[KB][kSrcSmall + 32];
   __shared__ __align__(128) uint8_t s_tile[kWide ? kTileBytes : 128];
   if (threadIdx.x == 0) sh.tile = kWide ? s_tile : nullptr;
+  zs::init_luts(Team{threadIdx.x, (uint32_t)NT}, &sh);
   const Team t{threadIdx.x, (uint32_t)NT};
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   uint8_t* lit = lit_scratch + (size_t)blockIdx.x * kLitStride;

@@ -16,7 +16,6 @@ struct ParShared {
   BlockRec recs[kGroup];
   GroupInfo gi;
   uint32_t predef[kGroup];
-  uint32_t pat_w[kParThreads / 32][kPatWords];
   uint32_t item, status, pos_after, err, done;
   alignas(128) uint8_t tile[kTileBytes];
   alignas(16) uint8_t src[kSrcStage + 32];
@@ -25,12 +24,20 @@ struct ParShared {
 static_assert(sizeof(ParShared) <= 227 * 1024, "ParShared must fit one SM's shared memory");
 
 // Lane-parallel execution of one block of short sequences.  Team-uniform entry; returns S_OK / S_DECODE_ERROR.
+//
+// The block is assembled IN SHARED MEMORY: during phase B nobody needs the slots' entropy tables, so their 148 KB
+// hold the block's (<= 128 KiB) output.  Every dependence between the block's sequences is then served at
+// shared-memory latency instead of a round trip through L2, bytes that precede the block come from global memory
+// (final since the previous block), and the finished block leaves with one coalesced copy.
 ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, const SeqOut* seqs, uint8_t* out,
                                const uint8_t* lit, uint32_t frame_start) {
+  static_assert(sizeof(ps->slot) >= kZstdBlockMax + 16, "slots must be able to hold one decoded block");
+  uint8_t* obuf = reinterpret_cast<uint8_t*>(ps->slot);
   const uint32_t warp = t.tid >> 5, lane = t.tid & 31u, nw = t.n >> 5;
-  const Team wt{lane, 32u};
   const uint32_t base = r.base_out, nseq = r.nseq, nb = (nseq + 31u) >> 5;
+  const uint32_t dec = r.matched + (r.lit_len - r.lit_used);
   const int rle = r.lit_rle;
+  const uint8_t* gout = out + base;  // gout[p] for p < 0: bytes of earlier blocks
   volatile uint32_t* done = &ps->done;
   if (t.tid == 0) { ps->done = 0; ps->err = 0; }
   team_sync(t);
@@ -41,84 +48,90 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
     SeqOut q;
     q.out_rel = q.lit_rel = q.ll = q.ml = 0; q.off = 1;
     if (act) q = seqs[s];
-    const uint32_t d = base + q.out_rel;
-    if (act && q.ml && (q.off == 0 || q.off > d + q.ll - frame_start)) ps->err = 1;
+    if (act && q.ml && (q.off == 0 || q.off > base + q.out_rel + q.ll - frame_start)) ps->err = 1;
     if (act && q.ll <= kLaneMax) {
-      if (rle >= 0) for (uint32_t i = 0; i < q.ll; i++) out[d + i] = (uint8_t)rle;
-      else for (uint32_t i = 0; i < q.ll; i++) out[d + i] = lit[q.lit_rel + i];
+      if (rle >= 0) for (uint32_t i = 0; i < q.ll; i++) obuf[q.out_rel + i] = (uint8_t)rle;
+      else for (uint32_t i = 0; i < q.ll; i++) obuf[q.out_rel + i] = lit[q.lit_rel + i];
     }
     uint32_t m = __ballot_sync(0xFFFFFFFFu, act && q.ll > kLaneMax);
     while (m) {
       const uint32_t sl = (uint32_t)__ffs((int)m) - 1u;
       m &= m - 1u;
-      const uint32_t dd = __shfl_sync(0xFFFFFFFFu, d, sl), lr = __shfl_sync(0xFFFFFFFFu, q.lit_rel, sl),
+      const uint32_t dd = __shfl_sync(0xFFFFFFFFu, q.out_rel, sl), lr = __shfl_sync(0xFFFFFFFFu, q.lit_rel, sl),
                      l = __shfl_sync(0xFFFFFFFFu, q.ll, sl);
-      if (rle >= 0) team_fill(wt, out + dd, (uint32_t)rle, l);
-      else team_copy(wt, out + dd, lit + lr, l);
+      for (uint32_t k = lane; k < l; k += 32) obuf[dd + k] = rle >= 0 ? (uint8_t)rle : lit[lr + k];
     }
   }
-  {
-    const uint32_t rest = r.lit_len - r.lit_used;
-    if (rest) {
-      if (rle >= 0) team_fill(t, out + base + r.matched, (uint32_t)rle, rest);
-      else team_copy(t, out + base + r.matched, lit + r.lit_used, rest);
-    }
-  }
+  for (uint32_t k = t.tid; k < r.lit_len - r.lit_used; k += t.n)
+    obuf[r.matched + k] = rle >= 0 ? (uint8_t)rle : lit[r.lit_used + k];
   team_sync(t);
   ZN_TP(34);
-  if (ps->err) return S_DECODE_ERROR;
+  uint32_t rc = ps->err ? S_DECODE_ERROR : S_OK;
   // ---- pass 2: matches, one lane per sequence, batches published in order
-  for (uint32_t b = warp; b < nb; b += nw) {
+  for (uint32_t b = warp; rc == S_OK && b < nb; b += nw) {
     const uint32_t s = b * 32u + lane;
     const bool act = s < nseq;
     SeqOut q;
     q.out_rel = q.lit_rel = q.ll = q.ml = 0; q.off = 1;
     if (act) q = seqs[s];
-    const uint32_t dst = base + q.out_rel + q.ll;
-    const uint32_t src_end = q.off >= q.ml ? dst - q.off + q.ml : dst;
+    const int32_t dst = (int32_t)(q.out_rel + q.ll);                  // block-relative
+    const int32_t src = dst - (int32_t)q.off;                         // may be negative: earlier blocks
+    const int32_t src_end = q.off >= q.ml ? src + (int32_t)q.ml : dst;
     bool pending = act && q.ml > 0;
     while (__any_sync(0xFFFFFFFFu, pending)) {
       const uint32_t dn = *done;
       bool ready;
       if (dn >= b) {  // every earlier batch is complete: bytes below the first pending lane's match are final
         const uint32_t k = (uint32_t)__ffs((int)__ballot_sync(0xFFFFFFFFu, pending)) - 1u;
-        const uint32_t wm = __shfl_sync(0xFFFFFFFFu, dst, k);
+        const int32_t wm = __shfl_sync(0xFFFFFFFFu, dst, k);
         ready = pending && (src_end <= wm || lane == k);
       } else {        // only sources wholly below the oldest unfinished batch are safe
-        const uint32_t wm = base + seqs[dn * 32u].out_rel;
+        const int32_t wm = (int32_t)seqs[dn * 32u].out_rel;
         ready = pending && src_end <= wm;
       }
       if (!__any_sync(0xFFFFFFFFu, ready)) {
-        __nanosleep(200);  // waiting for an earlier batch: do not steal issue slots from the warps that work
+        __nanosleep(100);  // waiting for an earlier batch: do not steal issue slots from the warps that work
         continue;
       }
       __threadfence_block();  // order the reads below after the observation of `done`
       if (ready && q.ml <= kLaneMax) {
-        const uint8_t* sp = out + dst - q.off;
-        uint8_t* dp = out + dst;
-        for (uint32_t i = 0; i < q.ml; i++) dp[i] = sp[i];
+        // byte-serial in one lane: also correct for self-overlapping matches (off < ml)
+        for (uint32_t i = 0; i < q.ml; i++) {
+          const int32_t p = src + (int32_t)i;
+          obuf[dst + (int32_t)i] = p >= 0 ? obuf[p] : gout[p];
+        }
       }
       uint32_t m = __ballot_sync(0xFFFFFFFFu, ready && q.ml > kLaneMax);
-      while (m) {
+      while (m) {  // long match: whole warp; byte k reads window[k mod off], which existed before the match began
         const uint32_t sl = (uint32_t)__ffs((int)m) - 1u;
         m &= m - 1u;
-        const uint32_t dd = __shfl_sync(0xFFFFFFFFu, dst, sl), oo = __shfl_sync(0xFFFFFFFFu, q.off, sl),
-                       l = __shfl_sync(0xFFFFFFFFu, q.ml, sl);
-        __syncwarp();
-        team_match(wt, out + dd, oo, l, ps->pat_w[warp], nullptr);
+        const int32_t dd = __shfl_sync(0xFFFFFFFFu, dst, sl);
+        const uint32_t oo = __shfl_sync(0xFFFFFFFFu, q.off, sl), l = __shfl_sync(0xFFFFFFFFu, q.ml, sl);
+        for (uint32_t k = lane; k < l; k += 32) {
+          const int32_t p = dd - (int32_t)oo + (int32_t)(oo >= l ? k : k % oo);
+          obuf[dd + (int32_t)k] = p >= 0 ? obuf[p] : gout[p];
+        }
       }
       pending = pending && !ready;
       __syncwarp();
     }
     __threadfence_block();
     if (lane == 0) {
-      while (*done != b) __nanosleep(100);
+      while (*done != b) __nanosleep(50);
       *done = b + 1u;
     }
     __syncwarp();
   }
   team_sync(t);
-  return S_OK;
+  if (rc == S_OK) team_copy(t, out + base, obuf, dec);
+  team_sync(t);
+  // the slots were used as the output buffer: restore what the next walk / team executor expects
+  if (t.tid < (uint32_t)kGroup) { ps->predef[t.tid] = 0; ps->slot[t.tid].huf.valid = 0; ps->slot[t.tid].tile = nullptr; }
+  for (int j = 0; j < kGroup; j++) zs::init_luts(t, &ps->slot[j]);
+  team_sync(t);
+  if (t.tid == 0) ps->slot[0].tile = ps->tile;
+  team_sync(t);
+  return rc;
 }
 
 // Team executor for a block of long sequences: records -> ring -> exec_batch (vector copies, TMA bulk stores).
@@ -288,6 +301,7 @@ __global__ void __launch_bounds__(kParThreads, 1) k_decode_par(const BlobDesc* _
   uint8_t* my_scratch = scratch + (size_t)blockIdx.x * kParScratchPerCta;
   if (threadIdx.x < (uint32_t)kGroup) { ps->predef[threadIdx.x] = 0; ps->slot[threadIdx.x].tile = nullptr; }
   if (threadIdx.x == 0) ps->slot[0].tile = ps->tile;
+  for (int j = 0; j < kGroup; j++) zs::init_luts(t, &ps->slot[j]);
   for (;;) {
     if (threadIdx.x == 0) ps->item = atomicAdd(work_counter, 1u);
     __syncthreads();

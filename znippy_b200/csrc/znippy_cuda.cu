@@ -382,6 +382,12 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
     const uint32_t nd = p->grp_dec_off[g + 1] - p->grp_dec_off[g];
     if (nd) {
       const uint32_t* list = p->d_list_dec + p->grp_dec_off[g];
+      const char* force = getenv("ZN_DECODE_KERNEL");  // development override: par | team | warp
+      if (force && !strcmp(force, "warp")) {
+        const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
+        k_decode<32, 2><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+                                             p->d_counter + g);
+      } else
       if (p->big_blobs && p->entropy_heavy && !getenv("ZN_NO_PAR")) {  // large blobs: block-parallel decode, one CTA per SM
         const uint32_t max_grid = (uint32_t)c->sm_count;
         if (!c->d_par && cudaMalloc(&c->d_par, (size_t)max_grid * par::kParScratchPerCta) != cudaSuccess) {

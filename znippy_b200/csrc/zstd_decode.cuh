@@ -40,6 +40,7 @@ struct DecShared {
   uint16_t next_seq[64]; // scratch of the sequence-table builds (sequence decoder; the two may run concurrently)
   int16_t norm[64];
   uint8_t weights[256];
+  uint32_t lut_ll[36], lut_ml[53];  // length code -> baseline | extra bits << 24 (shared-memory copy: LDS, not indexed LDC)
   // single-writer mailboxes (thread 0 -> team); each has its own slot so that a fast thread 0 can never overwrite
   // one before a slow thread has read it (there is at least one barrier between a read and the slot's next write)
   uint32_t huf_used;    // bytes of the Huffman tree description, ~0u = malformed
@@ -80,6 +81,12 @@ inline const PredefTables* predef_tables() {
 #endif
 
 namespace zs {
+
+// Fills the length-code lookup tables of `sh`; strided over the team (call before the first block, then barrier).
+ZN_HD void init_luts(const Team& t, DecShared* sh) {
+  for (uint32_t i = t.tid; i < 36; i += t.n) sh->lut_ll[i] = kLLBase[i] | ((uint32_t)kLLBits[i] << 24);
+  for (uint32_t i = t.tid; i < 53; i += t.n) sh->lut_ml[i] = kMLBase[i] | ((uint32_t)kMLBits[i] << 24);
+}
 
 // cursors of one frame that thread 0's sequence decoder and the executors both advance
 struct ExecState {
@@ -291,8 +298,9 @@ ZN_HD uint32_t decode_seq_batch(DecShared* sh, SeqDecoder& d, uint32_t first, ui
     const uint32_t obits = d.b.read(oc);
     const uint64_t ov = ((uint64_t)1 << oc) + obits;
     d.b.refill();
-    const uint32_t ml = kMLBase[mc] + d.b.read(kMLBits[mc]);
-    const uint32_t ll = kLLBase[lc] + d.b.read(kLLBits[lc]);
+    const uint32_t xm = sh->lut_ml[mc], xl = sh->lut_ll[lc];
+    const uint32_t ml = (xm & 0xFFFFFFu) + d.b.read(xm >> 24);
+    const uint32_t ll = (xl & 0xFFFFFFu) + d.b.read(xl >> 24);
     if (first + i + 1 < nseq) {
       d.b.refill();
       d.sl = fse_base(el) + d.b.read(fse_nbits(el));

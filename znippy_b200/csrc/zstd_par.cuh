@@ -234,8 +234,9 @@ ZN_HD void decode_block_sequences(const uint8_t* src, uint32_t src_len, BlockRec
     b.refill();
     const uint32_t ov = (1u << oc) + b.read(oc);
     b.refill();
-    const uint32_t ml = zs::kMLBase[mc] + b.read(zs::kMLBits[mc]);
-    const uint32_t ll = zs::kLLBase[lc] + b.read(zs::kLLBits[lc]);
+    const uint32_t xm = sh->lut_ml[mc], xl = sh->lut_ll[lc];
+    const uint32_t ml = (xm & 0xFFFFFFu) + b.read(xm >> 24);
+    const uint32_t ll = (xl & 0xFFFFFFu) + b.read(xl >> 24);
     if (i + 1 < nseq) {
       b.refill();
       sl = zs::fse_base(el) + b.read(zs::fse_nbits(el));
@@ -458,7 +459,7 @@ inline uint32_t host_decode_frames_par(const uint8_t* src, uint32_t src_len, uin
     const uint32_t block_max = window < kZstdBlockMax ? (uint32_t)window : kZstdBlockMax;
     Defs defs{kDefNone, {kDefNone, kDefNone, kDefNone}};
     uint32_t rep[3] = {1, 4, 8};
-    for (int j = 0; j < kGroup; j++) slots[j].huf.valid = 0;
+    for (int j = 0; j < kGroup; j++) { slots[j].huf.valid = 0; zs::init_luts(t, &slots[j]); }
     for (;;) {
       GroupInfo gi;
       walk_group(src, src_len, ip, block_max, defs, recs, &gi);
