@@ -11,6 +11,12 @@
 #endif
 __device__ unsigned long long g_trace[4096];
 __device__ unsigned int g_trace_n;
+__device__ unsigned long long g_cnt[16];
+#if defined(__CUDA_ARCH__)
+#define ZN_CNT(i, v) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_cnt[i], (unsigned long long)(v)); } while (0)
+#else
+#define ZN_CNT(i, v) do {} while (0)
+#endif
 #if defined(__CUDA_ARCH__)
 #define ZN_TP(id)                                                            \
   do {                                                                       \
@@ -91,5 +97,8 @@ int main(int argc, char** argv) {
     if (blocks >= first && blocks < first + 4) printf("  blk %d  tp %2u  +%llu cyc\n", blocks, id, prev ? c - prev : 0ull);
     prev = c;
   }
+  unsigned long long cnt[16];
+  cudaMemcpyFromSymbol(cnt, g_cnt, sizeof cnt);
+  for (int i = 0; i < 8; i++) printf("cnt[%d] = %llu\n", i, cnt[i]);
   return 0;
 }

@@ -11,6 +11,9 @@
 #define ZN_D inline
 #endif
 
+#ifndef ZN_CNT
+#define ZN_CNT(i, v) do {} while (0)  // debug counters, only live in tools/trace_decode.cu
+#endif
 #ifndef ZN_TP
 #define ZN_TP(id) do {} while (0)  // phase trace points, only live in tools/trace_decode.cu
 #endif

@@ -38,8 +38,7 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
   const uint32_t dec = r.matched + (r.lit_len - r.lit_used);
   const int rle = r.lit_rle;
   const uint8_t* gout = out + base;  // gout[p] for p < 0: bytes of earlier blocks
-  volatile uint32_t* done = &ps->done;
-  if (t.tid == 0) { ps->done = 0; ps->err = 0; }
+  if (t.tid == 0) ps->err = 0;
   team_sync(t);
   // ---- pass 1: literals (no dependences) + offset validation
   for (uint32_t b = warp; b < nb; b += nw) {
@@ -67,7 +66,19 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
   team_sync(t);
   ZN_TP(34);
   uint32_t rc = ps->err ? S_DECODE_ERROR : S_OK;
-  // ---- pass 2: matches, one lane per sequence, batches published in order
+  // ---- pass 2: matches, one lane per sequence, 32 sequences per batch, batches spread over the warps.
+  // Readiness is tracked exactly: a lane may copy as soon as every EARLIER BATCH that produced bytes of its source
+  // range is flagged done (bdone[]), and the part of its source inside its own batch lies below the first unfinished
+  // lane's match.  Far matches therefore never wait, and a batch only waits for the few lanes that really depend on
+  // its predecessors.  bstart[c] = block-relative output position where batch c begins.
+  uint32_t* bstart = reinterpret_cast<uint32_t*>(ps->tile);                 // nb + 1 <= 1377 entries (8 KiB tile)
+  volatile uint8_t* bdone = reinterpret_cast<volatile uint8_t*>(ps->src);   // nb <= 1376 flags
+  static_assert(kTileBytes >= (kMaxSeq / 32 + 2) * 4 && kSrcStage >= kMaxSeq / 32 + 1, "scratch too small for batch tables");
+  for (uint32_t c = t.tid; c <= nb; c += t.n) {
+    bstart[c] = c < nb ? seqs[c * 32u].out_rel : r.matched;
+    if (c < nb) bdone[c] = 0;
+  }
+  team_sync(t);
   for (uint32_t b = warp; rc == S_OK && b < nb; b += nw) {
     const uint32_t s = b * 32u + lane;
     const bool act = s < nseq;
@@ -75,25 +86,49 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
     q.out_rel = q.lit_rel = q.ll = q.ml = 0; q.off = 1;
     if (act) q = seqs[s];
     const int32_t dst = (int32_t)(q.out_rel + q.ll);                  // block-relative
-    const int32_t src = dst - (int32_t)q.off;                         // may be negative: earlier blocks
+    const int32_t src = dst - (int32_t)q.off;                         // may be negative: earlier blocks (final)
     const int32_t src_end = q.off >= q.ml ? src + (int32_t)q.ml : dst;
     bool pending = act && q.ml > 0;
-    while (__any_sync(0xFFFFFFFFu, pending)) {
-      const uint32_t dn = *done;
-      bool ready;
-      if (dn >= b) {  // every earlier batch is complete: bytes below the first pending lane's match are final
-        const uint32_t k = (uint32_t)__ffs((int)__ballot_sync(0xFFFFFFFFu, pending)) - 1u;
-        const int32_t wm = __shfl_sync(0xFFFFFFFFu, dst, k);
-        ready = pending && (src_end <= wm || lane == k);
-      } else {        // only sources wholly below the oldest unfinished batch are safe
-        const int32_t wm = (int32_t)seqs[dn * 32u].out_rel;
-        ready = pending && src_end <= wm;
+    // producer batches of the in-block part of the source: [c_lo, c_hi], restricted to batches before this one
+    uint32_t c_lo = 1, c_hi = 0;  // empty
+    if (pending && src_end > 0) {
+      const uint32_t plo = src > 0 ? (uint32_t)src : 0u, phi = (uint32_t)(src_end - 1);
+      uint32_t lo = 0, hi = b;  // batches > b cannot hold bytes below dst
+      while (hi > lo) { const uint32_t mid = (lo + hi + 1) >> 1; if (bstart[mid] <= plo) lo = mid; else hi = mid - 1; }
+      c_lo = lo;
+      lo = c_lo; hi = b;
+      while (hi > lo) { const uint32_t mid = (lo + hi + 1) >> 1; if (bstart[mid] <= phi) lo = mid; else hi = mid - 1; }
+      c_hi = lo;
+    }
+    const bool in_batch = pending && c_hi == b && c_lo <= c_hi;       // part of the source lies in this batch
+    const uint32_t c_end = c_hi == b ? b - 1u : c_hi;                  // (b == 0 and c_hi == 0: wraps; guarded below)
+    uint32_t pm;
+    ZN_CNT(0, 1);
+    const long long t_b0 = clock64();
+    while ((pm = __ballot_sync(0xFFFFFFFFu, pending)) != 0) {
+      ZN_CNT(1, 1);
+      bool ext_ok = true;
+      if (pending && c_lo <= c_hi && !(c_hi == b && b == 0) && c_lo <= c_end) {
+        while (c_lo <= c_end && bdone[c_lo]) c_lo++;
+        ext_ok = c_lo > c_end;
       }
+      // inside the batch: a lane must wait only for PENDING earlier lanes whose match output overlaps its source
+      bool in_ok = true;
+      for (uint32_t mm = pm; mm;) {
+        const uint32_t j = (uint32_t)__ffs((int)mm) - 1u;
+        mm &= mm - 1u;
+        const int32_t dj = __shfl_sync(0xFFFFFFFFu, dst, j);
+        const int32_t ej = dj + (int32_t)__shfl_sync(0xFFFFFFFFu, q.ml, j);
+        if (j < lane && dj < src_end && ej > src) in_ok = false;
+      }
+      const bool ready = pending && ext_ok && (!in_batch || in_ok);
       if (!__any_sync(0xFFFFFFFFu, ready)) {
-        __nanosleep(100);  // waiting for an earlier batch: do not steal issue slots from the warps that work
+        ZN_CNT(2, 1);
+        __nanosleep(20);
         continue;
       }
-      __threadfence_block();  // order the reads below after the observation of `done`
+      { const uint32_t nr__ = __popc(__ballot_sync(0xFFFFFFFFu, ready)); ZN_CNT(3, nr__); (void)nr__; }
+      __threadfence_block();  // order the reads below after the observation of bdone[]
       if (ready && q.ml <= kLaneMax) {
         // byte-serial in one lane: also correct for self-overlapping matches (off < ml)
         for (uint32_t i = 0; i < q.ml; i++) {
@@ -102,24 +137,22 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
         }
       }
       uint32_t m = __ballot_sync(0xFFFFFFFFu, ready && q.ml > kLaneMax);
-      while (m) {  // long match: whole warp; byte k reads window[k mod off], which existed before the match began
+      while (m) {  // long match: whole warp; byte j reads window[j mod off], which existed before the match began
         const uint32_t sl = (uint32_t)__ffs((int)m) - 1u;
         m &= m - 1u;
         const int32_t dd = __shfl_sync(0xFFFFFFFFu, dst, sl);
         const uint32_t oo = __shfl_sync(0xFFFFFFFFu, q.off, sl), l = __shfl_sync(0xFFFFFFFFu, q.ml, sl);
-        for (uint32_t k = lane; k < l; k += 32) {
-          const int32_t p = dd - (int32_t)oo + (int32_t)(oo >= l ? k : k % oo);
-          obuf[dd + (int32_t)k] = p >= 0 ? obuf[p] : gout[p];
+        for (uint32_t j = lane; j < l; j += 32) {
+          const int32_t p = dd - (int32_t)oo + (int32_t)(oo >= l ? j : j % oo);
+          obuf[dd + (int32_t)j] = p >= 0 ? obuf[p] : gout[p];
         }
       }
       pending = pending && !ready;
       __syncwarp();
     }
+    ZN_CNT(4, clock64() - t_b0);
     __threadfence_block();
-    if (lane == 0) {
-      while (*done != b) __nanosleep(50);
-      *done = b + 1u;
-    }
+    if (lane == 0) bdone[b] = 1;
     __syncwarp();
   }
   team_sync(t);
