@@ -95,7 +95,8 @@ int zn_hash_batch(zn_ctx* ctx, const uint8_t* base, const uint64_t* off, const u
 
 /*
  * For each blob i: if compressed[i], decode blobs_base[blob_off[i] .. +blob_len[i]) (capacity out_len[i]);
- * else the blob bytes are the content.  Then BLAKE3 the content, compare with expect_digest[i] when given,
+ * else the blob bytes are the content.  compressed[i] == 1: the codec is identified by the frame magic (Zstandard
+ * or LZ4 frame); compressed[i] == 2: the blob is one raw LZ4 block (no header; both sizes come from the index).  Then BLAKE3 the content, compare with expect_digest[i] when given,
  * and copy the content to out_base[out_off[i] ..] when out_base is given.
  *   expect_digest  nullable (n*32)  -> no compare (extract_file semantics, archive.rs:144-168)
  *   out_base       nullable         -> verify-only (decompress_archive with save_data=false)

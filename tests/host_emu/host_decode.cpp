@@ -47,3 +47,14 @@ extern "C" int zn_hostemu_decode_par(const uint8_t* src, uint32_t src_len, uint8
   free(in);
   return (int)st;
 }
+
+extern "C" int zn_hostemu_decode_lz4_block(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap, uint32_t* produced) {
+  zn::DecShared* sh = (zn::DecShared*)calloc(1, sizeof(zn::DecShared));
+  zn::Team t{0, 1};
+  uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 32);
+  memcpy(in + 8, src, src_len);
+  uint32_t st = zn::decode_lz4_block(t, sh, in + 8, src_len, out, cap, produced);
+  free(in);
+  free(sh);
+  return (int)st;
+}

@@ -268,3 +268,26 @@ def test_block_parallel_path_levels_and_fuzz(codec, oracle):
         assert (st[i] == 0) == ok_ref, (i, st[i], rc, len(o))
         if ok_ref:
             assert outb[ooff[i]:ooff[i] + cap].tobytes() == o
+
+
+def test_raw_lz4_blocks(codec, oracle):
+    """compressed[i] == 2: one raw LZ4 block per blob (LZ4_compress_default / _HC output, no frame), sizes from the index."""
+    O = oracle
+    l = O.liblz4()
+    frames = [f for f in json.load(open(os.path.join(GOLD, "frames.json")))["frames"] if f["codec"] == "lz4block"]
+    blobs = [base64.b64decode(f["blob_b64"]) for f in frames]
+    lens = [f["out_len"] for f in frames]
+    want = [bytes.fromhex(f["out_blake3"]) for f in frames]
+    for d in (O.real_text(700_000), O.gen_text(2 << 20), O.gen_binary(100_000), O.gen_random(50_000), O.gen_text(13)):
+        blobs.append(l.compress_block(d)); lens.append(len(d)); want.append(O.blake3(d))
+        blobs.append(l.compress_block(d, 9)); lens.append(len(d)); want.append(O.blake3(d))
+    buf, offs = _pack(blobs)
+    ooff = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    out = np.zeros(sum(lens) + 1, np.uint8)
+    st, dg = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs], [2] * len(blobs), lens, b"".join(want), out, ooff)
+    assert not st.any(), st
+    # a truncated block and a too-small destination are per-blob errors
+    st, _ = codec.decode_verify_batch(buf, offs[:1], [len(blobs[0]) - 3], [2], lens[:1], None, out, [0])
+    assert st[0] != 0
+    st, _ = codec.decode_verify_batch(buf, offs[:1], [len(blobs[0])], [2], [lens[0] - 1], None, out, [0])
+    assert st[0] in (codec.S_DST_TOO_SMALL, codec.S_DECODE_ERROR, codec.S_SIZE_MISMATCH)

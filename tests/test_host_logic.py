@@ -70,6 +70,7 @@ def emu():
     L.zn_hostemu_compress.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
     L.zn_hostemu_compress.restype = C.c_long
     L.zn_hostemu_decode_par.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.zn_hostemu_decode_lz4_block.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
 
     class E:
         @staticmethod
@@ -78,6 +79,14 @@ def emu():
             out = np.zeros(max(cap, 1) + 64, np.uint8)
             n = C.c_uint32(0)
             st = L.zn_hostemu_decode_at(a.ctypes.data, a.size, mis, out.ctypes.data, cap, C.byref(n))
+            return st, out[:n.value].tobytes()
+
+        @staticmethod
+        def decode_lz4_block(blob, cap):
+            a = np.frombuffer(blob, np.uint8)
+            out = np.zeros(max(cap, 1) + 64, np.uint8)
+            n = C.c_uint32(0)
+            st = L.zn_hostemu_decode_lz4_block(a.ctypes.data, a.size, out.ctypes.data, cap, C.byref(n))
             return st, out[:n.value].tobytes()
 
         @staticmethod
@@ -124,6 +133,22 @@ def test_hostemu_decoder_golden_and_corpora(emu, oracle):
     st, out = emu.decode(b, 90000)
     assert st == 0 and out == rt[:90000].tobytes()
     assert emu.decode(z.compress(rt[:50000], 3), 49999)[0] == 3  # DST_TOO_SMALL
+
+
+def test_hostemu_raw_lz4_blocks(emu, oracle):
+    O = oracle
+    for f in json.load(open(os.path.join(GOLD, "frames.json")))["frames"]:
+        if f["codec"] == "lz4block":
+            st, out = emu.decode_lz4_block(base64.b64decode(f["blob_b64"]), f["out_len"])
+            assert st == 0 and O.blake3_official(out).hex() == f["out_blake3"], f["name"]
+    d = O.real_text(300_000)
+    for hc in (None, 9):
+        b = O.liblz4().compress_block(d, hc)
+        st, out = emu.decode_lz4_block(b, len(d))
+        assert st == 0 and out == d.tobytes()
+        rc, o = O.lz4_block_decompress(b, len(d))
+        assert rc == 0 and o == out
+        assert emu.decode_lz4_block(b[:-5], len(d))[0] != 0
 
 
 def test_hostemu_bitflips_agree_with_oracle(emu, oracle):

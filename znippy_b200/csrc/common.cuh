@@ -33,7 +33,8 @@ enum : uint32_t {
 // blob flags in BlobDesc.flags
 enum : uint32_t {
   F_COMPRESSED = 1u,   // run the codec; otherwise content == blob bytes (store-as-is, decompress.rs:164-166)
-  F_HAS_EXPECT = 2u    // compare digest with expect[]
+  F_HAS_EXPECT = 2u,   // compare digest with expect[]
+  F_LZ4_BLOCK = 4u     // the blob is one raw LZ4 block (no frame, no magic): compressed[i] == 2 in the C ABI
 };
 
 // One row of the batch (index row: blob_offset, blob_size, uncompressed_size, compressed — index.rs:45-52).

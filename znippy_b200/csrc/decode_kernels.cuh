@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 16 : 512 / NT) k_decode(const B
           __syncthreads();
           src = s_src + 16;
         }
-        st = decode_blob(t, &sh, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, lit, predef, &got);
+        if (d.flags & F_LZ4_BLOCK)
+          st = decode_lz4_block(t, &sh, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, &got);
+        else
+          st = decode_blob(t, &sh, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, lit, predef, &got);
         if (st == S_OK && got != (uint32_t)d.dst_cap) st = S_SIZE_MISMATCH;
       }
       ZN_TP(22);

@@ -184,4 +184,15 @@ ZN_HD uint32_t decode_blob(const Team& t, DecShared* sh, const uint8_t* src, uin
   return zs::decode_frames(t, sh, src, src_len, out, cap, lit_scratch, predef, produced);
 }
 
+// A raw LZ4 block (LZ4_compress_default output): no header at all, the index supplies both sizes.
+ZN_HD uint32_t decode_lz4_block(const Team& t, DecShared* sh, const uint8_t* src, uint32_t src_len, uint8_t* out,
+                                uint32_t cap, uint32_t* produced) {
+  zs::ExecState es;
+  es.pos = 0; es.wm = 0; es.bulk = 0;
+  *produced = 0;
+  const uint32_t rc = lz::decode_block(t, sh, src, src_len, out, cap, 0u, es);
+  *produced = es.pos;
+  return rc;
+}
+
 }  // namespace zn

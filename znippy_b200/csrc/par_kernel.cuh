@@ -353,7 +353,10 @@ __global__ void __launch_bounds__(kParThreads, 1) k_decode_par(const BlobDesc* _
         __syncthreads();
         src = ps->src + 16;
       }
-      st = decode_blob_par(t, ps, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, my_scratch, &got);
+      if (d.flags & F_LZ4_BLOCK)
+        st = decode_lz4_block(t, &ps->slot[0], src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, &got);
+      else
+        st = decode_blob_par(t, ps, src, (uint32_t)d.src_len, out_base + d.dst_off, (uint32_t)d.dst_cap, my_scratch, &got);
       if (st == S_OK && got != (uint32_t)d.dst_cap) st = S_SIZE_MISMATCH;
     }
     if (threadIdx.x < kBulkIssuers) bulk_wait_all();

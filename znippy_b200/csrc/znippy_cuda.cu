@@ -269,7 +269,7 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     const uint64_t nc = std::max<uint64_t>(1, (d.dst_cap + kChunk - 1) / kChunk);
     d.n_chunks = (uint32_t)nc;
     d.cv_base = chunks;
-    d.flags = (comp ? F_COMPRESSED : 0u) | (expect ? F_HAS_EXPECT : 0u);
+    d.flags = (comp ? F_COMPRESSED : 0u) | (expect ? F_HAS_EXPECT : 0u) | (comp && compressed[i] == 2 ? F_LZ4_BLOCK : 0u);
     prefix[i] = (uint32_t)chunks;
     chunks += nc;
     if (chunks > 0xFFFFFFF0ull) { delete p; c->err = "batch too large (chunk count)"; return nullptr; }
