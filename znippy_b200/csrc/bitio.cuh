@@ -68,6 +68,38 @@ struct BackBits {
     pre = fetch(widx);
     return true;
   }
+#if defined(__CUDA_ARCH__)
+  // Device fast path: the 64-bit window is handled as two 32-bit halves with clamped funnel shifts (one SHF each)
+  // instead of multi-instruction 64-bit variable shifts.  When navail <= 32 every valid bit sits in the high half.
+  ZN_D void refill() {  // afterwards navail > 32, so any read of <= 32 bits is served from the window
+    if (navail <= 32) {
+      uint32_t hi = (uint32_t)(win >> 32);
+      const uint32_t n = (uint32_t)navail;
+      hi |= __funnelshift_rc(pre, 0u, n);                    // pre >> n          (0 when n == 32)
+      const uint32_t lo = __funnelshift_rc(0u, pre, n);      // pre << (32 - n)   (0 when n == 0)
+      win = ((uint64_t)hi << 32) | lo;
+      navail += 32;
+      widx--;
+      pre = fetch(widx);
+      if (navail <= 32) {  // the window was empty: take a second word
+        const uint32_t n2 = (uint32_t)navail;
+        uint32_t h2 = (uint32_t)(win >> 32);
+        h2 |= __funnelshift_rc(pre, 0u, n2);
+        win = ((uint64_t)h2 << 32) | __funnelshift_rc(0u, pre, n2);
+        navail += 32;
+        widx--;
+        pre = fetch(widx);
+      }
+    }
+  }
+  ZN_D uint32_t peek(uint32_t n) const { return __funnelshift_lc((uint32_t)(win >> 32), 0u, n); }  // n <= 32
+  ZN_D void skip(uint32_t n) {
+    const uint32_t hi = (uint32_t)(win >> 32), lo = (uint32_t)win;
+    win = ((uint64_t)__funnelshift_lc(lo, hi, n) << 32) | __funnelshift_lc(0u, lo, n);
+    navail -= (int32_t)n;
+    bits_left -= (int32_t)n;
+  }
+#else
   ZN_HD void refill() {  // afterwards navail > 32, so any read of <= 32 bits is served from the window
     while (navail <= 32) {
       win |= (uint64_t)pre << (32 - navail);
@@ -78,6 +110,7 @@ struct BackBits {
   }
   ZN_HD uint32_t peek(uint32_t n) const { return n ? (uint32_t)(win >> (64 - n)) : 0u; }  // n <= 32
   ZN_HD void skip(uint32_t n) { win <<= n; navail -= (int32_t)n; bits_left -= (int32_t)n; }
+#endif
   ZN_HD uint32_t read(uint32_t n) {  // n <= 32; caller guarantees a refill() since the last 32 bits consumed
     const uint32_t v = peek(n);
     skip(n);

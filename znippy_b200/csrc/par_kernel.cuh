@@ -102,6 +102,16 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
     }
     const bool in_batch = pending && c_hi == b && c_lo <= c_hi;       // part of the source lies in this batch
     const uint32_t c_end = c_hi == b ? b - 1u : c_hi;                  // (b == 0 and c_hi == 0: wraps; guarded below)
+    // earlier lanes of this batch whose match output [dst_j, dst_j + ml_j) overlaps my source range (computed once)
+    uint32_t dep_mask = 0;
+    if (__any_sync(0xFFFFFFFFu, in_batch)) {
+#pragma unroll 4
+      for (uint32_t j = 0; j < 31; j++) {
+        const int32_t dj = __shfl_sync(0xFFFFFFFFu, dst, j);
+        const int32_t ej = dj + (int32_t)__shfl_sync(0xFFFFFFFFu, q.ml, j);
+        if (in_batch && j < lane && dj < src_end && ej > src) dep_mask |= 1u << j;
+      }
+    }
     uint32_t pm;
     ZN_CNT(0, 1);
     const long long t_b0 = clock64();
@@ -112,16 +122,8 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
         while (c_lo <= c_end && bdone[c_lo]) c_lo++;
         ext_ok = c_lo > c_end;
       }
-      // inside the batch: a lane must wait only for PENDING earlier lanes whose match output overlaps its source
-      bool in_ok = true;
-      for (uint32_t mm = pm; mm;) {
-        const uint32_t j = (uint32_t)__ffs((int)mm) - 1u;
-        mm &= mm - 1u;
-        const int32_t dj = __shfl_sync(0xFFFFFFFFu, dst, j);
-        const int32_t ej = dj + (int32_t)__shfl_sync(0xFFFFFFFFu, q.ml, j);
-        if (j < lane && dj < src_end && ej > src) in_ok = false;
-      }
-      const bool ready = pending && ext_ok && (!in_batch || in_ok);
+      // inside the batch a lane waits only for PENDING earlier lanes whose match output overlaps its source
+      const bool ready = pending && ext_ok && (dep_mask & pm) == 0;
       if (!__any_sync(0xFFFFFFFFu, ready)) {
         ZN_CNT(2, 1);
         __nanosleep(20);
@@ -130,8 +132,21 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
       { const uint32_t nr__ = __popc(__ballot_sync(0xFFFFFFFFu, ready)); ZN_CNT(3, nr__); (void)nr__; }
       __threadfence_block();  // order the reads below after the observation of bdone[]
       if (ready && q.ml <= kLaneMax) {
-        // byte-serial in one lane: also correct for self-overlapping matches (off < ml)
-        for (uint32_t i = 0; i < q.ml; i++) {
+        uint32_t i = 0;
+        if (q.off >= 4) {  // 4 bytes per step: the loads of a step do not depend on its stores (distance >= 4)
+          for (; i + 4 <= q.ml; i += 4) {
+            const int32_t p = src + (int32_t)i;
+            uint8_t v0, v1, v2, v3;
+            if (p >= 0) { v0 = obuf[p]; v1 = obuf[p + 1]; v2 = obuf[p + 2]; v3 = obuf[p + 3]; }
+            else {
+              v0 = gout[p]; v1 = p + 1 >= 0 ? obuf[p + 1] : gout[p + 1]; v2 = p + 2 >= 0 ? obuf[p + 2] : gout[p + 2];
+              v3 = p + 3 >= 0 ? obuf[p + 3] : gout[p + 3];
+            }
+            uint8_t* o = obuf + dst + (int32_t)i;
+            o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
+          }
+        }
+        for (; i < q.ml; i++) {  // byte-serial tail / short distances: also correct for self-overlapping matches
           const int32_t p = src + (int32_t)i;
           obuf[dst + (int32_t)i] = p >= 0 ? obuf[p] : gout[p];
         }

@@ -266,7 +266,7 @@ ZN_HD void decode_block_sequences(const uint8_t* src, uint32_t src_len, BlockRec
       nsym++;
     }
     if (ll > rec->lit_len - lit_pos) return;  // lit_len was published by the walker from the literals header
-    if ((uint64_t)out_pos + ll + ml > kZstdBlockMax) return;
+    if (ll > kZstdBlockMax || ml > kZstdBlockMax + 3u || out_pos + ll + ml > kZstdBlockMax) return;
     SeqOut r;
     r.out_rel = out_pos; r.lit_rel = lit_pos; r.ll = ll; r.ml = ml; r.off = offset;
     out[i] = r;
