@@ -162,6 +162,25 @@ def build_workload(name: str, gib: float, rank: int):
         return blobs, lens, np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy(), np.ones(len(blobs), np.uint8), (
             f"real text (python stdlib sources, {tot >> 20} MiB cycled to {gib:g} GiB), {len(blobs)} rows x 8 MiB, zstd level 3 "
             "frames: Huffman literals + FSE-described sequence tables")
+    if name == "realsmall":  # the reference's only published entropy-coded corpus shape (backlog.md:322): ~41 k files of ~24 KB
+        import sysconfig
+        root = sysconfig.get_paths()["stdlib"]
+        data = np.frombuffer(b"".join(open(os.path.join(root, fn), "rb").read() for fn in sorted(os.listdir(root))
+                                      if fn.endswith(".py")), np.uint8)
+        rng = np.random.default_rng(5)
+        z = _libzstd()
+        n, uniq = 40_000, 2_000  # 2 000 distinct files (compressing 40 000 would dominate the bench's set-up time), cycled
+        files = []
+        for _ in range(uniq):
+            ln = int(rng.integers(2_000, 48_000))
+            o = int(rng.integers(0, data.size - ln))
+            sl = np.ascontiguousarray(data[o:o + ln])
+            files.append((_zstd_compress(z, sl, 3), ln, _digest(sl)))
+        blobs = [files[i % uniq][0] for i in range(n)]
+        lens = [files[i % uniq][1] for i in range(n)]
+        digs = np.frombuffer(b"".join(files[i % uniq][2] for i in range(n)), np.uint8).reshape(-1, 32).copy()
+        return blobs, lens, digs, np.ones(n, np.uint8), (
+            f"{n} real-text files of 2-48 KB ({sum(lens) >> 20} MiB, python sources), one zstd level-3 frame per file")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -326,14 +345,16 @@ def run_ours(args):
     in_buf, in_off = pack(blobs, 16)
     in_len = np.array([len(b) for b in blobs], np.uint64)
     out_len = np.array(lens, np.uint64)
-    out_off = np.concatenate([[0], np.cumsum(out_len)])[:-1].astype(np.uint64)
+    # output rows 16-byte aligned, as the host-buffer API and the archive loops lay them out
+    out_off = np.concatenate([[0], np.cumsum((out_len + np.uint64(15)) & ~np.uint64(15))])[:-1].astype(np.uint64)
     out_bytes = int(out_len.sum())
+    out_span = int(out_off[-1] + out_len[-1]) if n else 0
 
-    ctx = Ctx(local, staging_bytes=out_bytes + in_buf.size + (1 << 20))
+    ctx = Ctx(local, staging_bytes=out_span + in_buf.size + (1 << 20))
     stream = torch.cuda.Stream()  # a real (non-default) stream: kernels and the timing events share it
     torch.cuda.set_stream(stream)
     d_in = torch.from_numpy(in_buf).cuda()
-    d_out = torch.empty(out_bytes + 256, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(out_span + 256, dtype=torch.uint8, device="cuda")
     plan = Plan.decode_verify(ctx, in_off, in_len, comp, out_off, out_len, digs)
     plan.set_overlap(args.groups)  # decode of row range g+1 overlaps blake3 of range g (znippy_cuda.h)
 
@@ -387,7 +408,7 @@ def run_ours(args):
     pinned = ctx.pinned()
     h_in = pinned[: in_buf.size]
     h_in[:] = in_buf
-    h_out = pinned[in_buf.size + 4096 - in_buf.size % 4096:][:out_bytes]
+    h_out = pinned[in_buf.size + 4096 - in_buf.size % 4096:][:out_span]
     e2e_steps = max(3, min(args.steps, 20))
     codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)  # warm (allocations)
     sync_all()
@@ -444,7 +465,7 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu:
-        k = min(n, 64 if args.workload != "small100k" else 20000)
+        k = min(n, 64 if args.workload not in ("small100k", "realsmall") else 20000)
         gbs, threads, desc, _ = cpu_pipeline(blobs[:k], lens[:k], digs[:k], args.cpu_seconds, comp=comp[:k])
         cpu = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": desc}
 
@@ -474,7 +495,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed", "realtext"],
+    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed", "realtext", "realsmall"],
                     help="text2g = BASELINE configs[1] (the metric's config); the others are secondary report lines")
     ap.add_argument("--gib", type=float, default=2.0, help="uncompressed GiB per GPU (2 = BASELINE configs[1])")
     ap.add_argument("--groups", type=int, default=1, help="row groups of the overlapped decode/hash schedule (1 = serial)")

@@ -291,3 +291,20 @@ def test_raw_lz4_blocks(codec, oracle):
     assert st[0] != 0
     st, _ = codec.decode_verify_batch(buf, offs[:1], [len(blobs[0])], [2], [lens[0] - 1], None, out, [0])
     assert st[0] in (codec.S_DST_TOO_SMALL, codec.S_DECODE_ERROR, codec.S_SIZE_MISMATCH)
+
+
+def test_block_parallel_mixed_batch_with_small_sources(codec, oracle):
+    """A big-blob batch (block-parallel kernel) that also holds blobs whose COMPRESSED form is small enough to be staged
+    in shared memory, with short-sequence blocks (lane executor) and long-match blocks (team executor) interleaved."""
+    O = oracle
+    z = O.libzstd()
+    rt = O.real_text(2_500_000)
+    small_real = O.real_text(20_000)                     # ~6 KB compressed: staged source + lane executor
+    mix = np.concatenate([O.gen_text(400_000), rt[:300_000], O.gen_binary(300_000), rt[300_000:500_000]])
+    contents = [rt.tobytes(), small_real.tobytes(), mix.tobytes(), rt[:1_000_000].tobytes(), small_real[:5000].tobytes(),
+                rt[100:2_200_100].tobytes()]
+    blobs = [z.compress(c, 3) for c in contents]
+    st, dg, out, out_off = _run(codec, blobs, [1] * len(blobs), contents)
+    assert st.tolist() == [0] * len(blobs)
+    for i, c in enumerate(contents):
+        assert out[out_off[i]:out_off[i] + len(c)].tobytes() == c, i

@@ -71,9 +71,12 @@ ZN_D uint32_t exec_block_lanes(const Team& t, ParShared* ps, const BlockRec& r, 
   // range is flagged done (bdone[]), and the part of its source inside its own batch lies below the first unfinished
   // lane's match.  Far matches therefore never wait, and a batch only waits for the few lanes that really depend on
   // its predecessors.  bstart[c] = block-relative output position where batch c begins.
-  uint32_t* bstart = reinterpret_cast<uint32_t*>(ps->tile);                 // nb + 1 <= 1377 entries (8 KiB tile)
-  volatile uint8_t* bdone = reinterpret_cast<volatile uint8_t*>(ps->src);   // nb <= 1376 flags
-  static_assert(kTileBytes >= (kMaxSeq / 32 + 2) * 4 && kSrcStage >= kMaxSeq / 32 + 1, "scratch too small for batch tables");
+  // both tables live in the bulk-store tile, which is idle here (the caller drained bulk stores with mem_sync); the
+  // staged-source buffer ps->src must NOT be touched: the walker of the next group still parses from it
+  constexpr uint32_t kMaxBatches = kMaxSeq / 32;
+  uint32_t* bstart = reinterpret_cast<uint32_t*>(ps->tile);                                      // nb + 1 entries
+  volatile uint8_t* bdone = reinterpret_cast<volatile uint8_t*>(ps->tile + (kMaxBatches + 2) * 4);  // nb flags
+  static_assert(kTileBytes >= (kMaxBatches + 2) * 4 + kMaxBatches + 1, "tile too small for the batch tables");
   for (uint32_t c = t.tid; c <= nb; c += t.n) {
     bstart[c] = c < nb ? seqs[c * 32u].out_rel : r.matched;
     if (c < nb) bdone[c] = 0;
