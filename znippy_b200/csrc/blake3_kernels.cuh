@@ -67,13 +67,63 @@ ZN_D void b3_issue_stage(uint8_t* buf, const uint8_t* ptr, uint32_t len, uint32_
       uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
       for (uint32_t j = 0; j < 4; j++) {
-        if (j < nb) w0 |= (uint32_t)__ldg(src + j) << (8 * j);
-        if (j + 4 < nb) w1 |= (uint32_t)__ldg(src + j + 4) << (8 * j);
-        if (j + 8 < nb) w2 |= (uint32_t)__ldg(src + j + 8) << (8 * j);
-        if (j + 12 < nb) w3 |= (uint32_t)__ldg(src + j + 12) << (8 * j);
+        if (j < nb) w0 |= (uint32_t)src[j] << (8 * j);  // plain (coherent) loads: the fused decoder hashes its own output
+        if (j + 4 < nb) w1 |= (uint32_t)src[j + 4] << (8 * j);
+        if (j + 8 < nb) w2 |= (uint32_t)src[j + 8] << (8 * j);
+        if (j + 12 < nb) w3 |= (uint32_t)src[j + 12] << (8 * j);
       }
       *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
     }
+  }
+}
+
+// Chaining values of one warp tile: lane L hashes the (<= 1 KiB) chunk at `ptr` (len bytes, chunk counter ctr).
+// wbuf = this warp's kB3SmemPerWarp bytes of shared memory.  All 32 lanes must call (act = lane has a chunk).
+ZN_D void b3_warp_tile(uint8_t* wbuf, const uint8_t* ptr, uint32_t len, uint32_t ctr, bool root, bool act, uint32_t lane,
+                       uint32_t one, uint32_t (&cv)[8]) {
+  const uint32_t nblocks = act ? (len == 0 ? 1u : (len + 63u) >> 6) : 0u;
+  b3::set_iv(cv);
+  // ---- software pipeline over the 8 stages of a chunk
+  const uint8_t* base0 = reinterpret_cast<const uint8_t*>(
+      ((uintptr_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(reinterpret_cast<uintptr_t>(ptr) >> 32), 0) << 32) |
+      __shfl_sync(0xFFFFFFFFu, (uint32_t)reinterpret_cast<uintptr_t>(ptr), 0));
+  const bool regular = __all_sync(0xFFFFFFFFu, act && len == kChunk && ptr == base0 + (size_t)lane * kChunk) &&
+                       (reinterpret_cast<uintptr_t>(base0) & 15) == 0;
+  __syncwarp();
+  b3_issue_stage(wbuf, ptr, len, 0, lane, regular, base0);
+  cp_async_commit();
+#pragma unroll 1
+  for (uint32_t s = 0; s < kChunk / kB3RowBytes; s++) {
+    uint8_t* cur = wbuf + (s & 1u) * kB3StageBytes;
+    if (s + 1 < kChunk / kB3RowBytes) b3_issue_stage(wbuf + ((s + 1) & 1u) * kB3StageBytes, ptr, len, s + 1, lane, regular, base0);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint4* row = reinterpret_cast<const uint4*>(cur + lane * kB3RowStride);
+#pragma unroll
+    for (uint32_t j = 0; j < kB3RowBytes / 64; j++) {
+      const uint32_t b = s * (kB3RowBytes / 64) + j;
+      if (b < nblocks) {
+        uint32_t m[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint4 v = row[j * 4 + k];
+          m[4 * k] = v.x; m[4 * k + 1] = v.y; m[4 * k + 2] = v.z; m[4 * k + 3] = v.w;
+        }
+        const uint32_t n = min(64u, len - b * 64u);
+        if (n < 64u) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const int vb = (int)n - 4 * k;  // valid bytes in word k
+            m[k] = vb >= 4 ? m[k] : (vb <= 0 ? 0u : (m[k] & (0xFFFFFFFFu >> (8 * (4 - vb)))));
+          }
+        }
+        uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
+        if (b + 1 == nblocks) flags |= b3::CHUNK_END | (root ? b3::ROOT : 0u);
+        b3::compress(cv, m, ctr, 0u, n, flags, one);
+      }
+    }
+    __syncwarp();  // everyone is done with `cur` before the next iteration's copies land in it
   }
 }
 
@@ -96,7 +146,7 @@ __global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __r
     // ---- which chunk of which blob is mine
     const uint8_t* ptr = nullptr;
     uint32_t len = 0, ctr = 0;
-    bool root = false;
+    bool root = false, skip = false;
     if (act) {
       uint32_t lo = 0, hi = n_blobs;
       while (hi - lo > 1) {  // largest b with chunk_prefix[b] <= g
@@ -104,58 +154,17 @@ __global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __r
         if (__ldg(chunk_prefix + mid) <= g) lo = mid; else hi = mid;
       }
       const BlobDesc d = blobs[lo];
+      skip = (d.flags & F_HASHED) != 0;  // chaining values already produced by the fused decode kernel
       ctr = g - __ldg(chunk_prefix + lo);
       ptr = content_ptr(d, blobs_base, out_base) + (uint64_t)ctr * kChunk;
       const uint64_t remain = d.dst_cap - (uint64_t)ctr * kChunk;
       len = remain < kChunk ? (uint32_t)remain : kChunk;
       root = d.n_chunks == 1;
     }
-    const uint32_t nblocks = act ? (len == 0 ? 1u : (len + 63u) >> 6) : 0u;
+    if (__all_sync(0xFFFFFFFFu, !act || skip)) continue;
     uint32_t cv[8];
-    b3::set_iv(cv);
-    // ---- software pipeline over the 8 stages of a chunk
-    const uint8_t* base0 = reinterpret_cast<const uint8_t*>(
-        ((uintptr_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(reinterpret_cast<uintptr_t>(ptr) >> 32), 0) << 32) |
-        __shfl_sync(0xFFFFFFFFu, (uint32_t)reinterpret_cast<uintptr_t>(ptr), 0));
-    const bool regular = __all_sync(0xFFFFFFFFu, act && len == kChunk && ptr == base0 + (size_t)lane * kChunk) &&
-                         (reinterpret_cast<uintptr_t>(base0) & 15) == 0;
-    __syncwarp();
-    b3_issue_stage(wbuf, ptr, len, 0, lane, regular, base0);
-    cp_async_commit();
-#pragma unroll 1
-    for (uint32_t s = 0; s < kChunk / kB3RowBytes; s++) {
-      uint8_t* cur = wbuf + (s & 1u) * kB3StageBytes;
-      if (s + 1 < kChunk / kB3RowBytes) b3_issue_stage(wbuf + ((s + 1) & 1u) * kB3StageBytes, ptr, len, s + 1, lane, regular, base0);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      const uint4* row = reinterpret_cast<const uint4*>(cur + lane * kB3RowStride);
-#pragma unroll
-      for (uint32_t j = 0; j < kB3RowBytes / 64; j++) {
-        const uint32_t b = s * (kB3RowBytes / 64) + j;
-        if (b < nblocks) {
-          uint32_t m[16];
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint4 v = row[j * 4 + k];
-            m[4 * k] = v.x; m[4 * k + 1] = v.y; m[4 * k + 2] = v.z; m[4 * k + 3] = v.w;
-          }
-          const uint32_t n = min(64u, len - b * 64u);
-          if (n < 64u) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-              const int vb = (int)n - 4 * k;  // valid bytes in word k
-              m[k] = vb >= 4 ? m[k] : (vb <= 0 ? 0u : (m[k] & (0xFFFFFFFFu >> (8 * (4 - vb)))));
-            }
-          }
-          uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u);
-          if (b + 1 == nblocks) flags |= b3::CHUNK_END | (root ? b3::ROOT : 0u);
-          b3::compress(cv, m, ctr, 0u, n, flags, one);
-        }
-      }
-      __syncwarp();  // everyone is done with `cur` before the next iteration's copies land in it
-    }
-    if (act) b3::store_cv(cvs + (uint64_t)g * 8, cv);
+    b3_warp_tile(wbuf, ptr, len, ctr, root, act && !skip, lane, one, cv);
+    if (act && !skip) b3::store_cv(cvs + (uint64_t)g * 8, cv);
   }
 }
 

@@ -34,6 +34,7 @@ enum : uint32_t {
 enum : uint32_t {
   F_COMPRESSED = 1u,   // run the codec; otherwise content == blob bytes (store-as-is, decompress.rs:164-166)
   F_HAS_EXPECT = 2u,   // compare digest with expect[]
+  F_HASHED = 8u,       // chunk chaining values are written by the fused decode+hash kernel, k_b3_chunks skips the blob
   F_LZ4_BLOCK = 4u     // the blob is one raw LZ4 block (no frame, no magic): compressed[i] == 2 in the C ABI
 };
 

@@ -177,11 +177,25 @@ ZN_HD uint32_t decode_frame(const Team& t, DecShared* sh, const uint8_t* src, ui
 // Entry point of the codec for one blob: picks the payload format by its magic number.
 // `predef` (team-uniform, owned by the caller across blobs) records which sequence tables in `sh` hold the
 // predefined distributions, so consecutive blobs do not copy them again.
+template <class Hook>
+ZN_HD uint32_t decode_blob(const Team& t, DecShared* sh, const uint8_t* src, uint32_t src_len, uint8_t* out,
+                           uint32_t cap, uint8_t* lit_scratch, uint32_t& predef, uint32_t* produced, Hook& hook) {
+  *produced = 0;
+  if (src_len >= 4 && ld32le(src) == 0x184D2204u) {
+    const uint32_t rc = lz::decode_frame(t, sh, src, src_len, out, cap, produced);
+    if (rc == S_OK) {  // the LZ4 path has no per-block hook: everything is hashed at the end
+      zs::ExecState es;
+      es.pos = *produced; es.wm = 0; es.bulk = 1;  // force a full memory barrier (and bulk drain) in finish()
+      hook.finish(t, es);
+    }
+    return rc;
+  }
+  return zs::decode_frames(t, sh, src, src_len, out, cap, lit_scratch, predef, produced, hook);
+}
 ZN_HD uint32_t decode_blob(const Team& t, DecShared* sh, const uint8_t* src, uint32_t src_len, uint8_t* out,
                            uint32_t cap, uint8_t* lit_scratch, uint32_t& predef, uint32_t* produced) {
-  *produced = 0;
-  if (src_len >= 4 && ld32le(src) == 0x184D2204u) return lz::decode_frame(t, sh, src, src_len, out, cap, produced);
-  return zs::decode_frames(t, sh, src, src_len, out, cap, lit_scratch, predef, produced);
+  zs::NoHook h;
+  return decode_blob(t, sh, src, src_len, out, cap, lit_scratch, predef, produced, h);
 }
 
 // A raw LZ4 block (LZ4_compress_default output): no header at all, the index supplies both sizes.

@@ -60,6 +60,7 @@ struct zn_plan {
   cudaStream_t last_stream = nullptr;
   bool ran = false;
   bool big_blobs = false;    // mean decoded size >= 512 KiB: 256-thread teams
+  bool fused_hash = false;   // large, highly compressible blobs: chaining values come out of the fused decode kernel
   bool entropy_heavy = false;  // compressed size > 1/64 of decoded size: many sequences per block -> block-parallel decode
   bool small_blobs = false;  // mean decoded size <= 64 KiB: one-warp teams
   // overlapped schedule: blobs are cut into `groups` contiguous index ranges; group g+1 decodes (HBM-bound) on the
@@ -159,6 +160,7 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   build_predef(&pd);
   if (cudaMemcpyToSymbol(g_predef, &pd, sizeof pd) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
   cudaFuncSetAttribute(k_b3_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Warps * kB3SmemPerWarp);
+  cudaFuncSetAttribute(k_decode<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kB3SmemPerWarp);
   cudaFuncSetAttribute(par::k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(par::ParShared));
   compress_init_attrs();
   return c;
@@ -291,6 +293,11 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     uint64_t src_bytes = 0;
     for (uint32_t i : ldec) src_bytes += descs[i].src_len;
     p->entropy_heavy = src_bytes * 64 > dec_bytes;
+    // Fused decode+hash (K4) is parity-tested but opt-in: on the 2 GiB pattern file it measures 1.54 ms against 1.43 ms
+    // for decode and hash back to back, because a team cannot hash while it parses its next block.
+    p->fused_hash = p->big_blobs && !p->entropy_heavy && getenv("ZN_FUSE") != nullptr;
+    if (p->fused_hash)
+      for (uint32_t i : ldec) descs[i].flags |= F_HASHED;
     p->small_blobs = !ldec.empty() && dec_bytes / ldec.size() <= (64u << 10);
   }
   p->n_small = (uint32_t)lsmall.size();
@@ -385,8 +392,8 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
       const char* force = getenv("ZN_DECODE_KERNEL");  // development override: par | team | warp
       if (force && !strcmp(force, "warp")) {
         const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
-        k_decode<32, 2><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
-                                             p->d_counter + g);
+        k_decode<32, 2, false><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+                                             p->d_counter + g, nullptr, 1u);
       } else
       if (p->big_blobs && p->entropy_heavy && !getenv("ZN_NO_PAR")) {  // large blobs: block-parallel decode, one CTA per SM
         const uint32_t max_grid = (uint32_t)c->sm_count;
@@ -400,22 +407,26 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
                                                                                  p->d_status, p->d_produced, p->d_counter + g);
       } else if (p->big_blobs) {  // highly compressible large blobs (few, long sequences): one 256-thread team per blob
         const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
-        k_decode<256, 1><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
-                                            p->d_counter + g);
+        if (p->fused_hash)
+          k_decode<256, 1, true><<<grid, 256, 8 * kB3SmemPerWarp, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                                       p->d_produced, p->d_counter + g, p->d_cvs, 1u);
+        else
+          k_decode<256, 1, false><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                        p->d_produced, p->d_counter + g, nullptr, 1u);
       } else if (p->small_blobs) {  // many small blobs: one warp per blob, ~10 blobs in flight per SM
         const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
-        k_decode<32, 2><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
-                                             p->d_counter + g);
+        k_decode<32, 2, false><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+                                             p->d_counter + g, nullptr, 1u);
       } else {
         const uint32_t grid = std::min<uint32_t>((nd + 3) / 4, c->dec_grid);
-        k_decode<kDecodeThreads, 4><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
-                                                                  p->d_produced, p->d_counter + g);
+        k_decode<kDecodeThreads, 4, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit,
+                                                                         p->d_status, p->d_produced, p->d_counter + g, nullptr, 1u);
       }
       launches++;
     }
     if (g + 1 == p->groups) ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
     const uint32_t clo = p->grp_chunk_lo[g], chi = p->grp_chunk_lo[g + 1];
-    if (chi > clo) {
+    if (chi > clo && !(p->fused_hash && p->n_dec == p->n)) {
       cudaStream_t hs = st;
       if (overlap) {
         ZN_CUDA(c, cudaEventRecord(p->evg[g], st));

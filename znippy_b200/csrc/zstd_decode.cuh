@@ -434,10 +434,18 @@ ZN_HD uint32_t decode_block(const Team& t, DecShared* sh, const uint8_t* p, uint
 }
 
 
+// Hook called (team-uniform) after every block and once at the end; the fused decode+hash kernel hashes the chunks that
+// have become final (below es.wm) while later blocks' bulk stores are still in flight.
+struct NoHook {
+  ZN_HD void after_block(const Team&, ExecState&) {}
+  ZN_HD void finish(const Team&, ExecState&) {}
+};
+
 // All concatenated frames of one blob (skippable frames are skipped).  Team-uniform.
 // Returns the blob's status; *produced = bytes written to out.
+template <class Hook>
 ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, uint32_t src_len, uint8_t* out,
-                             uint32_t cap, uint8_t* lit_scratch, uint32_t& predef, uint32_t* produced) {
+                             uint32_t cap, uint8_t* lit_scratch, uint32_t& predef, uint32_t* produced, Hook& hook) {
   uint32_t ip = 0;
   ExecState es;
   es.pos = 0;
@@ -519,6 +527,7 @@ ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, u
         ip += bsize;
       }
       *produced = es.pos;
+      hook.after_block(t, es);
       if (last) break;
     }
     if (fb != 0 && (uint64_t)(es.pos - frame_start) != fcs) return S_SIZE_MISMATCH;
@@ -528,6 +537,7 @@ ZN_HD uint32_t decode_frames(const Team& t, DecShared* sh, const uint8_t* src, u
     }
   }
   *produced = es.pos;
+  hook.finish(t, es);
   return S_OK;
 }
 
