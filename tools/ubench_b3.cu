@@ -76,6 +76,29 @@ struct G<4> {  // rotr12 / rotr7 through a 64-bit IMAD.WIDE (x * 2^(32-r): hi|lo
   }
 };
 
+template <>
+struct G<5> {  // V1 + only rotr7 through IMAD.WIDE (x * 2^25: hi + lo = rotr 7), sum on the FMA pipe
+  static __device__ __forceinline__ void g(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t mx, uint32_t my, uint32_t one,
+                                           uint32_t, uint32_t m25) {
+    a = imad(mx, one, a + b); d = rotr16(d ^ a); c = c + d; b = rotr12(b ^ c);
+    a = imad(my, one, a + b); d = rotr8(d ^ a); c = c + d;
+    const uint64_t w = (uint64_t)(b ^ c) * m25;
+    b = imad((uint32_t)(w >> 32), one, (uint32_t)w);
+  }
+};
+template <>
+struct G<6> {  // V1 + rotr12 and rotr7 through IMAD.WIDE
+  static __device__ __forceinline__ void g(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t mx, uint32_t my, uint32_t one,
+                                           uint32_t m20, uint32_t m25) {
+    a = imad(mx, one, a + b); d = rotr16(d ^ a); c = c + d;
+    uint64_t w = (uint64_t)(b ^ c) * m20;
+    b = imad((uint32_t)(w >> 32), one, (uint32_t)w);
+    a = imad(my, one, a + b); d = rotr8(d ^ a); c = c + d;
+    w = (uint64_t)(b ^ c) * m25;
+    b = imad((uint32_t)(w >> 32), one, (uint32_t)w);
+  }
+};
+
 template <int V>
 __device__ __forceinline__ void compress(uint32_t (&cv)[8], const uint32_t (&m)[16], uint32_t ctr, uint32_t blen, uint32_t flags,
                                          uint32_t one, uint32_t m20, uint32_t m25) {
@@ -154,16 +177,18 @@ int main() {
     const int grid = sms * cps;
     cudaMalloc(&d_out, (size_t)grid * 256 * 4);
     std::vector<uint32_t> ref(256), got(256);
-    double ms[5];
+    double ms[7];
     ms[0] = run<0>(d_out, d_seed, grid, iters, ref.data());
     ms[1] = run<1>(d_out, d_seed, grid, iters, got.data()); bool ok1 = got == ref;
     ms[2] = run<2>(d_out, d_seed, grid, iters, got.data()); bool ok2 = got == ref;
     ms[3] = run<3>(d_out, d_seed, grid, iters, got.data()); bool ok3 = got == ref;
     ms[4] = run<4>(d_out, d_seed, grid, iters, got.data()); bool ok4 = got == ref;
+    ms[5] = run<5>(d_out, d_seed, grid, iters, got.data()); bool ok5 = got == ref;
+    ms[6] = run<6>(d_out, d_seed, grid, iters, got.data()); bool ok6 = got == ref;
     const double bytes = (double)grid * 256 * iters * 64;
     printf("ctas/sm=%d  ", cps);
-    for (int v = 0; v < 5; v++) printf("V%d %.3f ms %.0f GB/s  ", v, ms[v], bytes / ms[v] / 1e6);
-    printf(" agree=%d%d%d%d\n", ok1, ok2, ok3, ok4);
+    for (int v = 0; v < 7; v++) printf("V%d %.3f ms %.0f GB/s  ", v, ms[v], bytes / ms[v] / 1e6);
+    printf(" agree=%d%d%d%d%d%d\n", ok1, ok2, ok3, ok4, ok5, ok6);
     cudaFree(d_out);
   }
   return 0;

@@ -70,8 +70,8 @@ def decode_verify_batch(blobs, blob_off, blob_len, compressed, out_len, expect=N
             raise ValueError("output range outside out buffer")
     if b.size == 0:
         b = np.zeros(1, np.uint8)
-    st = np.zeros(n, np.uint32)
-    dg = np.zeros((n, 32), np.uint8)
+    st = np.empty(n, np.uint32)  # both fully written by the call
+    dg = np.empty((n, 32), np.uint8)
     ctx.check(N.lib().zn_decode_verify_batch(ctx.handle, N.ptr(b), N.ptr(bo), N.ptr(bl), N.ptr(cf), N.ptr(ol), N.ptr(ex),
                                              N.ptr(out), N.ptr(oo), n, N.ptr(st), N.ptr(dg)), "zn_decode_verify_batch")
     return st, dg

@@ -233,6 +233,10 @@ static int plan_set_groups(zn_plan* p, int groups) {
     p->grp_chunk_lo[g + 1] = p->h_prefix[b1];
     b0 = b1;
   }
+  if (groups > 1 && !p->ev_join) {  // events of the overlapped schedule are only created when it is used
+    for (int i = 0; i < zn_plan::kMaxGroups; i++) ZN_CUDA(c, cudaEventCreateWithFlags(&p->evg[i], cudaEventDisableTiming));
+    ZN_CUDA(c, cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  }
   p->groups = groups;
   if (!ldec.empty()) {
     ZN_CUDA(c, cudaMemcpyAsync(p->d_list_dec, ldec.data(), ldec.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -259,6 +263,10 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
   p->n = n;
   std::vector<BlobDesc> descs(n);
   std::vector<uint32_t> prefix(n + 1, 0), ldec, lsmall, llarge, pblob, pidx;
+  ldec.reserve(n);
+  lsmall.reserve(n);
+  p->h_cap.reserve(n);
+  p->h_comp.reserve(n);
   uint64_t chunks = 0;
   for (uint32_t i = 0; i < n; i++) {
     BlobDesc& d = descs[i];
@@ -304,7 +312,7 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
   p->n_large = (uint32_t)llarge.size();
   p->n_pieces = (uint32_t)pblob.size();
   bool ok = upload(c, &p->d_blobs, descs.data(), n) && upload(c, &p->d_chunk_prefix, prefix.data(), n + 1) &&
-            upload(c, &p->d_list_dec, ldec.data(), ldec.size()) && upload(c, &p->d_list_small, lsmall.data(), lsmall.size()) &&
+            upload(c, &p->d_list_dec, (const uint32_t*)nullptr, ldec.size()) && upload(c, &p->d_list_small, lsmall.data(), lsmall.size()) &&
             upload(c, &p->d_list_large, llarge.data(), llarge.size()) &&
             upload(c, &p->d_piece_blob, pblob.data(), pblob.size()) && upload(c, &p->d_piece_idx, pidx.data(), pidx.size()) &&
             upload(c, &p->d_expect, (const uint32_t*)expect, expect ? (size_t)n * 8 : 0) &&
@@ -313,8 +321,6 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
             upload(c, &p->d_counter, (const uint32_t*)nullptr, zn_plan::kMaxGroups);
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
-  for (int i = 0; ok && i < zn_plan::kMaxGroups; i++) ok = cudaEventCreateWithFlags(&p->evg[i], cudaEventDisableTiming) == cudaSuccess;
-  if (ok) ok = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) == cudaSuccess;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // host vectors go out of scope
   if (ok) {
     // default schedule: overlap decode and hash when the batch is large enough to pipeline
