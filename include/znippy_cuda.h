@@ -138,6 +138,44 @@ int zn_decompress_rows(zn_ctx* ctx, int archive_fd, uint64_t row_lo, uint64_t ro
                        const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd, size_t batch_bytes,
                        int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats);
 
+/* ---- `.znippy` v0.7 container, natively (csrc/container.cpp; no Arrow library): footer -> manifest -> sub-indexes
+ * (znippy-common/src/index.rs:245-441), rows of all sub-indexes concatenated, columns looked up by name. ---- */
+typedef struct zn_index zn_index;
+zn_index* zn_index_open(const char* path, char* err, size_t errcap); /* NULL on failure, message in err */
+void zn_index_close(zn_index* index);
+uint64_t zn_index_rows(const zn_index* index);
+/* col: 0 blob_offset, 1 blob_size, 2 fdata_offset, 3 uncompressed_size */
+const uint64_t* zn_index_u64(const zn_index* index, int col);
+const uint32_t* zn_index_chunk_seq(const zn_index* index);
+const uint8_t* zn_index_compressed(const zn_index* index); /* one byte per row, 0/1 */
+const uint8_t* zn_index_checksums(const zn_index* index);  /* rows * 32 */
+const char* zn_index_path(const zn_index* index, uint64_t row, uint32_t* len); /* not NUL terminated */
+uint64_t zn_index_groups(const zn_index* index);            /* manifest entries */
+int zn_index_group(const zn_index* index, uint64_t g, int8_t* pkg_type, const char** repo, uint64_t* index_offset,
+                   uint64_t* index_len, uint64_t* row_count);
+const char* zn_index_metadata(const zn_index* index, const char* key); /* schema key/value of the first sub-index */
+uint32_t zn_index_field_count(const zn_index* index);
+const char* zn_index_field_name(const zn_index* index, uint32_t i);
+
+/* writer tail (meta_sink.rs:71-118): sub-index per (pkg_type, repo) group -> manifest -> "ZNPYMIDX" + offset, fsync */
+typedef struct zn_index_writer zn_index_writer;
+zn_index_writer* zn_index_writer_create(int fd, uint64_t blob_end);
+int zn_index_writer_metadata(zn_index_writer* w, const char* key, const char* value); /* before the first group */
+int zn_index_writer_push_group(zn_index_writer* w, int8_t pkg_type, const char* repo, uint64_t n, const char* const* paths,
+                               const uint32_t* chunk_seq, const uint64_t* fdata_offset, const uint8_t* compressed,
+                               const uint64_t* uncompressed_size, const uint64_t* blob_offset, const uint64_t* blob_size,
+                               const uint8_t* checksums);
+int zn_index_writer_finish(zn_index_writer* w); /* also destroys w */
+
+/* decompress_archive (decompress.rs:39-222) end to end without Python: index -> output files -> zn_decompress_rows ->
+ * VerifyReport (index.rs:490-499).  Rows [row_lo, row_hi) (clamped): one call per GPU shard. */
+typedef struct {
+  uint64_t total_files, verified_files, corrupt_files, total_bytes, verified_bytes, corrupt_bytes, chunks;
+} zn_verify_report;
+int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int save_data, const char* out_dir, uint64_t row_lo,
+                          uint64_t row_hi, size_t batch_bytes, int io_threads, zn_verify_report* report, char* err,
+                          size_t errcap);
+
 /* ---- device-resident API (inputs and outputs already in HBM; used for the device GB/s metric and by
  *      callers that keep a batch resident).  d_* are device pointers; h_* host pointers. ---- */
 

@@ -122,3 +122,27 @@ def test_lz4_archive(A, tmp_path, oracle):
     assert vr.corrupt_files == 0 and vr.chunks == 3
     for p, d in entries:
         assert (tmp_path / "x" / p).read_bytes() == d
+
+
+def test_native_and_pyarrow_container_paths_agree(A, tmp_path, oracle):
+    """decompress_archive runs fully natively by default (container.cpp + zn_decompress_rows); the pyarrow-fronted path
+    and the pyarrow-written index must give the same reports and bytes."""
+    entries = [("t/a.txt", oracle.real_text(150_000).tobytes()), ("t/b.jar", oracle.gen_random(30_000).tobytes()),
+               ("big.bin", oracle.gen_binary(9 << 20).tobytes()), ("e.txt", b"")]
+    (tmp_path / "n").mkdir(); (tmp_path / "p").mkdir()
+    pn, _ = _pack(A, tmp_path / "n", entries, native_index=True)
+    pp, _ = _pack(A, tmp_path / "p", entries, native_index=False)
+    tn, tp = A.read_znippy_index(pn), A.read_znippy_index(pp)
+    assert tn.schema.names == tp.schema.names and tn.num_rows == tp.num_rows == 5
+    for col in tn.schema.names:
+        if col not in ("blob_offset",):
+            assert tn.column(col).to_pylist() == tp.column(col).to_pylist(), col
+    for path in (pn, pp):
+        r1 = A.decompress_archive(path, True, str(tmp_path / "o1"), native=True)
+        r2 = A.decompress_archive(path, True, str(tmp_path / "o2"), native=False)
+        assert r1 == r2 and r1.corrupt_files == 0 and r1.total_files == 4 and r1.chunks == 5
+        for p, d in entries:
+            assert (tmp_path / "o1" / p).read_bytes() == d and (tmp_path / "o2" / p).read_bytes() == d
+    # one shard of the rows (multi-GPU: one call per GPU)
+    r = A.decompress_archive(pn, False, "/dev/null", row_range=(1, 3))
+    assert r.chunks == 2

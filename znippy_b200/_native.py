@@ -19,6 +19,10 @@ EXPORTS = [
     "zn_last_error", "zn_ctx_pinned", "zn_ctx_kernel_launches", "zn_hash_batch", "zn_decode_verify_batch",
     "zn_compress_batch", "zn_compress_bound", "zn_frame_content_size", "zn_plan_decode_verify", "zn_plan_hash",
     "zn_plan_destroy", "zn_plan_run", "zn_plan_results", "zn_plan_launches", "zn_plan_last_ms", "zn_plan_set_overlap", "zn_ctx_last_compress_ms", "zn_decompress_rows",
+    "zn_index_open", "zn_index_close", "zn_index_rows", "zn_index_u64", "zn_index_chunk_seq", "zn_index_compressed",
+    "zn_index_checksums", "zn_index_path", "zn_index_groups", "zn_index_group", "zn_index_metadata", "zn_index_field_count",
+    "zn_index_field_name", "zn_index_writer_create", "zn_index_writer_metadata", "zn_index_writer_push_group",
+    "zn_index_writer_finish", "zn_archive_decompress",
 ]
 
 
@@ -77,6 +81,37 @@ def lib() -> C.CDLL:
     L.zn_plan_last_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     L.zn_plan_set_overlap.argtypes = [vp, C.c_int]
     L.zn_decompress_rows.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int, vp, vp]
+    L.zn_index_open.argtypes = [C.c_char_p, C.c_char_p, sz]
+    L.zn_index_open.restype = vp
+    L.zn_index_close.argtypes = [vp]
+    L.zn_index_close.restype = None
+    L.zn_index_rows.argtypes = [vp]
+    L.zn_index_rows.restype = u64
+    L.zn_index_u64.argtypes = [vp, C.c_int]
+    L.zn_index_u64.restype = C.POINTER(C.c_uint64)
+    L.zn_index_chunk_seq.argtypes = [vp]
+    L.zn_index_chunk_seq.restype = C.POINTER(C.c_uint32)
+    L.zn_index_compressed.argtypes = [vp]
+    L.zn_index_compressed.restype = C.POINTER(C.c_uint8)
+    L.zn_index_checksums.argtypes = [vp]
+    L.zn_index_checksums.restype = C.POINTER(C.c_uint8)
+    L.zn_index_path.argtypes = [vp, u64, C.POINTER(u32)]
+    L.zn_index_path.restype = C.POINTER(C.c_char)
+    L.zn_index_groups.argtypes = [vp]
+    L.zn_index_groups.restype = u64
+    L.zn_index_group.argtypes = [vp, u64, C.POINTER(C.c_int8), C.POINTER(C.c_char_p), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.zn_index_metadata.argtypes = [vp, C.c_char_p]
+    L.zn_index_metadata.restype = C.c_char_p
+    L.zn_index_field_count.argtypes = [vp]
+    L.zn_index_field_count.restype = u32
+    L.zn_index_field_name.argtypes = [vp, u32]
+    L.zn_index_field_name.restype = C.c_char_p
+    L.zn_index_writer_create.argtypes = [C.c_int, u64]
+    L.zn_index_writer_create.restype = vp
+    L.zn_index_writer_metadata.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.zn_index_writer_push_group.argtypes = [vp, C.c_int8, C.c_char_p, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.zn_index_writer_finish.argtypes = [vp]
+    L.zn_archive_decompress.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, u64, u64, sz, C.c_int, vp, C.c_char_p, sz]
     L.zn_ctx_last_compress_ms.argtypes = [vp]
     L.zn_ctx_last_compress_ms.restype = C.c_float
     if L.zn_abi_version() != 1:

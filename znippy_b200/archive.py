@@ -240,8 +240,26 @@ def decompress_rows(archive_fd: int, cols, lo: int, hi: int, save_files=None, ct
 
 
 def decompress_archive(index_path: str, save_data: bool, out_dir: str, ctx: Ctx | None = None,
-                       row_range=None) -> VerifyReport:
-    """decompress.rs:39-222.  `row_range` restricts the call to one shard (multi-GPU: one process per GPU)."""
+                       row_range=None, native: bool = True) -> VerifyReport:
+    """decompress.rs:39-222.  `row_range` restricts the call to one shard (multi-GPU: one process per GPU).
+
+    native=True (default): the whole function runs in libznippy_cuda.so (`zn_archive_decompress`: C++ container
+    reader, output-file creation, threaded pread/pwrite worker, batched GPU decode+verify) — no pyarrow, no Python
+    loop.  native=False keeps the pyarrow index reader in front of the same native worker (used by the tests to
+    cross-check the two readers)."""
+    if native:
+        import ctypes as C
+
+        from . import _native as N
+        ctx = ctx or default_ctx()
+        rep = (C.c_uint64 * 7)()
+        err = C.create_string_buffer(512)
+        lo, hi = row_range if row_range is not None else (0, (1 << 64) - 1)
+        rc = N.lib().zn_archive_decompress(ctx.handle, index_path.encode(), int(bool(save_data)), (out_dir or ".").encode(), lo, hi,
+                                           1 << 30, 8, C.byref(rep), err, 512)
+        if rc != 0:
+            raise N.NativeError(f"zn_archive_decompress: {err.value.decode(errors='replace')}")
+        return VerifyReport(*[int(x) for x in rep])
     table = read_znippy_index(index_path)
     cols = _columns(table)
     paths = table.column("relative_path").to_pylist()
@@ -383,7 +401,8 @@ class StreamCompressor:
     rounds go through `zn_hash_batch` only (stream_packer.rs:222-227)."""
 
     def __init__(self, output: str, no_skip: bool, level: int = 3, codec_id: int = codec.CODEC_ZSTD,
-                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20):
+                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20, native_index: bool = True):
+        self.native_index = native_index
         self.output = os.path.splitext(output)[0] + ".znippy"  # stream_packer.rs:132
         self.no_skip, self.level, self.codec_id, self.ctx, self.batch_bytes = no_skip, level, codec_id, ctx, batch_bytes
         self.entries: list[ArchiveEntry] = []
@@ -474,11 +493,37 @@ class StreamCompressor:
                 groups.setdefault(key, []).append((e.relative_path,) + b[1:])
             if not groups:
                 groups[(0, "")] = []
-            schema = INDEX_SCHEMA.with_metadata(config_metadata())
-            sink = ArrowIpcSink(f, out_cursor)
-            for key in sorted(groups):
-                sink.push_subindex(key, schema, [build_metadata_batch(groups[key], schema)])
-            sink.finish()
+            if self.native_index:  # container.cpp writer: sub-index per group -> manifest -> footer, no pyarrow
+                import ctypes as C
+
+                from . import _native as N
+                f.flush()
+                L = N.lib()
+                w = L.zn_index_writer_create(f.fileno(), out_cursor)
+                for k, v in config_metadata().items():
+                    L.zn_index_writer_metadata(w, k.encode(), v.encode())
+                for key in sorted(groups):
+                    rows = groups[key]
+                    n = len(rows)
+                    paths = (C.c_char_p * max(n, 1))(*[r[0].encode() for r in rows])
+                    seq = np.array([r[1] for r in rows], np.uint32)
+                    fo = np.array([r[2] for r in rows], np.uint64)
+                    cp = np.array([int(r[3]) for r in rows], np.uint8)
+                    us = np.array([r[4] for r in rows], np.uint64)
+                    bo = np.array([r[5] for r in rows], np.uint64)
+                    bs = np.array([r[6] for r in rows], np.uint64)
+                    ck = np.frombuffer(b"".join(r[7] for r in rows), np.uint8) if n else np.zeros(1, np.uint8)
+                    if L.zn_index_writer_push_group(w, key[0], key[1].encode(), n, paths, N.ptr(seq), N.ptr(fo), N.ptr(cp), N.ptr(us),
+                                                    N.ptr(bo), N.ptr(bs), N.ptr(ck)) != 0:
+                        raise IOError("zn_index_writer_push_group failed")
+                if L.zn_index_writer_finish(w) != 0:
+                    raise IOError("zn_index_writer_finish failed")
+            else:
+                schema = INDEX_SCHEMA.with_metadata(config_metadata())
+                sink = ArrowIpcSink(f, out_cursor)
+                for key in sorted(groups):
+                    sink.push_subindex(key, schema, [build_metadata_batch(groups[key], schema)])
+                sink.finish()
         return rep
 
 

@@ -22,7 +22,7 @@ def _nvcc() -> str:
 
 def sources() -> list[str]:
     inc = os.path.join(os.path.dirname(HERE), "include", "znippy_cuda.h")
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [inc]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".cpp"))] + [inc]
 
 
 def stale() -> bool:
@@ -34,7 +34,7 @@ def stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO, os.path.join(CSRC, "znippy_cuda.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO, os.path.join(CSRC, "znippy_cuda.cu"), os.path.join(CSRC, "container.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

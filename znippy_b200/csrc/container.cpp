@@ -1,0 +1,789 @@
+// `.znippy` v0.7 container in C++ (no Arrow library): footer, manifest and sub-index reader + writer.
+//
+// First "next" row of SURVEY.md §8(f): the container is the step on both sides of the hot path — it supplies every
+// batch descriptor (blob_offset, blob_size, compressed, uncompressed_size, checksum, fdata_offset).  Restates
+//   znippy-common/src/index.rs:43-54    sub-index schema (8 base columns, all non-nullable; plugin columns may follow)
+//   znippy-common/src/index.rs:245-277  "ZNPYMIDX" + LE u64 footer
+//   znippy-common/src/index.rs:279-367  manifest (pkg_type, repo, module_name, index_offset, index_len, row_count)
+//   znippy-common/src/index.rs:374-441  read_znippy_index: footer -> manifest -> every sub-index, rows concatenated
+//   znippy-common/src/meta_sink.rs:71-118  writer tail: sub-index(es) -> manifest -> magic + offset
+// The sub-indexes and the manifest are Arrow IPC *streams* (encapsulated messages: 0xFFFFFFFF, metadata length,
+// Message flatbuffer, 8-byte aligned body).  Only what this schema needs of Arrow is implemented: Schema and
+// RecordBatch messages; Utf8, Int/UInt 8-64, Bool, FixedSizeBinary columns; no dictionaries, no body compression.
+// Parity: pyarrow reads what this writes and this reads what pyarrow writes (tests/test_container_native.py).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/znippy_cuda.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ flatbuffer reading
+struct Span {
+  const uint8_t* p;
+  size_t n;
+};
+
+struct FbErr {};
+
+inline void need(const Span& s, size_t off, size_t len) {
+  if (off > s.n || len > s.n - off) throw FbErr();
+}
+template <typename T>
+inline T rd(const Span& s, size_t off) {
+  need(s, off, sizeof(T));
+  T v;
+  memcpy(&v, s.p + off, sizeof(T));
+  return v;
+}
+// position of field `id` inside table at `tbl`, 0 when absent
+inline size_t fb_field(const Span& s, size_t tbl, int id) {
+  const int32_t so = rd<int32_t>(s, tbl);
+  const size_t vt = (size_t)((int64_t)tbl - so);
+  const uint16_t vts = rd<uint16_t>(s, vt);
+  const size_t slot = 4 + 2 * (size_t)id;
+  if (slot + 2 > vts) return 0;
+  const uint16_t fo = rd<uint16_t>(s, vt + slot);
+  return fo ? tbl + fo : 0;
+}
+template <typename T>
+inline T fb_scalar(const Span& s, size_t tbl, int id, T def) {
+  const size_t f = fb_field(s, tbl, id);
+  return f ? rd<T>(s, f) : def;
+}
+inline size_t fb_indirect(const Span& s, size_t tbl, int id) {  // table / vector / string position, 0 when absent
+  const size_t f = fb_field(s, tbl, id);
+  return f ? f + rd<uint32_t>(s, f) : 0;
+}
+inline std::string fb_string(const Span& s, size_t pos) {
+  if (!pos) return std::string();
+  const uint32_t n = rd<uint32_t>(s, pos);
+  need(s, pos + 4, n);
+  return std::string((const char*)s.p + pos + 4, n);
+}
+
+enum ArrowType { T_INT = 2, T_FLOAT = 3, T_BINARY = 4, T_UTF8 = 5, T_BOOL = 6, T_FSB = 15, T_LBINARY = 19, T_LUTF8 = 20 };
+
+struct FieldInfo {
+  std::string name;
+  int type = 0;
+  int bit_width = 0;   // Int
+  int byte_width = 0;  // FixedSizeBinary
+  int n_buffers = 0;
+};
+
+struct Column {  // one decoded column of one record batch (views into the file image)
+  const uint8_t* data = nullptr;
+  uint64_t data_len = 0;
+  const uint8_t* offsets = nullptr;  // utf8
+  uint64_t offsets_len = 0;
+};
+
+struct IndexImpl {
+  uint64_t rows = 0;
+  std::vector<uint64_t> col[4];  // blob_offset, blob_size, fdata_offset, uncompressed_size
+  std::vector<uint32_t> chunk_seq;
+  std::vector<uint8_t> compressed;
+  std::vector<uint8_t> checksums;
+  std::vector<uint64_t> path_off;  // rows + 1
+  std::string paths;
+  struct Group {
+    int8_t pkg_type;
+    std::string repo, module_name;
+    uint64_t index_offset, index_len, row_count;
+  };
+  std::vector<Group> groups;
+  std::map<std::string, std::string> metadata;
+  std::vector<std::string> field_names;
+};
+
+struct Msg {
+  int header_type;
+  size_t header;  // position of the header table inside meta
+  Span meta;
+  Span body;
+};
+
+// Iterates the encapsulated messages of one IPC stream; returns false at end-of-stream.
+bool next_message(const Span& stream, size_t* pos, Msg* m) {
+  if (*pos + 8 > stream.n) return false;
+  uint32_t cont = rd<uint32_t>(stream, *pos);
+  int32_t mlen;
+  size_t hdr = 8;
+  if (cont == 0xFFFFFFFFu) mlen = rd<int32_t>(stream, *pos + 4);
+  else { mlen = (int32_t)cont; hdr = 4; }  // pre-0.15 framing without the continuation marker
+  if (mlen == 0) return false;
+  if (mlen < 0) throw FbErr();
+  need(stream, *pos + hdr, (size_t)mlen);
+  m->meta = Span{stream.p + *pos + hdr, (size_t)mlen};
+  const size_t root = rd<uint32_t>(m->meta, 0);
+  m->header_type = fb_scalar<uint8_t>(m->meta, root, 1, 0);
+  m->header = fb_indirect(m->meta, root, 2);
+  const int64_t blen = fb_scalar<int64_t>(m->meta, root, 3, 0);
+  if (blen < 0) throw FbErr();
+  need(stream, *pos + hdr + (size_t)mlen, (size_t)blen);
+  m->body = Span{stream.p + *pos + hdr + (size_t)mlen, (size_t)blen};
+  *pos += hdr + (size_t)mlen + (size_t)blen;
+  return true;
+}
+
+void parse_schema(const Msg& m, std::vector<FieldInfo>* fields, std::map<std::string, std::string>* kv) {
+  const Span& s = m.meta;
+  const size_t fv = fb_indirect(s, m.header, 1);
+  if (!fv) throw FbErr();
+  const uint32_t nf = rd<uint32_t>(s, fv);
+  for (uint32_t i = 0; i < nf; i++) {
+    const size_t slot = fv + 4 + 4 * (size_t)i;
+    const size_t ft = slot + rd<uint32_t>(s, slot);
+    FieldInfo f;
+    f.name = fb_string(s, fb_indirect(s, ft, 0));
+    f.type = fb_scalar<uint8_t>(s, ft, 2, 0);
+    const size_t tt = fb_indirect(s, ft, 3);
+    if (fb_indirect(s, ft, 4)) throw FbErr();  // dictionary-encoded columns are not part of this format
+    switch (f.type) {
+      case T_INT: f.bit_width = tt ? fb_scalar<int32_t>(s, tt, 0, 0) : 0; f.n_buffers = 2; break;
+      case T_FLOAT: f.n_buffers = 2; break;
+      case T_BOOL: f.n_buffers = 2; break;
+      case T_FSB: f.byte_width = tt ? fb_scalar<int32_t>(s, tt, 0, 0) : 0; f.n_buffers = 2; break;
+      case T_UTF8: case T_BINARY: case T_LUTF8: case T_LBINARY: f.n_buffers = 3; break;
+      default: throw FbErr();
+    }
+    fields->push_back(f);
+  }
+  if (kv) {
+    const size_t mv = fb_indirect(s, m.header, 2);
+    if (mv) {
+      const uint32_t nk = rd<uint32_t>(s, mv);
+      for (uint32_t i = 0; i < nk; i++) {
+        const size_t slot = mv + 4 + 4 * (size_t)i;
+        const size_t t = slot + rd<uint32_t>(s, slot);
+        (*kv)[fb_string(s, fb_indirect(s, t, 0))] = fb_string(s, fb_indirect(s, t, 1));
+      }
+    }
+  }
+}
+
+// Columns of one RecordBatch message, in schema order.  Returns the row count.
+uint64_t parse_batch(const Msg& m, const std::vector<FieldInfo>& fields, std::vector<Column>* cols) {
+  const Span& s = m.meta;
+  const int64_t length = fb_scalar<int64_t>(s, m.header, 0, 0);
+  if (fb_indirect(s, m.header, 3)) throw FbErr();  // body compression
+  const size_t nodes = fb_indirect(s, m.header, 1), bufs = fb_indirect(s, m.header, 2);
+  if (length < 0 || !nodes || !bufs) throw FbErr();
+  const uint32_t nn = rd<uint32_t>(s, nodes), nb = rd<uint32_t>(s, bufs);
+  if (nn != fields.size()) throw FbErr();
+  uint32_t bi = 0;
+  cols->assign(fields.size(), Column());
+  for (size_t f = 0; f < fields.size(); f++) {
+    const int64_t flen = rd<int64_t>(s, nodes + 4 + 16 * f), nulls = rd<int64_t>(s, nodes + 4 + 16 * f + 8);
+    if (flen != length || nulls < 0) throw FbErr();
+    if (bi + (uint32_t)fields[f].n_buffers > nb) throw FbErr();
+    auto buf = [&](uint32_t k, const uint8_t** p, uint64_t* n) {
+      const int64_t off = rd<int64_t>(s, bufs + 4 + 16 * (size_t)(bi + k)), len = rd<int64_t>(s, bufs + 4 + 16 * (size_t)(bi + k) + 8);
+      if (off < 0 || len < 0) throw FbErr();
+      need(m.body, (size_t)off, (size_t)len);
+      *p = m.body.p + off;
+      *n = (uint64_t)len;
+    };
+    Column& c = (*cols)[f];
+    if (fields[f].n_buffers == 3) { buf(1, &c.offsets, &c.offsets_len); buf(2, &c.data, &c.data_len); }
+    else buf(1, &c.data, &c.data_len);
+    bi += (uint32_t)fields[f].n_buffers;
+  }
+  return (uint64_t)length;
+}
+
+int find_field(const std::vector<FieldInfo>& f, const char* name) {
+  for (size_t i = 0; i < f.size(); i++)
+    if (f[i].name == name) return (int)i;
+  return -1;
+}
+
+uint64_t get_uint(const Column& c, int bits, uint64_t i) {
+  switch (bits) {
+    case 8: return c.data[i];
+    case 16: { uint16_t v; memcpy(&v, c.data + 2 * i, 2); return v; }
+    case 32: { uint32_t v; memcpy(&v, c.data + 4 * i, 4); return v; }
+    default: { uint64_t v; memcpy(&v, c.data + 8 * i, 8); return v; }
+  }
+}
+
+// Appends the rows of one sub-index stream to `ix` (columns looked up by NAME, as the reference does).
+void read_subindex(const Span& stream, IndexImpl* ix, bool first) {
+  size_t pos = 0;
+  Msg m;
+  if (!next_message(stream, &pos, &m) || m.header_type != 1) throw FbErr();
+  std::vector<FieldInfo> fields;
+  parse_schema(m, &fields, first ? &ix->metadata : nullptr);
+  if (first)
+    for (auto& f : fields) ix->field_names.push_back(f.name);
+  static const char* u64names[4] = {"blob_offset", "blob_size", "fdata_offset", "uncompressed_size"};
+  int fi_u64[4], fi_path = find_field(fields, "relative_path"), fi_seq = find_field(fields, "chunk_seq"),
+                 fi_comp = find_field(fields, "compressed"), fi_sum = find_field(fields, "checksum");
+  for (int k = 0; k < 4; k++) {
+    fi_u64[k] = find_field(fields, u64names[k]);
+    if (fi_u64[k] < 0 || fields[fi_u64[k]].type != T_INT) throw FbErr();
+  }
+  if (fi_path < 0 || fi_seq < 0 || fi_comp < 0 || fi_sum < 0) throw FbErr();
+  if (fields[fi_path].type != T_UTF8 || fields[fi_comp].type != T_BOOL || fields[fi_sum].type != T_FSB ||
+      fields[fi_sum].byte_width != 32 || fields[fi_seq].type != T_INT)
+    throw FbErr();
+  std::vector<Column> cols;
+  while (next_message(stream, &pos, &m)) {
+    if (m.header_type != 3) continue;  // only record batches carry rows
+    const uint64_t n = parse_batch(m, fields, &cols);
+    for (int k = 0; k < 4; k++) {
+      const Column& c = cols[fi_u64[k]];
+      const int bits = fields[fi_u64[k]].bit_width;
+      if (c.data_len < n * (uint64_t)(bits / 8)) throw FbErr();
+      for (uint64_t i = 0; i < n; i++) ix->col[k].push_back(get_uint(c, bits, i));
+    }
+    {
+      const Column& c = cols[fi_seq];
+      const int bits = fields[fi_seq].bit_width;
+      if (c.data_len < n * (uint64_t)(bits / 8)) throw FbErr();
+      for (uint64_t i = 0; i < n; i++) ix->chunk_seq.push_back((uint32_t)get_uint(c, bits, i));
+    }
+    {
+      const Column& c = cols[fi_comp];
+      if (c.data_len < (n + 7) / 8) throw FbErr();
+      for (uint64_t i = 0; i < n; i++) ix->compressed.push_back((c.data[i >> 3] >> (i & 7)) & 1);
+    }
+    {
+      const Column& c = cols[fi_sum];
+      if (c.data_len < n * 32) throw FbErr();
+      ix->checksums.insert(ix->checksums.end(), c.data, c.data + n * 32);
+    }
+    {
+      const Column& c = cols[fi_path];
+      if (c.offsets_len < (n + 1) * 4) throw FbErr();
+      for (uint64_t i = 0; i < n; i++) {
+        int32_t a, b;
+        memcpy(&a, c.offsets + 4 * i, 4);
+        memcpy(&b, c.offsets + 4 * (i + 1), 4);
+        if (a < 0 || b < a || (uint64_t)b > c.data_len) throw FbErr();
+        ix->paths.append((const char*)c.data + a, (size_t)(b - a));
+        ix->path_off.push_back(ix->paths.size());
+      }
+    }
+    ix->rows += n;
+  }
+}
+
+void read_manifest(const Span& stream, IndexImpl* ix) {
+  size_t pos = 0;
+  Msg m;
+  if (!next_message(stream, &pos, &m) || m.header_type != 1) throw FbErr();
+  std::vector<FieldInfo> fields;
+  parse_schema(m, &fields, nullptr);
+  const int f_pkg = find_field(fields, "pkg_type"), f_repo = find_field(fields, "repo"), f_mod = find_field(fields, "module_name"),
+            f_off = find_field(fields, "index_offset"), f_len = find_field(fields, "index_len"), f_rows = find_field(fields, "row_count");
+  if (f_pkg < 0 || f_repo < 0 || f_mod < 0 || f_off < 0 || f_len < 0 || f_rows < 0) throw FbErr();
+  std::vector<Column> cols;
+  while (next_message(stream, &pos, &m)) {
+    if (m.header_type != 3) continue;
+    const uint64_t n = parse_batch(m, fields, &cols);
+    auto str = [&](int f, uint64_t i) {
+      const Column& c = cols[f];
+      int32_t a, b;
+      if (c.offsets_len < (i + 2) * 4) throw FbErr();
+      memcpy(&a, c.offsets + 4 * i, 4);
+      memcpy(&b, c.offsets + 4 * (i + 1), 4);
+      if (a < 0 || b < a || (uint64_t)b > c.data_len) throw FbErr();
+      return std::string((const char*)c.data + a, (size_t)(b - a));
+    };
+    for (uint64_t i = 0; i < n; i++) {
+      IndexImpl::Group g;
+      g.pkg_type = (int8_t)get_uint(cols[f_pkg], 8, i);
+      g.repo = str(f_repo, i);
+      g.module_name = str(f_mod, i);
+      g.index_offset = get_uint(cols[f_off], 64, i);
+      g.index_len = get_uint(cols[f_len], 64, i);
+      g.row_count = get_uint(cols[f_rows], 64, i);
+      ix->groups.push_back(g);
+    }
+  }
+}
+
+bool read_range(int fd, uint64_t off, uint64_t len, std::vector<uint8_t>* out) {
+  out->resize(len);
+  uint64_t done = 0;
+  while (done < len) {
+    const ssize_t r = pread(fd, out->data() + done, len - done, (off_t)(off + done));
+    if (r <= 0) return false;
+    done += (uint64_t)r;
+  }
+  return true;
+}
+
+void set_err(char* err, size_t cap, const std::string& m) {
+  if (err && cap) snprintf(err, cap, "%s", m.c_str());
+}
+
+// ------------------------------------------------------------------------------------------------ flatbuffer writing
+// Forward builder: a table is written as [vtable][table] and its children after it, so every uoffset is positive.
+struct FbW {
+  std::vector<uint8_t> b;
+  void align(size_t a) { while (b.size() % a) b.push_back(0); }
+  template <typename T>
+  void put(T v) { const size_t n = b.size(); b.resize(n + sizeof(T)); memcpy(b.data() + n, &v, sizeof(T)); }
+  template <typename T>
+  void patch(size_t pos, T v) { memcpy(b.data() + pos, &v, sizeof(T)); }
+  // points the uoffset slot at `slot` to the current (aligned) end of the buffer
+  void point_here(size_t slot, size_t a = 4) { align(a); patch<uint32_t>(slot, (uint32_t)(b.size() - slot)); }
+  size_t string(const std::string& s) {  // returns position
+    align(4);
+    const size_t p = b.size();
+    put<uint32_t>((uint32_t)s.size());
+    b.insert(b.end(), s.begin(), s.end());
+    b.push_back(0);
+    return p;
+  }
+};
+
+// Table with explicit field layout: each field = (id, size, alignment).  Returns table position; slot positions of the
+// fields are returned through `slots` (absolute).  All fields are present.
+struct FieldSpec {
+  int id, size;
+};
+size_t fb_table(FbW& w, const std::vector<FieldSpec>& fs, std::vector<size_t>* slots) {
+  int max_id = -1;
+  for (auto& f : fs) max_id = f.id > max_id ? f.id : max_id;
+  // object layout: soffset (4) then fields in descending size order (keeps natural alignment)
+  std::vector<FieldSpec> order = fs;
+  for (size_t i = 0; i < order.size(); i++)
+    for (size_t j = i + 1; j < order.size(); j++)
+      if (order[j].size > order[i].size) std::swap(order[i], order[j]);
+  std::vector<uint16_t> foff((size_t)max_id + 1, 0);
+  size_t obj = 4, maxal = 4;
+  for (auto& f : order) {
+    const size_t al = (size_t)f.size;
+    if (al > maxal) maxal = al;
+  }
+  // the object starts (soffset word) at a position aligned to the widest field; fields are padded relative to it
+  for (auto& f : order) {
+    const size_t al = (size_t)f.size;
+    while (obj % al) obj++;
+    foff[(size_t)f.id] = (uint16_t)obj;
+    obj += (size_t)f.size;
+  }
+  const size_t vts = 4 + 2 * ((size_t)max_id + 1);
+  // place vtable so that the table that follows is aligned to maxal
+  w.align(2);
+  while ((w.b.size() + vts) % maxal) w.b.push_back(0);
+  const size_t vt = w.b.size();
+  w.put<uint16_t>((uint16_t)vts);
+  w.put<uint16_t>((uint16_t)obj);
+  for (int i = 0; i <= max_id; i++) w.put<uint16_t>(foff[(size_t)i]);
+  const size_t tbl = w.b.size();
+  w.put<int32_t>((int32_t)(tbl - vt));
+  w.b.resize(tbl + obj, 0);
+  slots->assign((size_t)max_id + 1, 0);
+  for (auto& f : fs) (*slots)[(size_t)f.id] = tbl + foff[(size_t)f.id];
+  return tbl;
+}
+
+struct ColSpec {
+  const char* name;
+  int type;   // ArrowType
+  int bits;   // Int
+  bool sign;  // Int
+  int width;  // FixedSizeBinary
+};
+
+// Schema message (metadata only, no body)
+std::vector<uint8_t> schema_message(const std::vector<ColSpec>& cols, const std::vector<std::pair<std::string, std::string>>& kv) {
+  FbW w;
+  w.put<uint32_t>(0);  // root uoffset, patched below
+  std::vector<size_t> ms;
+  // Message: version(0) i16, header_type(1) u8, header(2) off, bodyLength(3) i64
+  w.align(8);
+  const size_t msg = fb_table(w, {{0, 2}, {1, 1}, {2, 4}, {3, 8}}, &ms);
+  w.patch<uint32_t>(0, (uint32_t)msg);
+  w.patch<int16_t>(ms[0], 4);  // MetadataVersion V5
+  w.patch<uint8_t>(ms[1], 1);  // Schema
+  w.patch<int64_t>(ms[3], 0);
+  // Schema: endianness(0) i16, fields(1) off, custom_metadata(2) off
+  std::vector<size_t> ss;
+  const bool has_kv = !kv.empty();
+  w.align(4);
+  {
+    std::vector<FieldSpec> spec = {{0, 2}, {1, 4}};
+    if (has_kv) spec.push_back({2, 4});
+    const size_t pos_before = w.b.size();
+    (void)pos_before;
+    const size_t sch = fb_table(w, spec, &ss);
+    w.patch<uint32_t>(ms[2], (uint32_t)(sch - ms[2]));
+    w.patch<int16_t>(ss[0], 0);  // little endian
+  }
+  // fields vector
+  w.point_here(ss[1]);
+  w.put<uint32_t>((uint32_t)cols.size());
+  const size_t fvec = w.b.size();
+  for (size_t i = 0; i < cols.size(); i++) w.put<uint32_t>(0);
+  for (size_t i = 0; i < cols.size(); i++) {
+    const ColSpec& c = cols[i];
+    std::vector<size_t> fsl;
+    // Field: name(0) off, nullable(1) u8, type_type(2) u8, type(3) off, children(5) off
+    w.align(4);
+    const size_t ft = fb_table(w, {{0, 4}, {1, 1}, {2, 1}, {3, 4}, {5, 4}}, &fsl);
+    w.patch<uint32_t>(fvec + 4 * i, (uint32_t)(ft - (fvec + 4 * i)));
+    w.patch<uint8_t>(fsl[1], 0);
+    w.patch<uint8_t>(fsl[2], (uint8_t)c.type);
+    const size_t np = w.string(c.name);
+    w.patch<uint32_t>(fsl[0], (uint32_t)(np - fsl[0]));
+    // type table
+    std::vector<size_t> tsl;
+    w.align(4);
+    size_t tt;
+    if (c.type == T_INT) {
+      tt = fb_table(w, {{0, 4}, {1, 1}}, &tsl);
+      w.patch<int32_t>(tsl[0], c.bits);
+      w.patch<uint8_t>(tsl[1], c.sign ? 1 : 0);
+    } else if (c.type == T_FSB) {
+      tt = fb_table(w, {{0, 4}}, &tsl);
+      w.patch<int32_t>(tsl[0], c.width);
+    } else {
+      tt = fb_table(w, {}, &tsl);  // Utf8 / Bool: empty table
+    }
+    w.patch<uint32_t>(fsl[3], (uint32_t)(tt - fsl[3]));
+    w.point_here(fsl[5]);
+    w.put<uint32_t>(0);  // children: empty vector
+  }
+  if (has_kv) {
+    w.point_here(ss[2]);
+    w.put<uint32_t>((uint32_t)kv.size());
+    const size_t kvec = w.b.size();
+    for (size_t i = 0; i < kv.size(); i++) w.put<uint32_t>(0);
+    for (size_t i = 0; i < kv.size(); i++) {
+      std::vector<size_t> ks;
+      w.align(4);
+      const size_t kt = fb_table(w, {{0, 4}, {1, 4}}, &ks);
+      w.patch<uint32_t>(kvec + 4 * i, (uint32_t)(kt - (kvec + 4 * i)));
+      const size_t k = w.string(kv[i].first);
+      w.patch<uint32_t>(ks[0], (uint32_t)(k - ks[0]));
+      const size_t v = w.string(kv[i].second);
+      w.patch<uint32_t>(ks[1], (uint32_t)(v - ks[1]));
+    }
+  }
+  w.align(8);
+  return w.b;
+}
+
+// RecordBatch message metadata for `length` rows with the given buffers (offset, length pairs; one FieldNode per column)
+std::vector<uint8_t> batch_message(uint64_t length, size_t ncols, const std::vector<std::pair<uint64_t, uint64_t>>& buffers,
+                                   uint64_t body_len) {
+  FbW w;
+  w.put<uint32_t>(0);
+  std::vector<size_t> ms;
+  w.align(8);
+  const size_t msg = fb_table(w, {{0, 2}, {1, 1}, {2, 4}, {3, 8}}, &ms);
+  w.patch<uint32_t>(0, (uint32_t)msg);
+  w.patch<int16_t>(ms[0], 4);
+  w.patch<uint8_t>(ms[1], 3);  // RecordBatch
+  w.patch<int64_t>(ms[3], (int64_t)body_len);
+  std::vector<size_t> rs;
+  w.align(8);
+  const size_t rb = fb_table(w, {{0, 8}, {1, 4}, {2, 4}}, &rs);
+  w.patch<uint32_t>(ms[2], (uint32_t)(rb - ms[2]));
+  w.patch<int64_t>(rs[0], (int64_t)length);
+  // nodes: vector of struct {length i64, null_count i64}: the elements must be 8-aligned, the length word sits before
+  w.align(8);
+  w.put<uint32_t>(0);  // pad so that (len word at 8k+4) -> elements at 8(k+1)
+  w.patch<uint32_t>(rs[1], (uint32_t)(w.b.size() - rs[1]));
+  w.put<uint32_t>((uint32_t)ncols);
+  for (size_t i = 0; i < ncols; i++) { w.put<int64_t>((int64_t)length); w.put<int64_t>(0); }
+  w.align(8);
+  w.put<uint32_t>(0);
+  w.patch<uint32_t>(rs[2], (uint32_t)(w.b.size() - rs[2]));
+  w.put<uint32_t>((uint32_t)buffers.size());
+  for (auto& b : buffers) { w.put<int64_t>((int64_t)b.first); w.put<int64_t>((int64_t)b.second); }
+  w.align(8);
+  return w.b;
+}
+
+void append_message(std::vector<uint8_t>* out, const std::vector<uint8_t>& meta, const std::vector<uint8_t>& body) {
+  const uint32_t cont = 0xFFFFFFFFu;
+  const int32_t mlen = (int32_t)meta.size();  // already a multiple of 8
+  out->insert(out->end(), (const uint8_t*)&cont, (const uint8_t*)&cont + 4);
+  out->insert(out->end(), (const uint8_t*)&mlen, (const uint8_t*)&mlen + 4);
+  out->insert(out->end(), meta.begin(), meta.end());
+  out->insert(out->end(), body.begin(), body.end());
+}
+void append_eos(std::vector<uint8_t>* out) {
+  const uint32_t e[2] = {0xFFFFFFFFu, 0};
+  out->insert(out->end(), (const uint8_t*)e, (const uint8_t*)e + 8);
+}
+
+struct BodyW {
+  std::vector<uint8_t> b;
+  std::vector<std::pair<uint64_t, uint64_t>> bufs;
+  void add(const void* p, uint64_t n) {
+    bufs.push_back({b.size(), n});
+    b.insert(b.end(), (const uint8_t*)p, (const uint8_t*)p + n);
+    while (b.size() % 8) b.push_back(0);
+  }
+  void add_empty() { bufs.push_back({b.size(), 0}); }  // absent validity bitmap (no nulls)
+};
+
+bool write_all(int fd, const void* p, size_t n, uint64_t off) {
+  size_t done = 0;
+  while (done < n) {
+    const ssize_t r = pwrite(fd, (const uint8_t*)p + done, n - done, (off_t)(off + done));
+    if (r <= 0) return false;
+    done += (size_t)r;
+  }
+  return true;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI: reader
+struct zn_index {
+  IndexImpl ix;
+};
+
+extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errcap, "cannot open archive"); return nullptr; }
+  zn_index* h = new zn_index();
+  try {
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 16) throw std::string("not a znippy archive (too small)");
+    const uint64_t flen = (uint64_t)st.st_size;
+    std::vector<uint8_t> tail;
+    if (!read_range(fd, flen - 16, 16, &tail)) throw std::string("read error");
+    if (memcmp(tail.data(), "ZNPYMIDX", 8) != 0) throw std::string("v0.6 archives are not supported");  // index.rs:387-389
+    uint64_t moff;
+    memcpy(&moff, tail.data() + 8, 8);
+    if (moff > flen - 16) throw std::string("manifest offset outside file");
+    std::vector<uint8_t> mbytes;
+    if (!read_range(fd, moff, flen - 16 - moff, &mbytes)) throw std::string("read error");
+    read_manifest(Span{mbytes.data(), mbytes.size()}, &h->ix);
+    bool first = true;
+    std::vector<uint8_t> sub;
+    for (auto& g : h->ix.groups) {
+      if (g.index_offset > flen || g.index_len > flen - g.index_offset) throw std::string("sub-index outside file");
+      if (!read_range(fd, g.index_offset, g.index_len, &sub)) throw std::string("read error");
+      read_subindex(Span{sub.data(), sub.size()}, &h->ix, first);
+      first = false;
+    }
+    h->ix.path_off.insert(h->ix.path_off.begin(), 0);
+  } catch (const std::string& m) {
+    set_err(err, errcap, m);
+    delete h;
+    h = nullptr;
+  } catch (const FbErr&) {
+    set_err(err, errcap, "malformed Arrow IPC metadata in archive index");
+    delete h;
+    h = nullptr;
+  } catch (const std::exception& e) {
+    set_err(err, errcap, e.what());
+    delete h;
+    h = nullptr;
+  }
+  close(fd);
+  return h;
+}
+
+extern "C" void zn_index_close(zn_index* h) { delete h; }
+extern "C" uint64_t zn_index_rows(const zn_index* h) { return h ? h->ix.rows : 0; }
+extern "C" const uint64_t* zn_index_u64(const zn_index* h, int col) { return (h && col >= 0 && col < 4) ? h->ix.col[col].data() : nullptr; }
+extern "C" const uint32_t* zn_index_chunk_seq(const zn_index* h) { return h ? h->ix.chunk_seq.data() : nullptr; }
+extern "C" const uint8_t* zn_index_compressed(const zn_index* h) { return h ? h->ix.compressed.data() : nullptr; }
+extern "C" const uint8_t* zn_index_checksums(const zn_index* h) { return h ? h->ix.checksums.data() : nullptr; }
+extern "C" const char* zn_index_path(const zn_index* h, uint64_t row, uint32_t* len) {
+  if (!h || row >= h->ix.rows) return nullptr;
+  if (len) *len = (uint32_t)(h->ix.path_off[row + 1] - h->ix.path_off[row]);
+  return h->ix.paths.data() + h->ix.path_off[row];
+}
+extern "C" uint64_t zn_index_groups(const zn_index* h) { return h ? h->ix.groups.size() : 0; }
+extern "C" int zn_index_group(const zn_index* h, uint64_t g, int8_t* pkg_type, const char** repo, uint64_t* index_offset,
+                              uint64_t* index_len, uint64_t* row_count) {
+  if (!h || g >= h->ix.groups.size()) return ZN_E_ARG;
+  const auto& G = h->ix.groups[g];
+  if (pkg_type) *pkg_type = G.pkg_type;
+  if (repo) *repo = G.repo.c_str();
+  if (index_offset) *index_offset = G.index_offset;
+  if (index_len) *index_len = G.index_len;
+  if (row_count) *row_count = G.row_count;
+  return ZN_OK;
+}
+extern "C" const char* zn_index_metadata(const zn_index* h, const char* key) {
+  if (!h || !key) return nullptr;
+  auto it = h->ix.metadata.find(key);
+  return it == h->ix.metadata.end() ? nullptr : it->second.c_str();
+}
+extern "C" uint32_t zn_index_field_count(const zn_index* h) { return h ? (uint32_t)h->ix.field_names.size() : 0; }
+extern "C" const char* zn_index_field_name(const zn_index* h, uint32_t i) {
+  return (h && i < h->ix.field_names.size()) ? h->ix.field_names[i].c_str() : nullptr;
+}
+
+// ================================================================================================ C ABI: writer
+struct zn_index_writer {
+  int fd;
+  uint64_t cursor;
+  std::vector<IndexImpl::Group> groups;
+  std::vector<std::pair<std::string, std::string>> kv;
+};
+
+extern "C" zn_index_writer* zn_index_writer_create(int fd, uint64_t blob_end) {
+  zn_index_writer* w = new zn_index_writer();
+  w->fd = fd;
+  w->cursor = blob_end;
+  return w;
+}
+extern "C" int zn_index_writer_metadata(zn_index_writer* w, const char* key, const char* value) {
+  if (!w || !key || !value) return ZN_E_ARG;
+  w->kv.push_back({key, value});
+  return ZN_OK;
+}
+
+// One sub-index (one record batch) for a (pkg_type, repo) group: index.rs:131-191 + meta_sink.rs:71-101
+extern "C" int zn_index_writer_push_group(zn_index_writer* w, int8_t pkg_type, const char* repo, uint64_t n,
+                                          const char* const* paths, const uint32_t* chunk_seq, const uint64_t* fdata_offset,
+                                          const uint8_t* compressed, const uint64_t* uncompressed_size,
+                                          const uint64_t* blob_offset, const uint64_t* blob_size, const uint8_t* checksums) {
+  if (!w || (n && (!paths || !chunk_seq || !fdata_offset || !compressed || !uncompressed_size || !blob_offset || !blob_size || !checksums)))
+    return ZN_E_ARG;
+  static const std::vector<ColSpec> cols = {
+      {"relative_path", T_UTF8, 0, false, 0}, {"chunk_seq", T_INT, 32, false, 0}, {"fdata_offset", T_INT, 64, false, 0},
+      {"compressed", T_BOOL, 0, false, 0},    {"uncompressed_size", T_INT, 64, false, 0}, {"blob_offset", T_INT, 64, false, 0},
+      {"blob_size", T_INT, 64, false, 0},     {"checksum", T_FSB, 0, false, 32}};
+  std::vector<uint8_t> out;
+  append_message(&out, schema_message(cols, w->kv), {});
+  BodyW body;
+  {
+    std::vector<int32_t> offs(n + 1, 0);
+    std::string data;
+    for (uint64_t i = 0; i < n; i++) { data += paths[i]; offs[i + 1] = (int32_t)data.size(); }
+    body.add_empty(); body.add(offs.data(), (n + 1) * 4); body.add(data.data(), data.size());
+  }
+  body.add_empty(); body.add(chunk_seq, n * 4);
+  body.add_empty(); body.add(fdata_offset, n * 8);
+  {
+    std::vector<uint8_t> bits((n + 7) / 8, 0);
+    for (uint64_t i = 0; i < n; i++) if (compressed[i]) bits[i >> 3] |= (uint8_t)(1u << (i & 7));
+    body.add_empty(); body.add(bits.data(), bits.size());
+  }
+  body.add_empty(); body.add(uncompressed_size, n * 8);
+  body.add_empty(); body.add(blob_offset, n * 8);
+  body.add_empty(); body.add(blob_size, n * 8);
+  body.add_empty(); body.add(checksums, n * 32);
+  append_message(&out, batch_message(n, cols.size(), body.bufs, body.b.size()), body.b);
+  append_eos(&out);
+  if (!write_all(w->fd, out.data(), out.size(), w->cursor)) return ZN_E_ARG;
+  IndexImpl::Group g;
+  g.pkg_type = pkg_type;
+  g.repo = repo ? repo : "";
+  g.index_offset = w->cursor;
+  g.index_len = out.size();
+  g.row_count = n;
+  w->groups.push_back(g);
+  w->cursor += out.size();
+  return ZN_OK;
+}
+
+// manifest + footer + fsync (meta_sink.rs:103-118); destroys the writer
+extern "C" int zn_index_writer_finish(zn_index_writer* w) {
+  if (!w) return ZN_E_ARG;
+  static const std::vector<ColSpec> cols = {{"pkg_type", T_INT, 8, true, 0},      {"repo", T_UTF8, 0, false, 0},
+                                            {"module_name", T_UTF8, 0, false, 0}, {"index_offset", T_INT, 64, false, 0},
+                                            {"index_len", T_INT, 64, false, 0},   {"row_count", T_INT, 64, false, 0}};
+  const uint64_t n = w->groups.size();
+  std::vector<uint8_t> out;
+  append_message(&out, schema_message(cols, {}), {});
+  BodyW body;
+  std::vector<int8_t> pk(n);
+  std::vector<uint64_t> io(n), il(n), rc(n);
+  std::vector<int32_t> ro(n + 1, 0), mo(n + 1, 0);
+  std::string rd_, md_;
+  for (uint64_t i = 0; i < n; i++) {
+    pk[i] = w->groups[i].pkg_type; io[i] = w->groups[i].index_offset; il[i] = w->groups[i].index_len; rc[i] = w->groups[i].row_count;
+    rd_ += w->groups[i].repo; ro[i + 1] = (int32_t)rd_.size();
+    md_ += w->groups[i].module_name; mo[i + 1] = (int32_t)md_.size();
+  }
+  body.add_empty(); body.add(pk.data(), n);
+  body.add_empty(); body.add(ro.data(), (n + 1) * 4); body.add(rd_.data(), rd_.size());
+  body.add_empty(); body.add(mo.data(), (n + 1) * 4); body.add(md_.data(), md_.size());
+  body.add_empty(); body.add(io.data(), n * 8);
+  body.add_empty(); body.add(il.data(), n * 8);
+  body.add_empty(); body.add(rc.data(), n * 8);
+  append_message(&out, batch_message(n, cols.size(), body.bufs, body.b.size()), body.b);
+  append_eos(&out);
+  int rcode = ZN_OK;
+  if (!write_all(w->fd, out.data(), out.size(), w->cursor)) rcode = ZN_E_ARG;
+  uint8_t footer[16];
+  memcpy(footer, "ZNPYMIDX", 8);
+  memcpy(footer + 8, &w->cursor, 8);
+  if (rcode == ZN_OK && !write_all(w->fd, footer, 16, w->cursor + out.size())) rcode = ZN_E_ARG;
+  if (rcode == ZN_OK && ftruncate(w->fd, (off_t)(w->cursor + out.size() + 16)) != 0) rcode = ZN_E_ARG;
+  if (rcode == ZN_OK) fsync(w->fd);
+  delete w;
+  return rcode;
+}
+
+// ================================================================================================ native decompress_archive
+// decompress.rs:39-222 end to end: index -> (pre-create output files) -> zn_decompress_rows -> VerifyReport.
+extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int save_data, const char* out_dir, uint64_t row_lo,
+                                     uint64_t row_hi, size_t batch_bytes, int io_threads, zn_verify_report* report, char* err,
+                                     size_t errcap) {
+  if (!ctx || !index_path || !report) return ZN_E_ARG;
+  memset(report, 0, sizeof *report);
+  zn_index* h = zn_index_open(index_path, err, errcap);
+  if (!h) return ZN_E_ARG;
+  const IndexImpl& ix = h->ix;
+  if (row_hi > ix.rows) row_hi = ix.rows;
+  if (row_lo > row_hi) row_lo = row_hi;
+  std::unordered_set<std::string> uniq;
+  std::vector<int> fds;
+  std::map<std::string, int> open_files;
+  int rc = ZN_OK;
+  for (uint64_t r = row_lo; r < row_hi; r++) uniq.insert(std::string(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]));
+  if (save_data) {  // decompress.rs:74-101: one fd per path, indexed by row
+    fds.assign(ix.rows, -1);
+    for (uint64_t r = row_lo; r < row_hi && rc == ZN_OK; r++) {
+      const std::string rel(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]);
+      auto it = open_files.find(rel);
+      if (it == open_files.end()) {
+        const std::string full = std::string(out_dir ? out_dir : ".") + "/" + rel;
+        for (size_t p = 1; p < full.size(); p++)
+          if (full[p] == '/') mkdir(full.substr(0, p).c_str(), 0755);
+        const int fd = open(full.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644);
+        if (fd < 0) { set_err(err, errcap, "failed to open output file " + full); rc = ZN_E_ARG; break; }
+        it = open_files.emplace(rel, fd).first;
+      }
+      fds[r] = it->second;
+    }
+  }
+  const int afd = rc == ZN_OK ? open(index_path, O_RDONLY) : -1;
+  if (rc == ZN_OK && afd < 0) { set_err(err, errcap, "cannot open archive"); rc = ZN_E_ARG; }
+  if (rc == ZN_OK) {
+    zn_verify_stats st;
+    std::vector<uint64_t> corrupt(row_hi - row_lo + 1);
+    rc = zn_decompress_rows(ctx, afd, row_lo, row_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.compressed.data(),
+                            ix.col[3].data(), ix.checksums.data(), save_data ? fds.data() : nullptr, batch_bytes, io_threads,
+                            corrupt.data(), &st);
+    if (rc != ZN_OK) set_err(err, errcap, zn_last_error(ctx));
+    report->total_files = uniq.size();
+    report->corrupt_files = st.corrupt_rows;  // the reference counts corrupt ROWS here (decompress.rs:210)
+    report->verified_files = report->total_files > report->corrupt_files ? report->total_files - report->corrupt_files : 0;
+    report->total_bytes = st.total_written_bytes;
+    report->verified_bytes = st.verified_bytes;
+    report->corrupt_bytes = st.corrupt_bytes;
+    report->chunks = st.total_chunks;
+  }
+  if (afd >= 0) close(afd);
+  for (auto& kv : open_files) close(kv.second);
+  zn_index_close(h);
+  return rc;
+}
