@@ -176,6 +176,24 @@ int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int save_data, co
                           uint64_t row_hi, size_t batch_bytes, int io_threads, zn_verify_report* report, char* err,
                           size_t errcap);
 
+/* ---- native write pipeline: compress_stream (znippy-compress/src/stream_packer.rs:58-372).  Entries are cut into
+ * <= 8 MiB rounds into a pinned slot; each full slot is one zn_compress_batch (+ zn_hash_batch for store-as-is rounds),
+ * payloads are pwritten at a running cursor, finish() writes sub-indexes per (pkg_type, repo), manifest and footer. */
+typedef struct zn_archive_writer zn_archive_writer;
+typedef struct {
+  uint64_t total_files, compressed_files, uncompressed_files, chunks, total_bytes_in, total_bytes_out, compressed_bytes,
+      uncompressed_bytes;
+} zn_compression_report; /* CompressionReport, znippy-common/src/lib.rs:39-51 */
+zn_archive_writer* zn_archive_writer_create(zn_ctx* ctx, const char* output_path, int no_skip, int level, int codec,
+                                            size_t slot_bytes);
+int zn_archive_writer_add(zn_archive_writer* w, const char* relative_path, const uint8_t* data, uint64_t len, int has_pkg_type,
+                          int8_t pkg_type, const char* repo); /* data is consumed (copied into the slot) before returning */
+int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_report* report); /* also destroys w */
+const char* zn_archive_writer_error(const zn_archive_writer* w);
+/* pinned host memory (cudaHostAlloc) for callers that stage their own buffers */
+void* zn_ctx_pinned_alloc(size_t bytes);
+void zn_ctx_pinned_free(void* p);
+
 /* ---- device-resident API (inputs and outputs already in HBM; used for the device GB/s metric and by
  *      callers that keep a batch resident).  d_* are device pointers; h_* host pointers. ---- */
 

@@ -146,3 +146,30 @@ def test_native_and_pyarrow_container_paths_agree(A, tmp_path, oracle):
     # one shard of the rows (multi-GPU: one call per GPU)
     r = A.decompress_archive(pn, False, "/dev/null", row_range=(1, 3))
     assert r.chunks == 2
+
+
+def test_native_and_python_write_pipelines_agree(A, tmp_path, oracle):
+    """compress_stream natively (zn_archive_writer_*) vs the Python-driven pipeline: same index columns (blob offsets
+    may differ only by batching), same decoded bytes, same CompressionReport; multi-group archives (index.rs:533-581)."""
+    ents = [A.ArchiveEntry("m/a.pom", oracle.real_text(90_000).tobytes(), 1, "central"),
+            A.ArchiveEntry("m/b.jar", oracle.gen_random(70_000).tobytes(), 1, "central"),
+            A.ArchiveEntry("p/c.whl", oracle.gen_binary(10 << 20).tobytes(), 2, "pypi"),
+            A.ArchiveEntry("plain.txt", b"hello" * 1000), A.ArchiveEntry("empty.bin", b"")]
+    outs = {}
+    for name, native in (("n", True), ("p", False)):
+        (tmp_path / name).mkdir()
+        sc = A.compress_stream(str(tmp_path / name / "x.znippy"), False, native=native)
+        for e in ents:
+            sc.sender().send(e)
+        outs[name] = (sc.output, sc.finish())
+    (pn, rn), (pp, rp) = outs["n"], outs["p"]
+    assert rn == rp and rn.total_files == 5 and rn.uncompressed_files == 1 and rn.chunks == 6
+    tn, tp = A.read_znippy_index(pn), A.read_znippy_index(pp)
+    for col in ("relative_path", "chunk_seq", "fdata_offset", "compressed", "uncompressed_size", "blob_size", "checksum"):
+        assert tn.column(col).to_pylist() == tp.column(col).to_pylist(), col
+    assert [(e[0], e[1], e[5]) for e in A.read_znippy_manifest(pn)] == [(0, "", 2), (1, "central", 2), (2, "pypi", 2)]
+    ar = A.ZnippyArchive.open(pn)
+    for e in ents:
+        assert ar.extract_file(e.relative_path) == e.data
+    vr = A.verify_archive_integrity(pn)
+    assert vr.corrupt_files == 0 and vr.total_files == 5 and vr.chunks == 6

@@ -22,7 +22,8 @@ EXPORTS = [
     "zn_index_open", "zn_index_close", "zn_index_rows", "zn_index_u64", "zn_index_chunk_seq", "zn_index_compressed",
     "zn_index_checksums", "zn_index_path", "zn_index_groups", "zn_index_group", "zn_index_metadata", "zn_index_field_count",
     "zn_index_field_name", "zn_index_writer_create", "zn_index_writer_metadata", "zn_index_writer_push_group",
-    "zn_index_writer_finish", "zn_archive_decompress",
+    "zn_index_writer_finish", "zn_archive_decompress", "zn_archive_writer_create", "zn_archive_writer_add",
+    "zn_archive_writer_finish", "zn_archive_writer_error", "zn_ctx_pinned_alloc", "zn_ctx_pinned_free",
 ]
 
 
@@ -112,6 +113,16 @@ def lib() -> C.CDLL:
     L.zn_index_writer_push_group.argtypes = [vp, C.c_int8, C.c_char_p, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.zn_index_writer_finish.argtypes = [vp]
     L.zn_archive_decompress.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, u64, u64, sz, C.c_int, vp, C.c_char_p, sz]
+    L.zn_archive_writer_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, sz]
+    L.zn_archive_writer_create.restype = vp
+    L.zn_archive_writer_add.argtypes = [vp, C.c_char_p, vp, u64, C.c_int, C.c_int8, C.c_char_p]
+    L.zn_archive_writer_finish.argtypes = [vp, vp]
+    L.zn_archive_writer_error.argtypes = [vp]
+    L.zn_archive_writer_error.restype = C.c_char_p
+    L.zn_ctx_pinned_alloc.argtypes = [sz]
+    L.zn_ctx_pinned_alloc.restype = vp
+    L.zn_ctx_pinned_free.argtypes = [vp]
+    L.zn_ctx_pinned_free.restype = None
     L.zn_ctx_last_compress_ms.argtypes = [vp]
     L.zn_ctx_last_compress_ms.restype = C.c_float
     if L.zn_abi_version() != 1:

@@ -401,14 +401,37 @@ class StreamCompressor:
     rounds go through `zn_hash_batch` only (stream_packer.rs:222-227)."""
 
     def __init__(self, output: str, no_skip: bool, level: int = 3, codec_id: int = codec.CODEC_ZSTD,
-                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20, native_index: bool = True):
+                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20, native_index: bool = True, native: bool = True):
         self.native_index = native_index
+        self.native = native
+        self._w = None
         self.output = os.path.splitext(output)[0] + ".znippy"  # stream_packer.rs:132
         self.no_skip, self.level, self.codec_id, self.ctx, self.batch_bytes = no_skip, level, codec_id, ctx, batch_bytes
         self.entries: list[ArchiveEntry] = []
 
+    def _native_writer(self):
+        from . import _native as N
+        if self._w is None:
+            self._ctx = self.ctx or default_ctx()
+            self._w = N.lib().zn_archive_writer_create(self._ctx.handle, self.output.encode(), int(self.no_skip), self.level,
+                                                       self.codec_id, self.batch_bytes)
+            if not self._w:
+                raise IOError(f"cannot create {self.output}")
+        return self._w
+
     def send(self, entry: ArchiveEntry):
-        self.entries.append(entry)
+        """native=True: the entry is consumed immediately by the C++ pipeline (zn_archive_writer_add copies it into the
+        pinned slot and flushes full slots through the GPU), so nothing is retained on the Python side."""
+        if not self.native:
+            self.entries.append(entry)
+            return
+        from . import _native as N
+        w = self._native_writer()
+        d = N.u8(entry.data) if len(entry.data) else None
+        rc = N.lib().zn_archive_writer_add(w, entry.relative_path.encode(), None if d is None else N.ptr(d), len(entry.data),
+                                           int(entry.pkg_type is not None), entry.pkg_type or 0, (entry.repo or "").encode())
+        if rc != 0:
+            raise codec.NativeError("zn_archive_writer_add: " + N.lib().zn_archive_writer_error(w).decode())
 
     def sender(self):
         return self
@@ -424,6 +447,17 @@ class StreamCompressor:
                     yield _Round(fi, seq, start, start, min(SLICE_SIZE, n - start), skip)
 
     def finish(self) -> CompressionReport:
+        if self.native:
+            import ctypes as C
+
+            from . import _native as N
+            w = self._native_writer()
+            rep8 = (C.c_uint64 * 8)()
+            rc = N.lib().zn_archive_writer_finish(w, C.byref(rep8))
+            self._w = None
+            if rc != 0:
+                raise codec.NativeError(f"zn_archive_writer_finish failed ({rc})")
+            return CompressionReport(*[int(x) for x in rep8])
         rep = CompressionReport(total_files=len(self.entries))
         blobs_meta = []  # (file_index, chunk_seq, fdata_offset, compressed, usize, blob_offset, blob_size, checksum)
         out_cursor = 0

@@ -17,6 +17,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
+#include <cctype>
 #include <cstring>
 #include <map>
 #include <string>
@@ -785,5 +787,223 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
   if (afd >= 0) close(afd);
   for (auto& kv : open_files) close(kv.second);
   zn_index_close(h);
+  return rc;
+}
+
+// ================================================================================================ native write pipeline
+// compress_stream (znippy-compress/src/stream_packer.rs:58-372) as a C++ object: entries are cut into <= 8 MiB rounds
+// (:169-202) straight into a pinned staging slot (the Magazine slot of slotpool.rs:93-130); a full slot is ONE
+// zn_compress_batch (blake3 + frame per slice, the barrel body :217-232) plus one zn_hash_batch for the store-as-is
+// rounds (:222-227); the writer step pwrites the payloads at a running cursor (:252-285); finish() sorts the blob
+// metas by (file_index, chunk_seq), groups them by (pkg_type, repo) in BTreeMap order and emits sub-indexes, manifest
+// and footer (:293-346, meta_sink.rs:71-118).
+extern "C" void* zn_ctx_pinned_alloc(size_t bytes);
+extern "C" void zn_ctx_pinned_free(void* p);
+
+namespace {
+constexpr uint64_t kSliceSize = 8ull * 1024 * 1024;  // stream_packer.rs:31
+
+bool should_skip_compression(const std::string& path) {  // index.rs:470-488: last extension only, case-insensitive
+  static const char* ext[] = {"zip", "gz", "bz2", "xz", "lz", "lzma", "7z", "rar", "cab", "jar", "war", "ear", "zst", "sz",
+                              "lz4", "tgz", "txz", "tbz", "apk", "dmg", "deb", "rpm", "arrow", "mpeg", "mpg", "jpeg", "jpg",
+                              "gif", "bmp", "png", "crate", "znippy", "zdata", "parquet", "webp", "webm"};
+  const size_t slash = path.find_last_of('/');
+  const std::string base = slash == std::string::npos ? path : path.substr(slash + 1);
+  const size_t dot = base.find_last_of('.');
+  if (dot == std::string::npos) return false;
+  std::string e = base.substr(dot + 1);
+  for (auto& ch : e) ch = (char)tolower((unsigned char)ch);
+  for (const char* x : ext)
+    if (e == x) return true;
+  return false;
+}
+
+struct Round {
+  uint64_t file_index, fdata_offset, stage_off, len;
+  uint32_t chunk_seq;
+  bool skip;
+};
+struct BlobMetaRow {
+  uint64_t file_index, fdata_offset, usize, blob_offset, blob_size;
+  uint32_t chunk_seq;
+  bool compressed;
+  uint8_t checksum[32];
+};
+struct EntryInfo {
+  std::string path, repo;
+  int8_t pkg_type;
+  bool skip;
+};
+}  // namespace
+
+struct zn_archive_writer {
+  zn_ctx* ctx;
+  int fd;
+  bool no_skip;
+  int level, codec;
+  uint64_t slot_bytes, stage_used = 0, out_cursor = 0;
+  uint8_t* stage = nullptr;  // pinned: source slices
+  uint8_t* outb = nullptr;   // pinned: compressed frames of one batch
+  uint64_t outb_cap = 0;
+  std::vector<Round> rounds;
+  std::vector<BlobMetaRow> metas;
+  std::vector<EntryInfo> entries;
+  zn_compression_report rep;
+  std::string err;
+};
+
+static int writer_flush(zn_archive_writer* w) {
+  if (w->rounds.empty()) return ZN_OK;
+  const size_t n = w->rounds.size();
+  std::vector<uint64_t> c_off, c_len, s_off, s_len, d_off;
+  std::vector<size_t> c_idx, s_idx;
+  uint64_t dcur = 0;
+  for (size_t i = 0; i < n; i++) {
+    const Round& r = w->rounds[i];
+    if (r.skip) { s_idx.push_back(i); s_off.push_back(r.stage_off); s_len.push_back(r.len); }
+    else {
+      c_idx.push_back(i); c_off.push_back(r.stage_off); c_len.push_back(r.len);
+      d_off.push_back(dcur);
+      dcur += (zn_compress_bound(r.len, w->codec) + 15) & ~15ull;
+    }
+  }
+  d_off.push_back(dcur);
+  if (dcur > w->outb_cap) {
+    if (w->outb) zn_ctx_pinned_free(w->outb);
+    w->outb = (uint8_t*)zn_ctx_pinned_alloc(dcur + 4096);
+    w->outb_cap = w->outb ? dcur + 4096 : 0;
+    if (!w->outb) { w->err = "pinned output allocation failed"; return ZN_E_NOMEM; }
+  }
+  std::vector<uint64_t> c_out(c_idx.size());
+  std::vector<uint8_t> c_dig(c_idx.size() * 32), s_dig(s_idx.size() * 32);
+  std::vector<uint32_t> c_st(c_idx.size());
+  if (!c_idx.empty()) {
+    const int rc = zn_compress_batch(w->ctx, w->stage, c_off.data(), c_len.data(), (uint32_t)c_idx.size(), w->level, w->codec, w->outb,
+                                     d_off.data(), c_out.data(), c_dig.data(), c_st.data());
+    if (rc != ZN_OK) { w->err = zn_last_error(w->ctx); return rc; }
+    for (uint32_t s : c_st)
+      if (s != ZN_S_OK) { w->err = "compress failed for a slice"; return ZN_E_ARG; }  // `?` propagates, stream_packer.rs:230
+  }
+  if (!s_idx.empty()) {
+    const int rc = zn_hash_batch(w->ctx, w->stage, s_off.data(), s_len.data(), (uint32_t)s_idx.size(), s_dig.data());
+    if (rc != ZN_OK) { w->err = zn_last_error(w->ctx); return rc; }
+  }
+  size_t ci = 0, si = 0;
+  for (size_t i = 0; i < n; i++) {  // writer step, in round order
+    const Round& r = w->rounds[i];
+    BlobMetaRow m;
+    m.file_index = r.file_index; m.chunk_seq = r.chunk_seq; m.fdata_offset = r.fdata_offset; m.usize = r.len;
+    m.compressed = !r.skip; m.blob_offset = w->out_cursor;
+    const uint8_t* payload;
+    if (r.skip) { payload = w->stage + r.stage_off; m.blob_size = r.len; memcpy(m.checksum, s_dig.data() + 32 * si, 32); si++; }
+    else { payload = w->outb + d_off[ci]; m.blob_size = c_out[ci]; memcpy(m.checksum, c_dig.data() + 32 * ci, 32); ci++; }
+    if (m.blob_size && !write_all(w->fd, payload, m.blob_size, w->out_cursor)) { w->err = "pwrite failed"; return ZN_E_ARG; }
+    w->out_cursor += m.blob_size;
+    w->metas.push_back(m);
+    w->rep.chunks++;
+    w->rep.total_bytes_in += r.len;
+    w->rep.total_bytes_out += m.blob_size;
+    if (r.skip) w->rep.uncompressed_bytes += r.len; else w->rep.compressed_bytes += r.len;
+  }
+  w->rounds.clear();
+  w->stage_used = 0;
+  return ZN_OK;
+}
+
+extern "C" zn_archive_writer* zn_archive_writer_create(zn_ctx* ctx, const char* output_path, int no_skip, int level, int codec,
+                                                       size_t slot_bytes) {
+  if (!ctx || !output_path) return nullptr;
+  if (slot_bytes < 2 * kSliceSize) slot_bytes = 2 * kSliceSize;
+  const int fd = open(output_path, O_CREAT | O_RDWR | O_TRUNC, 0644);
+  if (fd < 0) return nullptr;
+  zn_archive_writer* w = new zn_archive_writer();
+  w->ctx = ctx; w->fd = fd; w->no_skip = no_skip != 0; w->level = level; w->codec = codec; w->slot_bytes = slot_bytes;
+  memset(&w->rep, 0, sizeof w->rep);
+  w->stage = (uint8_t*)zn_ctx_pinned_alloc(slot_bytes + 4096);
+  if (!w->stage) { close(fd); delete w; return nullptr; }
+  return w;
+}
+
+extern "C" const char* zn_archive_writer_error(const zn_archive_writer* w) { return w ? w->err.c_str() : "null writer"; }
+
+extern "C" int zn_archive_writer_add(zn_archive_writer* w, const char* relative_path, const uint8_t* data, uint64_t len,
+                                     int has_pkg_type, int8_t pkg_type, const char* repo) {
+  if (!w || !relative_path || (len && !data)) return ZN_E_ARG;
+  EntryInfo e;
+  e.path = relative_path;
+  e.repo = repo ? repo : "";
+  e.pkg_type = has_pkg_type ? pkg_type : 0;
+  e.skip = !w->no_skip && should_skip_compression(e.path);
+  const uint64_t fi = w->entries.size();
+  w->entries.push_back(e);
+  w->rep.total_files++;
+  if (e.skip) w->rep.uncompressed_files++; else w->rep.compressed_files++;
+  uint64_t off = 0;
+  uint32_t seq = 0;
+  do {  // an empty entry still yields one zero-length round (stream_packer.rs:169-183)
+    const uint64_t n = len - off < kSliceSize ? len - off : kSliceSize;
+    if (w->stage_used + n > w->slot_bytes) {
+      const int rc = writer_flush(w);
+      if (rc != ZN_OK) return rc;
+    }
+    Round r;
+    r.file_index = fi; r.chunk_seq = seq++; r.fdata_offset = off; r.stage_off = w->stage_used; r.len = n; r.skip = e.skip;
+    if (n) memcpy(w->stage + w->stage_used, data + off, n);
+    w->stage_used += (n + 15) & ~15ull;
+    w->rounds.push_back(r);
+    off += n;
+  } while (off < len);
+  return ZN_OK;
+}
+
+extern "C" int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_report* report) {
+  if (!w) return ZN_E_ARG;
+  int rc = writer_flush(w);
+  if (rc == ZN_OK) {
+    std::stable_sort(w->metas.begin(), w->metas.end(), [](const BlobMetaRow& a, const BlobMetaRow& b) {
+      return a.file_index != b.file_index ? a.file_index < b.file_index : a.chunk_seq < b.chunk_seq;
+    });
+    std::map<std::pair<int8_t, std::string>, std::vector<const BlobMetaRow*>> groups;  // BTreeMap order
+    for (auto& m : w->metas) groups[{w->entries[m.file_index].pkg_type, w->entries[m.file_index].repo}].push_back(&m);
+    if (groups.empty()) groups[{0, ""}];
+    zn_index_writer* iw = zn_index_writer_create(w->fd, w->out_cursor);
+    {  // config echoed into the schema metadata (index.rs:73-85)
+      const long cores = sysconf(_SC_NPROCESSORS_ONLN) > 0 ? sysconf(_SC_NPROCESSORS_ONLN) : 1;
+      zn_index_writer_metadata(iw, "znippy_format_version", "3");
+      zn_index_writer_metadata(iw, "max_core_in_flight", std::to_string((cores * 9 + 9) / 10).c_str());
+      zn_index_writer_metadata(iw, "max_core_in_compress", std::to_string(cores).c_str());
+      zn_index_writer_metadata(iw, "max_mem_allowed", "0");
+      zn_index_writer_metadata(iw, "min_free_memory_ratio", "0.1");
+      zn_index_writer_metadata(iw, "file_split_block_size", "10485760");
+      zn_index_writer_metadata(iw, "max_chunks", "128");
+      zn_index_writer_metadata(iw, "compression_level", "19");
+      zn_index_writer_metadata(iw, "zstd_output_buffer_size", "1048576");
+    }
+    for (auto& kv : groups) {
+      const auto& rows = kv.second;
+      const uint64_t n = rows.size();
+      std::vector<const char*> paths(n);
+      std::vector<uint32_t> seq(n);
+      std::vector<uint64_t> fo(n), us(n), bo(n), bs(n);
+      std::vector<uint8_t> cp(n), ck(n * 32);
+      for (uint64_t i = 0; i < n; i++) {
+        const BlobMetaRow* m = rows[i];
+        paths[i] = w->entries[m->file_index].path.c_str();
+        seq[i] = m->chunk_seq; fo[i] = m->fdata_offset; us[i] = m->usize; bo[i] = m->blob_offset; bs[i] = m->blob_size;
+        cp[i] = m->compressed ? 1 : 0;
+        memcpy(ck.data() + 32 * i, m->checksum, 32);
+      }
+      const int prc = zn_index_writer_push_group(iw, kv.first.first, kv.first.second.c_str(), n, paths.data(), seq.data(), fo.data(),
+                                                 cp.data(), us.data(), bo.data(), bs.data(), ck.data());
+      if (prc != ZN_OK && rc == ZN_OK) rc = prc;
+    }
+    const int frc = zn_index_writer_finish(iw);
+    if (frc != ZN_OK && rc == ZN_OK) rc = frc;
+  }
+  if (report) *report = w->rep;
+  close(w->fd);
+  if (w->stage) zn_ctx_pinned_free(w->stage);
+  if (w->outb) zn_ctx_pinned_free(w->outb);
+  delete w;
   return rc;
 }

@@ -191,6 +191,14 @@ extern "C" void* zn_ctx_pinned(zn_ctx* c, size_t* bytes) {
 
 extern "C" uint64_t zn_ctx_kernel_launches(const zn_ctx* c) { return c ? c->launches : 0; }
 
+// pinned host memory for the native pipelines of container.cpp (which is compiled without the CUDA runtime headers)
+extern "C" void* zn_ctx_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void zn_ctx_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 // --------------------------------------------------------------------------------------------- plans
 template <typename T>
 static bool upload(zn_ctx* c, T** dptr, const T* h, size_t count) {
