@@ -176,6 +176,19 @@ int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int save_data, co
                           uint64_t row_hi, size_t batch_bytes, int io_threads, zn_verify_report* report, char* err,
                           size_t errcap);
 
+/* ---- native random access: ZnippyArchive (znippy-common/src/archive.rs:20-168).  extract_files = every chunk of every
+ * requested file in one batch (no digest compare, as archive.rs:144-168), chunks concatenated in fdata_offset order at
+ * out_base + out_off[i] (capacity = zn_archive_file_size).  file_status[i]: 0 ok, 1 not in the archive,
+ * 2 | (blob status << 16) a chunk failed to decode. */
+typedef struct zn_archive zn_archive;
+zn_archive* zn_archive_open(const char* path, char* err, size_t errcap);
+void zn_archive_close(zn_archive* a);
+uint64_t zn_archive_file_count(const zn_archive* a);
+const char* zn_archive_file_name(const zn_archive* a, uint64_t i, uint64_t* size);
+int zn_archive_file_size(const zn_archive* a, const char* path, uint64_t* size); /* 1 = present */
+int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* const* paths, uint32_t n, uint8_t* out_base,
+                             const uint64_t* out_off, uint32_t* file_status);
+
 /* ---- native write pipeline: compress_stream (znippy-compress/src/stream_packer.rs:58-372).  Entries are cut into
  * <= 8 MiB rounds into a pinned slot; each full slot is one zn_compress_batch (+ zn_hash_batch for store-as-is rounds),
  * payloads are pwritten at a running cursor, finish() writes sub-indexes per (pkg_type, repo), manifest and footer. */

@@ -173,3 +173,34 @@ def test_native_and_python_write_pipelines_agree(A, tmp_path, oracle):
         assert ar.extract_file(e.relative_path) == e.data
     vr = A.verify_archive_integrity(pn)
     assert vr.corrupt_files == 0 and vr.total_files == 5 and vr.chunks == 6
+
+
+def test_native_random_access(A, tmp_path, oracle):
+    """ZnippyArchive over zn_archive_*: list / contains / file_size / extract_files incl. a missing path, a multi-chunk
+    file, an empty file and a corrupt chunk (archive.rs:20-168)."""
+    entries = [(f"f/{i:03d}.txt", oracle.real_text(1000 + 997 * i).tobytes()) for i in range(40)]
+    entries += [("big.bin", oracle.gen_binary(20 << 20).tobytes()), ("lib.jar", oracle.gen_random(12345).tobytes()), ("nil", b"")]
+    path, _ = _pack(A, tmp_path, entries)
+    ar = A.ZnippyArchive.open(path)
+    assert ar.list_files() == [p for p, _ in entries]
+    assert ar.contains("big.bin") and not ar.contains("nope") and ar.file_size("big.bin") == 20 << 20 and ar.file_size("nope") is None
+    want = dict(entries)
+    names = ["big.bin", "f/007.txt", "missing.txt", "nil", "lib.jar", "f/039.txt", "f/007.txt"]
+    got = ar.extract_files(names)
+    for nme, g in zip(names, got):
+        if nme == "missing.txt":
+            assert isinstance(g, KeyError)
+        else:
+            assert g == want[nme], nme
+    assert ar.extract_file("f/000.txt") == want["f/000.txt"]
+    ar.close()
+    # corrupt the second chunk of big.bin: that file fails, the others still extract
+    t = A.read_znippy_index(path)
+    rows = [(p, o, s) for p, o, s, q in zip(t.column("relative_path").to_pylist(), t.column("blob_offset").to_pylist(),
+                                          t.column("blob_size").to_pylist(), t.column("chunk_seq").to_pylist()) if p == "big.bin" and q == 1]
+    raw = bytearray(open(path, "rb").read())
+    raw[rows[0][1]] ^= 0xFF   # frame magic
+    open(path, "wb").write(raw)
+    ar = A.ZnippyArchive.open(path)
+    got = ar.extract_files(["big.bin", "f/001.txt"])
+    assert isinstance(got[0], Exception) and got[1] == want["f/001.txt"]

@@ -24,6 +24,8 @@ EXPORTS = [
     "zn_index_field_name", "zn_index_writer_create", "zn_index_writer_metadata", "zn_index_writer_push_group",
     "zn_index_writer_finish", "zn_archive_decompress", "zn_archive_writer_create", "zn_archive_writer_add",
     "zn_archive_writer_finish", "zn_archive_writer_error", "zn_ctx_pinned_alloc", "zn_ctx_pinned_free",
+    "zn_archive_open", "zn_archive_close", "zn_archive_file_count", "zn_archive_file_name", "zn_archive_file_size",
+    "zn_archive_extract_files",
 ]
 
 
@@ -113,6 +115,16 @@ def lib() -> C.CDLL:
     L.zn_index_writer_push_group.argtypes = [vp, C.c_int8, C.c_char_p, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.zn_index_writer_finish.argtypes = [vp]
     L.zn_archive_decompress.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, u64, u64, sz, C.c_int, vp, C.c_char_p, sz]
+    L.zn_archive_open.argtypes = [C.c_char_p, C.c_char_p, sz]
+    L.zn_archive_open.restype = vp
+    L.zn_archive_close.argtypes = [vp]
+    L.zn_archive_close.restype = None
+    L.zn_archive_file_count.argtypes = [vp]
+    L.zn_archive_file_count.restype = u64
+    L.zn_archive_file_name.argtypes = [vp, u64, C.POINTER(u64)]
+    L.zn_archive_file_name.restype = C.c_char_p
+    L.zn_archive_file_size.argtypes = [vp, C.c_char_p, C.POINTER(u64)]
+    L.zn_archive_extract_files.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.zn_archive_writer_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, sz]
     L.zn_archive_writer_create.restype = vp
     L.zn_archive_writer_add.argtypes = [vp, C.c_char_p, vp, u64, C.c_int, C.c_int8, C.c_char_p]

@@ -295,39 +295,52 @@ def verify_archive_integrity(path: str, ctx: Ctx | None = None) -> VerifyReport:
 
 
 class ZnippyArchive:
-    """archive.rs:46-168: random-access reader; `extract_files` is one GPU batch over all requested chunks."""
+    """archive.rs:46-168: random-access reader; `extract_files` is one GPU batch over all requested chunks.  Backed by
+    the native `zn_archive_*` (container.cpp): index, per-file chunk lists, pread, batch decode — no pyarrow."""
 
     def __init__(self, path: str, ctx: Ctx | None = None):
+        import ctypes as C
+
+        from . import _native as N
         self.path, self.ctx = path, ctx
-        table = read_znippy_index(path)
-        bo, bs, fo, comp, us, _ = _columns(table)
-        self.file_index: dict[str, dict] = {}
-        for r, p in enumerate(table.column("relative_path").to_pylist()):
-            e = self.file_index.setdefault(p, {"uncompressed_size": 0, "chunks": []})
-            e["uncompressed_size"] += int(us[r])
-            e["chunks"].append((int(fo[r]), int(bo[r]), int(bs[r]), bool(comp[r]), int(us[r])))
-        for e in self.file_index.values():
-            e["chunks"].sort(key=lambda c: c[0])  # archive.rs:131-133
-        self._fd = os.open(path, os.O_RDONLY)
+        err = C.create_string_buffer(512)
+        self._h = N.lib().zn_archive_open(path.encode(), err, 512)
+        if not self._h:
+            raise IOError(f"cannot open {path}: {err.value.decode(errors='replace')}")
 
     @classmethod
     def open(cls, path: str, ctx: Ctx | None = None) -> "ZnippyArchive":
         return cls(path, ctx)
 
     def close(self):
-        if self._fd is not None:
-            os.close(self._fd)
-            self._fd = None
+        from . import _native as N
+        if getattr(self, "_h", None):
+            N.lib().zn_archive_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def list_files(self):
-        return list(self.file_index.keys())
+        import ctypes as C
+
+        from . import _native as N
+        L = N.lib()
+        return [L.zn_archive_file_name(self._h, i, None).decode() for i in range(L.zn_archive_file_count(self._h))]
 
     def contains(self, relative_path: str) -> bool:
-        return relative_path in self.file_index
+        from . import _native as N
+        return bool(N.lib().zn_archive_file_size(self._h, relative_path.encode(), None))
 
     def file_size(self, relative_path: str):
-        e = self.file_index.get(relative_path)
-        return None if e is None else e["uncompressed_size"]
+        import ctypes as C
+
+        from . import _native as N
+        sz = C.c_uint64(0)
+        return int(sz.value) if N.lib().zn_archive_file_size(self._h, relative_path.encode(), C.byref(sz)) else None
 
     def extract_file(self, relative_path: str) -> bytes:
         r = self.extract_files([relative_path])[0]
@@ -338,41 +351,31 @@ class ZnippyArchive:
     def extract_files(self, paths):
         """archive.rs:27-29, batched: every chunk of every requested file in one zn_decode_verify_batch
         (expect_digest = NULL: extract_file does not verify, archive.rs:144-168)."""
-        results: list = [None] * len(paths)
-        bo, bl, cf, ol, oo, owner = [], [], [], [], [], []
-        out_cur = in_cur = 0
-        reads = []
-        for k, p in enumerate(paths):
-            e = self.file_index.get(p)
-            if e is None:
-                results[k] = KeyError(f"file not found in archive: {p}")
-                continue
-            for (_fo, boff, bsz, comp, usz) in e["chunks"]:
-                reads.append((boff, bsz, in_cur))
-                bo.append(in_cur); bl.append(bsz); cf.append(1 if comp else 0); ol.append(usz); oo.append(out_cur)
-                owner.append(k)
-                in_cur += (bsz + 15) & ~15
-                out_cur += usz  # chunks of one file are concatenated in fdata_offset order
-        if not bo:
-            return results
-        buf = np.zeros(max(in_cur, 1), np.uint8)
-        for (boff, bsz, at) in reads:
-            if bsz and os.preadv(self._fd, [memoryview(buf)[at: at + bsz]], boff) != bsz:
-                raise IOError("short read from archive")
-        out = np.zeros(max(out_cur, 1), np.uint8)
-        status, _ = codec.decode_verify_batch(buf, bo, bl, cf, ol, None, out, oo, self.ctx)
-        bad = {}
-        for i, k in enumerate(owner):
-            if status[i] != codec.S_OK and k not in bad:
-                bad[k] = codec.CodecError(int(status[i]), f"decompress chunk of {paths[k]}")
-        pos = 0
-        for k, p in enumerate(paths):
-            if results[k] is not None:
-                continue
-            size = self.file_index[p]["uncompressed_size"]
-            results[k] = bad.get(k, None) or out[pos: pos + size].tobytes()
-            pos += size
-        return results
+        import ctypes as C
+
+        from . import _native as N
+        ctx = self.ctx or default_ctx()
+        n = len(paths)
+        sizes = [self.file_size(p) for p in paths]
+        offs = np.zeros(max(n, 1), np.uint64)
+        cur = 0
+        for i, sz in enumerate(sizes):
+            offs[i] = cur
+            cur += (sz or 0)
+        out = np.zeros(max(cur, 1), np.uint8)
+        st = np.zeros(max(n, 1), np.uint32)
+        arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
+        ctx.check(N.lib().zn_archive_extract_files(ctx.handle, self._h, arr, n, N.ptr(out), N.ptr(offs), N.ptr(st)),
+                  "zn_archive_extract_files")
+        res = []
+        for i, p in enumerate(paths):
+            if st[i] == 1:
+                res.append(KeyError(f"file not found in archive: {p}"))
+            elif st[i] != 0:
+                res.append(codec.CodecError(int(st[i]) >> 16, f"decompress chunk of {p}"))
+            else:
+                res.append(out[int(offs[i]): int(offs[i]) + sizes[i]].tobytes())
+        return res
 
 
 # --------------------------------------------------------------------------------------------- write side

@@ -18,10 +18,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -1005,5 +1007,120 @@ extern "C" int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_rep
   if (w->stage) zn_ctx_pinned_free(w->stage);
   if (w->outb) zn_ctx_pinned_free(w->outb);
   delete w;
+  return rc;
+}
+
+// ================================================================================================ native random access
+// ZnippyArchive (znippy-common/src/archive.rs:46-168): open = index + per-file chunk lists sorted by fdata_offset
+// (:68-136); extract_files (:27-29) = every chunk of every requested file in ONE zn_decode_verify_batch, no digest
+// compare (extract_file does not verify, :144-168), chunks concatenated in fdata_offset order.
+struct zn_archive {
+  zn_index* index = nullptr;
+  int fd = -1;
+  struct FileEntry {
+    uint64_t size = 0;
+    std::vector<uint64_t> rows;  // sorted by fdata_offset
+  };
+  std::map<std::string, FileEntry> files;
+  std::vector<std::map<std::string, FileEntry>::const_iterator> order;  // first-seen order for listing
+};
+
+extern "C" zn_archive* zn_archive_open(const char* path, char* err, size_t errcap) {
+  zn_index* ix = zn_index_open(path, err, errcap);
+  if (!ix) return nullptr;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errcap, "cannot open archive"); zn_index_close(ix); return nullptr; }
+  zn_archive* a = new zn_archive();
+  a->index = ix;
+  a->fd = fd;
+  const IndexImpl& I = ix->ix;
+  for (uint64_t r = 0; r < I.rows; r++) {
+    const std::string p(I.paths.data() + I.path_off[r], I.path_off[r + 1] - I.path_off[r]);
+    auto ins = a->files.emplace(p, zn_archive::FileEntry());
+    if (ins.second) a->order.push_back(ins.first);
+    ins.first->second.size += I.col[3][r];
+    ins.first->second.rows.push_back(r);
+  }
+  for (auto& kv : a->files)
+    std::stable_sort(kv.second.rows.begin(), kv.second.rows.end(), [&](uint64_t x, uint64_t y) { return I.col[2][x] < I.col[2][y]; });
+  return a;
+}
+extern "C" void zn_archive_close(zn_archive* a) {
+  if (!a) return;
+  if (a->fd >= 0) close(a->fd);
+  zn_index_close(a->index);
+  delete a;
+}
+extern "C" uint64_t zn_archive_file_count(const zn_archive* a) { return a ? a->order.size() : 0; }
+extern "C" const char* zn_archive_file_name(const zn_archive* a, uint64_t i, uint64_t* size) {
+  if (!a || i >= a->order.size()) return nullptr;
+  if (size) *size = a->order[i]->second.size;
+  return a->order[i]->first.c_str();
+}
+extern "C" int zn_archive_file_size(const zn_archive* a, const char* path, uint64_t* size) {  // contains + file_size
+  if (!a || !path) return 0;
+  auto it = a->files.find(path);
+  if (it == a->files.end()) return 0;
+  if (size) *size = it->second.size;
+  return 1;
+}
+
+// file_status[i]: 0 ok, 1 not in archive, 2 a chunk failed to decode (first failing chunk's per-blob status in the high half)
+extern "C" int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* const* paths, uint32_t n, uint8_t* out_base,
+                                        const uint64_t* out_off, uint32_t* file_status) {
+  if (!ctx || !a || (n && (!paths || !out_base || !out_off || !file_status))) return ZN_E_ARG;
+  const IndexImpl& I = a->index->ix;
+  std::vector<uint64_t> rows, bo, bl, ol, oo;
+  std::vector<uint8_t> cf;
+  std::vector<uint32_t> owner;
+  uint64_t in_cur = 0;
+  for (uint32_t k = 0; k < n; k++) {
+    auto it = a->files.find(paths[k]);
+    if (it == a->files.end()) { file_status[k] = 1; continue; }
+    file_status[k] = 0;
+    uint64_t pos = out_off[k];
+    for (uint64_t r : it->second.rows) {
+      rows.push_back(r);
+      bo.push_back(in_cur); bl.push_back(I.col[1][r]); cf.push_back(I.compressed[r]); ol.push_back(I.col[3][r]); oo.push_back(pos);
+      owner.push_back(k);
+      in_cur += (I.col[1][r] + 15) & ~15ull;
+      pos += I.col[3][r];
+    }
+  }
+  if (rows.empty()) return ZN_OK;
+  uint8_t* stage = (uint8_t*)zn_ctx_pinned_alloc(in_cur + 4096);
+  if (!stage) return ZN_E_NOMEM;
+  std::atomic<int> io_err{0};
+  {
+    std::atomic<size_t> cur{0};
+    auto body = [&] {
+      for (;;) {
+        const size_t i = cur.fetch_add(1);
+        if (i >= rows.size()) break;
+        uint64_t done = 0;
+        const uint64_t len = bl[i], off = I.col[0][rows[i]];
+        while (done < len) {
+          const ssize_t r = pread(a->fd, stage + bo[i] + done, len - done, (off_t)(off + done));
+          if (r <= 0) { io_err = 1; return; }
+          done += (uint64_t)r;
+        }
+      }
+    };
+    std::vector<std::thread> ts;
+    const int nt = rows.size() >= 16 ? 4 : 1;
+    for (int t = 1; t < nt; t++) ts.emplace_back(body);
+    body();
+    for (auto& t : ts) t.join();
+  }
+  int rc = io_err ? ZN_E_ARG : ZN_OK;
+  if (rc == ZN_OK) {
+    std::vector<uint32_t> st(rows.size());
+    rc = zn_decode_verify_batch(ctx, stage, bo.data(), bl.data(), cf.data(), ol.data(), nullptr, out_base, oo.data(),
+                                (uint32_t)rows.size(), st.data(), nullptr);
+    if (rc == ZN_OK)
+      for (size_t i = 0; i < rows.size(); i++)
+        if (st[i] != ZN_S_OK && file_status[owner[i]] == 0) file_status[owner[i]] = 2u | (st[i] << 16);
+  }
+  zn_ctx_pinned_free(stage);
   return rc;
 }
