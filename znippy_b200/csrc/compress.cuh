@@ -17,6 +17,11 @@
 // Everything here is warp-uniform code over a `Warp` abstraction (32 lanes on the device, 1 lane on the host) so the
 // format logic is exercised on the CPU against stock libzstd / liblz4 (tests/host_emu).
 #pragma once
+#include <cmath>
+#ifndef ZN_CP
+#define ZN_CP_BEGIN() do {} while (0)
+#define ZN_CP(i) do {} while (0)
+#endif
 #include "bitio.cuh"
 #include "zstd_tables.cuh"
 
@@ -31,12 +36,37 @@ struct Warp {
 ZN_D uint32_t w_ballot(const Warp&, bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 ZN_D uint32_t w_shfl(const Warp&, uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
 ZN_D void w_sync(const Warp&) { __syncwarp(); }
+ZN_D uint32_t w_shfl_xor(const Warp&, uint32_t v, uint32_t d) { return __shfl_xor_sync(0xFFFFFFFFu, v, d); }
 ZN_D uint32_t ffs32(uint32_t v) { return (uint32_t)__ffs((int)v); }
+ZN_D void w_count(uint32_t* p) { atomicAdd(p, 1u); }
+ZN_D void w_or(uint32_t* p, uint32_t v) { if (v) atomicOr(p, v); }
+ZN_D uint32_t w_max(const Warp&, uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+// exclusive prefix sum over the lanes; *total = sum over the warp
+ZN_D uint32_t w_excl_scan(const Warp& w, uint32_t v, uint32_t* total) {
+  uint32_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((int)w.lane >= d) x += y; }
+  *total = __shfl_sync(0xFFFFFFFFu, x, 31);
+  return x - v;
+}
+constexpr bool kOnDevice = true;
+ZN_D uint32_t w_sum(const Warp&, uint32_t v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  return v;
+}
 #else
 inline uint32_t w_ballot(const Warp&, bool p) { return p ? 1u : 0u; }
 inline uint32_t w_shfl(const Warp&, uint32_t v, uint32_t) { return v; }
 inline void w_sync(const Warp&) {}
+inline uint32_t w_shfl_xor(const Warp&, uint32_t v, uint32_t) { return v; }
 inline uint32_t ffs32(uint32_t v) { return v ? (uint32_t)__builtin_ffs((int)v) : 0u; }
+inline void w_count(uint32_t* p) { (*p)++; }
+inline uint32_t w_sum(const Warp&, uint32_t v) { return v; }
+inline void w_or(uint32_t* p, uint32_t v) { *p |= v; }
+inline uint32_t w_max(const Warp&, uint32_t v) { return v; }
+inline uint32_t w_excl_scan(const Warp&, uint32_t v, uint32_t* total) { *total = v; return 0; }
+constexpr bool kOnDevice = false;
 #endif
 
 ZN_HD uint32_t hash4(uint32_t v, uint32_t hlog) { return (v * 2654435761u) >> (32 - hlog); }
@@ -45,9 +75,20 @@ constexpr uint32_t kLz4Block = 64u * 1024u;
 constexpr uint32_t kLz4Slot = kLz4Block + kLz4Block / 255u + 32u;  // worst-case LZ4 block
 constexpr uint32_t kLz4HashLog = 12;                                 // 4096 x u16 = 8 KiB per warp
 constexpr uint32_t kZstdHashLog = 12;                                // 4096 x u32 = 16 KiB per warp
+#ifndef ZN_LAZY_MATCH_W
+#define ZN_LAZY_MATCH_W 4
+#define ZN_LAZY_SKIP_W 8
+#endif
+constexpr uint32_t kLazyMatchWeight = ZN_LAZY_MATCH_W, kLazySkipWeight = ZN_LAZY_SKIP_W;
+constexpr uint32_t kLazyProbe = 36;                                  // bytes each candidate lane compares before the warp votes
 constexpr uint32_t kZstdPrime = 1024;                                // bytes of the previous block hashed in first
 constexpr uint32_t kZstdMaxSeq = 32768;                              // sequences per 128 KiB block (min match 4)
-constexpr uint32_t kZstdSlot = kZstdBlockMax + 64u;                  // staged block payload
+#ifndef ZN_CBLOCK
+#define ZN_CBLOCK kZstdBlockMax
+#endif
+constexpr uint32_t kZstdCBlock = ZN_CBLOCK;                          // input bytes per compressed block (<= 128 KiB)
+constexpr uint32_t kZstdHalf = kZstdCBlock + 64u;                  // one staging region
+constexpr uint32_t kZstdSlot = 2u * kZstdHalf;                       // region A: raw literals (+ sequences); region B: Huffman payload
 
 // Length of the common prefix of a[0..max) and b[0..max), found 4 bytes per lane per step.
 ZN_HD uint32_t match_extend(const Warp& w, const uint8_t* a, const uint8_t* b, uint32_t max) {
@@ -69,6 +110,33 @@ ZN_HD uint32_t match_extend(const Warp& w, const uint8_t* a, const uint8_t* b, u
     }
     len += 4u * w.n;
   }
+}
+
+
+// Common prefix length of a[0..lim) and b[0..lim), lim <= 32, one lane.  The device version works on aligned words
+// (9 loads per side, all in flight together) and may read up to 39 bytes past a / b, so the caller guarantees slack.
+ZN_HD uint32_t prefix32(const uint8_t* a, const uint8_t* b, uint32_t lim, bool slack) {
+#if defined(__CUDA_ARCH__)
+  if (slack) {
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+    const uint32_t* wb = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(b) & ~(uintptr_t)3);
+    const uint32_t sa = ((uint32_t)reinterpret_cast<uintptr_t>(a) & 3u) * 8u, sb = ((uint32_t)reinterpret_cast<uintptr_t>(b) & 3u) * 8u;
+    uint32_t ra[9], rb[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { ra[k] = wa[k]; rb[k] = wb[k]; }
+    uint32_t n = 32;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      const uint32_t x = __funnelshift_r(ra[k], ra[k + 1], sa) ^ __funnelshift_r(rb[k], rb[k + 1], sb);
+      if (x) n = 4u * k + (((uint32_t)__ffs((int)x) - 1u) >> 3);
+    }
+    return n < lim ? n : lim;
+  }
+#endif
+  (void)slack;
+  uint32_t n = 0;
+  while (n < lim && a[n] == b[n]) n++;
+  return n;
 }
 
 // dst[0..n) = src[0..n), spread over the warp (byte granular; the compressed side is small by construction)
@@ -167,7 +235,7 @@ ZN_HD uint32_t lz4_frame_header(uint8_t* dst, uint64_t content) {
 // ------------------------------------------------------------------------------------------------- FSE encoding
 // Compression tables for the three predefined distributions (RFC 8878 §3.1.1.3.2.2.1), built once on the host.
 struct FseCTable {
-  uint16_t state[64];      // next-state table (table size <= 64 for the predefined logs 6/5/6)
+  uint16_t state[512];     // next-state table (table log <= 9)
   int32_t delta_nb[53];    // per symbol: (maxBitsOut << 16) - minStatePlus
   int32_t delta_state[53]; // per symbol: first state slot - count
   uint32_t log;
@@ -175,12 +243,19 @@ struct FseCTable {
 struct PredefCTables {
   FseCTable ll, of, ml;
 };
+struct FseBuildScratch {
+  int32_t cumul[54];
+  uint8_t symtab[512];
+};
 
-inline void fse_build_ctable(FseCTable* ct, const int16_t* norm, int nsym, int log) {
+// One thread.  norm sums to 1 << log (entries of -1 count as 1); log 0 with a single symbol of count 1 gives the
+// zero-bit table the RLE mode needs.
+ZN_HD void fse_build_ctable(FseCTable* ct, const int16_t* norm, int nsym, int log, FseBuildScratch* sc) {
   const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
-  int cumul[64] = {0};
-  uint8_t symtab[64];
+  int32_t* cumul = sc->cumul;
+  uint8_t* symtab = sc->symtab;
   int high = size - 1;
+  cumul[0] = 0;
   for (int s = 0; s < nsym; s++) {
     if (norm[s] == -1) { cumul[s + 1] = cumul[s] + 1; symtab[high--] = (uint8_t)s; }
     else cumul[s + 1] = cumul[s] + norm[s];
@@ -209,9 +284,10 @@ inline void fse_build_ctable(FseCTable* ct, const int16_t* norm, int nsym, int l
 }
 
 inline void build_predef_ctables(PredefCTables* p) {
-  fse_build_ctable(&p->ll, zs::kLLDefault, 36, 6);
-  fse_build_ctable(&p->of, zs::kOFDefault, 29, 5);
-  fse_build_ctable(&p->ml, zs::kMLDefault, 53, 6);
+  FseBuildScratch sc;
+  fse_build_ctable(&p->ll, zs::kLLDefault, 36, 6, &sc);
+  fse_build_ctable(&p->of, zs::kOFDefault, 29, 5, &sc);
+  fse_build_ctable(&p->ml, zs::kMLDefault, 53, 6, &sc);
 }
 
 #if defined(__CUDACC__)
@@ -275,49 +351,444 @@ struct FseCState {
 // packed sequence: ll | ml << 20 | off << 40 (each < 2^20)
 ZN_HD uint64_t seq_pack(uint32_t ll, uint32_t ml, uint32_t off) { return (uint64_t)ll | ((uint64_t)ml << 20) | ((uint64_t)off << 40); }
 
-// Sequences section with predefined tables.  One thread.  Returns bytes written, or 0 as soon as the section
-// would exceed `limit` bytes (the block is then stored raw); the writer overshoots `limit` by < 16 bytes.
-ZN_HD uint32_t zstd_encode_sequences(uint8_t* dst, const uint64_t* seqs, uint32_t nseq, uint32_t limit) {
-  uint8_t* p = dst;
-  if (nseq < 128) *p++ = (uint8_t)nseq;
-  else if (nseq < 0x7F00) { *p++ = (uint8_t)((nseq >> 8) + 128); *p++ = (uint8_t)nseq; }
-  else { *p++ = 255; *p++ = (uint8_t)(nseq - 0x7F00); *p++ = (uint8_t)((nseq - 0x7F00) >> 8); }
-  if (nseq == 0) return (uint32_t)(p - dst);
-  *p++ = 0;  // LL, OF, ML all predefined
-  const PredefCTables* ct = predef_ctables();
-  BitWriter bw{p, 0, 0};
-  FseCState sl, so, sm;
-  for (uint32_t k = nseq; k-- > 0;) {
-    const uint64_t s = seqs[k];
-    const uint32_t ll = (uint32_t)(s & 0xFFFFF), ml = (uint32_t)((s >> 20) & 0xFFFFF), off = (uint32_t)(s >> 40);
-    const uint32_t ofb = off + 3u;  // never a repeat code
-    const uint32_t oc = (uint32_t)hibit32(ofb);
-    const uint32_t lc = len_code(ll, zs::kLLBase, zs::kLLBits, 16, 36);
-    const uint32_t mc = len_code(ml, zs::kMLBase, zs::kMLBits, 32, 53);
-    if (k == nseq - 1) {
-      sm.init(&ct->ml, mc);
-      so.init(&ct->of, oc);
-      sl.init(&ct->ll, lc);
-    } else {
-      so.encode(bw, &ct->of, oc);
-      sm.encode(bw, &ct->ml, mc);
-      sl.encode(bw, &ct->ll, lc);
-      bw.flush();
+// ---- FSE table description (RFC 8878 §4.1.1): the writer mirroring fse_read_ncount of the decoder.
+// alphabet = index of the last symbol with a non-zero count + 1.  Returns bytes written (< 96).
+ZN_HD uint32_t fse_write_ncount(uint8_t* out, const int16_t* norm, uint32_t alphabet, uint32_t log) {
+  uint8_t* p = out;
+  const int size = 1 << log;
+  uint32_t bits = log - 5u, nacc = 4;
+  int remaining = size + 1, threshold = size, nb = (int)log + 1;
+  uint32_t sym = 0;
+  bool prev0 = false;
+  while (sym < alphabet && remaining > 1) {
+    if (prev0) {  // run of zero-probability symbols: 2-bit repeat counts
+      uint32_t start = sym;
+      while (sym < alphabet && !norm[sym]) sym++;
+      if (sym == alphabet) break;
+      while (sym >= start + 24) {
+        start += 24;
+        bits += 0xFFFFu << nacc;
+        p[0] = (uint8_t)bits; p[1] = (uint8_t)(bits >> 8); p += 2;
+        bits >>= 16;
+      }
+      while (sym >= start + 3) { start += 3; bits += 3u << nacc; nacc += 2; }
+      bits += (sym - start) << nacc;
+      nacc += 2;
+      if (nacc > 16) { p[0] = (uint8_t)bits; p[1] = (uint8_t)(bits >> 8); p += 2; bits >>= 16; nacc -= 16; }
     }
-    bw.add(ll - zs::kLLBase[lc], zs::kLLBits[lc]);
-    bw.add(ml - zs::kMLBase[mc], zs::kMLBits[mc]);
-    bw.flush();
-    bw.add(ofb - (1u << oc), oc);
-    bw.flush();
-    if ((uint32_t)(bw.p - dst) > limit) return 0;
+    int count = norm[sym++];
+    const int mx = (2 * threshold - 1) - remaining;
+    remaining -= count < 0 ? -count : count;
+    count++;
+    if (count >= threshold) count += mx;
+    bits += (uint32_t)count << nacc;
+    nacc += (uint32_t)nb;
+    nacc -= (count < mx) ? 1u : 0u;
+    prev0 = (count == 1);
+    while (remaining < threshold) { nb--; threshold >>= 1; }
+    if (nacc > 16) { p[0] = (uint8_t)bits; p[1] = (uint8_t)(bits >> 8); p += 2; bits >>= 16; nacc -= 16; }
   }
-  sm.flush(bw, &ct->ml);
-  bw.flush();
-  so.flush(bw, &ct->of);
-  bw.flush();
-  sl.flush(bw, &ct->ll);
-  bw.close();
-  return (uint32_t)(bw.p - dst);
+  p[0] = (uint8_t)bits; p[1] = (uint8_t)(bits >> 8);
+  p += (nacc + 7) / 8;
+  return (uint32_t)(p - out);
+}
+
+// Scales a histogram (total > 0, >= 2 symbols present) to sum 1 << log with every present symbol >= 1.
+ZN_HD void fse_normalize(int16_t* norm, const uint32_t* cnt, uint32_t nsym, uint32_t total, uint32_t log) {
+  const uint32_t size = 1u << log;
+  uint32_t sum = 0, largest = 0;
+  for (uint32_t s = 0; s < nsym; s++) {
+    uint32_t q = 0;
+    if (cnt[s]) {
+      const uint64_t scaled = (uint64_t)cnt[s] * size;
+      q = (uint32_t)(scaled / total);
+      const uint32_t rem = (uint32_t)(scaled % total);
+      if (q == 0) q = 1;
+      else if (q < 8 && 2u * rem > total + total / (q + 1)) q++;  // small shares round to nearest-ish
+      if (cnt[s] > cnt[largest]) largest = s;
+    }
+    norm[s] = (int16_t)q;
+    sum += q;
+  }
+  if (sum <= size) { norm[largest] = (int16_t)(norm[largest] + (size - sum)); return; }
+  for (uint32_t excess = sum - size; excess; excess--) {  // shave the biggest shares
+    uint32_t big = 0;
+    for (uint32_t s = 1; s < nsym; s++) if (norm[s] > norm[big]) big = s;
+    norm[big]--;
+  }
+}
+
+// cost in bits of coding the histogram with a normalised table (-1 entries count as 1)
+ZN_HD float fse_cost(const uint32_t* cnt, const int16_t* norm, uint32_t nsym, uint32_t log) {
+  float c = (float)log;  // final state flush
+  for (uint32_t s = 0; s < nsym; s++)
+    if (cnt[s]) { const int q = norm[s] < 0 ? 1 : norm[s]; c += (float)cnt[s] * ((float)log - log2f((float)q)); }
+  return c;
+}
+
+struct SeqScratch {
+  FseCTable ct[3];
+  FseBuildScratch bs[3];
+  uint32_t cnt[3][53];
+  int16_t norm[3][54];
+  uint8_t hdr[3][96];
+  uint32_t mode[3], hlen[3];
+  uint32_t sbits[3][32];   // per chunk: FSE state bits of each sequence, value << 8 | count
+  uint8_t codes[3][32];    // per chunk: the three codes of each sequence
+  uint32_t bitbuf[88];     // per chunk: the assembled bitstream (<= 31 carried bits + 32 x 75)
+};
+
+// packed sequence after pass 1: ll:17 | ml - 4:17 | offset value:18 | ll code:6 | ml code:6   (ml is 4 .. 131072)
+ZN_HD uint64_t seq_pack2(uint32_t ll, uint32_t ml, uint32_t ofv, uint32_t lc, uint32_t mc) {
+  return (uint64_t)ll | ((uint64_t)(ml - 4u) << 17) | ((uint64_t)ofv << 34) | ((uint64_t)lc << 52) | ((uint64_t)mc << 58);
+}
+
+// Sequences section, called by the whole warp.  Offsets become repeat codes where the history written by THIS block
+// allows it (blocks are compressed independently, so the history inherited from the previous block is treated as
+// unknown); each of the three code tables is sent FSE-compressed, RLE or predefined, whichever is estimated cheapest.
+// The lanes load 32 sequences at a time (one coalesced access) and hand them to the serial parts through shuffles;
+// lanes 0-2 build one table each; lane 0 writes the bitstream.  Rewrites seqs[] in place.  Returns (on every lane)
+// bytes written, or 0 when the section would exceed `limit` bytes (the block is then stored raw); the writer
+// overshoots `limit` by < 16 bytes.
+ZN_HD uint32_t zstd_encode_sequences(const Warp& w, uint8_t* dst, uint64_t* seqs, uint32_t nseq, uint32_t limit, SeqScratch* sc) {
+  uint8_t* p = dst;
+  if (w.lane == 0) {
+    if (nseq < 128) *p++ = (uint8_t)nseq;
+    else if (nseq < 0x7F00) { *p++ = (uint8_t)((nseq >> 8) + 128); *p++ = (uint8_t)nseq; }
+    else { *p++ = 255; *p++ = (uint8_t)(nseq - 0x7F00); *p++ = (uint8_t)((nseq - 0x7F00) >> 8); }
+  }
+  if (nseq == 0) return w_shfl(w, (uint32_t)(p - dst), 0);
+  // pass 1: offset values + code histograms
+  for (uint32_t i = w.lane; i < 3 * 53; i += w.n) sc->cnt[i / 53][i % 53] = 0;
+  w_sync(w);
+  uint32_t r0 = 0, r1 = 0, r2 = 0;  // 0 = not known to this block; tracked identically by every lane
+  for (uint32_t base = 0; base < nseq; base += w.n) {
+    const uint32_t k = base + w.lane;
+    const uint64_t s = k < nseq ? seqs[k] : 0ull;
+    const uint32_t ll = (uint32_t)(s & 0xFFFFF), ml = (uint32_t)((s >> 20) & 0xFFFFF), off = (uint32_t)(s >> 40);
+    const uint32_t here = nseq - base < w.n ? nseq - base : w.n;
+    uint32_t v = 0;
+    for (uint32_t j = 0; j < here; j++) {
+      const uint32_t llj = w_shfl(w, ll, j), offj = w_shfl(w, off, j);
+      uint32_t vj;
+      if (llj) {
+        if (offj == r0) vj = 1;
+        else if (offj == r1) { vj = 2; r1 = r0; r0 = offj; }
+        else if (offj == r2) { vj = 3; r2 = r1; r1 = r0; r0 = offj; }
+        else { vj = offj + 3u; r2 = r1; r1 = r0; r0 = offj; }
+      } else {
+        if (offj == r1) { vj = 1; r1 = r0; r0 = offj; }
+        else if (offj == r2) { vj = 2; r2 = r1; r1 = r0; r0 = offj; }
+        else if (r0 > 1 && offj == r0 - 1u) { vj = 3; r2 = r1; r1 = r0; r0 = offj; }
+        else { vj = offj + 3u; r2 = r1; r1 = r0; r0 = offj; }
+      }
+      if (j == w.lane) v = vj;
+    }
+    if (k < nseq) {
+      const uint32_t lc = len_code(ll, zs::kLLBase, zs::kLLBits, 16, 36), mc = len_code(ml, zs::kMLBase, zs::kMLBits, 32, 53);
+      seqs[k] = seq_pack2(ll, ml, v, lc, mc);
+      w_count(&sc->cnt[0][lc]);
+      w_count(&sc->cnt[1][hibit32(v)]);
+      w_count(&sc->cnt[2][mc]);
+    }
+  }
+  w_sync(w);
+  // table choice: lane t builds table t
+  const PredefCTables* pd = predef_ctables();
+  const FseCTable* dct[3] = {&pd->ll, &pd->of, &pd->ml};
+  for (uint32_t t = w.lane; t < 3; t += w.n) {
+    const int16_t* dnorm = t == 0 ? zs::kLLDefault : (t == 1 ? zs::kOFDefault : zs::kMLDefault);
+    const uint32_t dsym = t == 0 ? 36u : (t == 1 ? 29u : 53u), dlog = t == 1 ? 5u : 6u, maxlog = t == 1 ? 8u : 9u;
+    sc->mode[t] = 0;
+    sc->hlen[t] = 0;
+    uint32_t present = 0, last = 0;
+    for (uint32_t q = 0; q < 53; q++) if (sc->cnt[t][q]) { present++; last = q; }
+    const float c_pre = last < dsym ? fse_cost(sc->cnt[t], dnorm, dsym, dlog) : 1e30f;
+    if (present == 1) {
+      if (c_pre <= 8.f) continue;
+      for (uint32_t q = 0; q <= last; q++) sc->norm[t][q] = 0;
+      sc->norm[t][last] = 1;
+      fse_build_ctable(&sc->ct[t], sc->norm[t], (int)last + 1, 0, &sc->bs[t]);
+      sc->hdr[t][0] = (uint8_t)last;
+      sc->hlen[t] = 1;
+      sc->mode[t] = 1;
+      continue;
+    }
+    uint32_t log = nseq > 1 ? (uint32_t)hibit32(nseq - 1) : 0u;
+    log = log > 7 ? log - 2 : 5;
+    if (log > maxlog) log = maxlog;
+    while ((1u << log) < 2u * present && log < maxlog) log++;
+    fse_normalize(sc->norm[t], sc->cnt[t], last + 1, nseq, log);
+    const uint32_t hl = fse_write_ncount(sc->hdr[t], sc->norm[t], last + 1, log);
+    const float c_fse = 8.f * (float)hl + fse_cost(sc->cnt[t], sc->norm[t], last + 1, log);
+    if (c_fse >= c_pre) continue;
+    fse_build_ctable(&sc->ct[t], sc->norm[t], (int)last + 1, (int)log, &sc->bs[t]);
+    sc->hlen[t] = hl;
+    sc->mode[t] = 2;
+  }
+  w_sync(w);
+  const FseCTable* ct[3];
+  for (int t = 0; t < 3; t++) ct[t] = sc->mode[t] ? &sc->ct[t] : dct[t];
+  if (w.lane == 0) {
+    *p++ = (uint8_t)((sc->mode[0] << 6) | (sc->mode[1] << 4) | (sc->mode[2] << 2));
+    for (int t = 0; t < 3; t++) for (uint32_t i = 0; i < sc->hlen[t]; i++) *p++ = sc->hdr[t][i];
+  }
+  // pass 2: the bitstream, last sequence first, 32 sequences per step.  Lanes 0-2 each advance one FSE state chain
+  // (the only serial dependence); then every lane assembles the bits of its own sequence — state bits of OF, ML, LL,
+  // then the extra bits of LL, ML, OF — at the bit offset given by a warp prefix sum, and the finished words leave
+  // as a byte-coalesced store.
+  uint32_t over = 0;
+  if (w.lane == 0) over = (uint32_t)(p - dst) > limit ? 1u : 0u;
+  over = w_shfl(w, over, 0);
+  p = dst + w_shfl(w, (uint32_t)(p - dst), 0);
+  for (uint32_t i = w.lane; i < 88; i += w.n) sc->bitbuf[i] = 0;
+  uint32_t stv[kOnDevice ? 1 : 3] = {0};
+  uint32_t carry = 0;  // bits pending in bitbuf[0]
+  w_sync(w);
+  for (uint32_t chunk = (nseq + w.n - 1) / w.n; chunk-- > 0 && !over;) {
+    const uint32_t base = chunk * w.n;
+    const uint32_t here = nseq - base < w.n ? nseq - base : w.n;
+    const bool mine = w.lane < here;
+    const uint64_t sj = mine ? seqs[base + (here - 1u - w.lane)] : 0ull;  // lane i takes the i-th sequence in coding order
+    const uint32_t ll = (uint32_t)(sj & 0x1FFFF), ml = 4u + (uint32_t)((sj >> 17) & 0x1FFFF), ofv = (uint32_t)((sj >> 34) & 0x3FFFF);
+    const uint32_t lc = (uint32_t)((sj >> 52) & 63), mc = (uint32_t)(sj >> 58);
+    const uint32_t oc = mine ? (uint32_t)hibit32(ofv) : 0u;
+    if (mine) { sc->codes[0][w.lane] = (uint8_t)lc; sc->codes[1][w.lane] = (uint8_t)oc; sc->codes[2][w.lane] = (uint8_t)mc; }
+    w_sync(w);
+    for (uint32_t t = w.lane; t < 3; t += w.n) {
+      const FseCTable* c = ct[t];
+      uint32_t v = stv[kOnDevice ? 0 : t];
+      for (uint32_t i = 0; i < here; i++) {
+        const uint32_t sym = sc->codes[t][i];
+        if (base + (here - 1u - i) == nseq - 1u) {  // the very first sequence coded only seeds the state
+          FseCState st0;
+          st0.init(c, sym);
+          v = st0.value;
+          sc->sbits[t][i] = 0;
+        } else {
+          const uint32_t nb = (uint32_t)((int32_t)v + c->delta_nb[sym]) >> 16;
+          sc->sbits[t][i] = ((v & ((1u << nb) - 1u)) << 8) | nb;
+          v = c->state[(int32_t)(v >> nb) + c->delta_state[sym]];
+        }
+      }
+      stv[kOnDevice ? 0 : t] = v;
+    }
+    w_sync(w);
+    uint64_t a = 0, b = 0;
+    uint32_t na = 0, nbx = 0;
+    if (mine) {
+      const uint32_t so_ = sc->sbits[1][w.lane], sm_ = sc->sbits[2][w.lane], sl_ = sc->sbits[0][w.lane];
+      a = (uint64_t)(so_ >> 8);
+      na = so_ & 255u;
+      a |= (uint64_t)(sm_ >> 8) << na;
+      na += sm_ & 255u;
+      a |= (uint64_t)(sl_ >> 8) << na;
+      na += sl_ & 255u;
+      const uint32_t llb = zs::kLLBits[lc], mlb = zs::kMLBits[mc];
+      b = (uint64_t)(ll - zs::kLLBase[lc]);
+      b |= (uint64_t)(ml - zs::kMLBase[mc]) << llb;
+      b |= (uint64_t)(ofv - (1u << oc)) << (llb + mlb);
+      nbx = llb + mlb + oc;
+    }
+    uint32_t tot = 0;
+    const uint32_t at = carry + w_excl_scan(w, na + nbx, &tot);
+    if (mine) {
+      for (int part = 0; part < 2; part++) {
+        const uint64_t v = part ? b : a;
+        const uint32_t n = part ? nbx : na, off = part ? at + na : at;
+        if (!n) continue;
+        const uint32_t wi = off >> 5, sh = off & 31u;
+        const uint64_t lo = v << sh;
+        w_or(&sc->bitbuf[wi], (uint32_t)lo);
+        if (n + sh > 32) w_or(&sc->bitbuf[wi + 1], (uint32_t)(lo >> 32));
+        if (n + sh > 64) w_or(&sc->bitbuf[wi + 2], (uint32_t)(v >> (64u - sh)));
+      }
+    }
+    w_sync(w);
+    const uint32_t bits = carry + tot, nw = bits >> 5;
+    if ((uint32_t)(p - dst) + 4u * nw > limit) { over = 1; break; }
+    for (uint32_t i = w.lane; i < 4u * nw; i += w.n) p[i] = (uint8_t)(sc->bitbuf[i >> 2] >> (8u * (i & 3u)));
+    const uint32_t keep = sc->bitbuf[nw];
+    w_sync(w);
+    for (uint32_t i = w.lane; i <= nw; i += w.n) sc->bitbuf[i] = i == 0 ? keep : 0u;
+    w_sync(w);
+    p += 4u * nw;
+    carry = bits & 31u;
+  }
+  // final states: ML, OF, LL, then the end mark
+  const uint32_t st_ll = kOnDevice ? w_shfl(w, stv[0], 0) : stv[0];
+  const uint32_t st_of = kOnDevice ? w_shfl(w, stv[0], 1) : stv[kOnDevice ? 0 : 1];
+  const uint32_t st_ml = kOnDevice ? w_shfl(w, stv[0], 2) : stv[kOnDevice ? 0 : 2];
+  uint32_t total = 0;
+  if (w.lane == 0 && !over) {
+    BitWriter bw{p, (uint64_t)sc->bitbuf[0], carry};
+    bw.add(st_ml, ct[2]->log);
+    bw.flush();
+    bw.add(st_of, ct[1]->log);
+    bw.flush();
+    bw.add(st_ll, ct[0]->log);
+    bw.close();
+    total = (uint32_t)(bw.p - dst);
+  }
+  return w_shfl(w, total, 0);
+}
+
+
+// ------------------------------------------------------------------------------------------------- Huffman literals
+// Literals section with Huffman-compressed literals (RFC 8878 §3.1.1.3.1, type 2): tree described by direct 4-bit
+// weights, 1 or 4 streams.  scratch = >= 1024 words of shared memory (the idle match-finder table).
+// Returns the section size written at dst, or 0 when Huffman coding is not applicable / does not pay.
+constexpr uint32_t kHufMaxBits = 11;
+
+// lane 0: code lengths (<= 11 bits) from the histogram; fills nb[256], code[256]; returns max_bits (0 = not applicable)
+ZN_HD uint32_t huf_build(const uint32_t* cnt, uint8_t* nb, uint16_t* code, uint32_t* work, uint32_t* last_sym_out) {
+  uint32_t present = 0, last = 0;
+  for (uint32_t s = 0; s < 256; s++) { nb[s] = 0; if (cnt[s]) { present++; last = s; } }
+  *last_sym_out = last;
+  if (present < 2 || last > 128) return 0;  // direct weights describe at most 128 symbols + the implied last one
+  // O(n^2) Huffman: weight[] / parent[] over <= 2*present-1 nodes
+  uint32_t* wt = work;                                   // 512 entries
+  uint16_t* parent = reinterpret_cast<uint16_t*>(work + 512);  // 512 entries
+  uint16_t* leaf_of = parent + 512;                      // present entries: symbol of leaf i
+  uint32_t nn = 0;
+  for (uint32_t s = 0; s <= last; s++) if (cnt[s]) { wt[nn] = cnt[s]; parent[nn] = 0xFFFF; leaf_of[nn] = (uint16_t)s; nn++; }
+  const uint32_t nleaf = nn;
+  for (uint32_t step = 0; step + 1 < nleaf; step++) {
+    uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < nn; i++) {
+      if (parent[i] != 0xFFFF) continue;
+      if (a == 0xFFFFFFFFu || wt[i] < wt[a]) { b = a; a = i; }
+      else if (b == 0xFFFFFFFFu || wt[i] < wt[b]) b = i;
+    }
+    wt[nn] = wt[a] + wt[b];
+    parent[nn] = 0xFFFF;
+    parent[a] = parent[b] = (uint16_t)nn;
+    nn++;
+  }
+  uint32_t maxd = 0;
+  for (uint32_t i = 0; i < nleaf; i++) {
+    uint32_t d = 0;
+    for (uint32_t j = i; parent[j] != 0xFFFF; j = parent[j]) d++;
+    nb[leaf_of[i]] = (uint8_t)(d > 255 ? 255 : d);
+    maxd = d > maxd ? d : maxd;
+  }
+  if (maxd > kHufMaxBits) {  // length-limit: clamp, then repair the Kraft sum (units of 2^-11)
+    int32_t total = 0;
+    for (uint32_t s = 0; s <= last; s++)
+      if (nb[s]) { if (nb[s] > kHufMaxBits) nb[s] = kHufMaxBits; total += 1 << (kHufMaxBits - nb[s]); }
+    while (total > (1 << kHufMaxBits)) {  // lengthen the cheapest code that is not yet at the limit
+      uint32_t best = 256;
+      for (uint32_t s = 0; s <= last; s++)
+        if (nb[s] && nb[s] < kHufMaxBits && (best == 256 || nb[s] > nb[best] || (nb[s] == nb[best] && cnt[s] < cnt[best]))) best = s;
+      if (best == 256) return 0;
+      total -= 1 << (kHufMaxBits - nb[best] - 1);
+      nb[best]++;
+    }
+    while (total < (1 << kHufMaxBits)) {  // give the slack back to the most frequent symbol it fits
+      uint32_t best = 256;
+      for (uint32_t s = 0; s <= last; s++)
+        if (nb[s] > 1 && total + (1 << (kHufMaxBits - nb[s])) <= (1 << kHufMaxBits) && (best == 256 || cnt[s] > cnt[best])) best = s;
+      if (best == 256) return 0;
+      total += 1 << (kHufMaxBits - nb[best]);
+      nb[best]--;
+    }
+    maxd = 0;
+    for (uint32_t s = 0; s <= last; s++) maxd = nb[s] > maxd ? nb[s] : maxd;
+  }
+  // canonical codes in the decoder's order: ascending weight (longest codes first), ascending symbol within a weight
+  uint32_t pos = 0;
+  for (uint32_t wgt = 1; wgt <= maxd; wgt++) {
+    const uint32_t len = maxd + 1 - wgt;
+    for (uint32_t s = 0; s <= last; s++)
+      if (nb[s] == len) { code[s] = (uint16_t)(pos >> (wgt - 1)); pos += 1u << (wgt - 1); }
+  }
+  return pos == (1u << maxd) ? maxd : 0;
+}
+
+ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nlit, uint8_t* dst, uint32_t* scratch) {
+  if (nlit < 64) return 0;
+  uint32_t* cnt = scratch;                                        // [0, 256)
+  uint8_t* nb = reinterpret_cast<uint8_t*>(scratch + 256);        // 256 bytes
+  uint16_t* code = reinterpret_cast<uint16_t*>(scratch + 320);    // 256 x u16
+  uint32_t* pub = scratch + 448;                                  // mailbox: [0] max_bits, [1] last_sym, [2..5] stream bits
+  uint32_t* work = scratch + 464;                                 // tree construction (< 1100 words)
+  for (uint32_t i = w.lane; i < 256; i += w.n) cnt[i] = 0;
+  w_sync(w);
+  for (uint32_t i = w.lane; i < nlit; i += w.n) w_count(&cnt[lit[i]]);
+  w_sync(w);
+  if (w.lane == 0) {
+    uint32_t last = 0;
+    pub[0] = huf_build(cnt, nb, code, work, &last);
+    pub[1] = last;
+  }
+  w_sync(w);
+  const uint32_t maxbits = pub[0], last = pub[1];
+  if (!maxbits) return 0;
+  const uint32_t ns = nlit >= 256 ? 4u : 1u;
+  const uint32_t seg = ns == 4 ? (nlit + 3) / 4 : nlit;
+  uint32_t sbytes[4] = {0, 0, 0, 0};
+  for (uint32_t k = 0; k < ns; k++) {  // exact stream sizes first, so that every stream is encoded in place
+    const uint32_t lo = k * seg, hi = (k == ns - 1) ? nlit : lo + seg;
+    uint32_t bits = 0;
+    for (uint32_t i = lo + w.lane; i < hi; i += w.n) bits += nb[lit[i]];
+    bits = w_sum(w, bits);
+    sbytes[k] = (bits + 8) >> 3;  // + end marker, rounded up
+  }
+  const uint32_t nweights = last;  // symbols 0..last-1 explicit, `last` implied
+  const uint32_t tree = 1 + (nweights + 1) / 2;
+  const uint32_t comp = tree + (ns == 4 ? 6u : 0u) + sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
+  uint32_t hdr, sf;
+  if (ns == 1) { if (comp >= 1024) return 0; hdr = 3; sf = 0; }
+  else if (nlit < 1024 && comp < 1024) { hdr = 3; sf = 1; }
+  else if (nlit < 16384 && comp < 16384) { hdr = 4; sf = 2; }
+  else { hdr = 5; sf = 3; }
+  if (hdr + comp + 8 >= nlit) return 0;  // does not pay
+  if (ns == 4 && (sbytes[0] > 0xFFFF || sbytes[1] > 0xFFFF || sbytes[2] > 0xFFFF)) return 0;
+  if (w.lane == 0) {
+    if (hdr == 3) { const uint32_t v = 2u | (sf << 2) | (nlit << 4) | (comp << 14); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); }
+    else if (hdr == 4) { const uint32_t v = 2u | (sf << 2) | (nlit << 4) | (comp << 18); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); }
+    else { const uint64_t v = 2ull | ((uint64_t)sf << 2) | ((uint64_t)nlit << 4) | ((uint64_t)comp << 22); for (int i = 0; i < 5; i++) dst[i] = (uint8_t)(v >> (8 * i)); }
+    uint8_t* t = dst + hdr;
+    t[0] = (uint8_t)(127 + nweights);
+    for (uint32_t i = 0; i < nweights; i += 2) {
+      const uint32_t w0 = nb[i] ? maxbits + 1 - nb[i] : 0, w1 = (i + 1 < nweights && nb[i + 1]) ? maxbits + 1 - nb[i + 1] : 0;
+      t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
+    }
+    if (ns == 4) {
+      uint8_t* j = t + tree;
+      j[0] = (uint8_t)sbytes[0]; j[1] = (uint8_t)(sbytes[0] >> 8); j[2] = (uint8_t)sbytes[1]; j[3] = (uint8_t)(sbytes[1] >> 8);
+      j[4] = (uint8_t)sbytes[2]; j[5] = (uint8_t)(sbytes[2] >> 8);
+    }
+  }
+  uint32_t soff[4];
+  soff[0] = hdr + tree + (ns == 4 ? 6u : 0u);
+  for (int k = 1; k < 4; k++) soff[k] = soff[k - 1] + sbytes[k - 1];
+  for (uint32_t k = w.lane; k < ns; k += w.n) {  // one lane per stream; symbols go in last-to-first
+    const uint32_t lo = k * seg, hi = (k == ns - 1) ? nlit : lo + seg;
+    BitWriter bw{dst + soff[k], 0, 0};
+    if (hi > lo) {  // aligned words, the next one fetched while the current one is coded
+      const uintptr_t first = reinterpret_cast<uintptr_t>(lit + lo), lastb = reinterpret_cast<uintptr_t>(lit + hi - 1);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(lastb & ~(uintptr_t)3);
+      const uint32_t* wlo = reinterpret_cast<const uint32_t*>(first & ~(uintptr_t)3);
+      uint32_t cur = *wp;
+      for (;;) {
+        const uint32_t nxt = wp > wlo ? wp[-1] : 0u;
+        const uintptr_t wb = reinterpret_cast<uintptr_t>(wp);
+        const int top = (int)((lastb < wb + 3 ? lastb : wb + 3) - wb), bot = (int)((first > wb ? first : wb) - wb);
+        for (int j = top; j >= bot; j--) {
+          const uint32_t s = (cur >> (8 * j)) & 255u;
+          bw.add(code[s], nb[s]);
+          if (bw.nbits >= 32) bw.flush();
+        }
+        if (wp == wlo) break;
+        wp--;
+        cur = nxt;
+      }
+    }
+    bw.close();
+  }
+  w_sync(w);
+  return hdr + comp;
 }
 
 // ------------------------------------------------------------------------------------------------- zstd block
@@ -331,12 +802,14 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
   const uint32_t wbase = bstart > kZstdPrime ? bstart - kZstdPrime : 0u;  // table positions are relative to wbase
   const uint8_t* in = slice + wbase;
   const uint32_t s0 = bstart - wbase, end = s0 + n;
+  ZN_CP_BEGIN();
   for (uint32_t i = w.lane; i < (1u << kZstdHashLog); i += w.n) tab[i] = 0xFFFFFFFFu;
   w_sync(w);
   // prime with the tail of the previous block
   for (uint32_t p = w.lane; p + 4u <= s0; p += w.n) tab[hash4(ld32le(in + p), kZstdHashLog)] = p;
   w_sync(w);
   uint8_t* lit = stage + 3;
+  ZN_CP(0);
   uint32_t nlit = 0, nseq = 0, anchor = s0, pos = s0;
   if (n >= 8) {
     const uint32_t mflimit = end - 7;  // a match needs 4 bytes to verify
@@ -348,22 +821,46 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       const uint32_t cand = valid ? tab[h] : 0xFFFFFFFFu;
       const bool ok = valid && cand < p && ld32le(in + cand) == v;
       const uint32_t m = w_ballot(w, ok);
-      const uint32_t f = m ? ffs32(m) - 1u : w.n;
+      ZN_CP(1);
+      // Parallel lazy matching: every lane that found a candidate measures its own match (up to kLazyProbe bytes), and
+      // the warp takes the lane with the best gain — bytes matched minus the positions skipped to get there — instead
+      // of the first lane with any 4-byte match.  Fewer, longer sequences; the window is 32 positions, where a serial
+      // lazy parser looks 1-2 ahead.
+      uint32_t probe = 0;
+      if (ok) {
+        const uint32_t lim = end - p < kLazyProbe ? end - p : kLazyProbe;
+        probe = 4u + prefix32(in + p + 4, in + cand + 4, lim - 4u, p + 48u <= end);
+      }
+      ZN_CP(2);
+      uint32_t f = w.n;
+      if (m) {
+        const uint32_t f0 = ffs32(m) - 1u;
+        // score: matched bytes x 4 - skipped positions x 3 (a literal costs less than a byte once Huffman coded)
+        const uint32_t score = ok ? probe * kLazyMatchWeight + kLazySkipWeight * (w.n - 1u - (w.lane - f0)) : 0u;
+        // warp arg-max in one reduction: key = score : (31 - lane), so the earliest lane wins ties
+        const uint32_t key = w_max(w, (score << 5) | (31u - w.lane));
+        f = 31u - (key & 31u);
+        if (w.n == 1) f = 0;
+      }
       w_sync(w);
       if (valid && w.lane <= f) tab[h] = p;  // see lz4_compress_block
       w_sync(w);
+      ZN_CP(3);
       if (!m) {
         pos += w.n;
         continue;
       }
       const uint32_t mp = pos + f, mc = w_shfl(w, cand, f);
-      const uint32_t ml = 4u + match_extend(w, in + mp + 4, in + mc + 4, end - (mp + 4));
+      uint32_t ml = w_shfl(w, probe, f);  // a probe that stopped short of its cap already is the match length
+      if (ml == kLazyProbe) ml += match_extend(w, in + mp + ml, in + mc + ml, end - (mp + ml));
       const uint32_t ll = mp - anchor;
+      ZN_CP(4);
       w_copy(w, lit + nlit, in + anchor, ll);
       nlit += ll;
       if (w.lane == 0) seqs[nseq] = seq_pack(ll, ml, mp - mc);
       nseq++;
       pos = anchor = mp + ml;
+      ZN_CP(5);
     }
   }
   const uint32_t rest = end - anchor;
@@ -371,6 +868,22 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
   nlit += rest;
   w_sync(w);
   if (nseq == 0) return 0;  // nothing found: raw block
+  // Huffman-compressed literals into region B when that pays; otherwise raw literals in place (region A)
+  uint8_t* regB = stage + kZstdHalf;
+  ZN_CP(6);
+  const uint32_t hsz = zstd_huf_literals(w, lit, nlit, regB, tab);
+  ZN_CP(7);
+  if (hsz) {
+    uint32_t total = 0;
+    if (hsz + 16u < n) {
+      const uint32_t ss = zstd_encode_sequences(w, regB + hsz, seqs, nseq, n - hsz - 16u, reinterpret_cast<SeqScratch*>(tab));
+      if (ss) total = hsz + ss;
+    }
+    w_sync(w);
+    ZN_CP(8);
+    *payload_off = kZstdHalf;
+    return (total && total < n) ? total : 0u;
+  }
   // literals section header (raw literals), placed right before the literal bytes
   const uint32_t hs = nlit < 32 ? 1u : (nlit < 4096 ? 2u : 3u);
   uint8_t* hp = stage + 3 - hs;
@@ -379,13 +892,12 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
     if (hs == 1) hp[0] = (uint8_t)(nlit << 3);
     else if (hs == 2) { hp[0] = (uint8_t)(0x04 | ((nlit & 0xF) << 4)); hp[1] = (uint8_t)(nlit >> 4); }
     else { hp[0] = (uint8_t)(0x0C | ((nlit & 0xF) << 4)); hp[1] = (uint8_t)(nlit >> 4); hp[2] = (uint8_t)(nlit >> 12); }
-    // the block must beat its raw form, which also keeps the section inside the slot
-    if (hs + nlit + 16u < n) {
-      const uint32_t ss = zstd_encode_sequences(lit + nlit, seqs, nseq, n - (hs + nlit) - 16u);
-      if (ss) total = hs + nlit + ss;
-    }
   }
-  total = w_shfl(w, total, 0);
+  // the block must beat its raw form, which also keeps the section inside the slot
+  if (hs + nlit + 16u < n) {
+    const uint32_t ss = zstd_encode_sequences(w, lit + nlit, seqs, nseq, n - (hs + nlit) - 16u, reinterpret_cast<SeqScratch*>(tab));
+    if (ss) total = hs + nlit + ss;
+  }
   w_sync(w);
   *payload_off = 3 - hs;
   return (total && total < n) ? total : 0u;

@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(kZstdWarpsPerCta * 32) k_zstd_blocks(const Sli
   for (uint32_t j = blockIdx.x * kZstdWarpsPerCta + warp; j < total_blocks; j += gridDim.x * kZstdWarpsPerCta) {
     const uint32_t si = slice_of_block(slices, n_slices, j);
     const SliceDesc s = slices[si];
-    const uint64_t o = (uint64_t)(j - s.blk_first) * kZstdBlockMax;
-    const uint32_t n = (uint32_t)(s.src_len - o < kZstdBlockMax ? s.src_len - o : kZstdBlockMax);
+    const uint64_t o = (uint64_t)(j - s.blk_first) * cz::kZstdCBlock;
+    const uint32_t n = (uint32_t)(s.src_len - o < cz::kZstdCBlock ? s.src_len - o : cz::kZstdCBlock);
     uint32_t poff = 0;
     const uint32_t c = cz::zstd_compress_block(w, src_base + s.src_off, (uint32_t)o, n, tmp + (size_t)j * cz::kZstdSlot, seqs,
                                                tabs[warp], &poff);
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(256) k_zstd_assemble(const SliceDesc* __restri
   uint64_t op = 13;
   for (uint32_t b = 0; b < s.n_blocks; b++) {
     const uint32_t j = s.blk_first + b;
-    const uint64_t o = (uint64_t)b * kZstdBlockMax;
-    const uint32_t n = (uint32_t)(s.src_len - o < kZstdBlockMax ? s.src_len - o : kZstdBlockMax);
+    const uint64_t o = (uint64_t)b * cz::kZstdCBlock;
+    const uint32_t n = (uint32_t)(s.src_len - o < cz::kZstdCBlock ? s.src_len - o : cz::kZstdCBlock);
     const uint32_t poff = meta[2 * j], c = meta[2 * j + 1];
     const uint32_t last = b + 1 == s.n_blocks ? 1u : 0u;
     if (c == 0) {
@@ -167,7 +167,7 @@ inline void compress_init_attrs() {
 // zn_compress_bound: raw-block fallback makes this exact
 inline size_t compress_bound(size_t n, int codec) {
   if (codec == 2) return n + 4 * ((n + cz::kLz4Block - 1) / cz::kLz4Block) + 32;
-  return n + 3 * ((n + kZstdBlockMax - 1) / kZstdBlockMax) + 32;
+  return n + 3 * ((n + cz::kZstdCBlock - 1) / cz::kZstdCBlock) + 32;
 }
 
 template <typename T>
@@ -187,7 +187,7 @@ inline int compress_run(CompressScratch* cs, cudaStream_t st, int sm_count, cons
                         const uint64_t* /*dst_cap*/, uint64_t* out_len, uint32_t* status, uint32_t* launches, std::string* err) {
   (void)level;  // one match-finder effort so far; the level is accepted for API parity
   const bool lz4 = codec == 2;
-  const uint64_t bsz = lz4 ? cz::kLz4Block : kZstdBlockMax;
+  const uint64_t bsz = lz4 ? cz::kLz4Block : cz::kZstdCBlock;
   std::vector<SliceDesc> sl(n);
   uint64_t total_blocks = 0;
   for (uint32_t i = 0; i < n; i++) {
