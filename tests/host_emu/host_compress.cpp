@@ -33,14 +33,15 @@ extern "C" long zn_hostemu_compress(int codec, const uint8_t* src, uint64_t n, u
     memcpy(dst, e, 9);
     return 9;
   }
-  std::vector<uint32_t> tab(1u << cz::kZstdHashLog);
+  std::vector<uint16_t> tab(1u << cz::kZstdHashLog);
+  std::vector<cz::V16> win(cz::WinHigh::kSmem / 16 + 2);
   std::vector<uint8_t> stage(cz::kZstdSlot + 64);
   std::vector<uint64_t> seqs(cz::kZstdMaxSeq);
   op = cz::zstd_frame_header(dst, n);
   for (uint64_t o = 0; o < n; o += cz::kZstdCBlock) {
     const uint32_t bn = (uint32_t)(n - o < cz::kZstdCBlock ? n - o : cz::kZstdCBlock);
     uint32_t poff = 0;
-    const uint32_t c = cz::zstd_compress_block(w, src, (uint32_t)o, bn, stage.data(), seqs.data(), tab.data(), &poff);
+    const uint32_t c = (codec == 12 ? cz::zstd_compress_block<cz::WinHigh> : codec == 11 ? cz::zstd_compress_block<cz::WinMid> : cz::zstd_compress_block<cz::WinFast>)(w, src, (uint32_t)o, bn, stage.data(), seqs.data(), reinterpret_cast<uint8_t*>(win.data()), tab.data(), &poff);
     const uint32_t last = o + bn == n;
     if (c == 0) {
       cz::zstd_block_header(dst + op, last, 0, bn);

@@ -66,15 +66,22 @@ def test_frames_decode_with_reference_decoders(codec, oracle, codec_name):
 
 
 def test_ratio_against_reference_libraries(codec, oracle):
-    """Ratio gap vs the reference libraries, stated: pattern corpora within 25 % of libzstd level 19 / liblz4; real
-    text within 60 % of libzstd level 1 (raw literals, greedy single-probe match finder — DESIGN.md)."""
+    """Ratio gap vs the reference libraries, stated: pattern corpora within 10 % of libzstd level 19 / liblz4; real
+    text within 25 % of libzstd level 1 at every effort (Huffman literals, FSE-described sequence tables, repeat
+    offsets, warp-wide lazy match selection in a 20-56 KiB window — DESIGN.md §4.3)."""
     O = oracle
     z, l = O.libzstd(), O.liblz4()
-    for name, d, ref_level, slack in [("text", O.gen_text(8 << 20), 19, 1.25), ("binary", O.gen_binary(8 << 20), 19, 1.25),
-                                      ("real", O.real_text(2_000_000), 1, 1.60)]:
-        ours = len(codec.CompressCtx(3).compress(d))
+    for name, d, ref_level, slack in [("text", O.gen_text(8 << 20), 19, 1.10), ("binary", O.gen_binary(8 << 20), 19, 1.10),
+                                      ("real", O.real_text(2_000_000), 1, 1.25)]:
         ref = len(z.compress(d, ref_level))
-        assert ours <= ref * slack + 64, (name, ours, ref)
+        sizes = []
+        for level in (1, 3, 19):  # the three efforts of the zstd match finder
+            b = codec.CompressCtx(level).compress(d)
+            assert z.decompress(b, len(d)) == d.tobytes()
+            assert len(b) <= ref * slack + 64, (name, level, len(b), ref)
+            sizes.append(len(b))
+        if name == "real":
+            assert sizes[2] <= sizes[0], sizes  # more window, no worse
         ours4 = len(codec.CompressCtx(3, codec.CODEC_LZ4).compress(d))
         ref4 = len(l.compress_frame(d))
         assert ours4 <= ref4 * 1.10 + 64, (name, ours4, ref4)

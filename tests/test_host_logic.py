@@ -211,6 +211,8 @@ def test_hostemu_compressors_decode_with_stock_libraries(emu, oracle):
              O.gen_binary((1 << 20) + 17), O.real_text(400_000), O.gen_random(200_000), np.zeros(300_000, np.uint8),
              O.gen_small_alphabet(150_000), O.gen_rle_literals()]
     for d in cases:
+        for codec in (11, 12):  # the two larger window geometries of the zstd match finder (levels 3..9, >= 10)
+            assert z.decompress(emu.compress(codec, d), len(d)) == d.tobytes()
         b = emu.compress(1, d)
         assert z.decompress(b, len(d)) == d.tobytes()
         rc, o = O.zstd_decompress(b, len(d))

@@ -10,7 +10,7 @@ for name, d in [('real3.5m', O.real_text(3_500_000)), ('real700k', O.real_text(7
                 ('text1m', O.gen_text(1 << 20)), ('bin8m', O.gen_binary(8 << 20))]:
     d = np.ascontiguousarray(d)
     out = np.zeros(d.size + d.size // 2 + 4096, np.uint8)
-    n = L.zn_hostemu_compress(0, d.ctypes.data, d.size, out.ctypes.data)
+    n = L.zn_hostemu_compress(int(sys.argv[1]) if len(sys.argv) > 1 else 1, d.ctypes.data, d.size, out.ctypes.data)
     b = out[:n].tobytes()
     assert z.decompress(b, d.size) == d.tobytes()
     rc, o, st = O.zstd_decompress(b, d.size, want_stats=True)

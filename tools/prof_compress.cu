@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
   for (int rep = 0; rep < 2; rep++) {
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_cprof, z, sizeof z);
-    int rc = compress_run(&cs, 0, pr.multiProcessorCount, d_src, &so, &sl, 1, 1, 1, d_dst, &dofs, &dcap, &olen, &st, &launches, &err);
+    int rc = compress_run(&cs, 0, pr.multiProcessorCount, d_src, &so, &sl, 1, argc > 3 ? atoi(argv[3]) : 1, 1, d_dst, &dofs, &dcap, &olen, &st, &launches, &err);
     printf("rep %d rc %d: %zu -> %llu bytes, %.3f ms (%.2f GB/s) %s\n", rep, rc, n, (unsigned long long)olen, cs.last_ms, n / cs.last_ms / 1e6, err.c_str());
   }
   unsigned long long c[16];

@@ -41,6 +41,13 @@ ZN_D uint32_t ffs32(uint32_t v) { return (uint32_t)__ffs((int)v); }
 ZN_D void w_count(uint32_t* p) { atomicAdd(p, 1u); }
 ZN_D void w_or(uint32_t* p, uint32_t v) { if (v) atomicOr(p, v); }
 ZN_D uint32_t w_max(const Warp&, uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+ZN_D uint32_t w_min(const Warp&, uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+ZN_D uint32_t w_shfl_up(const Warp&, uint32_t v, uint32_t d) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+// unaligned 32-bit little-endian load from shared memory through two aligned words (the buffer has slack behind it)
+ZN_D uint32_t ld32s(const uint8_t* p) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+  return __funnelshift_r(w[0], w[1], ((uint32_t)reinterpret_cast<uintptr_t>(p) & 3u) * 8u);
+}
 // exclusive prefix sum over the lanes; *total = sum over the warp
 ZN_D uint32_t w_excl_scan(const Warp& w, uint32_t v, uint32_t* total) {
   uint32_t x = v;
@@ -65,6 +72,9 @@ inline void w_count(uint32_t* p) { (*p)++; }
 inline uint32_t w_sum(const Warp&, uint32_t v) { return v; }
 inline void w_or(uint32_t* p, uint32_t v) { *p |= v; }
 inline uint32_t w_max(const Warp&, uint32_t v) { return v; }
+inline uint32_t w_min(const Warp&, uint32_t v) { return v; }
+inline uint32_t w_shfl_up(const Warp&, uint32_t v, uint32_t) { return v; }
+inline uint32_t ld32s(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline uint32_t w_excl_scan(const Warp&, uint32_t v, uint32_t* total) { *total = v; return 0; }
 constexpr bool kOnDevice = false;
 #endif
@@ -74,14 +84,27 @@ ZN_HD uint32_t hash4(uint32_t v, uint32_t hlog) { return (v * 2654435761u) >> (3
 constexpr uint32_t kLz4Block = 64u * 1024u;
 constexpr uint32_t kLz4Slot = kLz4Block + kLz4Block / 255u + 32u;  // worst-case LZ4 block
 constexpr uint32_t kLz4HashLog = 12;                                 // 4096 x u16 = 8 KiB per warp
-constexpr uint32_t kZstdHashLog = 12;                                // 4096 x u32 = 16 KiB per warp
+constexpr uint32_t kZstdHashLog = 12;                                // 4096 x u16 = 8 KiB per warp
 #ifndef ZN_LAZY_MATCH_W
 #define ZN_LAZY_MATCH_W 4
 #define ZN_LAZY_SKIP_W 8
 #endif
 constexpr uint32_t kLazyMatchWeight = ZN_LAZY_MATCH_W, kLazySkipWeight = ZN_LAZY_SKIP_W;
-constexpr uint32_t kLazyProbe = 36;                                  // bytes each candidate lane compares before the warp votes
-constexpr uint32_t kZstdPrime = 1024;                                // bytes of the previous block hashed in first
+constexpr uint32_t kLazyProbeWords = 5;                              // words compared beyond the 4 verified bytes
+constexpr uint32_t kLazyProbe = 4u + 4u * kLazyProbeWords;                                  // bytes each candidate lane compares before the warp votes
+// Window geometry of the zstd match finder (see zstd_compress_block): W fresh bytes per window, H bytes of history
+// kept when it slides.  Shared memory per warp = H + W + 80 bytes + the 8 KiB table, which sets how many warps an
+// SM holds — the compressor is latency-bound, so speed follows the warp count and ratio follows W + H.
+template <uint32_t W, uint32_t H>
+struct Win {
+  static constexpr uint32_t kBytes = W, kHist = H;
+  static constexpr uint32_t kData = H + W + 16u;   // staged bytes (multiple of 16; + alignment slop)
+  static constexpr uint32_t kSmem = kData + 64u;   // + slack for the word-wise probes
+  static_assert(kData % 16u == 0 && kData < 65535u && H + 160u < W, "window geometry");
+};
+using WinFast = Win<16384, 4096>;    // levels <= 2
+using WinMid = Win<32768, 8192>;     // levels 3..9
+using WinHigh = Win<49152, 14336>;   // levels >= 10
 constexpr uint32_t kZstdMaxSeq = 32768;                              // sequences per 128 KiB block (min match 4)
 #ifndef ZN_CBLOCK
 #define ZN_CBLOCK kZstdBlockMax
@@ -113,30 +136,29 @@ ZN_HD uint32_t match_extend(const Warp& w, const uint8_t* a, const uint8_t* b, u
 }
 
 
-// Common prefix length of a[0..lim) and b[0..lim), lim <= 32, one lane.  The device version works on aligned words
-// (9 loads per side, all in flight together) and may read up to 39 bytes past a / b, so the caller guarantees slack.
-ZN_HD uint32_t prefix32(const uint8_t* a, const uint8_t* b, uint32_t lim, bool slack) {
+// Common prefix length of a[0..lim) and b[0..lim), lim <= 4*K, one lane.  The device version works on aligned words
+// (K+1 loads per side, all in flight together) and may read up to 4*K+7 bytes past a / b: the caller guarantees slack.
+template <int K>
+ZN_HD uint32_t prefix_words(const uint8_t* a, const uint8_t* b, uint32_t lim) {
 #if defined(__CUDA_ARCH__)
-  if (slack) {
-    const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
-    const uint32_t* wb = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(b) & ~(uintptr_t)3);
-    const uint32_t sa = ((uint32_t)reinterpret_cast<uintptr_t>(a) & 3u) * 8u, sb = ((uint32_t)reinterpret_cast<uintptr_t>(b) & 3u) * 8u;
-    uint32_t ra[9], rb[9];
+  const uint32_t* wa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+  const uint32_t* wb = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(b) & ~(uintptr_t)3);
+  const uint32_t sa = ((uint32_t)reinterpret_cast<uintptr_t>(a) & 3u) * 8u, sb = ((uint32_t)reinterpret_cast<uintptr_t>(b) & 3u) * 8u;
+  uint32_t ra[K + 1], rb[K + 1];
 #pragma unroll
-    for (int k = 0; k < 9; k++) { ra[k] = wa[k]; rb[k] = wb[k]; }
-    uint32_t n = 32;
+  for (int k = 0; k <= K; k++) { ra[k] = wa[k]; rb[k] = wb[k]; }
+  uint32_t n = 4u * K;
 #pragma unroll
-    for (int k = 7; k >= 0; k--) {
-      const uint32_t x = __funnelshift_r(ra[k], ra[k + 1], sa) ^ __funnelshift_r(rb[k], rb[k + 1], sb);
-      if (x) n = 4u * k + (((uint32_t)__ffs((int)x) - 1u) >> 3);
-    }
-    return n < lim ? n : lim;
+  for (int k = K - 1; k >= 0; k--) {
+    const uint32_t x = __funnelshift_r(ra[k], ra[k + 1], sa) ^ __funnelshift_r(rb[k], rb[k + 1], sb);
+    if (x) n = 4u * k + (((uint32_t)__ffs((int)x) - 1u) >> 3);
   }
-#endif
-  (void)slack;
+  return n < lim ? n : lim;
+#else
   uint32_t n = 0;
   while (n < lim && a[n] == b[n]) n++;
   return n;
+#endif
 }
 
 // dst[0..n) = src[0..n), spread over the warp (byte granular; the compressed side is small by construction)
@@ -468,6 +490,22 @@ ZN_HD uint32_t zstd_encode_sequences(const Warp& w, uint8_t* dst, uint64_t* seqs
     const uint32_t ll = (uint32_t)(s & 0xFFFFF), ml = (uint32_t)((s >> 20) & 0xFFFFF), off = (uint32_t)(s >> 40);
     const uint32_t here = nseq - base < w.n ? nseq - base : w.n;
     uint32_t v = 0;
+    // Fast path: a repeat code needs an offset equal to one of the three before it (r0 - 1 included), which is rare
+    // and which every lane can test against its three predecessors at once.
+    bool maybe = false;
+    if (w.n > 1) {
+      const uint32_t o1 = w_shfl_up(w, off, 1), o2 = w_shfl_up(w, off, 2), o3 = w_shfl_up(w, off, 3);
+      const uint32_t q1 = w.lane >= 1 ? o1 : (w.lane == 0 ? r0 : 0u);
+      const uint32_t q2 = w.lane >= 2 ? o2 : (w.lane == 1 ? r0 : r1);
+      const uint32_t q3 = w.lane >= 3 ? o3 : (w.lane == 2 ? r0 : (w.lane == 1 ? r1 : r2));
+      maybe = k < nseq && (off == q1 || off == q2 || off == q3 || off + 1u == q1);
+    }
+    if (w.n > 1 && !w_ballot(w, maybe)) {
+      v = off + 3u;
+      if (here >= 3) { r0 = w_shfl(w, off, here - 1); r1 = w_shfl(w, off, here - 2); r2 = w_shfl(w, off, here - 3); }
+      else if (here == 2) { r2 = r0; r0 = w_shfl(w, off, 1); r1 = w_shfl(w, off, 0); }
+      else { r2 = r1; r1 = r0; r0 = w_shfl(w, off, 0); }
+    } else
     for (uint32_t j = 0; j < here; j++) {
       const uint32_t llj = w_shfl(w, ll, j), offj = w_shfl(w, off, j);
       uint32_t vj;
@@ -640,38 +678,55 @@ ZN_HD uint32_t zstd_encode_sequences(const Warp& w, uint8_t* dst, uint64_t* seqs
 // Returns the section size written at dst, or 0 when Huffman coding is not applicable / does not pay.
 constexpr uint32_t kHufMaxBits = 11;
 
-// lane 0: code lengths (<= 11 bits) from the histogram; fills nb[256], code[256]; returns max_bits (0 = not applicable)
-ZN_HD uint32_t huf_build(const uint32_t* cnt, uint8_t* nb, uint16_t* code, uint32_t* work, uint32_t* last_sym_out) {
-  uint32_t present = 0, last = 0;
-  for (uint32_t s = 0; s < 256; s++) { nb[s] = 0; if (cnt[s]) { present++; last = s; } }
-  *last_sym_out = last;
-  if (present < 2 || last > 128) return 0;  // direct weights describe at most 128 symbols + the implied last one
-  // O(n^2) Huffman: weight[] / parent[] over <= 2*present-1 nodes
-  uint32_t* wt = work;                                   // 512 entries
+// Code lengths (<= 11 bits) and canonical codes from the histogram, whole warp; fills nb[256], code[256] and
+// res[0] = max_bits (0 = not applicable), res[1] = last symbol present.  The merge loop finds the two lightest
+// roots with two warp min-reductions per step.
+ZN_HD void huf_build(const Warp& w, const uint32_t* cnt, uint8_t* nb, uint16_t* code, uint32_t* work, uint32_t* res) {
+  uint32_t my_present = 0, my_last = 0;
+  for (uint32_t s = w.lane; s < 256; s += w.n) { nb[s] = 0; if (cnt[s]) { my_present++; my_last = s; } }
+  const uint32_t present = w_sum(w, my_present), last = w_max(w, my_last);
+  if (w.lane == 0) { res[0] = 0; res[1] = last; }
+  w_sync(w);
+  if (present < 2 || last > 128) return;  // direct weights describe at most 128 symbols + the implied last one
+  uint32_t* wt = work;                                         // 512 entries
   uint16_t* parent = reinterpret_cast<uint16_t*>(work + 512);  // 512 entries
-  uint16_t* leaf_of = parent + 512;                      // present entries: symbol of leaf i
-  uint32_t nn = 0;
-  for (uint32_t s = 0; s <= last; s++) if (cnt[s]) { wt[nn] = cnt[s]; parent[nn] = 0xFFFF; leaf_of[nn] = (uint16_t)s; nn++; }
-  const uint32_t nleaf = nn;
-  for (uint32_t step = 0; step + 1 < nleaf; step++) {
-    uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;
-    for (uint32_t i = 0; i < nn; i++) {
-      if (parent[i] != 0xFFFF) continue;
-      if (a == 0xFFFFFFFFu || wt[i] < wt[a]) { b = a; a = i; }
-      else if (b == 0xFFFFFFFFu || wt[i] < wt[b]) b = i;
-    }
-    wt[nn] = wt[a] + wt[b];
-    parent[nn] = 0xFFFF;
-    parent[a] = parent[b] = (uint16_t)nn;
-    nn++;
+  uint16_t* leaf_of = parent + 512;                            // present entries: symbol of leaf i
+  if (w.lane == 0) {
+    uint32_t k = 0;
+    for (uint32_t s = 0; s <= last; s++) if (cnt[s]) { wt[k] = cnt[s]; parent[k] = 0xFFFF; leaf_of[k] = (uint16_t)s; k++; }
   }
-  uint32_t maxd = 0;
-  for (uint32_t i = 0; i < nleaf; i++) {
+  w_sync(w);
+  const uint32_t nleaf = present;
+  uint32_t nn = nleaf;
+  for (uint32_t step = 0; step + 1 < nleaf; step++) {
+    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;  // this lane's two lightest roots, as weight << 9 | node
+    for (uint32_t i = w.lane; i < nn; i += w.n) {
+      if (parent[i] != 0xFFFF) continue;
+      const uint32_t key = (wt[i] << 9) | i;
+      if (key < k1) { k2 = k1; k1 = key; }
+      else if (key < k2) k2 = key;
+    }
+    const uint32_t ka = w_min(w, k1);
+    const uint32_t kb = w_min(w, k1 == ka ? k2 : k1);
+    w_sync(w);
+    if (w.lane == 0) {
+      wt[nn] = (ka >> 9) + (kb >> 9);
+      parent[nn] = 0xFFFF;
+      parent[ka & 511u] = parent[kb & 511u] = (uint16_t)nn;
+    }
+    nn++;
+    w_sync(w);
+  }
+  uint32_t my_maxd = 0;
+  for (uint32_t i = w.lane; i < nleaf; i += w.n) {
     uint32_t d = 0;
     for (uint32_t j = i; parent[j] != 0xFFFF; j = parent[j]) d++;
     nb[leaf_of[i]] = (uint8_t)(d > 255 ? 255 : d);
-    maxd = d > maxd ? d : maxd;
+    my_maxd = d > my_maxd ? d : my_maxd;
   }
+  uint32_t maxd = w_max(w, my_maxd);
+  w_sync(w);
+  if (w.lane != 0) return;
   if (maxd > kHufMaxBits) {  // length-limit: clamp, then repair the Kraft sum (units of 2^-11)
     int32_t total = 0;
     for (uint32_t s = 0; s <= last; s++)
@@ -680,7 +735,7 @@ ZN_HD uint32_t huf_build(const uint32_t* cnt, uint8_t* nb, uint16_t* code, uint3
       uint32_t best = 256;
       for (uint32_t s = 0; s <= last; s++)
         if (nb[s] && nb[s] < kHufMaxBits && (best == 256 || nb[s] > nb[best] || (nb[s] == nb[best] && cnt[s] < cnt[best]))) best = s;
-      if (best == 256) return 0;
+      if (best == 256) return;
       total -= 1 << (kHufMaxBits - nb[best] - 1);
       nb[best]++;
     }
@@ -688,7 +743,7 @@ ZN_HD uint32_t huf_build(const uint32_t* cnt, uint8_t* nb, uint16_t* code, uint3
       uint32_t best = 256;
       for (uint32_t s = 0; s <= last; s++)
         if (nb[s] > 1 && total + (1 << (kHufMaxBits - nb[s])) <= (1 << kHufMaxBits) && (best == 256 || cnt[s] > cnt[best])) best = s;
-      if (best == 256) return 0;
+      if (best == 256) return;
       total += 1 << (kHufMaxBits - nb[best]);
       nb[best]--;
     }
@@ -702,7 +757,7 @@ ZN_HD uint32_t huf_build(const uint32_t* cnt, uint8_t* nb, uint16_t* code, uint3
     for (uint32_t s = 0; s <= last; s++)
       if (nb[s] == len) { code[s] = (uint16_t)(pos >> (wgt - 1)); pos += 1u << (wgt - 1); }
   }
-  return pos == (1u << maxd) ? maxd : 0;
+  res[0] = pos == (1u << maxd) ? maxd : 0u;
 }
 
 ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nlit, uint8_t* dst, uint32_t* scratch) {
@@ -716,11 +771,7 @@ ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nli
   w_sync(w);
   for (uint32_t i = w.lane; i < nlit; i += w.n) w_count(&cnt[lit[i]]);
   w_sync(w);
-  if (w.lane == 0) {
-    uint32_t last = 0;
-    pub[0] = huf_build(cnt, nb, code, work, &last);
-    pub[1] = last;
-  }
+  huf_build(w, cnt, nb, code, work, pub);
   w_sync(w);
   const uint32_t maxbits = pub[0], last = pub[1];
   if (!maxbits) return 0;
@@ -795,31 +846,72 @@ ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nli
 // Compresses slice[bstart .. bstart+n) (n <= 128 KiB) into the payload of one compressed block.
 //   stage   kZstdSlot bytes: literals are written from stage+3, the block payload ends up at stage + *payload_off
 //   seqs    kZstdMaxSeq packed sequences (global scratch)
-//   tab     2^kZstdHashLog x u32 (shared memory)
+//   D       WN::kSmem bytes of shared memory, 16-byte aligned: the input window the match finder works in
+//   tab     2^kZstdHashLog x u16 (shared memory): window position of the latest occurrence of each hash
+// The match finder never touches global memory: the input slides through D in windows of WN::kBytes, each keeping the
+// last WN::kHist bytes of history (16-byte copies, the window keeps the source's alignment).  Offsets therefore stay
+// below WN::kHist + WN::kBytes.  A match cut by a window edge is picked up again by the next window and merged back
+// into one sequence, so periodic data still costs one sequence per block.
 // Returns the payload size, or 0 when the block should be stored raw.
+struct alignas(16) V16 { uint32_t a, b, c, d; };
+
+template <class WN>
 ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t bstart, uint32_t n, uint8_t* stage,
-                                   uint64_t* seqs, uint32_t* tab, uint32_t* payload_off) {
-  const uint32_t wbase = bstart > kZstdPrime ? bstart - kZstdPrime : 0u;  // table positions are relative to wbase
-  const uint8_t* in = slice + wbase;
-  const uint32_t s0 = bstart - wbase, end = s0 + n;
-  ZN_CP_BEGIN();
-  for (uint32_t i = w.lane; i < (1u << kZstdHashLog); i += w.n) tab[i] = 0xFFFFFFFFu;
-  w_sync(w);
-  // prime with the tail of the previous block
-  for (uint32_t p = w.lane; p + 4u <= s0; p += w.n) tab[hash4(ld32le(in + p), kZstdHashLog)] = p;
-  w_sync(w);
+                                   uint64_t* seqs, uint8_t* D, uint16_t* tab, uint32_t* payload_off) {
+  constexpr uint32_t kWinHist = WN::kHist, kWinData = WN::kData;
+  const uint32_t hist = bstart < kWinHist ? bstart : kWinHist;
+  const uint8_t* g = slice + bstart - hist;  // global address of D[0] (made 16-byte aligned just below)
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+  g -= mis;
+  uint32_t dlo = mis;                  // first valid byte of D
+  uint32_t pos = mis + hist, anchor = pos;
+  uint32_t bend = pos + n;             // block end in window coordinates (beyond the window until the last one)
+  uint32_t filled = 0;                 // bytes of D staged so far (multiple of 16)
   uint8_t* lit = stage + 3;
-  ZN_CP(0);
-  uint32_t nlit = 0, nseq = 0, anchor = s0, pos = s0;
-  if (n >= 8) {
-    const uint32_t mflimit = end - 7;  // a match needs 4 bytes to verify
-    while (pos < mflimit && nseq < kZstdMaxSeq) {
+  uint32_t nlit = 0, nseq = 0, ll_carry = 0;
+  uint32_t p_ll = 0, p_ml = 0, p_off = 0;  // the sequence not yet written out (it may still grow across a window edge)
+  uint32_t cont_off = 0;                   // offset of a match that ran into the window edge
+  bool have = false, first = true;
+  ZN_CP_BEGIN();
+  for (;;) {
+    // ---- stage D[filled .. target)
+    const uint32_t want = (bend + 15u) & ~15u;
+    const uint32_t target = want < kWinData ? want : kWinData;
+    for (uint32_t c = filled / 16u + w.lane; c < target / 16u; c += w.n) {
+      const uint32_t lo = c * 16u;
+      if (lo >= dlo && lo + 16u <= bend) *reinterpret_cast<V16*>(D + lo) = *reinterpret_cast<const V16*>(g + lo);
+      else for (uint32_t i = lo < dlo ? dlo : lo; i < lo + 16u && i < bend; i++) D[i] = g[i];
+    }
+    filled = target;
+    const uint32_t dend = bend < filled ? bend : filled;
+    w_sync(w);
+    if (first) {  // empty table, then the history of the previous block
+      for (uint32_t i = w.lane; i < (1u << kZstdHashLog); i += w.n) tab[i] = 0xFFFFu;
+      w_sync(w);
+      for (uint32_t p = dlo + w.lane; p + 4u <= pos; p += w.n) tab[hash4(ld32s(D + p), kZstdHashLog)] = (uint16_t)p;
+      w_sync(w);
+      first = false;
+    }
+    const bool final = dend == bend;
+    if (cont_off) {  // carry the cut match on (the table has no entry for the bytes a match covered)
+      if (cont_off <= pos - dlo && pos < dend) {
+        const uint32_t more = match_extend(w, D + pos, D + pos - cont_off, dend - pos);
+        p_ml += more;
+        pos = anchor = pos + more;
+        if (!final && pos == dend && more) { /* still running: keep cont_off */ } else cont_off = 0;
+      } else cont_off = 0;
+    }
+    ZN_CP(0);
+    // positions below plimit are parsed in this window: a match needs 4 bytes to verify, and a window that is not
+    // the last keeps 64 bytes of look-ahead for the probes
+    const uint32_t plimit = final ? (n >= 8 ? bend - 7u : pos) : dend - 64u;
+    while (pos < plimit) {
       const uint32_t p = pos + w.lane;
-      const bool valid = p < mflimit;
-      const uint32_t v = valid ? ld32le(in + p) : 0u;
+      const bool valid = p < plimit;
+      const uint32_t v = valid ? ld32s(D + p) : 0u;
       const uint32_t h = hash4(v, kZstdHashLog);
-      const uint32_t cand = valid ? tab[h] : 0xFFFFFFFFu;
-      const bool ok = valid && cand < p && ld32le(in + cand) == v;
+      const uint32_t cand = valid ? tab[h] : 0xFFFFu;
+      const bool ok = valid && cand < p && ld32s(D + cand) == v;
       const uint32_t m = w_ballot(w, ok);
       ZN_CP(1);
       // Parallel lazy matching: every lane that found a candidate measures its own match (up to kLazyProbe bytes), and
@@ -828,41 +920,84 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       // lazy parser looks 1-2 ahead.
       uint32_t probe = 0;
       if (ok) {
-        const uint32_t lim = end - p < kLazyProbe ? end - p : kLazyProbe;
-        probe = 4u + prefix32(in + p + 4, in + cand + 4, lim - 4u, p + 48u <= end);
+        const uint32_t lim = dend - p < kLazyProbe ? dend - p : kLazyProbe;
+        probe = 4u + prefix_words<kLazyProbeWords>(D + p + 4, D + cand + 4, lim - 4u);
       }
       ZN_CP(2);
-      uint32_t f = w.n;
-      if (m) {
-        const uint32_t f0 = ffs32(m) - 1u;
-        // score: matched bytes x 4 - skipped positions x 3 (a literal costs less than a byte once Huffman coded)
-        const uint32_t score = ok ? probe * kLazyMatchWeight + kLazySkipWeight * (w.n - 1u - (w.lane - f0)) : 0u;
-        // warp arg-max in one reduction: key = score : (31 - lane), so the earliest lane wins ties
-        const uint32_t key = w_max(w, (score << 5) | (31u - w.lane));
-        f = 31u - (key & 31u);
-        if (w.n == 1) f = 0;
-      }
-      w_sync(w);
-      if (valid && w.lane <= f) tab[h] = p;  // see lz4_compress_block
-      w_sync(w);
-      ZN_CP(3);
       if (!m) {
+        if (valid) tab[h] = (uint16_t)p;
+        w_sync(w);
         pos += w.n;
+        ZN_CP(3);
         continue;
       }
-      const uint32_t mp = pos + f, mc = w_shfl(w, cand, f);
-      uint32_t ml = w_shfl(w, probe, f);  // a probe that stopped short of its cap already is the match length
-      if (ml == kLazyProbe) ml += match_extend(w, in + mp + ml, in + mc + ml, end - (mp + ml));
-      const uint32_t ll = mp - anchor;
+      // One look-up round serves every match that starts inside these 32 positions: pick the best lane, emit its
+      // sequence, then pick again among the lanes behind the end of that match.
+      uint32_t lo = 0, f = 0, next = pos + w.n;
+      for (;;) {
+        const uint32_t mm = lo < 32u ? (m >> lo) << lo : 0u;
+        if (!mm) { f = w.n - 1u; break; }  // nothing more starts here: the rest of the window is literals
+        const uint32_t f0 = ffs32(mm) - 1u;
+        // score: matched bytes x 4 - skipped positions x 8 (a literal costs less than a byte once Huffman coded)
+        const uint32_t score = (ok && w.lane >= lo) ? probe * kLazyMatchWeight + kLazySkipWeight * (w.n - 1u - (w.lane - f0)) : 0u;
+        // warp arg-max in one reduction: key = score : (31 - lane), so the earliest lane wins ties
+        const uint32_t key = w_max(w, (score << 5) | (31u - w.lane));
+        f = w.n == 1 ? 0u : 31u - (key & 31u);
+        const uint32_t mp = pos + f, mc = w_shfl(w, cand, f);
+        uint32_t ml = w_shfl(w, probe, f);  // a probe that stopped short of its cap already is the match length
+        if (ml == kLazyProbe) ml += match_extend(w, D + mp + ml, D + mc + ml, dend - (mp + ml));
+        const uint32_t run = mp - anchor, ll = ll_carry + run, off = mp - mc;
+        w_copy(w, lit + nlit, D + anchor, run);
+        nlit += run;
+        ll_carry = 0;
+        if (have && ll == 0 && off == p_off) p_ml += ml;  // the continuation of the match a window edge cut
+        else {
+          if (have) {
+            if (w.lane == 0) seqs[nseq] = seq_pack(p_ll, p_ml, p_off);
+            nseq++;
+          }
+          p_ll = ll; p_ml = ml; p_off = off;
+          have = true;
+        }
+        anchor = mp + ml;
+        if (!final && anchor == dend) cont_off = off;
+        if (anchor >= pos + w.n) { next = anchor; break; }
+        lo = anchor - pos;
+      }
       ZN_CP(4);
-      w_copy(w, lit + nlit, in + anchor, ll);
-      nlit += ll;
-      if (w.lane == 0) seqs[nseq] = seq_pack(ll, ml, mp - mc);
-      nseq++;
-      pos = anchor = mp + ml;
+      if (valid && w.lane <= f) tab[h] = (uint16_t)p;  // positions behind the last match start are not entered (see lz4_compress_block)
+      w_sync(w);
+      pos = next;
       ZN_CP(5);
     }
+    if (final) break;
+    // ---- slide: the literals seen so far leave, the last kWinHist bytes stay
+    if (pos > anchor) {
+      w_copy(w, lit + nlit, D + anchor, pos - anchor);
+      nlit += pos - anchor;
+      ll_carry += pos - anchor;
+      anchor = pos;
+    }
+    const uint32_t S = (pos - kWinHist) & ~15u;  // pos >= kWinData - 64 - 32 > kWinHist here
+    w_sync(w);
+    for (uint32_t c = w.lane; c < (filled - S) / 16u; c += w.n)  // source and destination never overlap: S > filled - S
+      *reinterpret_cast<V16*>(D + 16u * c) = *reinterpret_cast<const V16*>(D + S + 16u * c);
+    for (uint32_t i = w.lane; i < (1u << kZstdHashLog); i += w.n) {
+      const uint32_t e = tab[i];
+      tab[i] = (e != 0xFFFFu && e >= S) ? (uint16_t)(e - S) : (uint16_t)0xFFFFu;
+    }
+    g += S;
+    pos -= S; anchor -= S; bend -= S; filled -= S;
+    dlo = dlo > S ? dlo - S : 0u;
+    w_sync(w);
   }
+  if (have) {
+    if (w.lane == 0) seqs[nseq] = seq_pack(p_ll, p_ml, p_off);
+    nseq++;
+  }
+  uint32_t* tabw = reinterpret_cast<uint32_t*>(D);  // the window is idle from here on: scratch for the entropy stages
+  const uint32_t end = bend;
+  const uint8_t* in = D;
   const uint32_t rest = end - anchor;
   w_copy(w, lit + nlit, in + anchor, rest);
   nlit += rest;
@@ -871,12 +1006,12 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
   // Huffman-compressed literals into region B when that pays; otherwise raw literals in place (region A)
   uint8_t* regB = stage + kZstdHalf;
   ZN_CP(6);
-  const uint32_t hsz = zstd_huf_literals(w, lit, nlit, regB, tab);
+  const uint32_t hsz = zstd_huf_literals(w, lit, nlit, regB, tabw);
   ZN_CP(7);
   if (hsz) {
     uint32_t total = 0;
     if (hsz + 16u < n) {
-      const uint32_t ss = zstd_encode_sequences(w, regB + hsz, seqs, nseq, n - hsz - 16u, reinterpret_cast<SeqScratch*>(tab));
+      const uint32_t ss = zstd_encode_sequences(w, regB + hsz, seqs, nseq, n - hsz - 16u, reinterpret_cast<SeqScratch*>(tabw));
       if (ss) total = hsz + ss;
     }
     w_sync(w);
@@ -895,7 +1030,7 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
   }
   // the block must beat its raw form, which also keeps the section inside the slot
   if (hs + nlit + 16u < n) {
-    const uint32_t ss = zstd_encode_sequences(w, lit + nlit, seqs, nseq, n - (hs + nlit) - 16u, reinterpret_cast<SeqScratch*>(tab));
+    const uint32_t ss = zstd_encode_sequences(w, lit + nlit, seqs, nseq, n - (hs + nlit) - 16u, reinterpret_cast<SeqScratch*>(tabw));
     if (ss) total = hs + nlit + ss;
   }
   w_sync(w);

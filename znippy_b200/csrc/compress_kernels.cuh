@@ -20,7 +20,13 @@ struct SliceDesc {
 };
 
 constexpr int kLz4WarpsPerCta = 4;
-constexpr int kZstdWarpsPerCta = 2;
+constexpr int kZstdWarpsPerCta = 1;
+template <class WN>
+struct ZstdLaunch {
+  static constexpr uint32_t kWindow = (WN::kSmem + 127u) & ~127u;
+  static constexpr uint32_t kSmemBytes = kWindow + (2u << cz::kZstdHashLog);
+  static constexpr uint32_t kCtasPerSm = (228u * 1024u) / (kSmemBytes + 1024u);
+};
 
 // which slice owns global block j (slices' blk_first ascending)
 ZN_D uint32_t slice_of_block(const SliceDesc* __restrict__ s, uint32_t n_slices, uint32_t j) {
@@ -80,22 +86,23 @@ __global__ void __launch_bounds__(256) k_lz4_assemble(const SliceDesc* __restric
 }
 
 // ---- zstd: every 128 KiB block of every slice -> staged payload; meta[2j] = payload offset in the slot, meta[2j+1] = size (0 = raw)
-__global__ void __launch_bounds__(kZstdWarpsPerCta * 32) k_zstd_blocks(const SliceDesc* __restrict__ slices, uint32_t n_slices,
-                                                                       uint32_t total_blocks,
-                                                                       const uint8_t* __restrict__ src_base, uint8_t* tmp,
-                                                                       uint64_t* seq_scratch, uint32_t* meta) {
-  __shared__ uint32_t tabs[kZstdWarpsPerCta][1u << cz::kZstdHashLog];
-  const uint32_t warp = threadIdx.x >> 5;
-  const cz::Warp w{threadIdx.x & 31u, 32u};
-  uint64_t* seqs = seq_scratch + (size_t)(blockIdx.x * kZstdWarpsPerCta + warp) * cz::kZstdMaxSeq;
-  for (uint32_t j = blockIdx.x * kZstdWarpsPerCta + warp; j < total_blocks; j += gridDim.x * kZstdWarpsPerCta) {
+template <class WN>
+__global__ void __launch_bounds__(32) k_zstd_blocks(const SliceDesc* __restrict__ slices, uint32_t n_slices, uint32_t total_blocks,
+                                                    const uint8_t* __restrict__ src_base, uint8_t* tmp, uint64_t* seq_scratch,
+                                                    uint32_t* meta) {
+  extern __shared__ __align__(16) uint8_t zsm[];  // one warp per CTA: the input window, then the hash table
+  uint8_t* D = zsm;
+  uint16_t* tab = reinterpret_cast<uint16_t*>(zsm + ZstdLaunch<WN>::kWindow);
+  const cz::Warp w{threadIdx.x, 32u};
+  uint64_t* seqs = seq_scratch + (size_t)blockIdx.x * cz::kZstdMaxSeq;
+  for (uint32_t j = blockIdx.x; j < total_blocks; j += gridDim.x) {
     const uint32_t si = slice_of_block(slices, n_slices, j);
     const SliceDesc s = slices[si];
     const uint64_t o = (uint64_t)(j - s.blk_first) * cz::kZstdCBlock;
     const uint32_t n = (uint32_t)(s.src_len - o < cz::kZstdCBlock ? s.src_len - o : cz::kZstdCBlock);
     uint32_t poff = 0;
-    const uint32_t c = cz::zstd_compress_block(w, src_base + s.src_off, (uint32_t)o, n, tmp + (size_t)j * cz::kZstdSlot, seqs,
-                                               tabs[warp], &poff);
+    const uint32_t c = cz::zstd_compress_block<WN>(w, src_base + s.src_off, (uint32_t)o, n, tmp + (size_t)j * cz::kZstdSlot, seqs, D, tab,
+                                               &poff);
     if (w.lane == 0) { meta[2 * j] = poff; meta[2 * j + 1] = c; }
     __syncwarp();
   }
@@ -162,6 +169,9 @@ inline void compress_init_attrs() {
   cz::PredefCTables ct;
   cz::build_predef_ctables(&ct);
   cudaMemcpyToSymbol(cz::g_predef_c, &ct, sizeof ct);
+  cudaFuncSetAttribute(k_zstd_blocks<cz::WinFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZstdLaunch<cz::WinFast>::kSmemBytes);
+  cudaFuncSetAttribute(k_zstd_blocks<cz::WinMid>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZstdLaunch<cz::WinMid>::kSmemBytes);
+  cudaFuncSetAttribute(k_zstd_blocks<cz::WinHigh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZstdLaunch<cz::WinHigh>::kSmemBytes);
 }
 
 // zn_compress_bound: raw-block fallback makes this exact
@@ -185,7 +195,8 @@ static bool grow(T** p, size_t* cap, size_t need_bytes) {
 inline int compress_run(CompressScratch* cs, cudaStream_t st, int sm_count, const uint8_t* d_src, const uint64_t* src_off,
                         const uint64_t* src_len, uint32_t n, int level, int codec, uint8_t* d_dst, const uint64_t* dst_off,
                         const uint64_t* /*dst_cap*/, uint64_t* out_len, uint32_t* status, uint32_t* launches, std::string* err) {
-  (void)level;  // one match-finder effort so far; the level is accepted for API parity
+  // zstd: the level picks the window geometry of the match finder (three efforts); LZ4 has one effort
+  const int effort = level <= 2 ? 0 : (level <= 9 ? 1 : 2);
   const bool lz4 = codec == 2;
   const uint64_t bsz = lz4 ? cz::kLz4Block : cz::kZstdCBlock;
   std::vector<SliceDesc> sl(n);
@@ -204,7 +215,9 @@ inline int compress_run(CompressScratch* cs, cudaStream_t st, int sm_count, cons
   const uint32_t nb = (uint32_t)total_blocks;
   const size_t slot = lz4 ? cz::kLz4Slot : cz::kZstdSlot;
   const uint32_t wpc = lz4 ? kLz4WarpsPerCta : kZstdWarpsPerCta;
-  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((nb + wpc - 1) / wpc, (uint32_t)sm_count * (lz4 ? 6u : 6u)));
+  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((nb + wpc - 1) / wpc, (uint32_t)sm_count * (lz4 ? 6u : (effort == 0 ? ZstdLaunch<cz::WinFast>::kCtasPerSm
+                                                                  : effort == 1 ? ZstdLaunch<cz::WinMid>::kCtasPerSm
+                                                                                : ZstdLaunch<cz::WinHigh>::kCtasPerSm))));
   const size_t small_bytes = (size_t)n * sizeof(SliceDesc) + (size_t)nb * 8 + (size_t)n * 8 + 64;
   if (!grow(&cs->tmp, &cs->tmp_cap, std::max<size_t>(1, (size_t)nb * slot)) ||
       !grow((uint8_t**)&cs->small, &cs->small_cap, small_bytes) ||
@@ -225,7 +238,12 @@ inline int compress_run(CompressScratch* cs, cudaStream_t st, int sm_count, cons
   cudaEventRecord(cs->ev[0], st);
   if (nb) {
     if (lz4) k_lz4_blocks<<<grid, kLz4WarpsPerCta * 32, 0, st>>>(d_sl, n, nb, d_src, cs->tmp, d_meta);
-    else k_zstd_blocks<<<grid, kZstdWarpsPerCta * 32, 0, st>>>(d_sl, n, nb, d_src, cs->tmp, cs->seqs, d_meta);
+    else if (effort == 0)
+      k_zstd_blocks<cz::WinFast><<<grid, 32, ZstdLaunch<cz::WinFast>::kSmemBytes, st>>>(d_sl, n, nb, d_src, cs->tmp, cs->seqs, d_meta);
+    else if (effort == 1)
+      k_zstd_blocks<cz::WinMid><<<grid, 32, ZstdLaunch<cz::WinMid>::kSmemBytes, st>>>(d_sl, n, nb, d_src, cs->tmp, cs->seqs, d_meta);
+    else
+      k_zstd_blocks<cz::WinHigh><<<grid, 32, ZstdLaunch<cz::WinHigh>::kSmemBytes, st>>>(d_sl, n, nb, d_src, cs->tmp, cs->seqs, d_meta);
     (*launches)++;
   }
   if (lz4) k_lz4_assemble<<<n, 256, 0, st>>>(d_sl, d_src, cs->tmp, d_meta, d_dst, d_len);
