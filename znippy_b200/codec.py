@@ -122,7 +122,7 @@ def blake3_hash(data, ctx: Ctx | None = None) -> bytes:
 
 class CompressCtx:
     """codec.rs:8-55.  `level` follows the reference's meaning (higher = more effort); the GPU match finder has
-    three effort settings, so levels <= 1, 2..9 and >= 10 map onto them."""
+    three effort settings (window geometries), so levels <= 2, 3..9 and >= 10 map onto them."""
 
     def __init__(self, compression_level: int, codec: int = CODEC_ZSTD, ctx: Ctx | None = None):
         self.level = int(compression_level)

@@ -456,7 +456,8 @@ struct SeqScratch {
   uint8_t hdr[3][96];
   uint32_t mode[3], hlen[3];
   uint32_t sbits[3][32];   // per chunk: FSE state bits of each sequence, value << 8 | count
-  uint8_t codes[3][32];    // per chunk: the three codes of each sequence
+  int32_t dnb[3][32];      // per chunk: delta_nb / delta_state of each sequence's three codes, fetched by the lanes so
+  int32_t dst[3][32];      //            that the serial state chains only wait for the state table itself
   uint32_t bitbuf[88];     // per chunk: the assembled bitstream (<= 31 carried bits + 32 x 75)
 };
 
@@ -591,23 +592,27 @@ ZN_HD uint32_t zstd_encode_sequences(const Warp& w, uint8_t* dst, uint64_t* seqs
     const uint32_t ll = (uint32_t)(sj & 0x1FFFF), ml = 4u + (uint32_t)((sj >> 17) & 0x1FFFF), ofv = (uint32_t)((sj >> 34) & 0x3FFFF);
     const uint32_t lc = (uint32_t)((sj >> 52) & 63), mc = (uint32_t)(sj >> 58);
     const uint32_t oc = mine ? (uint32_t)hibit32(ofv) : 0u;
-    if (mine) { sc->codes[0][w.lane] = (uint8_t)lc; sc->codes[1][w.lane] = (uint8_t)oc; sc->codes[2][w.lane] = (uint8_t)mc; }
+    if (mine) {
+      sc->dnb[0][w.lane] = ct[0]->delta_nb[lc]; sc->dst[0][w.lane] = ct[0]->delta_state[lc];
+      sc->dnb[1][w.lane] = ct[1]->delta_nb[oc]; sc->dst[1][w.lane] = ct[1]->delta_state[oc];
+      sc->dnb[2][w.lane] = ct[2]->delta_nb[mc]; sc->dst[2][w.lane] = ct[2]->delta_state[mc];
+    }
     w_sync(w);
     for (uint32_t t = w.lane; t < 3; t += w.n) {
-      const FseCTable* c = ct[t];
+      const uint16_t* stt = ct[t]->state;
       uint32_t v = stv[kOnDevice ? 0 : t];
-      for (uint32_t i = 0; i < here; i++) {
-        const uint32_t sym = sc->codes[t][i];
-        if (base + (here - 1u - i) == nseq - 1u) {  // the very first sequence coded only seeds the state
-          FseCState st0;
-          st0.init(c, sym);
-          v = st0.value;
-          sc->sbits[t][i] = 0;
-        } else {
-          const uint32_t nb = (uint32_t)((int32_t)v + c->delta_nb[sym]) >> 16;
-          sc->sbits[t][i] = ((v & ((1u << nb) - 1u)) << 8) | nb;
-          v = c->state[(int32_t)(v >> nb) + c->delta_state[sym]];
-        }
+      uint32_t i = 0;
+      if (base + here == nseq) {  // the very first sequence coded only seeds the state (FseCState::init)
+        const int32_t dnb = sc->dnb[t][0];
+        const uint32_t nb = (uint32_t)(dnb + (1 << 15)) >> 16;
+        v = stt[(int32_t)(((nb << 16) - (uint32_t)dnb) >> nb) + sc->dst[t][0]];
+        sc->sbits[t][0] = 0;
+        i = 1;
+      }
+      for (; i < here; i++) {
+        const uint32_t nb = (uint32_t)((int32_t)v + sc->dnb[t][i]) >> 16;
+        sc->sbits[t][i] = ((v & ((1u << nb) - 1u)) << 8) | nb;
+        v = stt[(int32_t)(v >> nb) + sc->dst[t][i]];
       }
       stv[kOnDevice ? 0 : t] = v;
     }
