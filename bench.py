@@ -457,11 +457,22 @@ def run_ours(args):
                         "gbs": round(k_hash_bytes / (stage_ms[2] * 1e-3) / 1e9, 1) if stage_ms[2] > 0 else None},
         "k_b3_tree": {"ms": round(float(stage_ms[3]), 4)}}
     dom = "k_b3_chunks" if stage_ms[2] >= stage_ms[1] else "k_decode"
+    note = "blake3 is int-ALU bound (~10.5 int ops/byte), see DESIGN.md; hbm frac reported as asked"
+    if plan.fused():
+        # decode and hash are ONE kernel (fused_ws.cuh): algorithmic bytes of decode+verify per SURVEY §8(d) = blob read +
+        # content written + one 32 B chaining value per KiB; the hash's read of the fresh output is not algorithmic
+        fused_bytes = k_decode_bytes + 32 * (out_bytes // 1024)
+        kernels = {"k_decode_ws": {"ms": round(float(stage_ms[1]), 4), "alg_bytes": fused_bytes,
+                                   "gbs": round(fused_bytes / (stage_ms[1] * 1e-3) / 1e9, 1)},
+                   "k_b3_tree": {"ms": round(float(stage_ms[3]), 4)}}
+        dom = "k_decode_ws"
+        note = ("decode + blake3 chunk hashing fused in one warp-specialised kernel; its floor is the int-ALU pipe (the "
+                "standalone hash kernel needs 0.99 ms for this batch at 89 % ALU utilisation), not HBM; hbm frac reported as asked")
     achieved = kernels[dom]["gbs"]
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
-                "frac_of_nominal_8000": round(achieved / 8000.0, 4), "kernels": kernels,
-                "note": "blake3 is int-ALU bound (~10.5 int ops/byte), see DESIGN.md; hbm frac reported as asked"}
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom) if args.workload == "text2g" else None,
+                "peak_source": peak_src,
+                "frac_of_nominal_8000": round(achieved / 8000.0, 4), "kernels": kernels, "note": note}
 
     cpu = None
     if not args.no_cpu:

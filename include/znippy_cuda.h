@@ -231,6 +231,10 @@ int zn_plan_results(zn_plan* plan, uint32_t* h_status, uint8_t* h_digests);
 int zn_plan_set_overlap(zn_plan* plan, int groups);
 /* kernels launched by one zn_plan_run of this plan */
 uint32_t zn_plan_launches(const zn_plan* plan);
+/* 1 when the plan decodes and hashes in ONE kernel (batches of large, highly compressible blobs: decode warps feed
+ * hash warps through a device-wide tile queue, fused_ws.cuh); the decode stage of zn_plan_last_ms then covers both
+ * and the hash stage is empty.  Environment: ZN_FUSE=0 keeps the two kernels apart. */
+int zn_plan_fused(const zn_plan* plan);
 /* device time of the most recent completed run, per stage, in ms (CUDA events on the run's stream):
  * [0] total, [1] decode stage, [2] hash stage (chunks), [3] tree+compare stage.  Synchronises. */
 int zn_plan_last_ms(zn_plan* plan, float ms[4]);

@@ -308,3 +308,41 @@ def test_block_parallel_mixed_batch_with_small_sources(codec, oracle):
     assert st.tolist() == [0] * len(blobs)
     for i, c in enumerate(contents):
         assert out[out_off[i]:out_off[i] + len(c)].tobytes() == c, i
+
+
+@pytest.mark.parametrize("mode", ["ws", "team", "0"])
+def test_fused_decode_hash_kernels(codec, oracle, mode, monkeypatch):
+    """Large, highly compressible blobs through the fused decode+hash kernels (ZN_FUSE: `ws` = warp-specialised K4w, the
+    default; `team` = the interleaved K4; `0` = decode and hash as two kernels): same bytes, same digests, same status
+    rules on all three; a small grid makes every decode team take several blobs."""
+    O = oracle
+    z, l = O.libzstd(), O.liblz4()
+    monkeypatch.setenv("ZN_FUSE", mode)
+    monkeypatch.setenv("ZN_WS_GRID", "3")
+    datas = [O.gen_text(8 << 20), O.gen_binary(8 << 20), O.gen_text((1 << 20) + 17), O.gen_binary(700_000),
+             np.zeros(3 << 20, np.uint8), O.gen_text(5_000_001), O.gen_binary((4 << 20) - 1), O.gen_text(2 << 20),
+             O.gen_binary(6 << 20), O.gen_text(1_234_567), O.gen_text(4 << 20)]
+    blobs = [z.compress(d, 19 if i % 2 == 0 else 3) for i, d in enumerate(datas)]
+    blobs[7] = l.compress_frame(datas[7])
+    contents = [d.tobytes() for d in datas]
+    st, dg, out, out_off = _run(codec, blobs, [1] * len(blobs), contents)
+    assert st.tolist() == [0] * len(blobs)
+    for i, c in enumerate(contents):
+        assert dg[i].tobytes() == O.blake3(c), i
+        assert out[out_off[i]:out_off[i] + len(c)].tobytes() == c, i
+    # 16-byte aligned rows (the bench layout), digest only compared on the device
+    buf, offs = _pack(blobs)
+    lens = [len(c) for c in contents]
+    ooff = np.concatenate([[0], np.cumsum([(n + 15) // 16 * 16 for n in lens])])[:-1]
+    out2 = np.zeros(int(ooff[-1]) + lens[-1] + 16, np.uint8)
+    st, dg2 = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs], [1] * len(blobs), lens,
+                                        b"".join(O.blake3(c) for c in contents), out2, ooff)
+    assert st.tolist() == [0] * len(blobs) and (dg2 == dg).all()
+    # one corrupted blob, one wrong expectation: only those rows fail
+    bad = bytearray(blobs[2]); bad[len(bad) // 2] ^= 0x10
+    blobs2 = list(blobs); blobs2[2] = bytes(bad)
+    buf, offs = _pack(blobs2)
+    ex = [O.blake3(c) for c in contents]; ex[5] = bytes(32)
+    st, _ = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs2], [1] * len(blobs2), lens, b"".join(ex), out2, ooff)
+    assert st[5] == codec.S_DIGEST_MISMATCH and st[2] != 0
+    assert [int(x) for i, x in enumerate(st) if i not in (2, 5)] == [0] * (len(blobs) - 2)

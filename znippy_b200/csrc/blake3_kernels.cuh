@@ -67,10 +67,12 @@ ZN_D void b3_issue_stage(uint8_t* buf, const uint8_t* ptr, uint32_t len, uint32_
       uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
       for (uint32_t j = 0; j < 4; j++) {
-        if (j < nb) w0 |= (uint32_t)src[j] << (8 * j);  // plain (coherent) loads: the fused decoder hashes its own output
-        if (j + 4 < nb) w1 |= (uint32_t)src[j + 4] << (8 * j);
-        if (j + 8 < nb) w2 |= (uint32_t)src[j + 8] << (8 * j);
-        if (j + 12 < nb) w3 |= (uint32_t)src[j + 12] << (8 * j);
+        // L2 loads (never the non-coherent path, never L1): the fused decoders hash their own output, and a sector that
+        // straddles two tiles must not be served from an L1 copy taken before its second half was written
+        if (j < nb) w0 |= (uint32_t)__ldcg(src + j) << (8 * j);
+        if (j + 4 < nb) w1 |= (uint32_t)__ldcg(src + j + 4) << (8 * j);
+        if (j + 8 < nb) w2 |= (uint32_t)__ldcg(src + j + 8) << (8 * j);
+        if (j + 12 < nb) w3 |= (uint32_t)__ldcg(src + j + 12) << (8 * j);
       }
       *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
     }

@@ -16,13 +16,16 @@ constexpr uint32_t kBulkIssuers = 32;   // threads that may issue (and must ther
 
 struct Team {
   uint32_t tid, n;
+  uint32_t bar = 0;  // 0: the team is the whole CTA (bar.sync 0); else the named barrier of a sub-CTA team of n threads
 };
 
 #if defined(__CUDA_ARCH__)
 
 // A team is either a whole CTA or, for small blobs, a CTA of exactly one warp.
 ZN_D void team_sync(const Team& t) {
-  if (t.n == 32) __syncwarp(); else __syncthreads();
+  if (t.n == 32) __syncwarp();
+  else if (t.bar == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(t.bar), "r"(t.n) : "memory");
 }
 
 // ---- TMA bulk stores (cp.async.bulk shared -> global): one instruction moves up to a whole tile, so a 128 KiB

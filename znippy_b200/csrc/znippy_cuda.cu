@@ -18,6 +18,7 @@
 #include "compress_kernels.cuh"
 #include "decode_kernels.cuh"
 #include "par_kernel.cuh"
+#include "fused_ws.cuh"
 
 using namespace zn;
 
@@ -55,7 +56,8 @@ struct zn_plan {
   uint32_t *d_list_dec = nullptr, *d_list_small = nullptr, *d_list_large = nullptr;
   uint32_t *d_piece_blob = nullptr, *d_piece_idx = nullptr;
   uint32_t *d_cvs = nullptr, *d_digests = nullptr, *d_expect = nullptr, *d_status = nullptr, *d_produced = nullptr,
-           *d_counter = nullptr;
+           *d_counter = nullptr, *d_wsq = nullptr;  // d_wsq: tile queue of the warp-specialised fused kernel (fused_ws.cuh)
+  uint32_t ws_tiles = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool ran = false;
@@ -161,6 +163,7 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   if (cudaMemcpyToSymbol(g_predef, &pd, sizeof pd) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
   cudaFuncSetAttribute(k_b3_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Warps * kB3SmemPerWarp);
   cudaFuncSetAttribute(k_decode<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kB3SmemPerWarp);
+  cudaFuncSetAttribute(k_decode_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes);
   cudaFuncSetAttribute(par::k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(par::ParShared));
   compress_init_attrs();
   return c;
@@ -309,11 +312,15 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     uint64_t src_bytes = 0;
     for (uint32_t i : ldec) src_bytes += descs[i].src_len;
     p->entropy_heavy = src_bytes * 64 > dec_bytes;
-    // Fused decode+hash (K4) is parity-tested but opt-in: on the 2 GiB pattern file it measures 1.54 ms against 1.43 ms
-    // for decode and hash back to back, because a team cannot hash while it parses its next block.
-    p->fused_hash = p->big_blobs && !p->entropy_heavy && getenv("ZN_FUSE") != nullptr;
+    // Large, highly compressible blobs go through the fused decode+hash kernel (fused_ws.cuh): on the 2 GiB pattern file
+    // 1.32 ms per step against 1.53 ms for decode and hash back to back.  ZN_FUSE=0 keeps the two kernels apart,
+    // ZN_FUSE=team selects the older fused kernel in which one team alternates between decoding and hashing (1.65 ms).
+    {
+      const char* fz = getenv("ZN_FUSE");
+      p->fused_hash = p->big_blobs && !p->entropy_heavy && !(fz && !strcmp(fz, "0"));
+    }
     if (p->fused_hash)
-      for (uint32_t i : ldec) descs[i].flags |= F_HASHED;
+      for (uint32_t i : ldec) { descs[i].flags |= F_HASHED; p->ws_tiles += (descs[i].n_chunks + 31u) / 32u; }
     p->small_blobs = !ldec.empty() && dec_bytes / ldec.size() <= (64u << 10);
   }
   p->n_small = (uint32_t)lsmall.size();
@@ -327,7 +334,8 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_cvs, (const uint32_t*)nullptr, (size_t)chunks * 8) &&
             upload(c, &p->d_digests, (const uint32_t*)nullptr, (size_t)n * 8) &&
             upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
-            upload(c, &p->d_counter, (const uint32_t*)nullptr, zn_plan::kMaxGroups);
+            upload(c, &p->d_counter, (const uint32_t*)nullptr, zn_plan::kMaxGroups) &&
+            upload(c, &p->d_wsq, (const uint32_t*)nullptr, p->fused_hash ? 4 + 2 * (size_t)p->ws_tiles : 0);
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // host vectors go out of scope
   if (ok) {
@@ -364,12 +372,14 @@ extern "C" zn_plan* zn_plan_hash(zn_ctx* ctx, uint32_t n, const uint64_t* h_off,
   return plan_build(ctx, PLAN_HASH, n, h_off, h_len, nullptr, nullptr, nullptr, h_expect_digest, false);
 }
 
+extern "C" int zn_plan_fused(const zn_plan* p) { return p && p->fused_hash ? 1 : 0; }
+
 extern "C" void zn_plan_destroy(zn_plan* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   if (p->ran) cudaStreamSynchronize(p->last_stream);
   void* ptrs[] = {p->d_blobs, p->d_chunk_prefix, p->d_list_dec, p->d_list_small, p->d_list_large, p->d_piece_blob,
-                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter};
+                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter, p->d_wsq};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, p->ctx->stream);
   for (auto& e : p->ev)
@@ -419,9 +429,24 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
         const uint32_t grid = std::min<uint32_t>(nd, max_grid);
         par::k_decode_par<<<grid, par::kParThreads, sizeof(par::ParShared), st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_par,
                                                                                  p->d_status, p->d_produced, p->d_counter + g);
+      } else if (force && !strcmp(force, "team128")) {  // development: 128-thread teams for everything
+        const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid);
+        k_decode<kDecodeThreads, 1, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit,
+                                                                         p->d_status, p->d_produced, p->d_counter + g, nullptr, 1u);
       } else if (p->big_blobs) {  // highly compressible large blobs (few, long sequences): one 256-thread team per blob
-        const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
-        if (p->fused_hash)
+        uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
+        if (const char* gs = getenv("ZN_WS_GRID")) grid = std::max(1, std::min<int>((int)grid, atoi(gs)));  // tests: several blobs per CTA
+        const char* fm = getenv("ZN_FUSE");
+        if (p->fused_hash && p->groups == 1 && !(fm && !strcmp(fm, "team"))) {
+          // warp-specialised fused kernel: one CTA per SM, two decode teams each; its tile queue starts empty
+          ZN_CUDA(c, cudaMemsetAsync(p->d_wsq, 0, 16 + 8 * (size_t)p->ws_tiles, st));
+          WsQueue q{p->d_wsq, reinterpret_cast<unsigned long long*>(p->d_wsq + 4), p->ws_tiles};
+          uint32_t wgrid = (uint32_t)c->sm_count;  // every SM hashes, whether or not one of its teams gets a blob
+          if (const char* gs = getenv("ZN_WS_GRID")) wgrid = std::max(1, std::min<int>((int)wgrid, atoi(gs)));
+          k_decode_ws<<<wgrid, kWsThreads, kWsSmemBytes, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                               p->d_produced, p->d_counter + g, p->d_cvs, q, 1u);
+        }
+        else if (p->fused_hash)
           k_decode<256, 1, true><<<grid, 256, 8 * kB3SmemPerWarp, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
                                                                        p->d_produced, p->d_counter + g, p->d_cvs, 1u);
         else
@@ -859,3 +884,16 @@ extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, ui
   }
   return ZN_OK;
 }
+
+#ifdef ZN_WS_DEBUG
+// development only (tools/ws_times.py): reset / read the fused kernel's phase stamps
+extern "C" void zn_debug_ws_times(unsigned long long* out, int reset) {
+  if (reset) {
+    unsigned long long init[4] = {~0ull, 0, 0, 0};
+    cudaMemcpyToSymbol(g_ws_dbg, init, sizeof init);
+  } else {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_ws_dbg, 32);
+  }
+}
+#endif
