@@ -102,7 +102,10 @@ ZN_D void b3_warp_tile(uint8_t* wbuf, const uint8_t* ptr, uint32_t len, uint32_t
     cp_async_wait<1>();
     __syncwarp();
     const uint4* row = reinterpret_cast<const uint4*>(cur + lane * kB3RowStride);
-#pragma unroll
+    // NOT unrolled: one copy of the 7-round compression (~13 KB of code) instead of two.  Instruction fetch is what
+    // limits the hash warps once other code runs on the SM too: in the fused kernel (fused_ws.cuh) 15 % of the warp
+    // samples were "no instruction" stalls with the unrolled body, and the kernel went from 1.22 to 1.08 ms without it.
+#pragma unroll 1
     for (uint32_t j = 0; j < kB3RowBytes / 64; j++) {
       const uint32_t b = s * (kB3RowBytes / 64) + j;
       if (b < nblocks) {
