@@ -91,7 +91,7 @@ def compress_batch(src, src_off, src_len, level: int = 1, codec: int = CODEC_ZST
     caps = np.array([compress_bound(int(x), codec) for x in sl], dtype=np.uint64)
     doff = np.zeros(n + 1, np.uint64)
     np.cumsum(caps, out=doff[1:])
-    dst = np.zeros(int(doff[-1]) + 1, np.uint8)
+    dst = np.empty(int(doff[-1]) + 1, np.uint8)  # every byte that is read back below was written by the call
     dlen = np.zeros(n, np.uint64)
     dg = np.zeros((n, 32), np.uint8)
     st = np.zeros(n, np.uint32)

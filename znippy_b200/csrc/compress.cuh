@@ -90,6 +90,14 @@ constexpr uint32_t kZstdHashLog = 12;                                // 4096 x u
 #define ZN_LAZY_SKIP_W 8
 #endif
 constexpr uint32_t kLazyMatchWeight = ZN_LAZY_MATCH_W, kLazySkipWeight = ZN_LAZY_SKIP_W;
+#ifndef ZN_MIN_MATCH
+#define ZN_MIN_MATCH 4
+#endif
+constexpr uint32_t kZstdMinMatch = ZN_MIN_MATCH;                     // shortest match the zstd parser emits
+#ifndef ZN_INSERT_SPAN
+#define ZN_INSERT_SPAN 64
+#endif
+constexpr uint32_t kZstdInsertSpan = ZN_INSERT_SPAN;                 // positions of a long match entered beyond the round
 constexpr uint32_t kLazyProbeWords = 5;                              // words compared beyond the 4 verified bytes
 constexpr uint32_t kLazyProbe = 4u + 4u * kLazyProbeWords;                                  // bytes each candidate lane compares before the warp votes
 // Window geometry of the zstd match finder (see zstd_compress_block): W fresh bytes per window, H bytes of history
@@ -916,8 +924,7 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       const uint32_t v = valid ? ld32s(D + p) : 0u;
       const uint32_t h = hash4(v, kZstdHashLog);
       const uint32_t cand = valid ? tab[h] : 0xFFFFu;
-      const bool ok = valid && cand < p && ld32s(D + cand) == v;
-      const uint32_t m = w_ballot(w, ok);
+      bool ok = valid && cand < p && ld32s(D + cand) == v;
       ZN_CP(1);
       // Parallel lazy matching: every lane that found a candidate measures its own match (up to kLazyProbe bytes), and
       // the warp takes the lane with the best gain — bytes matched minus the positions skipped to get there — instead
@@ -927,7 +934,11 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       if (ok) {
         const uint32_t lim = dend - p < kLazyProbe ? dend - p : kLazyProbe;
         probe = 4u + prefix_words<kLazyProbeWords>(D + p + 4, D + cand + 4, lim - 4u);
+        // Minimum match (tunable, ZN_MIN_MATCH): a sequence costs ~21 bits once entropy coded, so on skewed small-alphabet
+        // data 6-7 pays (78 -> 54 KB on the test corpus), while on source text the host emulation measures 4 best.
+        ok = probe >= kZstdMinMatch;
       }
+      const uint32_t m = w_ballot(w, ok);
       ZN_CP(2);
       if (!m) {
         if (valid) tab[h] = (uint16_t)p;
@@ -970,7 +981,16 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
         lo = anchor - pos;
       }
       ZN_CP(4);
-      if (valid && w.lane <= f) tab[h] = (uint16_t)p;  // positions behind the last match start are not entered (see lz4_compress_block)
+      // Every position of the round enters the table, the ones covered by matches included (most bytes of compressible
+      // data lie inside matches: leaving them out hides them from every later look-up).  The next round starts at `next`,
+      // so none of these lanes is looked up again and can find itself.  The part of a long match that reaches beyond the
+      // round is entered too, up to kZstdInsertSpan positions.
+      (void)f;
+      if (valid && p < next) tab[h] = (uint16_t)p;
+      if (next > pos + w.n) {
+        const uint32_t lim = next < pos + w.n + kZstdInsertSpan ? next : pos + w.n + kZstdInsertSpan;
+        for (uint32_t q = pos + w.n + w.lane; q < lim && q + 4u <= dend; q += w.n) tab[hash4(ld32s(D + q), kZstdHashLog)] = (uint16_t)q;
+      }
       w_sync(w);
       pos = next;
       ZN_CP(5);
