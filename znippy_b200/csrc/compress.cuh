@@ -87,7 +87,7 @@ constexpr uint32_t kLz4HashLog = 12;                                 // 4096 x u
 constexpr uint32_t kZstdHashLog = 12;                                // 4096 x u16 = 8 KiB per warp
 #ifndef ZN_LAZY_MATCH_W
 #define ZN_LAZY_MATCH_W 4
-#define ZN_LAZY_SKIP_W 8
+#define ZN_LAZY_SKIP_W 16
 #endif
 constexpr uint32_t kLazyMatchWeight = ZN_LAZY_MATCH_W, kLazySkipWeight = ZN_LAZY_SKIP_W;
 #ifndef ZN_MIN_MATCH
@@ -954,7 +954,7 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
         const uint32_t mm = lo < 32u ? (m >> lo) << lo : 0u;
         if (!mm) { f = w.n - 1u; break; }  // nothing more starts here: the rest of the window is literals
         const uint32_t f0 = ffs32(mm) - 1u;
-        // score: matched bytes x 4 - skipped positions x 8 (a literal costs less than a byte once Huffman coded)
+        // score: matched bytes x 4 - skipped positions x 16 (measured optimum; a literal costs less than a byte once Huffman coded)
         const uint32_t score = (ok && w.lane >= lo) ? probe * kLazyMatchWeight + kLazySkipWeight * (w.n - 1u - (w.lane - f0)) : 0u;
         // warp arg-max in one reduction: key = score : (31 - lane), so the earliest lane wins ties
         const uint32_t key = w_max(w, (score << 5) | (31u - w.lane));
