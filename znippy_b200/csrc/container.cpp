@@ -12,6 +12,7 @@
 // RecordBatch messages; Utf8, Int/UInt 8-64, Bool, FixedSizeBinary columns; no dictionaries, no body compression.
 // Parity: pyarrow reads what this writes and this reads what pyarrow writes (tests/test_container_native.py).
 #include <fcntl.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -749,45 +750,75 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
   if (row_hi > ix.rows) row_hi = ix.rows;
   if (row_lo > row_hi) row_lo = row_hi;
   std::unordered_set<std::string> uniq;
-  std::vector<int> fds;
-  std::map<std::string, int> open_files;
   int rc = ZN_OK;
   for (uint64_t r = row_lo; r < row_hi; r++) uniq.insert(std::string(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]));
-  if (save_data) {  // decompress.rs:74-101: one fd per path, indexed by row
-    fds.assign(ix.rows, -1);
-    for (uint64_t r = row_lo; r < row_hi && rc == ZN_OK; r++) {
-      const std::string rel(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]);
-      auto it = open_files.find(rel);
-      if (it == open_files.end()) {
-        const std::string full = std::string(out_dir ? out_dir : ".") + "/" + rel;
-        for (size_t p = 1; p < full.size(); p++)
-          if (full[p] == '/') mkdir(full.substr(0, p).c_str(), 0755);
-        const int fd = open(full.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644);
-        if (fd < 0) { set_err(err, errcap, "failed to open output file " + full); rc = ZN_E_ARG; break; }
-        it = open_files.emplace(rel, fd).first;
-      }
-      fds[r] = it->second;
+  // decompress.rs:74-101 keeps one fd per path for the whole run.  With 100 000 small files that needs a raised
+  // RLIMIT_NOFILE, so here the row range is worked off in windows of at most `max_open` distinct paths (rows of a
+  // file are adjacent in the index): same files, same bytes, any descriptor limit.
+  size_t max_open = 4096;
+  {
+    struct rlimit rl;
+    if (getrlimit(RLIMIT_NOFILE, &rl) == 0) {
+      if (rl.rlim_cur < rl.rlim_max) { rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_NOFILE, &rl); getrlimit(RLIMIT_NOFILE, &rl); }
+      const size_t lim = rl.rlim_cur == RLIM_INFINITY ? 65536 : (size_t)rl.rlim_cur;
+      max_open = std::max<size_t>(16, std::min<size_t>(lim > 128 ? (lim - 64) / 2 : 16, 16384));
     }
   }
-  const int afd = rc == ZN_OK ? open(index_path, O_RDONLY) : -1;
-  if (rc == ZN_OK && afd < 0) { set_err(err, errcap, "cannot open archive"); rc = ZN_E_ARG; }
+  const int afd = open(index_path, O_RDONLY);
+  if (afd < 0) { set_err(err, errcap, "cannot open archive"); rc = ZN_E_ARG; }
+  zn_verify_stats total;
+  memset(&total, 0, sizeof total);
+  std::vector<int> fds;
+  if (save_data) fds.assign(ix.rows, -1);
+  std::vector<uint64_t> corrupt(row_hi - row_lo + 1);
+  std::unordered_set<std::string> created;  // a path met again in a later window is re-opened without truncation
+  for (uint64_t w_lo = row_lo; w_lo < row_hi && rc == ZN_OK;) {
+    std::map<std::string, int> open_files;
+    uint64_t w_hi = w_lo;
+    if (save_data) {
+      for (; w_hi < row_hi && rc == ZN_OK; w_hi++) {
+        const std::string rel(ix.paths.data() + ix.path_off[w_hi], ix.path_off[w_hi + 1] - ix.path_off[w_hi]);
+        auto it = open_files.find(rel);
+        if (it == open_files.end()) {
+          if (open_files.size() >= max_open) break;
+          const std::string full = std::string(out_dir ? out_dir : ".") + "/" + rel;
+          for (size_t p = 1; p < full.size(); p++)
+            if (full[p] == '/') mkdir(full.substr(0, p).c_str(), 0755);
+          const bool again = !created.insert(rel).second;
+          const int fd = open(full.c_str(), O_CREAT | O_WRONLY | (again ? 0 : O_TRUNC), 0644);
+          if (fd < 0) { set_err(err, errcap, "failed to open output file " + full); rc = ZN_E_ARG; break; }
+          it = open_files.emplace(rel, fd).first;
+        }
+        fds[w_hi] = it->second;
+      }
+    } else {
+      w_hi = row_hi;
+    }
+    if (rc == ZN_OK) {
+      zn_verify_stats st;
+      rc = zn_decompress_rows(ctx, afd, w_lo, w_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.compressed.data(),
+                              ix.col[3].data(), ix.checksums.data(), save_data ? fds.data() : nullptr, batch_bytes, io_threads,
+                              corrupt.data(), &st);
+      if (rc != ZN_OK) set_err(err, errcap, zn_last_error(ctx));
+      total.corrupt_rows += st.corrupt_rows;
+      total.total_written_bytes += st.total_written_bytes;
+      total.verified_bytes += st.verified_bytes;
+      total.corrupt_bytes += st.corrupt_bytes;
+      total.total_chunks += st.total_chunks;
+    }
+    for (auto& kv : open_files) close(kv.second);
+    w_lo = w_hi;
+  }
   if (rc == ZN_OK) {
-    zn_verify_stats st;
-    std::vector<uint64_t> corrupt(row_hi - row_lo + 1);
-    rc = zn_decompress_rows(ctx, afd, row_lo, row_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.compressed.data(),
-                            ix.col[3].data(), ix.checksums.data(), save_data ? fds.data() : nullptr, batch_bytes, io_threads,
-                            corrupt.data(), &st);
-    if (rc != ZN_OK) set_err(err, errcap, zn_last_error(ctx));
     report->total_files = uniq.size();
-    report->corrupt_files = st.corrupt_rows;  // the reference counts corrupt ROWS here (decompress.rs:210)
+    report->corrupt_files = total.corrupt_rows;  // the reference counts corrupt ROWS here (decompress.rs:210)
     report->verified_files = report->total_files > report->corrupt_files ? report->total_files - report->corrupt_files : 0;
-    report->total_bytes = st.total_written_bytes;
-    report->verified_bytes = st.verified_bytes;
-    report->corrupt_bytes = st.corrupt_bytes;
-    report->chunks = st.total_chunks;
+    report->total_bytes = total.total_written_bytes;
+    report->verified_bytes = total.verified_bytes;
+    report->corrupt_bytes = total.corrupt_bytes;
+    report->chunks = total.total_chunks;
   }
   if (afd >= 0) close(afd);
-  for (auto& kv : open_files) close(kv.second);
   zn_index_close(h);
   return rc;
 }

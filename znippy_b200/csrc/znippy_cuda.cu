@@ -9,8 +9,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/znippy_cuda.h"
@@ -195,12 +197,67 @@ extern "C" void* zn_ctx_pinned(zn_ctx* c, size_t* bytes) {
 extern "C" uint64_t zn_ctx_kernel_launches(const zn_ctx* c) { return c ? c->launches : 0; }
 
 // pinned host memory for the native pipelines of container.cpp (which is compiled without the CUDA runtime headers)
+// cudaHostAlloc costs ~0.3 ms per MiB (page pinning), i.e. more than moving the bytes over PCIe: the staging buffers of
+// the read worker and of the archive writer are therefore recycled through a small process-wide cache (the reference
+// keeps its Magazine slots for the life of the process for the same reason, slotpool.rs:93-130).
+namespace {
+struct PinnedCache {
+  std::mutex mu;
+  struct Buf { void* p; size_t cap; };
+  std::vector<Buf> free_list;                       // idle buffers, at most kKeep of them
+  std::unordered_map<void*, size_t> live;           // capacity of every buffer handed out
+  static constexpr size_t kKeep = 6;
+} g_pinned;
+}  // namespace
+
 extern "C" void* zn_ctx_pinned_alloc(size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_pinned.mu);
+    size_t best = SIZE_MAX;
+    for (size_t i = 0; i < g_pinned.free_list.size(); i++) {
+      const size_t cap = g_pinned.free_list[i].cap;
+      if (cap >= bytes && cap <= 2 * bytes + (64u << 20) && (best == SIZE_MAX || cap < g_pinned.free_list[best].cap)) best = i;
+    }
+    if (best != SIZE_MAX) {
+      PinnedCache::Buf b = g_pinned.free_list[best];
+      g_pinned.free_list.erase(g_pinned.free_list.begin() + (long)best);
+      g_pinned.live[b.p] = b.cap;
+      return b.p;
+    }
+  }
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    // memory pressure: drop the idle buffers and try once more
+    std::vector<PinnedCache::Buf> drop;
+    { std::lock_guard<std::mutex> lk(g_pinned.mu); drop.swap(g_pinned.free_list); }
+    for (auto& b : drop) cudaFreeHost(b.p);
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  std::lock_guard<std::mutex> lk(g_pinned.mu);
+  g_pinned.live[p] = bytes;
   return p;
 }
-extern "C" void zn_ctx_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void zn_ctx_pinned_free(void* p) {
+  if (!p) return;
+  void* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pinned.mu);
+    auto it = g_pinned.live.find(p);
+    if (it == g_pinned.live.end()) { evict = p; }
+    else {
+      g_pinned.free_list.push_back({p, it->second});
+      g_pinned.live.erase(it);
+      if (g_pinned.free_list.size() > PinnedCache::kKeep) {  // drop the smallest idle buffer
+        size_t k = 0;
+        for (size_t i = 1; i < g_pinned.free_list.size(); i++) if (g_pinned.free_list[i].cap < g_pinned.free_list[k].cap) k = i;
+        evict = g_pinned.free_list[k].p;
+        g_pinned.free_list.erase(g_pinned.free_list.begin() + (long)k);
+      }
+    }
+  }
+  if (evict) cudaFreeHost(evict);
+}
 
 // --------------------------------------------------------------------------------------------- plans
 template <typename T>
@@ -774,19 +831,17 @@ extern "C" int zn_compress_batch(zn_ctx* c, const uint8_t* src_base, const uint6
 #include <thread>
 
 namespace {
-struct Pinned {
+struct Pinned {  // staging buffer from the process-wide pinned cache
   uint8_t* p = nullptr;
   size_t cap = 0;
   bool ensure(size_t need) {
     if (cap >= need) return true;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    if (cudaHostAlloc((void**)&p, need + 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
-    cap = need + 4096;
-    return true;
+    if (p) zn_ctx_pinned_free(p);
+    p = (uint8_t*)zn_ctx_pinned_alloc(need + 4096);
+    cap = p ? need + 4096 : 0;
+    return p != nullptr;
   }
-  ~Pinned() { if (p) cudaFreeHost(p); }
+  ~Pinned() { if (p) zn_ctx_pinned_free(p); }
 };
 
 template <typename F>
@@ -816,14 +871,36 @@ extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, ui
   memset(stats, 0, sizeof *stats);
   if (batch_bytes < (64u << 20)) batch_bytes = 64u << 20;
   if (io_threads < 1) io_threads = 1;
-  Pinned pin_in, pin_out;
-  std::vector<uint64_t> in_off, out_off;
-  std::vector<uint32_t> status;
+  // Three stages — pread into pinned memory, GPU decode+verify, pwrite from pinned memory — over two sets of staging
+  // buffers: while the GPU works on batch k, helper threads read batch k+1 and write batch k-1 (the reference overlaps
+  // the same three through its reader / worker / writer threads, decompress.rs:105-192).  A range that fits one
+  // staging budget is still cut into a few batches so that there is something to overlap.
+  {
+    // ... but only where I/O is worth hiding: many rows, or hundreds of MiB of blobs to read / of cheaply decoded bytes to
+    // write.  Entropy-coded data (the slow decode) keeps its rows together: its kernels need every blob they can get.
+    uint64_t in_b = 0, out_b = 0;
+    for (uint64_t r = row_lo; r < row_hi; r++) { in_b += blob_size[r]; out_b += uncompressed_size[r]; }
+    const uint64_t rows = row_hi - row_lo;
+    const bool cheap_decode = in_b <= out_b / 16 || in_b >= out_b - out_b / 10;
+    const bool split = rows >= 1200 || in_b >= (256ull << 20) || (out_fd && cheap_decode && out_b >= (256ull << 20));
+    if (split) {
+      const uint64_t quarter = std::max<uint64_t>((in_b + out_b) / 4 + 32 * rows, 64u << 20);
+      if (quarter < batch_bytes) batch_bytes = (size_t)quarter;
+    }
+  }
+  struct Batch {
+    uint64_t a = 0, b = 0;
+    uint32_t n = 0;
+    Pinned pin_in, pin_out;
+    std::vector<uint64_t> in_off, out_off;
+    std::vector<uint32_t> status;
+    std::thread reader, writer;
+  } bt[2];
   std::atomic<int> io_err{0};
-  uint64_t a = row_lo;
-  while (a < row_hi) {
+  auto join = [](std::thread& t) { if (t.joinable()) t.join(); };
+  auto claim = [&](Batch& B, uint64_t a) -> bool {  // next row range whose blobs + outputs fit the staging budget
     uint64_t b = a, need = 0, in_bytes = 0, out_bytes = 0;
-    while (b < row_hi) {  // claim the next row range whose blobs + outputs fit the staging budget
+    while (b < row_hi) {
       const uint64_t r = blob_size[b] + uncompressed_size[b] + 32;
       if (b > a && need + r > batch_bytes) break;
       need += r;
@@ -831,58 +908,92 @@ extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, ui
       out_bytes += (uncompressed_size[b] + 15) & ~15ull;
       b++;
     }
-    const uint32_t n = (uint32_t)(b - a);
-    if (!pin_in.ensure(in_bytes + 16) || (out_fd && !pin_out.ensure(out_bytes + 16))) { c->err = "pinned staging allocation failed"; return ZN_E_NOMEM; }
-    in_off.resize(n);
-    out_off.resize(n);
-    status.assign(n, 0);
+    B.a = a; B.b = b; B.n = (uint32_t)(b - a);
+    if (!B.pin_in.ensure(in_bytes + 16) || (out_fd && !B.pin_out.ensure(out_bytes + 16))) return false;
+    B.in_off.resize(B.n);
+    B.out_off.resize(B.n);
+    B.status.assign(B.n, 0);
     uint64_t ci = 0, co = 0;
-    for (uint32_t i = 0; i < n; i++) {
-      in_off[i] = ci; ci += (blob_size[a + i] + 15) & ~15ull;
-      out_off[i] = co; co += (uncompressed_size[a + i] + 15) & ~15ull;
+    for (uint32_t i = 0; i < B.n; i++) {
+      B.in_off[i] = ci; ci += (blob_size[a + i] + 15) & ~15ull;
+      B.out_off[i] = co; co += (uncompressed_size[a + i] + 15) & ~15ull;
     }
-    parallel_rows(n, io_threads, [&](uint32_t i) {  // pread (decompress.rs:148-153)
-      uint64_t done = 0, len = blob_size[a + i];
-      while (done < len) {
-        const ssize_t r = pread(archive_fd, pin_in.p + in_off[i] + done, len - done, (off_t)(blob_offset[a + i] + done));
-        if (r <= 0) { io_err = 1; return; }
-        done += (uint64_t)r;
-      }
-    });
-    if (io_err) { c->err = "failed to read blob from archive"; return ZN_E_ARG; }
-    const int rc = zn_decode_verify_batch(c, pin_in.p, in_off.data(), blob_size + a, compressed + a, uncompressed_size + a,
-                                          checksums + 32 * a, out_fd ? pin_out.p : nullptr, out_fd ? out_off.data() : nullptr, n,
-                                          status.data(), nullptr);
-    if (rc != ZN_OK) return rc;
-    for (uint32_t i = 0; i < n; i++) {  // fold, decompress.rs:140,156-184
-      stats->total_chunks++;
-      const uint32_t s = status[i];
-      if (s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) { stats->decode_errors++; continue; }
-      const uint64_t len = uncompressed_size[a + i];
-      stats->total_written_bytes += len;
-      if (s == ZN_S_OK) stats->verified_bytes += len;
-      else {
-        stats->corrupt_bytes += len;
-        if (corrupt_rows_out) corrupt_rows_out[stats->corrupt_rows] = a + i;
-        stats->corrupt_rows++;
-      }
-    }
-    if (out_fd) {
-      parallel_rows(n, io_threads, [&](uint32_t i) {  // pwrite at fdata_offset (decompress.rs:186-189)
-        const uint32_t s = status[i];
-        if ((s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) || out_fd[a + i] < 0) return;
-        uint64_t done = 0, len = uncompressed_size[a + i];
+    return true;
+  };
+  auto start_read = [&](Batch& B) {
+    B.reader = std::thread([&B, &io_err, archive_fd, blob_size, blob_offset, io_threads]() {
+      parallel_rows(B.n, io_threads, [&](uint32_t i) {  // pread (decompress.rs:148-153)
+        uint64_t done = 0, len = blob_size[B.a + i];
         while (done < len) {
-          const ssize_t r = pwrite(out_fd[a + i], pin_out.p + out_off[i] + done, len - done, (off_t)(fdata_offset[a + i] + done));
+          const ssize_t r = pread(archive_fd, B.pin_in.p + B.in_off[i] + done, len - done, (off_t)(blob_offset[B.a + i] + done));
           if (r <= 0) { io_err = 1; return; }
           done += (uint64_t)r;
         }
       });
-      if (io_err) { c->err = "pwrite to output file failed"; return ZN_E_ARG; }
-    }
-    a = b;
+    });
+  };
+  auto start_write = [&](Batch& B) {
+    B.writer = std::thread([&B, &io_err, out_fd, uncompressed_size, fdata_offset, io_threads]() {
+      parallel_rows(B.n, io_threads, [&](uint32_t i) {  // pwrite at fdata_offset (decompress.rs:186-189)
+        const uint32_t s = B.status[i];
+        if ((s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) || out_fd[B.a + i] < 0) return;
+        uint64_t done = 0, len = uncompressed_size[B.a + i];
+        while (done < len) {
+          const ssize_t r = pwrite(out_fd[B.a + i], B.pin_out.p + B.out_off[i] + done, len - done, (off_t)(fdata_offset[B.a + i] + done));
+          if (r <= 0) { io_err = 1; return; }
+          done += (uint64_t)r;
+        }
+      });
+    });
+  };
+  int rc = ZN_OK;
+  uint64_t next = row_lo;
+  int cur = 0;
+  bool have = false;
+  if (next < row_hi) {
+    if (!claim(bt[0], next)) { c->err = "pinned staging allocation failed"; return ZN_E_NOMEM; }
+    next = bt[0].b;
+    start_read(bt[0]);
+    have = true;
   }
-  return ZN_OK;
+  while (have && rc == ZN_OK) {
+    Batch& B = bt[cur];
+    Batch& O = bt[cur ^ 1];
+    join(B.reader);
+    if (io_err) { c->err = "failed to read blob from archive"; rc = ZN_E_ARG; break; }
+    bool more = false;
+    if (next < row_hi) {  // the other buffer set is free once its writer is done
+      join(O.writer);
+      if (io_err) { c->err = "pwrite to output file failed"; rc = ZN_E_ARG; break; }
+      if (!claim(O, next)) { c->err = "pinned staging allocation failed"; rc = ZN_E_NOMEM; break; }
+      next = O.b;
+      start_read(O);
+      more = true;
+    }
+    rc = zn_decode_verify_batch(c, B.pin_in.p, B.in_off.data(), blob_size + B.a, compressed + B.a, uncompressed_size + B.a,
+                                checksums + 32 * B.a, out_fd ? B.pin_out.p : nullptr, out_fd ? B.out_off.data() : nullptr, B.n,
+                                B.status.data(), nullptr);
+    if (rc != ZN_OK) break;
+    for (uint32_t i = 0; i < B.n; i++) {  // fold, decompress.rs:140,156-184
+      stats->total_chunks++;
+      const uint32_t s = B.status[i];
+      if (s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) { stats->decode_errors++; continue; }
+      const uint64_t len = uncompressed_size[B.a + i];
+      stats->total_written_bytes += len;
+      if (s == ZN_S_OK) stats->verified_bytes += len;
+      else {
+        stats->corrupt_bytes += len;
+        if (corrupt_rows_out) corrupt_rows_out[stats->corrupt_rows] = B.a + i;
+        stats->corrupt_rows++;
+      }
+    }
+    if (out_fd) start_write(B);
+    have = more;
+    cur ^= 1;
+  }
+  for (auto& B : bt) { join(B.reader); join(B.writer); }
+  if (rc == ZN_OK && io_err) { c->err = "pwrite to output file failed"; rc = ZN_E_ARG; }
+  return rc;
 }
 
 #ifdef ZN_WS_DEBUG
