@@ -33,7 +33,7 @@ extern "C" long zn_hostemu_compress(int codec, const uint8_t* src, uint64_t n, u
     memcpy(dst, e, 9);
     return 9;
   }
-  std::vector<uint16_t> tab(1u << cz::kZstdHashLog);
+  std::vector<uint16_t> tab(1u << 14);
   std::vector<cz::V16> win(cz::WinHigh::kSmem / 16 + 2);
   std::vector<uint8_t> stage(cz::kZstdSlot + 64);
   std::vector<uint64_t> seqs(cz::kZstdMaxSeq);

@@ -84,7 +84,7 @@ ZN_HD uint32_t hash4(uint32_t v, uint32_t hlog) { return (v * 2654435761u) >> (3
 constexpr uint32_t kLz4Block = 64u * 1024u;
 constexpr uint32_t kLz4Slot = kLz4Block + kLz4Block / 255u + 32u;  // worst-case LZ4 block
 constexpr uint32_t kLz4HashLog = 12;                                 // 4096 x u16 = 8 KiB per warp
-constexpr uint32_t kZstdHashLog = 12;                                // 4096 x u16 = 8 KiB per warp
+constexpr uint32_t kZstdHashLog = 12;                                // default table: 4096 x u16 = 8 KiB per warp (Win::kHashLog)
 #ifndef ZN_LAZY_MATCH_W
 #define ZN_LAZY_MATCH_W 4
 #define ZN_LAZY_SKIP_W 16
@@ -103,16 +103,20 @@ constexpr uint32_t kLazyProbe = 4u + 4u * kLazyProbeWords;                      
 // Window geometry of the zstd match finder (see zstd_compress_block): W fresh bytes per window, H bytes of history
 // kept when it slides.  Shared memory per warp = H + W + 80 bytes + the 8 KiB table, which sets how many warps an
 // SM holds — the compressor is latency-bound, so speed follows the warp count and ratio follows W + H.
-template <uint32_t W, uint32_t H>
+#ifndef ZN_FAST_HASHLOG
+#define ZN_FAST_HASHLOG 12
+#endif
+template <uint32_t W, uint32_t H, uint32_t HL>
 struct Win {
   static constexpr uint32_t kBytes = W, kHist = H;
+  static constexpr uint32_t kHashLog = HL;           // 2^HL u16 table entries
   static constexpr uint32_t kData = H + W + 16u;   // staged bytes (multiple of 16; + alignment slop)
   static constexpr uint32_t kSmem = kData + 64u;   // + slack for the word-wise probes
   static_assert(kData % 16u == 0 && kData < 65535u && H + 160u < W, "window geometry");
 };
-using WinFast = Win<16384, 4096>;    // levels <= 2
-using WinMid = Win<32768, 8192>;     // levels 3..9
-using WinHigh = Win<49152, 14336>;   // levels >= 10
+using WinFast = Win<16384, 4096, ZN_FAST_HASHLOG>;    // levels <= 2
+using WinMid = Win<32768, 8192, 12>;     // levels 3..9
+using WinHigh = Win<49152, 14336, 12>;   // levels >= 10
 constexpr uint32_t kZstdMaxSeq = 32768;                              // sequences per 128 KiB block (min match 4)
 #ifndef ZN_CBLOCK
 #define ZN_CBLOCK kZstdBlockMax
@@ -860,7 +864,7 @@ ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nli
 //   stage   kZstdSlot bytes: literals are written from stage+3, the block payload ends up at stage + *payload_off
 //   seqs    kZstdMaxSeq packed sequences (global scratch)
 //   D       WN::kSmem bytes of shared memory, 16-byte aligned: the input window the match finder works in
-//   tab     2^kZstdHashLog x u16 (shared memory): window position of the latest occurrence of each hash
+//   tab     2^WN::kHashLog x u16 (shared memory): window position of the latest occurrence of each hash
 // The match finder never touches global memory: the input slides through D in windows of WN::kBytes, each keeping the
 // last WN::kHist bytes of history (16-byte copies, the window keeps the source's alignment).  Offsets therefore stay
 // below WN::kHist + WN::kBytes.  A match cut by a window edge is picked up again by the next window and merged back
@@ -871,7 +875,7 @@ struct alignas(16) V16 { uint32_t a, b, c, d; };
 template <class WN>
 ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t bstart, uint32_t n, uint8_t* stage,
                                    uint64_t* seqs, uint8_t* D, uint16_t* tab, uint32_t* payload_off) {
-  constexpr uint32_t kWinHist = WN::kHist, kWinData = WN::kData;
+  constexpr uint32_t kWinHist = WN::kHist, kWinData = WN::kData, kHashLog = WN::kHashLog;
   const uint32_t hist = bstart < kWinHist ? bstart : kWinHist;
   const uint8_t* g = slice + bstart - hist;  // global address of D[0] (made 16-byte aligned just below)
   const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
@@ -899,9 +903,9 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
     const uint32_t dend = bend < filled ? bend : filled;
     w_sync(w);
     if (first) {  // empty table, then the history of the previous block
-      for (uint32_t i = w.lane; i < (1u << kZstdHashLog); i += w.n) tab[i] = 0xFFFFu;
+      for (uint32_t i = w.lane; i < (1u << kHashLog); i += w.n) tab[i] = 0xFFFFu;
       w_sync(w);
-      for (uint32_t p = dlo + w.lane; p + 4u <= pos; p += w.n) tab[hash4(ld32s(D + p), kZstdHashLog)] = (uint16_t)p;
+      for (uint32_t p = dlo + w.lane; p + 4u <= pos; p += w.n) tab[hash4(ld32s(D + p), kHashLog)] = (uint16_t)p;
       w_sync(w);
       first = false;
     }
@@ -922,7 +926,7 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       const uint32_t p = pos + w.lane;
       const bool valid = p < plimit;
       const uint32_t v = valid ? ld32s(D + p) : 0u;
-      const uint32_t h = hash4(v, kZstdHashLog);
+      const uint32_t h = hash4(v, kHashLog);
       const uint32_t cand = valid ? tab[h] : 0xFFFFu;
       bool ok = valid && cand < p && ld32s(D + cand) == v;
       ZN_CP(1);
@@ -989,7 +993,7 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
       if (valid && p < next) tab[h] = (uint16_t)p;
       if (next > pos + w.n) {
         const uint32_t lim = next < pos + w.n + kZstdInsertSpan ? next : pos + w.n + kZstdInsertSpan;
-        for (uint32_t q = pos + w.n + w.lane; q < lim && q + 4u <= dend; q += w.n) tab[hash4(ld32s(D + q), kZstdHashLog)] = (uint16_t)q;
+        for (uint32_t q = pos + w.n + w.lane; q < lim && q + 4u <= dend; q += w.n) tab[hash4(ld32s(D + q), kHashLog)] = (uint16_t)q;
       }
       w_sync(w);
       pos = next;
@@ -1007,7 +1011,7 @@ ZN_HD uint32_t zstd_compress_block(const Warp& w, const uint8_t* slice, uint32_t
     w_sync(w);
     for (uint32_t c = w.lane; c < (filled - S) / 16u; c += w.n)  // source and destination never overlap: S > filled - S
       *reinterpret_cast<V16*>(D + 16u * c) = *reinterpret_cast<const V16*>(D + S + 16u * c);
-    for (uint32_t i = w.lane; i < (1u << kZstdHashLog); i += w.n) {
+    for (uint32_t i = w.lane; i < (1u << kHashLog); i += w.n) {
       const uint32_t e = tab[i];
       tab[i] = (e != 0xFFFFu && e >= S) ? (uint16_t)(e - S) : (uint16_t)0xFFFFu;
     }

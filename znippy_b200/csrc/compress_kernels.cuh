@@ -24,7 +24,7 @@ constexpr int kZstdWarpsPerCta = 1;
 template <class WN>
 struct ZstdLaunch {
   static constexpr uint32_t kWindow = (WN::kSmem + 127u) & ~127u;
-  static constexpr uint32_t kSmemBytes = kWindow + (2u << cz::kZstdHashLog);
+  static constexpr uint32_t kSmemBytes = kWindow + (2u << WN::kHashLog);
   static constexpr uint32_t kCtasPerSm = (228u * 1024u) / (kSmemBytes + 1024u);
 };
 
