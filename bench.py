@@ -119,14 +119,17 @@ def build_rows(entries, level_for):
     return blobs, lens, np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy(), np.array(comp, np.uint8)
 
 
+def text2g_desc(gib: float, rows: int) -> str:
+    return (f"configs[1]: single {gib:g} GiB text-pattern file per GPU = {rows} rows x 8 MiB slices, zstd L19 frames "
+            "(libzstd 1.5.5), decode + blake3 + 32-byte compare, output materialised in HBM")
+
+
 def build_workload(name: str, gib: float, rank: int):
     """Returns (blobs, lens, digests, compressed flags, description)."""
     if name == "text2g":
         total = int(gib * (1 << 30))
         blobs, lens, digs = build_text_corpus(total, first_byte=rank * total)
-        return blobs, lens, digs, np.ones(len(blobs), np.uint8), (
-            f"configs[1]: single {gib:g} GiB text-pattern file per GPU = {len(blobs)} rows x 8 MiB slices, zstd L19 frames "
-            "(libzstd 1.5.5), decode + blake3 + 32-byte compare, output materialised in HBM")
+        return blobs, lens, digs, np.ones(len(blobs), np.uint8), text2g_desc(gib, len(blobs))
     if name == "small100k":  # configs[0] shape: 100 000 x text(10 240) (perf_bench.rs:133-141), one row per file
         s = text_slice(0, 10240)
         b, d = _zstd_compress(_libzstd(), s, 19), _digest(s)
@@ -315,9 +318,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * t_tot / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": {"workload": "configs[1]: single 2 GiB text-pattern file, zstd L19 frames, decode + blake3 verify",
-                   "note": "reference CPU worker loop (decompress.rs:105-192) restated in C over libzstd 1.5.5; the Rust "
-                           "reference itself cannot be built in this image (no cargo, OpenZL fetched at build time)"},
+        "config": {"workload": text2g_desc(args.gib, int(args.gib * (1 << 30)) // SLICE),  # same string as our arm's
+                   "note": "reference CPU worker loop (decompress.rs:105-192) restated in C over libzstd 1.5.5, output "
+                           "materialised in host memory; the Rust reference itself cannot be built in this image (no "
+                           "cargo, OpenZL fetched at build time); each step is a bounded sample of the workload"},
         "cpu_baseline": {"value": round(v, 3), "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"{sample_rows} rows x 8 MiB per step ({sample_rows * 8} MiB of the 2 GiB file)"},
         "e2e": {"value": round(v, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
