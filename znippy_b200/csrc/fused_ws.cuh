@@ -43,7 +43,8 @@ constexpr uint32_t kWsTeamBytes =
 constexpr uint32_t kWsSmemBytes = kWsTeams * kWsTeamBytes + kWsHashWarps * kB3SmemPerWarp;
 static_assert(kWsSmemBytes <= 227u * 1024u, "one CTA per SM");
 
-// Device-wide tile queue of one plan run: ctl[0] = head (consumers), ctl[1] = tail (producers), ent[i] = 0 until filled,
+// Device-wide tile queue of one plan run: ctl[0] = head (consumers), ctl[1] = tail (producers), ctl[2] = stall flag
+// (watchdog), ent[i] = 0 until filled,
 // then (list index << 32) | (tile + 1).  Zeroed before every launch.
 struct WsQueue {
   uint32_t* ctl;
@@ -160,7 +161,17 @@ __global__ void __launch_bounds__(kWsThreads, 1)
       idx = atomicAdd(q.ctl, 1u);
       if (idx < q.total) {
         unsigned long long e;
-        while ((e = *reinterpret_cast<volatile unsigned long long*>(q.ent + idx)) == 0ull) __nanosleep(100);
+        uint32_t spins = 0;
+        while ((e = *reinterpret_cast<volatile unsigned long long*>(q.ent + idx)) == 0ull) {
+          __nanosleep(100);
+          // Watchdog: producers never wait, so an entry that stays empty for seconds means a bug, not load.  Give up
+          // (ctl[2] != 0 makes zn_plan_results fail) instead of hanging the GPU.
+          if (++spins > (1u << 25) || *reinterpret_cast<volatile uint32_t*>(q.ctl + 2)) {
+            atomicExch(q.ctl + 2, 1u);
+            idx = 0xFFFFFFFFu;
+            break;
+          }
+        }
         __threadfence();
         e_lo = (uint32_t)e;
         e_hi = (uint32_t)(e >> 32);

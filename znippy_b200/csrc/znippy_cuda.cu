@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -60,6 +61,7 @@ struct zn_plan {
   uint32_t *d_cvs = nullptr, *d_digests = nullptr, *d_expect = nullptr, *d_status = nullptr, *d_produced = nullptr,
            *d_counter = nullptr, *d_wsq = nullptr;  // d_wsq: tile queue of the warp-specialised fused kernel (fused_ws.cuh)
   uint32_t ws_tiles = 0;
+  bool ran_ws = false;             // the last run used the warp-specialised fused kernel
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool ran = false;
@@ -75,6 +77,7 @@ struct zn_plan {
   uint32_t grp_chunk_lo[kMaxGroups + 1] = {0};
   cudaEvent_t evg[kMaxGroups] = {nullptr};
   cudaEvent_t ev_join = nullptr;
+  bool uploads_synced = false;  // the plan's arrays (uploaded on the ctx stream) are known to have landed
   std::vector<uint64_t> h_cap;
   std::vector<uint8_t> h_comp;
   std::vector<uint32_t> h_prefix;
@@ -307,8 +310,10 @@ static int plan_set_groups(zn_plan* p, int groups) {
   }
   p->groups = groups;
   if (!ldec.empty()) {
+    // pageable source: the call returns once the bytes sit in the driver's staging buffer, so `ldec` may go out of
+    // scope; the copy itself is ordered before the kernels on the stream (no host-side wait for the DMA)
     ZN_CUDA(c, cudaMemcpyAsync(p->d_list_dec, ldec.data(), ldec.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    ZN_CUDA(c, cudaStreamSynchronize(c->stream));
+    p->uploads_synced = false;  // zn_plan_run waits for them if it is given another stream
   }
   return ZN_OK;
 }
@@ -454,6 +459,10 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
   cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
   if (p->n && !d_blobs) return ZN_E_ARG;
   if (p->n_dec && !d_out) return ZN_E_ARG;
+  if (st != c->stream && !p->uploads_synced) {  // the plan was uploaded on the ctx stream: order it before this stream's kernels
+    ZN_CUDA(c, cudaStreamSynchronize(c->stream));
+    p->uploads_synced = true;
+  }
   uint32_t launches = 0;
   ZN_CUDA(c, cudaEventRecord(p->ev[0], st));
   if (p->n) {
@@ -497,6 +506,7 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
         if (p->fused_hash && p->groups == 1 && !(fm && !strcmp(fm, "team"))) {
           // warp-specialised fused kernel: one CTA per SM, two decode teams each; its tile queue starts empty
           ZN_CUDA(c, cudaMemsetAsync(p->d_wsq, 0, 16 + 8 * (size_t)p->ws_tiles, st));
+          p->ran_ws = true;
           WsQueue q{p->d_wsq, reinterpret_cast<unsigned long long*>(p->d_wsq + 4), p->ws_tiles};
           uint32_t wgrid = (uint32_t)c->sm_count;  // every SM hashes, whether or not one of its teams gets a blob
           if (const char* gs = getenv("ZN_WS_GRID")) wgrid = std::max(1, std::min<int>((int)wgrid, atoi(gs)));
@@ -568,7 +578,10 @@ extern "C" int zn_plan_results(zn_plan* p, uint32_t* h_status, uint8_t* h_digest
   cudaSetDevice(c->device);
   if (h_status && p->n) ZN_CUDA(c, cudaMemcpyAsync(h_status, p->d_status, (size_t)p->n * 4, cudaMemcpyDeviceToHost, p->last_stream));
   if (h_digests && p->n) ZN_CUDA(c, cudaMemcpyAsync(h_digests, p->d_digests, (size_t)p->n * 32, cudaMemcpyDeviceToHost, p->last_stream));
+  uint32_t stall = 0;
+  if (p->d_wsq && p->ran_ws) ZN_CUDA(c, cudaMemcpyAsync(&stall, p->d_wsq + 2, 4, cudaMemcpyDeviceToHost, p->last_stream));
   ZN_CUDA(c, cudaStreamSynchronize(p->last_stream));
+  if (stall) { c->err = "fused decode+hash kernel stalled (internal error): results are incomplete"; return ZN_E_CUDA; }
   return ZN_OK;
 }
 
@@ -689,6 +702,10 @@ extern "C" int zn_decode_verify_batch(zn_ctx* c, const uint8_t* blobs_base, cons
   if (out_base && n && !out_off) return ZN_E_ARG;
   if (n == 0) return ZN_OK;
   cudaSetDevice(c->device);
+  const bool prof = getenv("ZN_HOST_PROF") != nullptr;  // development: host-side stage times of this call on stderr
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tp[8] = {0};
+  tp[0] = now();
   Layout Li = make_layout(blob_off, blob_len, n);
   // output layout: mirror the caller's when it is compact, so that one D2H copy returns everything
   Layout Lo;
@@ -703,16 +720,20 @@ extern "C" int zn_decode_verify_batch(zn_ctx* c, const uint8_t* blobs_base, cons
     for (uint32_t i = 0; i < n; i++) { Lo.dev_off[i] = cur; cur += (need[i] + 15) & ~15ull; }
     Lo.total = cur;
   }
+  tp[1] = now();
   int rc = ensure(c, &c->d_in, &c->d_in_cap, Li.total);
   if (rc) return rc;
   rc = ensure(c, &c->d_out, &c->d_out_cap, Lo.total);
   if (rc) return rc;
   rc = copy_in(c, c->d_in, blobs_base, blob_off, blob_len, n, Li);
   if (rc) return rc;
+  tp[2] = now();
   zn_plan* p = plan_build(c, PLAN_DECODE_VERIFY, n, Li.dev_off.data(), blob_len, compressed, Lo.dev_off.data(), out_len,
                           expect_digest, out_base != nullptr);
   if (!p) return ZN_E_NOMEM;
+  tp[3] = now();
   rc = zn_plan_run(p, c->d_in, c->d_out, nullptr);
+  tp[4] = now();
   if (rc == ZN_OK && out_base) {
     if (Lo.span) {
       if (Lo.span_bytes)
@@ -728,7 +749,12 @@ extern "C" int zn_decode_verify_batch(zn_ctx* c, const uint8_t* blobs_base, cons
     if (rc != ZN_OK) c->err = std::string("D2H: ") + cudaGetErrorString(cudaGetLastError());
   }
   if (rc == ZN_OK) rc = zn_plan_results(p, status, digest_out);
+  tp[5] = now();
   zn_plan_destroy(p);
+  tp[6] = now();
+  if (prof)
+    fprintf(stderr, "zn_decode_verify_batch n=%u: layout %.3f  ensure+copy_in %.3f  plan_build %.3f  enqueue %.3f  wait+results %.3f  destroy %.3f ms\n",
+            n, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], tp[6] - tp[5]);
   return rc;
 }
 
