@@ -204,3 +204,34 @@ def test_native_random_access(A, tmp_path, oracle):
     ar = A.ZnippyArchive.open(path)
     got = ar.extract_files(["big.bin", "f/001.txt"])
     assert isinstance(got[0], Exception) and got[1] == want["f/001.txt"]
+
+
+def test_read_worker_pipeline_and_file_windows(A, tmp_path, oracle, monkeypatch):
+    """The native read worker beyond one staging batch and beyond one window of open output files: a 288 MiB pattern file
+    (extract: 4-5 batches, pread / GPU / pwrite overlapped over two buffer sets), 272 MiB of incompressible data (verify:
+    batches cut on the blob bytes), and 60 small files extracted with at most 7 descriptors open at a time."""
+    O = oracle
+    big = O.gen_text(288 << 20)
+    rnd = O.gen_random(272 << 20)
+    small = [(f"s/{i % 5}/f{i}.txt", (f"file {i} " * (50 + 37 * i)).encode()) for i in range(60)]
+    path, rep = _pack(A, tmp_path, [("big.txt", big), ("rnd.bin", rnd)] + small)
+    assert rep.total_files == 62
+    vr = A.decompress_archive(path, False, str(tmp_path))
+    total = big.size + rnd.size + sum(len(d) for _, d in small)
+    assert vr.corrupt_files == 0 and vr.verified_bytes == total and vr.chunks == 36 + 34 + 60
+    monkeypatch.setenv("ZN_MAX_OPEN_FILES", "7")
+    out = tmp_path / "x"
+    vr = A.decompress_archive(path, True, str(out))
+    assert vr.corrupt_files == 0 and vr.total_files == 62 and vr.total_bytes == total
+    assert O.blake3((out / "big.txt").read_bytes()) == O.blake3(big)
+    assert O.blake3((out / "rnd.bin").read_bytes()) == O.blake3(rnd)
+    for p, d in small:
+        assert (out / p).read_bytes() == d
+    # a flipped byte inside a late batch is still attributed to its row
+    with open(path, "r+b") as f:
+        f.seek(200 << 20)
+        b = f.read(1)
+        f.seek(200 << 20)
+        f.write(bytes([b[0] ^ 0x40]))
+    vr = A.decompress_archive(path, False, str(tmp_path))
+    assert vr.corrupt_files == 1 and vr.verified_bytes == total - (8 << 20)

@@ -763,6 +763,7 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
       const size_t lim = rl.rlim_cur == RLIM_INFINITY ? 65536 : (size_t)rl.rlim_cur;
       max_open = std::max<size_t>(16, std::min<size_t>(lim > 128 ? (lim - 64) / 2 : 16, 16384));
     }
+    if (const char* e = getenv("ZN_MAX_OPEN_FILES")) max_open = std::max(1, atoi(e));  // tests: force several windows
   }
   const int afd = open(index_path, O_RDONLY);
   if (afd < 0) { set_err(err, errcap, "cannot open archive"); rc = ZN_E_ARG; }
