@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
           __nanosleep(100);
           // Watchdog: producers never wait, so an entry that stays empty for seconds means a bug, not load.  Give up
           // (ctl[2] != 0 makes zn_plan_results fail) instead of hanging the GPU.
-          if (++spins > (1u << 25) || *reinterpret_cast<volatile uint32_t*>(q.ctl + 2)) {
+          if (++spins > (1u << 25) || ((spins & 4095u) == 0 && *reinterpret_cast<volatile uint32_t*>(q.ctl + 2))) {
             atomicExch(q.ctl + 2, 1u);
             idx = 0xFFFFFFFFu;
             break;
