@@ -216,40 +216,39 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
   finish_blob(d, blob, o, digests, expect, status);
 }
 
-// K3c: large blobs: one CTA per blob, every level spread over the CTA, in place (read -> barrier -> write).
+// K3c: large blobs: one CTA per blob, every level spread over the CTA.  Levels ping-pong between the blob's slots in
+// `cvs` and in `cvs2` (same layout), so a level needs no barrier between its items — the 8 warps run their (load, load,
+// compress, store) items independently and hide each other's L2 round trips — only one barrier per level.
 __global__ void __launch_bounds__(256) k_b3_tree_large(const BlobDesc* __restrict__ blobs,
                                                        const uint32_t* __restrict__ list,
-                                                       uint32_t* cvs, uint32_t* __restrict__ digests,
+                                                       uint32_t* cvs, uint32_t* cvs2, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
                                                        uint32_t* __restrict__ status, uint32_t one) {
   const uint32_t blob = list[blockIdx.x];
   const BlobDesc d = blobs[blob];
-  uint32_t* base = cvs + d.cv_base * 8;
+  uint32_t* src = cvs + d.cv_base * 8;
+  uint32_t* dst = cvs2 + d.cv_base * 8;
   uint32_t n = d.n_chunks;
   uint32_t l[8], r[8], o[8];
   while (n > 1) {
     const uint32_t pairs = n >> 1, items = pairs + (n & 1);  // the odd tail is a pass-through item
-    for (uint32_t j0 = 0; j0 < items; j0 += blockDim.x) {
-      const uint32_t j = j0 + threadIdx.x;
-      const bool act = j < items;
-      if (act) {
-        b3::load_cv(base + (uint64_t)(2 * j) * 8, l);
-        if (j < pairs) {
-          b3::load_cv(base + (uint64_t)(2 * j + 1) * 8, r);
-          b3::parent(l, r, n == 2, o, one);
-        } else {
+    for (uint32_t j = threadIdx.x; j < items; j += blockDim.x) {
+      b3::load_cv(src + (uint64_t)(2 * j) * 8, l);
+      if (j < pairs) {
+        b3::load_cv(src + (uint64_t)(2 * j + 1) * 8, r);
+        b3::parent(l, r, n == 2, o, one);
+      } else {
 #pragma unroll
-          for (int i = 0; i < 8; i++) o[i] = l[i];
-        }
+        for (int i = 0; i < 8; i++) o[i] = l[i];
       }
-      __syncthreads();  // reads of slots [2*j0, 2*j0+2*blockDim) are done before slots [j0, j0+blockDim) are overwritten
-      if (act) b3::store_cv(base + (uint64_t)j * 8, o);
+      b3::store_cv(dst + (uint64_t)j * 8, o);
     }
     __syncthreads();
+    uint32_t* t = src; src = dst; dst = t;
     n = items;
   }
   if (threadIdx.x == 0) {
-    b3::load_cv(base, o);
+    b3::load_cv(src, o);
     finish_blob(d, blob, o, digests, expect, status);
   }
 }

@@ -59,7 +59,8 @@ struct zn_plan {
   uint32_t *d_list_dec = nullptr, *d_list_small = nullptr, *d_list_large = nullptr;
   uint32_t *d_piece_blob = nullptr, *d_piece_idx = nullptr;
   uint32_t *d_cvs = nullptr, *d_digests = nullptr, *d_expect = nullptr, *d_status = nullptr, *d_produced = nullptr,
-           *d_counter = nullptr, *d_wsq = nullptr;  // d_wsq: tile queue of the warp-specialised fused kernel (fused_ws.cuh)
+           *d_counter = nullptr, *d_wsq = nullptr, *d_cvs2 = nullptr;
+  // d_wsq: tile queue of the warp-specialised fused kernel (fused_ws.cuh); d_cvs2: second level buffer of the large-blob tree
   uint32_t ws_tiles = 0;
   bool ran_ws = false;             // the last run used the warp-specialised fused kernel
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -394,6 +395,7 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_piece_blob, pblob.data(), pblob.size()) && upload(c, &p->d_piece_idx, pidx.data(), pidx.size()) &&
             upload(c, &p->d_expect, (const uint32_t*)expect, expect ? (size_t)n * 8 : 0) &&
             upload(c, &p->d_cvs, (const uint32_t*)nullptr, (size_t)chunks * 8) &&
+            upload(c, &p->d_cvs2, (const uint32_t*)nullptr, llarge.empty() ? 0 : (size_t)chunks * 8) &&
             upload(c, &p->d_digests, (const uint32_t*)nullptr, (size_t)n * 8) &&
             upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
             upload(c, &p->d_counter, (const uint32_t*)nullptr, zn_plan::kMaxGroups) &&
@@ -441,7 +443,7 @@ extern "C" void zn_plan_destroy(zn_plan* p) {
   cudaSetDevice(p->ctx->device);
   if (p->ran) cudaStreamSynchronize(p->last_stream);
   void* ptrs[] = {p->d_blobs, p->d_chunk_prefix, p->d_list_dec, p->d_list_small, p->d_list_large, p->d_piece_blob,
-                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter, p->d_wsq};
+                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter, p->d_wsq, p->d_cvs2};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, p->ctx->stream);
   for (auto& e : p->ev)
@@ -559,7 +561,7 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
     launches++;
   }
   if (p->n_large) {
-    k_b3_tree_large<<<p->n_large, 256, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_digests, p->d_expect, p->d_status, 1u);
+    k_b3_tree_large<<<p->n_large, 256, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_cvs2, p->d_digests, p->d_expect, p->d_status, 1u);
     launches++;
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[3], st));
