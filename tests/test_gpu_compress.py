@@ -2,6 +2,7 @@
 (stock libzstd 1.5.5 / liblz4 1.9.4 and the oracle restatements) to identical bytes, the digest must be the blake3 of
 the ORIGINAL bytes (stream_packer.rs:219), and the GPU decoder must round-trip its own output.  Also the reference's
 own codec unit tests (codec.rs:84-123) through the mirrored API."""
+import sys
 import threading
 
 import numpy as np
@@ -22,7 +23,15 @@ def _cases(O):
         "empty": np.zeros(0, np.uint8), "one": np.array([7], np.uint8), "t11": O.gen_text(11), "t13": O.gen_text(13),
         "text10k": O.gen_text(10240), "text3m": O.gen_text(3 << 20), "bin1m+17": O.gen_binary((1 << 20) + 17),
         "real": O.real_text(1_500_000), "rand": O.gen_random(300_000), "zeros": np.zeros(500_000, np.uint8),
-        "small": O.gen_small_alphabet(200_000), "rle": O.gen_rle_literals(), "inc": O.gen_incompressible(100_000, 3)}
+        "small": O.gen_small_alphabet(200_000), "rle": O.gen_rle_literals(), "inc": O.gen_incompressible(100_000, 3),
+        # more than 128 literal symbols: the Huffman tree goes out as FSE-compressed weights
+        "skew256": _skew256(400_000), "exe": np.fromfile(sys.executable, np.uint8)[:900_000]}
+
+
+def _skew256(n, seed=5):
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, 257) ** 1.1
+    return rng.choice(256, n, p=p / p.sum()).astype(np.uint8)
 
 
 @pytest.mark.parametrize("codec_name", ["zstd", "lz4"])

@@ -204,12 +204,20 @@ def test_hostemu_block_parallel_pipeline(emu, oracle):
             assert out == oo
 
 
+def _skew256(n, seed=5):
+    """Zipf-like bytes over all 256 values: compressible literals whose Huffman tree needs more than 128 weights."""
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, 257) ** 1.1
+    return rng.choice(256, n, p=p / p.sum()).astype(np.uint8)
+
+
 def test_hostemu_compressors_decode_with_stock_libraries(emu, oracle):
     O = oracle
     z, l = O.libzstd(), O.liblz4()
     cases = [np.zeros(0, np.uint8), np.array([7], np.uint8), O.gen_text(13), O.gen_text(10240), O.gen_text(1 << 20),
              O.gen_binary((1 << 20) + 17), O.real_text(400_000), O.gen_random(200_000), np.zeros(300_000, np.uint8),
-             O.gen_small_alphabet(150_000), O.gen_rle_literals()]
+             O.gen_small_alphabet(150_000), O.gen_rle_literals(), _skew256(300_000),
+             np.fromfile(sys.executable, np.uint8)[:700_000]]  # > 128 literal symbols: FSE-compressed Huffman weights
     for d in cases:
         for codec in (11, 12):  # the two larger window geometries of the zstd match finder (levels 3..9, >= 10)
             assert z.decompress(emu.compress(codec, d), len(d)) == d.tobytes()

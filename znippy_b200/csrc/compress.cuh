@@ -704,7 +704,7 @@ ZN_HD void huf_build(const Warp& w, const uint32_t* cnt, uint8_t* nb, uint16_t* 
   const uint32_t present = w_sum(w, my_present), last = w_max(w, my_last);
   if (w.lane == 0) { res[0] = 0; res[1] = last; }
   w_sync(w);
-  if (present < 2 || last > 128) return;  // direct weights describe at most 128 symbols + the implied last one
+  if (present < 2) return;
   uint32_t* wt = work;                                         // 512 entries
   uint16_t* parent = reinterpret_cast<uint16_t*>(work + 512);  // 512 entries
   uint16_t* leaf_of = parent + 512;                            // present entries: symbol of leaf i
@@ -777,6 +777,51 @@ ZN_HD void huf_build(const Warp& w, const uint32_t* cnt, uint8_t* nb, uint16_t* 
   res[0] = pos == (1u << maxd) ? maxd : 0u;
 }
 
+// Huffman weights, FSE-compressed (RFC 8878 §4.2.1.1: table log <= 6, two interleaved states, header byte = size of the
+// stream < 128).  One thread.  Writes header byte + table description + stream at `out` and returns the byte count, or 0
+// when this form is not possible (fewer than two distinct weights, or 128 bytes and more).
+ZN_HD uint32_t huf_write_weights_fse(uint8_t* out, const uint8_t* wts, uint32_t n, uint32_t* scratch) {
+  if (n < 2) return 0;
+  uint32_t* cnt = scratch;                                    // 16 words
+  int16_t* norm = reinterpret_cast<int16_t*>(scratch + 16);   // 16 entries
+  FseCTable* ct = reinterpret_cast<FseCTable*>(scratch + 32);
+  FseBuildScratch* bs = reinterpret_cast<FseBuildScratch*>(scratch + 32 + (sizeof(FseCTable) + 3) / 4);
+  for (int k = 0; k < 16; k++) cnt[k] = 0;
+  uint32_t maxw = 0, present = 0;
+  for (uint32_t k = 0; k < n; k++) { if (!cnt[wts[k]]++) present++; if (wts[k] > maxw) maxw = wts[k]; }
+  if (present < 2) return 0;
+  int hb = hibit32(n - 1) - 2;
+  const uint32_t log = hb < 5 ? 5u : (hb > 6 ? 6u : (uint32_t)hb);
+  fse_normalize(norm, cnt, maxw + 1, n, log);
+  const uint32_t hdr = fse_write_ncount(out + 1, norm, maxw + 1, log);
+  fse_build_ctable(ct, norm, (int)maxw + 1, (int)log, bs);
+  BitWriter bw{out + 1 + hdr, 0, 0};
+  FseCState s1, s2;
+  uint32_t k = n;
+  if (n & 1u) {
+    s1.init(ct, wts[--k]);
+    s2.init(ct, wts[--k]);
+    s1.encode(bw, ct, wts[--k]);
+    bw.flush();
+  } else {
+    s2.init(ct, wts[--k]);
+    s1.init(ct, wts[--k]);
+  }
+  while (k > 0) {
+    s2.encode(bw, ct, wts[--k]);
+    s1.encode(bw, ct, wts[--k]);
+    bw.flush();
+  }
+  s2.flush(bw, ct);
+  bw.flush();
+  s1.flush(bw, ct);
+  bw.close();
+  const uint32_t size = (uint32_t)(bw.p - (out + 1));
+  if (size == 0 || size >= 128) return 0;
+  out[0] = (uint8_t)size;
+  return 1 + size;
+}
+
 ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nlit, uint8_t* dst, uint32_t* scratch) {
   if (nlit < 64) return 0;
   uint32_t* cnt = scratch;                                        // [0, 256)
@@ -803,7 +848,26 @@ ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nli
     sbytes[k] = (bits + 8) >> 3;  // + end marker, rounded up
   }
   const uint32_t nweights = last;  // symbols 0..last-1 explicit, `last` implied
-  const uint32_t tree = 1 + (nweights + 1) / 2;
+  // tree description: direct 4-bit weights (<= 128 of them) or FSE-compressed weights, whichever is smaller
+  uint8_t* tdesc = reinterpret_cast<uint8_t*>(scratch + 1600);  // <= 130 bytes
+  if (w.lane == 0) {
+    uint8_t* wts = reinterpret_cast<uint8_t*>(scratch + 1640);  // 256 bytes
+    for (uint32_t i = 0; i < nweights; i++) wts[i] = nb[i] ? (uint8_t)(maxbits + 1 - nb[i]) : (uint8_t)0;
+    const uint32_t direct = nweights <= 128 ? 1 + (nweights + 1) / 2 : 0u;
+    uint32_t sz = huf_write_weights_fse(tdesc, wts, nweights, scratch + 1712);
+    if (!sz || (direct && direct <= sz)) {
+      sz = direct;
+      if (direct) {
+        tdesc[0] = (uint8_t)(127 + nweights);
+        for (uint32_t i = 0; i < nweights; i += 2)
+          tdesc[1 + i / 2] = (uint8_t)((wts[i] << 4) | (i + 1 < nweights ? wts[i + 1] : 0));
+      }
+    }
+    pub[6] = sz;
+  }
+  w_sync(w);
+  const uint32_t tree = pub[6];
+  if (!tree) return 0;
   const uint32_t comp = tree + (ns == 4 ? 6u : 0u) + sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
   uint32_t hdr, sf;
   if (ns == 1) { if (comp >= 1024) return 0; hdr = 3; sf = 0; }
@@ -817,11 +881,7 @@ ZN_HD uint32_t zstd_huf_literals(const Warp& w, const uint8_t* lit, uint32_t nli
     else if (hdr == 4) { const uint32_t v = 2u | (sf << 2) | (nlit << 4) | (comp << 18); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); }
     else { const uint64_t v = 2ull | ((uint64_t)sf << 2) | ((uint64_t)nlit << 4) | ((uint64_t)comp << 22); for (int i = 0; i < 5; i++) dst[i] = (uint8_t)(v >> (8 * i)); }
     uint8_t* t = dst + hdr;
-    t[0] = (uint8_t)(127 + nweights);
-    for (uint32_t i = 0; i < nweights; i += 2) {
-      const uint32_t w0 = nb[i] ? maxbits + 1 - nb[i] : 0, w1 = (i + 1 < nweights && nb[i + 1]) ? maxbits + 1 - nb[i + 1] : 0;
-      t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
-    }
+    for (uint32_t i = 0; i < tree; i++) t[i] = tdesc[i];
     if (ns == 4) {
       uint8_t* j = t + tree;
       j[0] = (uint8_t)sbytes[0]; j[1] = (uint8_t)(sbytes[0] >> 8); j[2] = (uint8_t)sbytes[1]; j[3] = (uint8_t)(sbytes[1] >> 8);
