@@ -76,7 +76,7 @@ def test_frames_decode_with_reference_decoders(codec, oracle, codec_name):
 
 def test_ratio_against_reference_libraries(codec, oracle):
     """Ratio gap vs the reference libraries, stated: pattern corpora within 10 % of libzstd level 19 / liblz4; real
-    text within 25 % of libzstd level 1 at every effort (Huffman literals, FSE-described sequence tables, repeat
+    text within 25 % of libzstd level 1 at every effort (Huffman literals with FSE-compressed or direct weights, FSE-described sequence tables, repeat
     offsets, warp-wide lazy match selection in a 20-56 KiB window — DESIGN.md §4.3)."""
     O = oracle
     z, l = O.libzstd(), O.liblz4()
