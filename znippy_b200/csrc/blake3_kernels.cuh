@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
 // K3c: large blobs: one CTA per blob, every level spread over the CTA.  Levels ping-pong between the blob's slots in
 // `cvs` and in `cvs2` (same layout), so a level needs no barrier between its items — the 8 warps run their (load, load,
 // compress, store) items independently and hide each other's L2 round trips — only one barrier per level.
-__global__ void __launch_bounds__(256) k_b3_tree_large(const BlobDesc* __restrict__ blobs,
+__global__ void __launch_bounds__(512) k_b3_tree_large(const BlobDesc* __restrict__ blobs,
                                                        const uint32_t* __restrict__ list,
                                                        uint32_t* cvs, uint32_t* cvs2, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,

@@ -561,7 +561,7 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
     launches++;
   }
   if (p->n_large) {
-    k_b3_tree_large<<<p->n_large, 256, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_cvs2, p->d_digests, p->d_expect, p->d_status, 1u);
+    k_b3_tree_large<<<p->n_large, 512, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_cvs2, p->d_digests, p->d_expect, p->d_status, 1u);
     launches++;
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[3], st));
