@@ -346,3 +346,36 @@ def test_fused_decode_hash_kernels(codec, oracle, mode, monkeypatch):
     st, _ = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs2], [1] * len(blobs2), lens, b"".join(ex), out2, ooff)
     assert st[5] == codec.S_DIGEST_MISMATCH and st[2] != 0
     assert [int(x) for i, x in enumerate(st) if i not in (2, 5)] == [0] * (len(blobs) - 2)
+
+
+def test_fused_kernel_survives_corrupt_blobs(codec, oracle):
+    """Bit flips in large pattern blobs through the default (warp-specialised fused) path: the call returns, damaged rows
+    report an error or a digest mismatch, every other row stays bit-exact (a producer that fails must still queue all of
+    its tiles, or the hash warps would wait for ever — the kernel's watchdog would turn that into an error return)."""
+    O = oracle
+    z = O.libzstd()
+    datas = [O.gen_text(4 << 20), O.gen_binary(3 << 20), O.gen_text((2 << 20) + 5), O.gen_binary(5 << 20), O.gen_text(1 << 20),
+             O.gen_binary(2 << 20)]
+    good = [z.compress(d, 19) for d in datas]
+    want = [O.blake3(d.tobytes()) for d in datas]
+    lens = [d.size for d in datas]
+    ooff = np.concatenate([[0], np.cumsum([(n + 15) // 16 * 16 for n in lens])])[:-1]
+    out = np.zeros(int(ooff[-1]) + lens[-1] + 16, np.uint8)
+    rng = random.Random(11)
+    for trial in range(16):
+        victim = rng.randrange(len(good))
+        bad = bytearray(good[victim])
+        pos = rng.randrange(4, len(bad))
+        bad[pos] ^= 1 << rng.randrange(8)
+        blobs = list(good)
+        blobs[victim] = bytes(bad)
+        buf, offs = _pack(blobs)
+        st, dg = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs], [1] * len(blobs), lens, b"".join(want), out, ooff)
+        for i in range(len(blobs)):
+            if i != victim:
+                assert st[i] == 0 and dg[i].tobytes() == want[i], (trial, i)
+        ref_rc, ref_out = O.zstd_decompress(bytes(bad), lens[victim])
+        if ref_rc == 0 and ref_out == datas[victim].tobytes():
+            assert st[victim] == 0  # the flip hit a bit that does not matter (e.g. the unverified frame checksum)
+        else:
+            assert st[victim] != 0, (trial, victim, pos)
