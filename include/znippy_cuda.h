@@ -224,11 +224,17 @@ void zn_plan_destroy(zn_plan* plan);
 int zn_plan_run(zn_plan* plan, const uint8_t* d_blobs, uint8_t* d_out, void* stream);
 /* Waits for the last run and copies results back. status / digests nullable. */
 int zn_plan_results(zn_plan* plan, uint32_t* h_status, uint8_t* h_digests);
-/* Schedule of a decode+verify plan.  groups <= 1: decode, then hash, then tree, back to back on one stream (per-stage
- * times of zn_plan_last_ms are then exact).  groups > 1 (opt-in; env ZN_OVERLAP_GROUPS sets the default for batches >= 256 MiB):
- * rows are cut into `groups` contiguous ranges and the HBM-bound decode of range g+1 overlaps the ALU-bound blake3 of
- * range g on a second stream of the context. */
+/* Kept for ABI stability; has no effect.  (Round 1 offered a stream-overlapped decode/hash schedule here; it measured
+ * slower than the stages back to back on every corpus and was replaced by per-row kernel classes.) */
 int zn_plan_set_overlap(zn_plan* plan, int groups);
+/* Rows of a decode+verify plan per decode class, chosen per row from the index columns alone (the reference's worker
+ * treats every row alike, decompress.rs:156-166; here the row's sizes pick its kernel):
+ *   [0] entropy-coded Zstandard frames      -> device-wide pipeline (csrc/zpipe.cuh)
+ *   [1] large, highly compressible frames   -> fused decode+hash kernel (csrc/fused_ws.cuh)
+ *   [2] large raw-block / LZ4 blobs         -> block-parallel team kernel
+ *   [3] decoded size <= 64 KiB              -> one-warp teams
+ *   [4] the rest                            -> 128-thread teams */
+int zn_plan_class_counts(const zn_plan* plan, uint32_t counts[5]);
 /* kernels launched by one zn_plan_run of this plan */
 uint32_t zn_plan_launches(const zn_plan* plan);
 /* 1 when the plan decodes and hashes in ONE kernel (batches of large, highly compressible blobs: decode warps feed

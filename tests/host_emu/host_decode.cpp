@@ -6,6 +6,7 @@
 
 #include "../../znippy_b200/csrc/lz4_decode.cuh"
 #include "../../znippy_b200/csrc/zstd_par.cuh"
+#include "../../znippy_b200/csrc/zpipe.cuh"
 
 extern "C" int zn_hostemu_decode(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap,
                                  uint32_t* produced) {
@@ -57,4 +58,17 @@ extern "C" int zn_hostemu_decode_lz4_block(const uint8_t* src, uint32_t src_len,
   free(in);
   free(sh);
   return (int)st;
+}
+
+// device-wide pipeline (zpipe.cuh: walk, fat tables, lane-per-block sequences, lane-per-stream literals, chain), serial
+// emulation for one blob.  Returns 0 = decoded by the pipeline, 1 = the pipeline hands the blob to the legacy decoder.
+extern "C" int zn_hostemu_decode_pipe(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap, uint64_t* stats) {
+  static zn::zp::FseD predef[zn::zp::kTabSet];
+  static bool init = false;
+  if (!init) { zn::zp::build_predef_set(predef); init = true; }
+  uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 32);
+  memcpy(in + 8, src, src_len);
+  const int rc = zn::zp::host_pipeline(in + 8, src_len, out, cap, predef, stats);
+  free(in);
+  return rc;
 }

@@ -71,8 +71,18 @@ def emu():
     L.zn_hostemu_compress.restype = C.c_long
     L.zn_hostemu_decode_par.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.zn_hostemu_decode_lz4_block.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.zn_hostemu_decode_pipe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
 
     class E:
+        @staticmethod
+        def decode_pipe(blob, cap):
+            """0 = decoded by the device-wide pipeline logic, 1 = handed to the legacy decoder"""
+            a = np.frombuffer(blob, np.uint8)
+            out = np.zeros(max(cap, 1) + 64, np.uint8)
+            stats = np.zeros(4, np.uint64)
+            rc = L.zn_hostemu_decode_pipe(a.ctypes.data, a.size, out.ctypes.data, cap, stats.ctypes.data)
+            return rc, out[:cap].tobytes(), stats
+
         @staticmethod
         def decode(blob, cap, mis=0):
             a = np.frombuffer(blob, np.uint8)
@@ -202,6 +212,47 @@ def test_hostemu_block_parallel_pipeline(emu, oracle):
         assert (st == 0) == (rc == 0)
         if st == 0:
             assert out == oo
+
+
+def test_hostemu_device_wide_pipeline(emu, oracle):
+    """zpipe.cuh on the CPU: walk (table provenance, pool needs), fat FSE tables, lane-per-block sequence decode with
+    symbolic repeat offsets, word-storing Huffman streams, chain — every format path, all levels, multi-frame blobs; and
+    under bit-flips the pipeline either hands the blob to the legacy decoder or produces exactly the oracle's bytes."""
+    import random
+    O, z = oracle, oracle.libzstd()
+    rt = O.real_text(600_000)
+    corpora = [
+        (O.gen_text(300_000), 19), (O.gen_random(300_000), 3), (O.real_text(3 << 20), 19), (rt, 1), (rt, 3), (rt, 7), (rt, -5),
+        (np.concatenate([np.full(200_000, 65, np.uint8), rt[:5000], np.full(150_000, 66, np.uint8)]), 3),
+        (rt[:300], 3), (rt[:2000], 19), (np.zeros(0, np.uint8), 3),
+        (np.frombuffer(bytes(np.random.default_rng(3).choice([97, 98, 99, 100], 50000).astype(np.uint8)), np.uint8), 3),
+        (np.tile(rt[:50], 40), 1), (O.gen_rle_literals(), 19), (O.gen_small_alphabet(300), 1), (O.gen_small_alphabet(3000), 1),
+        (O.gen_periodic_noise(2000, 200, 12), 3), (O.gen_periodic_noise(20000, 64, 8), 19), (_skew256(400_000), 3)]
+    nseq = 0
+    for d, lvl in corpora:
+        blob = z.compress(d, lvl)
+        rc, out, stats = emu.decode_pipe(blob, len(d))
+        assert rc == 0 and out == d.tobytes(), (lvl, len(d))
+        nseq += int(stats[1])
+    assert nseq > 100_000
+    b = z.compress(rt[:50000], 3, checksum=True) + b"\x50\x2a\x4d\x18\x03\x00\x00\x00abc" + z.compress(rt[50000:90000], 19)
+    rc, out, _ = emu.decode_pipe(b, 90000)
+    assert rc == 0 and out == rt[:90000].tobytes()
+    assert emu.decode_pipe(oracle.liblz4().compress_frame(rt[:5000].tobytes()), 5000)[0] == 1  # not a zstd frame: legacy decoder
+    assert emu.decode_pipe(z.compress(rt[:5000], 3), 4999)[0] == 1 and emu.decode_pipe(z.compress(rt[:5000], 3), 5001)[0] == 1
+    base = z.compress(rt[:300_000], 3)
+    rnd = random.Random(2)
+    handed = 0
+    for _ in range(200):
+        c = bytearray(base)
+        c[rnd.randrange(len(c))] ^= 1 << rnd.randrange(8)
+        rc, out, _ = emu.decode_pipe(bytes(c), 300_000)
+        orc, oo = O.zstd_decompress(bytes(c), 300_000)
+        if rc == 0:  # accepted by the pipeline: must be what the oracle produces
+            assert orc == 0 and out == oo
+        else:
+            handed += 1
+    assert handed > 50
 
 
 def _skew256(n, seed=5):

@@ -56,6 +56,7 @@ struct HashHook {
   }
 };
 
+// `only_if` (nullable): word only_if[i * only_stride] != 0 selects list item i; null = every item.
 // NT threads per team; the CTA claims KB work items per atomic and its first KB warps fetch their descriptors (and
 // stage blobs <= kSrcSmall) in parallel, so the three dependent global round trips (counter -> list -> descriptor ->
 // bytes) are paid once per KB blobs instead of once per blob.  This is what bounds the 100 000 x 10 KiB-file corpus.
@@ -63,7 +64,8 @@ template <int NT, int KB, bool FUSE>
 __global__ void __launch_bounds__(NT, NT == 32 ? 16 : 512 / NT) k_decode(const BlobDesc* __restrict__ blobs, const uint32_t* __restrict__ list,
                                                          uint32_t n_list, const uint8_t* blobs_base, uint8_t* out_base,
                                                          uint8_t* lit_scratch, uint32_t* status, uint32_t* produced,
-                                                         uint32_t* work_counter, uint32_t* cvs, uint32_t one) {
+                                                         uint32_t* work_counter, uint32_t* cvs, uint32_t one,
+                                                         const uint32_t* only_if, uint32_t only_stride) {
   extern __shared__ __align__(16) uint8_t hash_stage[];  // FUSE only: (NT / 32) x kB3SmemPerWarp
   __shared__ DecShared sh;
   __shared__ uint32_t s_base;
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 16 : 512 / NT) k_decode(const B
     __syncthreads();
     ZN_TP(21);
     for (uint32_t k = 0; k < (uint32_t)KB && base + k < n_list; k++) {
+      // second pass behind the device-wide pipeline (zpipe.cuh): only the rows it handed back (flag word != 0)
+      if (only_if && only_if[(size_t)(base + k) * only_stride] == 0) continue;
       const uint32_t blob = s_blob[k];
       const BlobDesc d = s_desc[k];
       uint32_t st, got = 0;

@@ -22,6 +22,7 @@
 #include "decode_kernels.cuh"
 #include "par_kernel.cuh"
 #include "fused_ws.cuh"
+#include "zpipe_kernels.cuh"
 
 using namespace zn;
 
@@ -42,11 +43,30 @@ struct zn_ctx {
   uint8_t* d_out = nullptr;
   size_t d_out_cap = 0;
   CompressScratch cs;        // compressor work space (grown on demand)
+  // scratch of the device-wide zstd pipeline (zpipe.cuh), grown on demand: block table, work list, fat FSE tables,
+  // sequence records, regenerated literals, pool counters
+  struct ZScratch {
+    zp::ZBlock* blocks = nullptr; uint32_t* comp_list = nullptr; size_t slots = 0;
+    zp::FseD* tabs = nullptr; size_t tab_sets = 0;
+    zp::SeqRec16* recs = nullptr; size_t seqs = 0;
+    uint8_t* lits = nullptr; size_t lit16 = 0;
+    zp::ZPools* pools = nullptr;
+  } zs;
   uint64_t launches = 0;
   std::string err;
 };
 
 enum PlanKind { PLAN_DECODE_VERIFY = 1, PLAN_HASH = 2 };
+
+// decode classes: every compressed row of a batch is routed by its own sizes (index columns only, no device feedback)
+enum DecClass {
+  DC_PIPE = 0,  // entropy-coded Zstandard frames: device-wide pipeline (zpipe.cuh)
+  DC_BIGPAT,    // large and highly compressible (pattern corpora): fused decode+hash, TMA bulk stores
+  DC_BIGRAW,    // large, not compressible (frames of raw blocks) or LZ4: block-parallel / team kernel
+  DC_SMALL,     // decoded size <= 64 KiB: one-warp teams
+  DC_MID,       // the rest: 128-thread teams
+  DC_COUNT
+};
 
 struct zn_plan {
   zn_ctx* ctx = nullptr;
@@ -59,29 +79,22 @@ struct zn_plan {
   uint32_t *d_list_dec = nullptr, *d_list_small = nullptr, *d_list_large = nullptr;
   uint32_t *d_piece_blob = nullptr, *d_piece_idx = nullptr;
   uint32_t *d_cvs = nullptr, *d_digests = nullptr, *d_expect = nullptr, *d_status = nullptr, *d_produced = nullptr,
-           *d_counter = nullptr, *d_wsq = nullptr, *d_cvs2 = nullptr;
+           *d_counter = nullptr, *d_wsq = nullptr, *d_cvs2 = nullptr, *d_status0 = nullptr;  // d_status0: initial statuses (rows rejected by the planner)
   // d_wsq: tile queue of the warp-specialised fused kernel (fused_ws.cuh); d_cvs2: second level buffer of the large-blob tree
   uint32_t ws_tiles = 0;
   bool ran_ws = false;             // the last run used the warp-specialised fused kernel
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool ran = false;
-  bool big_blobs = false;    // mean decoded size >= 512 KiB: 256-thread teams
-  bool fused_hash = false;   // large, highly compressible blobs: chaining values come out of the fused decode kernel
-  bool entropy_heavy = false;  // compressed size > 1/64 of decoded size: many sequences per block -> block-parallel decode
-  bool small_blobs = false;  // mean decoded size <= 64 KiB: one-warp teams
-  // overlapped schedule: blobs are cut into `groups` contiguous index ranges; group g+1 decodes (HBM-bound) on the
-  // caller's stream while group g is hashed (int-ALU-bound) on the context's second stream
-  static const int kMaxGroups = 16;
-  int groups = 1;
-  uint32_t grp_dec_off[kMaxGroups + 1] = {0};
-  uint32_t grp_chunk_lo[kMaxGroups + 1] = {0};
-  cudaEvent_t evg[kMaxGroups] = {nullptr};
-  cudaEvent_t ev_join = nullptr;
+  uint32_t cls_off[DC_COUNT + 1] = {0};  // class c = d_list_dec[cls_off[c] .. cls_off[c + 1]), largest blobs first
+  bool fused_hash = false;   // the DC_BIGPAT rows' chaining values come out of the fused decode kernel
+  uint32_t n_hashed = 0;     // rows whose chunks k_b3_chunks may skip
+  // device-wide pipeline (DC_PIPE rows)
+  zp::ZBlob* d_zb = nullptr;
+  uint32_t nzb = 0;
+  size_t z_slots = 0, z_tabs = 0, z_seqs = 0, z_lit16 = 0;
+  uint64_t z_mean = 0;       // mean decoded size of the pipeline rows (picks the exec team size)
   bool uploads_synced = false;  // the plan's arrays (uploaded on the ctx stream) are known to have landed
-  std::vector<uint64_t> h_cap;
-  std::vector<uint8_t> h_comp;
-  std::vector<uint32_t> h_prefix;
   uint32_t launches_per_run = 0;
 };
 
@@ -171,6 +184,14 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   cudaFuncSetAttribute(k_decode<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kB3SmemPerWarp);
   cudaFuncSetAttribute(k_decode_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes);
   cudaFuncSetAttribute(par::k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(par::ParShared));
+  {
+    static zp::FseD zset[zp::kTabSet];
+    zp::build_predef_set(zset);
+    if (cudaMemcpyToSymbol(zp::g_zpredef, zset, sizeof zset) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
+  }
+  cudaFuncSetAttribute(zp::k_zlit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zp::kLitSmem);
+  cudaFuncSetAttribute(zp::k_zexec<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(zp::ExecShared<512>));
+  cudaFuncSetAttribute(zp::k_zexec<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(zp::ExecShared<128>));
   compress_init_attrs();
   return c;
 }
@@ -181,6 +202,8 @@ extern "C" void zn_ctx_destroy(zn_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->d_lit) cudaFree(c->d_lit);
   if (c->d_par) cudaFree(c->d_par);
+  for (void* q : {(void*)c->zs.blocks, (void*)c->zs.comp_list, (void*)c->zs.tabs, (void*)c->zs.recs, (void*)c->zs.lits, (void*)c->zs.pools})
+    if (q) cudaFree(q);
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   c->cs.release();
@@ -274,56 +297,17 @@ static bool upload(zn_ctx* c, T** dptr, const T* h, size_t count) {
   return true;
 }
 
-// (Re)builds the decode work list for `groups` contiguous blob-index ranges of equal decoded bytes: within a group
-// blobs are ordered largest first (dynamic work counter), groups are laid out back to back.
-static int plan_set_groups(zn_plan* p, int groups) {
-  zn_ctx* c = p->ctx;
-  const uint32_t n = p->n;
-  if (groups < 1) groups = 1;
-  if (groups > zn_plan::kMaxGroups) groups = zn_plan::kMaxGroups;
-  if (p->n_dec < 8u * (uint32_t)groups) groups = 1;
-  uint64_t total = 0;
-  for (uint32_t i = 0; i < n; i++) total += p->h_cap[i];
-  std::vector<uint32_t> ldec;
-  ldec.reserve(p->n_dec);
-  uint32_t b0 = 0;
-  uint64_t acc = 0;
-  p->grp_dec_off[0] = 0;
-  p->grp_chunk_lo[0] = 0;
-  for (int g = 0; g < groups; g++) {
-    uint32_t b1 = b0;
-    const uint64_t target = total * (uint64_t)(g + 1) / (uint64_t)groups;
-    while (b1 < n && (g + 1 == groups || acc + p->h_cap[b1] <= target || b1 == b0)) acc += p->h_cap[b1++];
-    const size_t first = ldec.size();
-    for (uint32_t i = b0; i < b1; i++)
-      if (p->h_comp[i]) ldec.push_back(i);
-    bool sorted_desc = true;  // largest first for the dynamic work counter; uniform sizes need no sort
-    for (size_t k = first + 1; k < ldec.size() && sorted_desc; k++) sorted_desc = p->h_cap[ldec[k]] <= p->h_cap[ldec[k - 1]];
-    if (!sorted_desc)
-      std::stable_sort(ldec.begin() + first, ldec.end(), [&](uint32_t a, uint32_t b) { return p->h_cap[a] > p->h_cap[b]; });
-    p->grp_dec_off[g + 1] = (uint32_t)ldec.size();
-    p->grp_chunk_lo[g + 1] = p->h_prefix[b1];
-    b0 = b1;
-  }
-  if (groups > 1 && !p->ev_join) {  // events of the overlapped schedule are only created when it is used
-    for (int i = 0; i < zn_plan::kMaxGroups; i++) ZN_CUDA(c, cudaEventCreateWithFlags(&p->evg[i], cudaEventDisableTiming));
-    ZN_CUDA(c, cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-  }
-  p->groups = groups;
-  if (!ldec.empty()) {
-    // pageable source: the call returns once the bytes sit in the driver's staging buffer, so `ldec` may go out of
-    // scope; the copy itself is ordered before the kernels on the stream (no host-side wait for the DMA)
-    ZN_CUDA(c, cudaMemcpyAsync(p->d_list_dec, ldec.data(), ldec.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    p->uploads_synced = false;  // zn_plan_run waits for them if it is given another stream
-  }
-  return ZN_OK;
+extern "C" int zn_plan_set_overlap(zn_plan* p, int groups) {
+  // Kept for ABI stability.  The stream-overlapped decode/hash schedule of round 1 measured slower than stages back to
+  // back on every corpus and was removed together with the batch-wide kernel choice: classes of rows now
+  // get their own kernels, and the pattern class fuses decode and hash in one kernel.
+  (void)groups;
+  return p ? ZN_OK : ZN_E_ARG;
 }
 
-extern "C" int zn_plan_set_overlap(zn_plan* p, int groups) {
-  if (!p) return ZN_E_ARG;
-  cudaSetDevice(p->ctx->device);
-  if (p->ran) cudaStreamSynchronize(p->last_stream);
-  return plan_set_groups(p, groups);
+static bool env_off(const char* name) {
+  const char* e = getenv(name);
+  return e && !strcmp(e, "0");
 }
 
 static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_off, const uint64_t* src_len,
@@ -336,12 +320,12 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
   p->kind = kind;
   p->n = n;
   std::vector<BlobDesc> descs(n);
-  std::vector<uint32_t> prefix(n + 1, 0), ldec, lsmall, llarge, pblob, pidx;
-  ldec.reserve(n);
+  std::vector<uint32_t> prefix(n + 1, 0), lsmall, llarge, pblob, pidx, cls[DC_COUNT];
+  std::vector<uint32_t> status0(n, 0);
   lsmall.reserve(n);
-  p->h_cap.reserve(n);
-  p->h_comp.reserve(n);
+  const bool use_pipe = !env_off("ZN_PIPE"), use_fuse = !env_off("ZN_FUSE");
   uint64_t chunks = 0;
+  bool any_status = false;
   for (uint32_t i = 0; i < n; i++) {
     BlobDesc& d = descs[i];
     const bool comp = kind == PLAN_DECODE_VERIFY && compressed && compressed[i];
@@ -349,48 +333,87 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     d.src_len = src_len[i];
     d.dst_off = out_off ? out_off[i] : 0;
     d.dst_cap = kind == PLAN_DECODE_VERIFY ? (out_len ? out_len[i] : 0) : src_len[i];
-    if (!comp && kind == PLAN_DECODE_VERIFY && d.dst_cap != d.src_len) d.dst_cap = d.src_len;  // index invariant
+    bool skip = false;
+    if (!comp && kind == PLAN_DECODE_VERIFY && d.dst_cap != d.src_len) {
+      // store-as-is row whose index sizes disagree (blob_size != uncompressed_size): the reference would hand back
+      // blob_size bytes for a file region of uncompressed_size — a corrupt index row.  Nothing is gathered or hashed.
+      status0[i] = S_SIZE_MISMATCH;
+      any_status = true;
+      skip = true;
+      d.src_len = 0;
+      d.dst_cap = 0;
+    }
     const uint64_t nc = std::max<uint64_t>(1, (d.dst_cap + kChunk - 1) / kChunk);
     d.n_chunks = (uint32_t)nc;
     d.cv_base = chunks;
-    d.flags = (comp ? F_COMPRESSED : 0u) | (expect ? F_HAS_EXPECT : 0u) | (comp && compressed[i] == 2 ? F_LZ4_BLOCK : 0u);
+    d.flags = (comp ? F_COMPRESSED : 0u) | (expect && !skip ? F_HAS_EXPECT : 0u) | (comp && compressed[i] == 2 ? F_LZ4_BLOCK : 0u);
     prefix[i] = (uint32_t)chunks;
     chunks += nc;
     if (chunks > 0xFFFFFFF0ull) { delete p; c->err = "batch too large (chunk count)"; return nullptr; }
-    if (comp) ldec.push_back(i);
-    else if (gather_raw && kind == PLAN_DECODE_VERIFY)
+    if (comp) {
+      const bool big = d.dst_cap >= (512u << 10), pat = d.src_len * 64 <= d.dst_cap, lz4b = (d.flags & F_LZ4_BLOCK) != 0;
+      int k;
+      if (big && pat && !lz4b) k = DC_BIGPAT;
+      else if (use_pipe && !lz4b && !pat && d.src_len < d.dst_cap && d.dst_cap >= 4096 && d.dst_cap < 0xFFFFFFF0ull) k = DC_PIPE;
+      else if (big) k = DC_BIGRAW;
+      else if (d.dst_cap <= (64u << 10)) k = DC_SMALL;
+      else k = DC_MID;
+      cls[k].push_back(i);
+    } else if (gather_raw && kind == PLAN_DECODE_VERIFY && !skip)
       for (uint64_t o = 0, k = 0; o < d.dst_cap; o += kGatherPiece, k++) { pblob.push_back(i); pidx.push_back((uint32_t)k); }
     (nc <= kTreeSmallMax ? lsmall : llarge).push_back(i);
-    p->h_cap.push_back(d.dst_cap);
-    p->h_comp.push_back(comp ? 1 : 0);
   }
   prefix[n] = (uint32_t)chunks;
-  p->h_prefix = prefix;
   p->total_chunks = (uint32_t)chunks;
+  // class lists back to back, largest first inside a class (dynamic work counters)
+  std::vector<uint32_t> ldec;
+  for (int k = 0; k < DC_COUNT; k++) {
+    auto& L = cls[k];
+    bool sorted_desc = true;
+    for (size_t j = 1; j < L.size() && sorted_desc; j++) sorted_desc = descs[L[j]].dst_cap <= descs[L[j - 1]].dst_cap;
+    if (!sorted_desc) std::stable_sort(L.begin(), L.end(), [&](uint32_t x, uint32_t y) { return descs[x].dst_cap > descs[y].dst_cap; });
+    p->cls_off[k] = (uint32_t)ldec.size();
+    ldec.insert(ldec.end(), L.begin(), L.end());
+  }
+  p->cls_off[DC_COUNT] = (uint32_t)ldec.size();
   p->n_dec = (uint32_t)ldec.size();
+  // Large, highly compressible blobs go through the fused decode+hash kernel (fused_ws.cuh).  ZN_FUSE=0 keeps the two
+  // kernels apart, ZN_FUSE=team selects the older fused kernel in which one team alternates between decoding and hashing.
+  p->fused_hash = use_fuse && !cls[DC_BIGPAT].empty();
+  if (p->fused_hash)
+    for (uint32_t i : cls[DC_BIGPAT]) { descs[i].flags |= F_HASHED; p->ws_tiles += (descs[i].n_chunks + 31u) / 32u; p->n_hashed++; }
+  // device-wide pipeline: per-blob block-table slots and pool budgets (zpipe.cuh; anything that does not fit is decoded
+  // by the one-team kernel instead)
+  std::vector<zp::ZBlob> zb(cls[DC_PIPE].size());
   {
-    uint64_t dec_bytes = 0;
-    for (uint32_t i : ldec) dec_bytes += descs[i].dst_cap;
-    p->big_blobs = !ldec.empty() && dec_bytes / ldec.size() >= (512u << 10);
-    uint64_t src_bytes = 0;
-    for (uint32_t i : ldec) src_bytes += descs[i].src_len;
-    p->entropy_heavy = src_bytes * 64 > dec_bytes;
-    // Large, highly compressible blobs go through the fused decode+hash kernel (fused_ws.cuh): on the 2 GiB pattern file
-    // 1.32 ms per step against 1.53 ms for decode and hash back to back.  ZN_FUSE=0 keeps the two kernels apart,
-    // ZN_FUSE=team selects the older fused kernel in which one team alternates between decoding and hashing (1.65 ms).
-    {
-      const char* fz = getenv("ZN_FUSE");
-      p->fused_hash = p->big_blobs && !p->entropy_heavy && !(fz && !strcmp(fz, "0"));
+    uint64_t slots = 0, seqs = 0, lit16 = 0, tabs = 0, bytes = 0;
+    for (size_t j = 0; j < zb.size(); j++) {
+      const uint64_t cap = descs[cls[DC_PIPE][j]].dst_cap;
+      const uint32_t sc = (uint32_t)(cap / 16384 + 8);  // level >= 16 frames split their 128 KiB blocks
+      memset(&zb[j], 0, sizeof zb[j]);
+      zb[j].blob = cls[DC_PIPE][j];
+      zb[j].slot0 = (uint32_t)slots;
+      zb[j].slot_cap = sc;
+      slots += sc;
+      seqs += cap / 5 + 64;
+      lit16 += cap / 16 + 2ull * sc + 2;
+      tabs += cap / 32768 + 2;
+      bytes += cap;
     }
-    if (p->fused_hash)
-      for (uint32_t i : ldec) { descs[i].flags |= F_HASHED; p->ws_tiles += (descs[i].n_chunks + 31u) / 32u; }
-    p->small_blobs = !ldec.empty() && dec_bytes / ldec.size() <= (64u << 10);
+    const uint64_t lim = 0xFFFFFFF0ull;
+    p->nzb = (uint32_t)zb.size();
+    p->z_slots = (size_t)std::min(slots, lim);
+    p->z_seqs = (size_t)std::min(seqs, lim);
+    p->z_lit16 = (size_t)std::min(lit16, lim);
+    p->z_tabs = (size_t)std::min(tabs, lim);
+    p->z_mean = zb.empty() ? 0 : bytes / zb.size();
+    if (slots > lim) { delete p; c->err = "batch too large (zstd block slots)"; return nullptr; }
   }
   p->n_small = (uint32_t)lsmall.size();
   p->n_large = (uint32_t)llarge.size();
   p->n_pieces = (uint32_t)pblob.size();
   bool ok = upload(c, &p->d_blobs, descs.data(), n) && upload(c, &p->d_chunk_prefix, prefix.data(), n + 1) &&
-            upload(c, &p->d_list_dec, (const uint32_t*)nullptr, ldec.size()) && upload(c, &p->d_list_small, lsmall.data(), lsmall.size()) &&
+            upload(c, &p->d_list_dec, ldec.data(), ldec.size()) && upload(c, &p->d_list_small, lsmall.data(), lsmall.size()) &&
             upload(c, &p->d_list_large, llarge.data(), llarge.size()) &&
             upload(c, &p->d_piece_blob, pblob.data(), pblob.size()) && upload(c, &p->d_piece_idx, pidx.data(), pidx.size()) &&
             upload(c, &p->d_expect, (const uint32_t*)expect, expect ? (size_t)n * 8 : 0) &&
@@ -398,28 +421,18 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_cvs2, (const uint32_t*)nullptr, llarge.empty() ? 0 : (size_t)chunks * 8) &&
             upload(c, &p->d_digests, (const uint32_t*)nullptr, (size_t)n * 8) &&
             upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
-            upload(c, &p->d_counter, (const uint32_t*)nullptr, zn_plan::kMaxGroups) &&
-            upload(c, &p->d_wsq, (const uint32_t*)nullptr, p->fused_hash ? 4 + 2 * (size_t)p->ws_tiles : 0);
+            upload(c, &p->d_counter, (const uint32_t*)nullptr, 16) &&
+            upload(c, &p->d_wsq, (const uint32_t*)nullptr, p->fused_hash ? 4 + 2 * (size_t)p->ws_tiles : 0) &&
+            upload(c, &p->d_zb, zb.data(), zb.size());
+  if (ok && any_status) ok = upload(c, &p->d_status0, status0.data(), n);
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // host vectors go out of scope
-  if (ok) {
-    // default schedule: overlap decode and hash when the batch is large enough to pipeline
-    uint64_t dec_bytes = 0;
-    for (uint32_t i = 0; i < n; i++) dec_bytes += p->h_comp[i] ? p->h_cap[i] : 0;
-    // default: stages back to back.  The overlapped schedule only pays once a blob's decode latency is well below
-    // the hash time of its group ("overlap"); opt in with zn_plan_set_overlap or ZN_OVERLAP_GROUPS.
-    int g = 1;
-    if (dec_bytes >= (256ull << 20)) {
-      const char* e = getenv("ZN_OVERLAP_GROUPS");
-      if (e) g = atoi(e);
-    }
-    ok = plan_set_groups(p, g) == ZN_OK;
-  }
   if (!ok) {
     c->err = std::string("plan allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     zn_plan_destroy(p);
     return nullptr;
   }
+  p->uploads_synced = true;
   return p;
 }
 
@@ -438,20 +451,112 @@ extern "C" zn_plan* zn_plan_hash(zn_ctx* ctx, uint32_t n, const uint64_t* h_off,
 
 extern "C" int zn_plan_fused(const zn_plan* p) { return p && p->fused_hash ? 1 : 0; }
 
+extern "C" int zn_plan_class_counts(const zn_plan* p, uint32_t counts[5]) {
+  if (!p || !counts) return ZN_E_ARG;
+  for (int k = 0; k < DC_COUNT; k++) counts[k] = p->cls_off[k + 1] - p->cls_off[k];
+  return ZN_OK;
+}
+
 extern "C" void zn_plan_destroy(zn_plan* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   if (p->ran) cudaStreamSynchronize(p->last_stream);
   void* ptrs[] = {p->d_blobs, p->d_chunk_prefix, p->d_list_dec, p->d_list_small, p->d_list_large, p->d_piece_blob,
-                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter, p->d_wsq, p->d_cvs2};
+                  p->d_piece_idx, p->d_cvs, p->d_digests, p->d_expect, p->d_status, p->d_produced, p->d_counter, p->d_wsq, p->d_cvs2,
+                  p->d_zb, p->d_status0};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, p->ctx->stream);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
-  for (auto& e : p->evg)
-    if (e) cudaEventDestroy(e);
-  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
+}
+
+template <typename T>
+static bool zgrow(T** ptr, size_t* have, size_t want, size_t bytes_per) {
+  if (*have >= want) return true;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  const size_t cap = want + want / 8 + 16;
+  if (cudaMalloc((void**)ptr, cap * bytes_per) != cudaSuccess) { cudaGetLastError(); return false; }
+  *have = cap;
+  return true;
+}
+
+__global__ void k_zinit(zp::ZPools* pools, uint32_t seq_cap, uint32_t lit_cap16, uint32_t tab_cap, uint32_t comp_cap) {
+  zp::ZPools z;
+  z.seq_used = 0; z.seq_cap = seq_cap;
+  z.lit_used16 = 0; z.lit_cap16 = lit_cap16;
+  z.tab_used = 0; z.tab_cap = tab_cap;
+  z.comp_used = 0; z.comp_cap = comp_cap;
+  *pools = z;
+}
+
+// DC_PIPE rows: the device-wide pipeline, then the one-team decoder for whatever the pipeline handed back.
+static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cudaStream_t st, uint32_t* launches) {
+  zn_ctx* c = p->ctx;
+  auto& z = c->zs;
+  if (!z.pools && cudaMalloc((void**)&z.pools, sizeof(zp::ZPools)) != cudaSuccess) { c->err = "zstd pipeline scratch allocation failed"; cudaGetLastError(); return ZN_E_NOMEM; }
+  {
+    const size_t slots_before = z.slots;
+    size_t dummy = slots_before;
+    if (!zgrow(&z.blocks, &z.slots, p->z_slots, sizeof(zp::ZBlock)) || !zgrow(&z.comp_list, &dummy, p->z_slots, 4) ||
+        !zgrow(&z.tabs, &z.tab_sets, p->z_tabs, sizeof(zp::FseD) * zp::kTabSet) || !zgrow(&z.recs, &z.seqs, p->z_seqs, sizeof(zp::SeqRec16)) ||
+        !zgrow(&z.lits, &z.lit16, p->z_lit16 + 4, 16)) {
+      c->err = "zstd pipeline scratch allocation failed";
+      return ZN_E_NOMEM;
+    }
+  }
+  zp::ZArgs a;
+  a.blobs = p->d_blobs; a.blobs_base = d_blobs; a.zb = p->d_zb; a.nzb = p->nzb; a.blocks = z.blocks; a.pools = z.pools;
+  a.comp_list = z.comp_list; a.tabs = z.tabs; a.recs = z.recs; a.lits = z.lits;
+  const uint32_t sms = (uint32_t)c->sm_count, slots = (uint32_t)p->z_slots;
+  // development: ZN_ZPROF=1 prints the device time of every pipeline kernel of this run on stderr (synchronises)
+  const bool prof = getenv("ZN_ZPROF") != nullptr;
+  cudaEvent_t pe[9];
+  int npe = 0;
+  auto mark = [&]() { if (prof) { cudaEventCreate(&pe[npe]); cudaEventRecord(pe[npe], st); npe++; } };
+  mark();
+  k_zinit<<<1, 1, 0, st>>>(z.pools, (uint32_t)p->z_seqs, (uint32_t)p->z_lit16, (uint32_t)p->z_tabs, slots);
+  zp::k_zwalk<<<(p->nzb + 63) / 64, 64, 0, st>>>(a);
+  mark();
+  zp::k_ztables<<<std::min<uint32_t>((slots + zp::kTabWarps - 1) / zp::kTabWarps, sms * 8), zp::kTabWarps * 32, 0, st>>>(a);
+  mark();
+  zp::k_zseq<<<(slots + 63) / 64, 64, 0, st>>>(a);
+  mark();
+  zp::k_zlit<<<std::min<uint32_t>((slots + zp::kLitBlocks - 1) / zp::kLitBlocks, sms * 3), zp::kLitBlocks * 4, zp::kLitSmem, st>>>(a);
+  mark();
+  zp::k_zchain<<<(p->nzb + 63) / 64, 64, 0, st>>>(a);
+  mark();
+  uint32_t* ctr = p->d_counter + DC_COUNT;  // [0] exec, [1] legacy pass
+  if (p->z_mean >= (256u << 10))
+    zp::k_zexec<512><<<std::min<uint32_t>(p->nzb, sms * 2), 512, sizeof(zp::ExecShared<512>), st>>>(a, d_out, p->d_produced, ctr);
+  else
+    zp::k_zexec<128><<<std::min<uint32_t>(p->nzb, sms * 6), 128, sizeof(zp::ExecShared<128>), st>>>(a, d_out, p->d_produced, ctr);
+  mark();
+  // rows the pipeline handed back (ZBlob.state != 0): the one-team decoder, which also produces their status
+  const uint32_t* list = p->d_list_dec + p->cls_off[DC_PIPE];
+  const uint32_t grid = std::min<uint32_t>(p->nzb, c->dec_grid);
+  k_decode<kDecodeThreads, 1, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, p->nzb, d_blobs, d_out, c->d_lit, p->d_status,
+                                                                   p->d_produced, ctr + 1, nullptr, 1u, &p->d_zb[0].state,
+                                                                   (uint32_t)(sizeof(zp::ZBlob) / 4));
+  mark();
+  if (prof) {
+    cudaEventSynchronize(pe[npe - 1]);
+    static const char* names[] = {"walk", "tables", "seq", "lit", "chain", "exec", "legacy"};
+    zp::ZPools hp;
+    cudaMemcpy(&hp, z.pools, sizeof hp, cudaMemcpyDeviceToHost);
+    std::vector<zp::ZBlob> hz(p->nzb);
+    cudaMemcpy(hz.data(), p->d_zb, sizeof(zp::ZBlob) * p->nzb, cudaMemcpyDeviceToHost);
+    uint32_t handed = 0;
+    for (auto& b : hz) handed += b.state != 0;
+    fprintf(stderr, "zpipe: %u blobs (%u handed back), %u blocks, %u seqs, %u table sets, %u lit16 |", p->nzb, handed, hp.comp_used, hp.seq_used, hp.tab_used, hp.lit_used16);
+    for (int i = 0; i + 1 < npe; i++) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
+    fprintf(stderr, " ms\n");
+    for (int i = 0; i < npe; i++) cudaEventDestroy(pe[i]);
+  }
+  *launches += 8;
+  return ZN_OK;
 }
 
 extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, void* stream_v) {
@@ -468,91 +573,75 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
   uint32_t launches = 0;
   ZN_CUDA(c, cudaEventRecord(p->ev[0], st));
   if (p->n) {
-    ZN_CUDA(c, cudaMemsetAsync(p->d_status, 0, (size_t)p->n * 4, st));
-    ZN_CUDA(c, cudaMemsetAsync(p->d_counter, 0, 4 * zn_plan::kMaxGroups, st));
+    if (p->d_status0) ZN_CUDA(c, cudaMemcpyAsync(p->d_status, p->d_status0, (size_t)p->n * 4, cudaMemcpyDeviceToDevice, st));
+    else ZN_CUDA(c, cudaMemsetAsync(p->d_status, 0, (size_t)p->n * 4, st));
+    ZN_CUDA(c, cudaMemsetAsync(p->d_counter, 0, 4 * 16, st));
   }
   if (p->n_pieces && d_out) {
     const uint32_t grid = std::min<uint32_t>(p->n_pieces, (uint32_t)c->sm_count * 16u);
     k_gather_raw<<<grid, 256, 0, st>>>(p->d_blobs, p->d_piece_blob, p->d_piece_idx, p->n_pieces, d_blobs, d_out);
     launches++;
   }
-  const bool overlap = p->groups > 1;
-  for (int g = 0; g < p->groups; g++) {
-    const uint32_t nd = p->grp_dec_off[g + 1] - p->grp_dec_off[g];
-    if (nd) {
-      const uint32_t* list = p->d_list_dec + p->grp_dec_off[g];
-      const char* force = getenv("ZN_DECODE_KERNEL");  // development override: par | team | warp
-      if (force && !strcmp(force, "warp")) {
-        const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
-        k_decode<32, 2, false><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
-                                             p->d_counter + g, nullptr, 1u);
-      } else
-      if (p->big_blobs && p->entropy_heavy && !getenv("ZN_NO_PAR")) {  // large blobs: block-parallel decode, one CTA per SM
-        const uint32_t max_grid = (uint32_t)c->sm_count;
-        if (!c->d_par && cudaMalloc(&c->d_par, (size_t)max_grid * par::kParScratchPerCta) != cudaSuccess) {
-          c->err = "block-parallel decode scratch allocation failed";
-          cudaGetLastError();
-          return ZN_E_NOMEM;
-        }
-        const uint32_t grid = std::min<uint32_t>(nd, max_grid);
-        par::k_decode_par<<<grid, par::kParThreads, sizeof(par::ParShared), st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_par,
-                                                                                 p->d_status, p->d_produced, p->d_counter + g);
-      } else if (force && !strcmp(force, "team128")) {  // development: 128-thread teams for everything
-        const uint32_t grid = std::min<uint32_t>(nd, c->dec_grid);
-        k_decode<kDecodeThreads, 1, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit,
-                                                                         p->d_status, p->d_produced, p->d_counter + g, nullptr, 1u);
-      } else if (p->big_blobs) {  // highly compressible large blobs (few, long sequences): one 256-thread team per blob
-        uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
-        if (const char* gs = getenv("ZN_WS_GRID")) grid = std::max(1, std::min<int>((int)grid, atoi(gs)));  // tests: several blobs per CTA
-        const char* fm = getenv("ZN_FUSE");
-        if (p->fused_hash && p->groups == 1 && !(fm && !strcmp(fm, "team"))) {
-          // warp-specialised fused kernel: one CTA per SM, two decode teams each; its tile queue starts empty
-          ZN_CUDA(c, cudaMemsetAsync(p->d_wsq, 0, 16 + 8 * (size_t)p->ws_tiles, st));
-          p->ran_ws = true;
-          WsQueue q{p->d_wsq, reinterpret_cast<unsigned long long*>(p->d_wsq + 4), p->ws_tiles};
-          uint32_t wgrid = (uint32_t)c->sm_count;  // every SM hashes, whether or not one of its teams gets a blob
-          if (const char* gs = getenv("ZN_WS_GRID")) wgrid = std::max(1, std::min<int>((int)wgrid, atoi(gs)));
-          k_decode_ws<<<wgrid, kWsThreads, kWsSmemBytes, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
-                                                               p->d_produced, p->d_counter + g, p->d_cvs, q, 1u);
-        }
-        else if (p->fused_hash)
-          k_decode<256, 1, true><<<grid, 256, 8 * kB3SmemPerWarp, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
-                                                                       p->d_produced, p->d_counter + g, p->d_cvs, 1u);
-        else
-          k_decode<256, 1, false><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
-                                                        p->d_produced, p->d_counter + g, nullptr, 1u);
-      } else if (p->small_blobs) {  // many small blobs: one warp per blob, ~10 blobs in flight per SM
-        const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
-        k_decode<32, 2, false><<<grid, 32, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
-                                             p->d_counter + g, nullptr, 1u);
-      } else {
-        const uint32_t grid = std::min<uint32_t>((nd + 3) / 4, c->dec_grid);
-        k_decode<kDecodeThreads, 4, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit,
-                                                                         p->d_status, p->d_produced, p->d_counter + g, nullptr, 1u);
-      }
-      launches++;
-    }
-    if (g + 1 == p->groups) ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
-    const uint32_t clo = p->grp_chunk_lo[g], chi = p->grp_chunk_lo[g + 1];
-    if (chi > clo && !(p->fused_hash && p->n_dec == p->n)) {
-      cudaStream_t hs = st;
-      if (overlap) {
-        ZN_CUDA(c, cudaEventRecord(p->evg[g], st));
-        ZN_CUDA(c, cudaStreamWaitEvent(c->stream2, p->evg[g], 0));
-        hs = c->stream2;
-      }
-      const uint32_t tiles = (chi - clo + 31u) / 32u;
-      const uint32_t ctas = (tiles + kB3Warps - 1) / kB3Warps;
-      // 3 hash CTAs fill an SM's shared memory; when decode CTAs must co-reside (overlapped schedule) leave room
-      const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * (overlap ? 2u : 3u));
-      k_b3_chunks<<<grid, kB3Warps * 32, kB3Warps * kB3SmemPerWarp, hs>>>(p->d_blobs, p->d_chunk_prefix, p->n, clo, chi, d_blobs,
-                                                                         d_out, p->d_cvs, 1u);
-      launches++;
-    }
+  auto cls_n = [&](int k) { return p->cls_off[k + 1] - p->cls_off[k]; };
+  auto cls_list = [&](int k) { return p->d_list_dec + p->cls_off[k]; };
+  if (p->nzb) {
+    const int rc = run_pipeline(p, d_blobs, d_out, st, &launches);
+    if (rc != ZN_OK) return rc;
   }
-  if (overlap) {
-    ZN_CUDA(c, cudaEventRecord(p->ev_join, c->stream2));
-    ZN_CUDA(c, cudaStreamWaitEvent(st, p->ev_join, 0));
+  if (const uint32_t nd = cls_n(DC_BIGPAT)) {  // highly compressible large blobs (few, long sequences)
+    const uint32_t* list = cls_list(DC_BIGPAT);
+    uint32_t grid = std::min<uint32_t>(nd, c->dec_grid / 2);
+    if (const char* gs = getenv("ZN_WS_GRID")) grid = std::max(1, std::min<int>((int)grid, atoi(gs)));  // tests: several blobs per CTA
+    const char* fm = getenv("ZN_FUSE");
+    if (p->fused_hash && !(fm && !strcmp(fm, "team"))) {
+      // warp-specialised fused kernel: one CTA per SM, two decode teams each; its tile queue starts empty
+      ZN_CUDA(c, cudaMemsetAsync(p->d_wsq, 0, 16 + 8 * (size_t)p->ws_tiles, st));
+      p->ran_ws = true;
+      WsQueue q{p->d_wsq, reinterpret_cast<unsigned long long*>(p->d_wsq + 4), p->ws_tiles};
+      uint32_t wgrid = (uint32_t)c->sm_count;  // every SM hashes, whether or not one of its teams gets a blob
+      if (const char* gs = getenv("ZN_WS_GRID")) wgrid = std::max(1, std::min<int>((int)wgrid, atoi(gs)));
+      k_decode_ws<<<wgrid, kWsThreads, kWsSmemBytes, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                           p->d_produced, p->d_counter + DC_BIGPAT, p->d_cvs, q, 1u);
+    } else if (p->fused_hash)
+      k_decode<256, 1, true><<<grid, 256, 8 * kB3SmemPerWarp, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                                   p->d_produced, p->d_counter + DC_BIGPAT, p->d_cvs, 1u, nullptr, 0u);
+    else
+      k_decode<256, 1, false><<<grid, 256, 0, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
+                                                    p->d_produced, p->d_counter + DC_BIGPAT, nullptr, 1u, nullptr, 0u);
+    launches++;
+  }
+  if (const uint32_t nd = cls_n(DC_BIGRAW)) {  // large raw-block / LZ4 / (pipeline off) entropy-coded blobs: one CTA per SM
+    const uint32_t max_grid = (uint32_t)c->sm_count;
+    if (!c->d_par && cudaMalloc(&c->d_par, (size_t)max_grid * par::kParScratchPerCta) != cudaSuccess) {
+      c->err = "block-parallel decode scratch allocation failed";
+      cudaGetLastError();
+      return ZN_E_NOMEM;
+    }
+    par::k_decode_par<<<std::min<uint32_t>(nd, max_grid), par::kParThreads, sizeof(par::ParShared), st>>>(
+        p->d_blobs, cls_list(DC_BIGRAW), nd, d_blobs, d_out, c->d_par, p->d_status, p->d_produced, p->d_counter + DC_BIGRAW);
+    launches++;
+  }
+  if (const uint32_t nd = cls_n(DC_SMALL)) {  // many small blobs: one warp per blob, ~10 blobs in flight per SM
+    const uint32_t grid = std::min<uint32_t>((nd + 1) / 2, c->dec_grid_small);
+    k_decode<32, 2, false><<<grid, 32, 0, st>>>(p->d_blobs, cls_list(DC_SMALL), nd, d_blobs, d_out, c->d_lit, p->d_status, p->d_produced,
+                                                p->d_counter + DC_SMALL, nullptr, 1u, nullptr, 0u);
+    launches++;
+  }
+  if (const uint32_t nd = cls_n(DC_MID)) {
+    const uint32_t grid = std::min<uint32_t>((nd + 3) / 4, c->dec_grid);
+    k_decode<kDecodeThreads, 4, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, cls_list(DC_MID), nd, d_blobs, d_out, c->d_lit,
+                                                                     p->d_status, p->d_produced, p->d_counter + DC_MID, nullptr, 1u,
+                                                                     nullptr, 0u);
+    launches++;
+  }
+  ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
+  if (p->total_chunks && p->n_hashed != p->n) {
+    const uint32_t tiles = (p->total_chunks + 31u) / 32u;
+    const uint32_t ctas = (tiles + kB3Warps - 1) / kB3Warps;
+    const uint32_t grid = std::min<uint32_t>(ctas, (uint32_t)c->sm_count * 3u);  // 3 hash CTAs fill an SM's shared memory
+    k_b3_chunks<<<grid, kB3Warps * 32, kB3Warps * kB3SmemPerWarp, st>>>(p->d_blobs, p->d_chunk_prefix, p->n, 0u, p->total_chunks,
+                                                                       d_blobs, d_out, p->d_cvs, 1u);
+    launches++;
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[2], st));
   if (p->n_small) {

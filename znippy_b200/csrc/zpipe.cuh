@@ -1,0 +1,849 @@
+// Device-wide Zstandard decode pipeline ("zpipe"): the entropy-coded path of codec::decompress_into
+// (znippy-common/src/codec.rs:67-78, called per row by decompress.rs:156-166 and archive.rs:159-164) for a whole
+// batch of index rows at once.  The arithmetic on the reference path lives in openzl-sys-rs 0.2.0 -> zstd (not
+// vendored); this is written from RFC 8878.
+//
+// The one-CTA-per-blob decoders (zstd_decode.cuh, zstd_par.cuh) leave an entropy-coded batch bound by a handful of
+// serial bit-stream decoders per SM.  Here every phase runs over EVERY block of EVERY blob of the batch at once:
+//
+//   walk     one thread per blob hops over frame and block headers and fills a global block table: where each block's
+//            literals / Huffman tree / sequence tables are DEFINED (own section, an earlier block for treeless and
+//            repeat modes, or the predefined distribution) — which removes the table dependence between blocks — and
+//            bump-allocates the blob's sequence records, literal bytes and table sets from batch-wide pools;
+//   tables   one warp per compressed block parses the three FSE table descriptions and builds "fat" decoding tables
+//            (next-state base, state bits, extra bits, value baseline in one 8-byte entry) in global memory;
+//   seq      ONE LANE PER BLOCK runs the three interleaved FSE state machines: 32 independent bit streams per warp,
+//            thousands per device.  Repeat offsets that reach back before the block are kept SYMBOLIC (history entry
+//            i minus k), so no block waits for its predecessor.  Output: one 16-byte record per sequence;
+//   lit      ONE LANE PER HUFFMAN STREAM (4 per block), the block's decoding table in shared memory;
+//   chain    one thread per blob: block output offsets (prefix sum of the regenerated sizes), true repeat-offset
+//            history entering every block, frame content sizes;
+//   exec     one CTA per blob executes the sequences group by group in shared memory (zpipe_kernels.cuh).
+//
+// Anything irregular (LZ4 frames, dictionaries, more blocks than budgeted, any malformed field) marks the blob for the
+// legacy one-team decoder, which then produces the status exactly as before: the pipeline only has to be right for
+// well-formed frames and conservative for everything else.
+//
+// Everything in this file is scalar code that also compiles for the host (tests/host_emu runs the phases serially and
+// checks them against the oracle on the CPU).
+#pragma once
+#include "zstd_tables.cuh"
+
+namespace zn {
+namespace zp {
+
+constexpr uint32_t kDefPredef = 0xFFFFFFFEu;  // table source: predefined distribution
+constexpr uint32_t kDefNone = 0xFFFFFFFFu;    // table source: nothing defined yet in this frame
+constexpr uint32_t kSymBit = 0x80000000u;     // offset is symbolic: incoming history entry (v & 3) minus ((v >> 2) & 0x1FFFFFFF)
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+
+constexpr uint32_t kTabLL = 512, kTabOF = 256, kTabML = 512;      // entries per table (max table logs 9 / 8 / 9)
+constexpr uint32_t kTabSet = kTabLL + kTabOF + kTabML;             // entries of one block's table set
+constexpr uint32_t kTabOffLL = 0, kTabOffOF = kTabLL, kTabOffML = kTabLL + kTabOF;
+
+// fat FSE decoding-table entry: x = next-state base | state bits << 16 | extra bits << 24, y = value baseline
+struct alignas(8) FseD {
+  uint32_t x, y;
+};
+ZN_HD uint32_t fd_base(uint32_t x) { return x & 0xFFFFu; }
+ZN_HD uint32_t fd_nbits(uint32_t x) { return (x >> 16) & 0xFFu; }
+ZN_HD uint32_t fd_extra(uint32_t x) { return x >> 24; }
+
+// block flags
+enum : uint32_t {
+  ZB_TYPE_MASK = 3u,      // 0 raw, 1 RLE, 2 compressed
+  ZB_LAST = 4u,           // last block of its frame
+  ZB_FIRST = 8u,          // first block of its frame
+  ZB_LIT_SHIFT = 4,       // bits 4-5: literals type (0 raw, 1 RLE, 2 Huffman, 3 treeless)
+  ZB_STREAMS4 = 64u,      // four Huffman streams
+  ZB_HAS_FCS = 128u,      // (first block) the frame header carries a content size
+  ZB_MODES_SHIFT = 8      // bits 8-15: Symbol_Compression_Modes byte
+};
+
+struct ZBlock {
+  uint32_t src_off;     // block content, offset from the blob's first byte
+  uint32_t len;         // Block_Size (RLE: regenerated size)
+  uint32_t flags;
+  uint32_t lit_regen;   // regenerated literal bytes
+  uint32_t lit_off;     // raw: offset of the literal bytes; RLE: the byte; Huffman: offset of the streams area
+  uint32_t lit_clen;    // Huffman: bytes of the streams area (jump table + streams)
+  uint32_t huf_desc;    // Huffman: offset of the tree description (type 2 only)
+  uint32_t huf_dlen;    //          and its length
+  uint32_t huf_def;     // blob-relative index of the block whose tree description this block uses
+  uint32_t nseq;
+  uint32_t seq_off;     // offset of the first byte after the modes byte
+  uint32_t seq_def[3];  // LL / OF / ML: blob-relative index of the block whose table set holds the table, kDefPredef, kDefNone
+  uint32_t seq_base;    // first record of this block in the sequence pool
+  uint32_t lit_base16;  // Huffman: literal pool offset of the regenerated literals, in 16-byte units
+  uint32_t tab_slot;    // table set of this block (it defines at least one table), else kNoSlot
+  uint32_t fcs_lo, fcs_hi;  // first block of a frame: Frame_Content_Size
+  // ---- tables phase
+  uint32_t bits_off;    // offset of the sequence bit stream; ~0u: the table descriptions are malformed
+  uint32_t tlogs;       // table logs of this block's set, LL | OF << 8 | ML << 16
+  // ---- seq / lit phases
+  uint32_t matched;     // bytes produced by the sequences (literals + matches)
+  uint32_t lit_used;    // literals consumed by the sequences
+  uint32_t rep_fin[3];  // history after the block (possibly symbolic)
+  uint32_t st_seq;      // 0 = sequences decoded fine
+  uint32_t st_lit;      // Huffman streams still to be decoded fine (0 = literals ready)
+  // ---- chain phase
+  uint32_t out_base;    // first output byte of the block, relative to the blob's output
+  uint32_t rep_in[3];   // true history entering the block
+  uint32_t frame_start; // output offset where the block's frame began
+  uint32_t pad[3];
+};
+static_assert(sizeof(ZBlock) == 144, "ZBlock layout");
+
+// per pipeline blob (host fills blob / slot0 / slot_cap, the walk fills the rest)
+struct ZBlob {
+  uint32_t blob;      // index of the BlobDesc
+  uint32_t slot0;     // first ZBlock of this blob
+  uint32_t slot_cap;  // ZBlocks available
+  uint32_t n_blocks;
+  uint32_t state;     // 0: pipeline; != 0: legacy decoder takes the blob
+  uint32_t pad[3];
+};
+
+// batch-wide bump allocators + capacities
+struct ZPools {
+  uint32_t seq_used, seq_cap;      // sequence records
+  uint32_t lit_used16, lit_cap16;  // Huffman literal bytes / 16
+  uint32_t tab_used, tab_cap;      // table sets
+  uint32_t comp_used, comp_cap;    // compressed blocks (work list of the tables / seq / lit phases)
+};
+
+// 16-byte sequence record
+struct alignas(16) SeqRec16 {
+  uint32_t w0, w1, w2, w3;
+};
+ZN_HD SeqRec16 rec_pack(uint32_t out_rel, uint32_t lit_rel, uint32_t ll, uint32_t ml, uint32_t off) {
+  SeqRec16 r;
+  r.w0 = off;
+  r.w1 = out_rel | ((ll & 0x3FFFu) << 18);
+  r.w2 = lit_rel | ((ml & 0x3FFFu) << 18);
+  r.w3 = (ll >> 14) | ((ml >> 14) << 8);
+  return r;
+}
+ZN_HD uint32_t rec_off(const SeqRec16& r) { return r.w0; }
+ZN_HD uint32_t rec_out(const SeqRec16& r) { return r.w1 & 0x3FFFFu; }
+ZN_HD uint32_t rec_lit(const SeqRec16& r) { return r.w2 & 0x3FFFFu; }
+ZN_HD uint32_t rec_ll(const SeqRec16& r) { return (r.w1 >> 18) | ((r.w3 & 0xFFu) << 14); }
+ZN_HD uint32_t rec_ml(const SeqRec16& r) { return (r.w2 >> 18) | ((r.w3 >> 8) << 14); }
+
+ZN_HD bool is_sym(uint32_t v) { return (v & kSymBit) != 0; }
+ZN_HD uint32_t sym_make(uint32_t i) { return kSymBit | i; }
+ZN_HD uint32_t sym_minus1(uint32_t v) { return v + 4u; }
+// value of a (possibly symbolic) offset given the true incoming history; 0 = corrupt
+ZN_HD uint32_t sym_resolve(uint32_t v, uint32_t r0, uint32_t r1, uint32_t r2) {
+  if (!is_sym(v)) return v;
+  const uint32_t i = v & 3u, k = (v >> 2) & 0x1FFFFFFFu;
+  const uint32_t base = i == 0 ? r0 : (i == 1 ? r1 : r2);
+  return base > k ? base - k : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------------------ walk
+// Literals section header (RFC 8878 §3.1.1.3.1.1).  Fills the literal fields of `b`; *consumed = bytes of the whole
+// literals section.  false = malformed.
+ZN_HD bool walk_literals(const uint8_t* p, uint32_t len, uint32_t blk_off, ZBlock* b, uint32_t* lit_type, uint32_t* consumed) {
+  if (len < 1) return false;
+  const uint32_t b0 = p[0], type = b0 & 3, sf = (b0 >> 2) & 3;
+  *lit_type = type;
+  b->lit_clen = 0; b->huf_desc = 0; b->huf_dlen = 0;
+  if (type < 2) {
+    uint32_t hdr, regen;
+    if ((sf & 1) == 0) { hdr = 1; regen = b0 >> 3; }
+    else if (sf == 1) { if (len < 2) return false; hdr = 2; regen = (b0 >> 4) | ((uint32_t)p[1] << 4); }
+    else { if (len < 3) return false; hdr = 3; regen = (b0 >> 4) | ((uint32_t)p[1] << 4) | ((uint32_t)p[2] << 12); }
+    if (regen > kZstdBlockMax) return false;
+    b->lit_regen = regen;
+    if (type == 0) {
+      if (hdr + regen > len) return false;
+      b->lit_off = blk_off + hdr;
+      *consumed = hdr + regen;
+    } else {
+      if (hdr + 1 > len) return false;
+      b->lit_off = p[hdr];
+      *consumed = hdr + 1;
+    }
+    return true;
+  }
+  uint32_t hdr, regen, comp, streams;
+  if (sf <= 1) {
+    if (len < 3) return false;
+    const uint32_t v = ld24le(p);
+    hdr = 3; regen = (v >> 4) & 0x3FF; comp = (v >> 14) & 0x3FF; streams = sf == 0 ? 1 : 4;
+  } else if (sf == 2) {
+    if (len < 4) return false;
+    const uint32_t v = ld32le(p);
+    hdr = 4; regen = (v >> 4) & 0x3FFF; comp = v >> 18; streams = 4;
+  } else {
+    if (len < 5) return false;
+    const uint64_t v = (uint64_t)ld32le(p) | ((uint64_t)p[4] << 32);
+    hdr = 5; regen = (uint32_t)(v >> 4) & 0x3FFFF; comp = (uint32_t)(v >> 22); streams = 4;
+  }
+  if (regen > kZstdBlockMax || hdr + comp > len) return false;
+  b->lit_regen = regen;
+  uint32_t desc = 0;
+  if (type == 2) {
+    if (comp < 1) return false;
+    const uint32_t hb = p[hdr];
+    desc = hb < 128 ? 1 + hb : 1 + ((hb - 127) + 1) / 2;
+    if (desc > comp) return false;
+    b->huf_desc = blk_off + hdr;
+    b->huf_dlen = desc;
+  }
+  b->lit_off = blk_off + hdr + desc;
+  b->lit_clen = comp - desc;
+  if (streams == 4) b->flags |= ZB_STREAMS4;
+  *consumed = hdr + comp;
+  return true;
+}
+
+// Number_of_Sequences at q; returns bytes used (0 = malformed).
+ZN_HD uint32_t walk_nseq(const uint8_t* q, uint32_t avail, uint32_t* nseq) {
+  if (avail < 1) return 0;
+  const uint32_t n = q[0];
+  if (n < 128) { *nseq = n; return 1; }
+  if (n == 255) { if (avail < 3) return 0; *nseq = (uint32_t)q[1] + ((uint32_t)q[2] << 8) + 0x7F00u; return 3; }
+  if (avail < 2) return 0;
+  *nseq = ((n - 128) << 8) + q[1];
+  return 2;
+}
+
+struct WalkNeeds {
+  uint32_t nseq, lit16, tabs, comp;
+};
+
+// Walks every frame of one blob.  blocks[0 .. slot_cap) receive the block table (allocation fields blob-relative:
+// seq_base / lit_base16 / tab_slot count from 0 and are rebased by the caller once the pools have been bumped).
+// Returns the number of blocks, or ~0u when the blob has to go to the legacy decoder.
+ZN_HD uint32_t walk_blob(const uint8_t* src, uint32_t src_len, uint32_t slot_cap, ZBlock* blocks, WalkNeeds* needs) {
+  needs->nseq = needs->lit16 = needs->tabs = needs->comp = 0;
+  uint32_t ip = 0, nb = 0;
+  if (src_len == 0) return ~0u;
+  while (ip < src_len) {
+    if (src_len - ip >= 8) {
+      const uint32_t magic = ld32le(src + ip);
+      if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+        const uint32_t sz = ld32le(src + ip + 4);
+        if (sz > src_len - ip - 8) return ~0u;
+        ip += 8 + sz;
+        continue;
+      }
+    }
+    if (src_len - ip < 5) return ~0u;
+    if (ld32le(src + ip) != 0xFD2FB528u) return ~0u;  // LZ4 frame, unknown magic: legacy decoder decides
+    const uint32_t fhd = src[ip + 4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did_flag = fhd & 3;
+    if (fhd & 0x08) return ~0u;
+    const uint32_t checksum = (fhd >> 2) & 1;
+    uint32_t hp = ip + 5;
+    uint64_t window = 0;
+    if (!single) {
+      if (src_len < hp + 1) return ~0u;
+      const uint32_t wd = src[hp++], e = wd >> 3, m = wd & 7;
+      const uint64_t base = 1ull << (10 + e);
+      window = base + (base >> 3) * m;
+    }
+    const uint32_t db = did_flag == 3 ? 4u : did_flag;
+    if (src_len < hp + db) return ~0u;
+    uint32_t did = 0;
+    for (uint32_t i = 0; i < db; i++) did |= (uint32_t)src[hp + i] << (8 * i);
+    hp += db;
+    if (did != 0) return ~0u;
+    const uint32_t fb = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2u : (fcs_flag == 2 ? 4u : 8u));
+    if (src_len < hp + fb) return ~0u;
+    uint64_t fcs = 0;
+    for (uint32_t i = 0; i < fb; i++) fcs |= (uint64_t)src[hp + i] << (8 * i);
+    if (fb == 2) fcs += 256;
+    hp += fb;
+    if (single) window = fcs;
+    ip = hp;
+    const uint32_t block_max = window < kZstdBlockMax ? (uint32_t)window : kZstdBlockMax;
+    uint32_t def_huf = kDefNone, def_seq[3] = {kDefNone, kDefNone, kDefNone};
+    bool first = true;
+    for (;;) {
+      if (src_len - ip < 3) return ~0u;
+      if (nb >= slot_cap) return ~0u;
+      const uint32_t bh = ld24le(src + ip);
+      ip += 3;
+      const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+      if (type == 3) return ~0u;
+      ZBlock* b = &blocks[nb];
+      b->src_off = ip; b->len = bsize;
+      b->flags = type | (last ? ZB_LAST : 0u) | (first ? ZB_FIRST : 0u) | (first && fb ? ZB_HAS_FCS : 0u);
+      b->fcs_lo = (uint32_t)fcs; b->fcs_hi = (uint32_t)(fcs >> 32);
+      b->lit_regen = 0; b->lit_off = 0; b->lit_clen = 0; b->huf_desc = 0; b->huf_dlen = 0; b->huf_def = kDefNone;
+      b->nseq = 0; b->seq_off = 0; b->seq_def[0] = b->seq_def[1] = b->seq_def[2] = kDefNone;
+      b->seq_base = needs->nseq; b->lit_base16 = needs->lit16; b->tab_slot = kNoSlot;
+      b->bits_off = ~0u; b->tlogs = 0;
+      b->matched = 0; b->lit_used = 0;
+      b->rep_fin[0] = sym_make(0); b->rep_fin[1] = sym_make(1); b->rep_fin[2] = sym_make(2);
+      b->st_seq = 0; b->st_lit = 0;
+      b->out_base = 0; b->rep_in[0] = b->rep_in[1] = b->rep_in[2] = 0; b->frame_start = 0;
+      first = false;
+      if (type == 1) {
+        if (src_len - ip < 1) return ~0u;
+        ip += 1;
+      } else {
+        if (bsize > src_len - ip) return ~0u;
+        if (type == 2) {
+          if (bsize > block_max || bsize < 2) return ~0u;
+          const uint8_t* p = src + ip;
+          uint32_t lit_type, consumed;
+          if (!walk_literals(p, bsize, ip, b, &lit_type, &consumed)) return ~0u;
+          b->flags |= lit_type << ZB_LIT_SHIFT;
+          if (lit_type == 2) def_huf = nb;
+          if (lit_type >= 2) {
+            if (def_huf == kDefNone) return ~0u;
+            b->huf_def = def_huf;
+            b->st_lit = (b->flags & ZB_STREAMS4) ? 4u : 1u;
+            needs->lit16 += (b->lit_regen + 15u) / 16u + 1u;  // + 1: word stores may touch the next aligned word
+          }
+          uint32_t nseq;
+          const uint32_t used = walk_nseq(p + consumed, bsize - consumed, &nseq);
+          if (!used) return ~0u;
+          b->nseq = nseq;
+          if (nseq == 0) {
+            if (consumed + used != bsize) return ~0u;
+          } else {
+            if (consumed + used >= bsize) return ~0u;
+            if (nseq > kZstdBlockMax / 3 + 1) return ~0u;
+            const uint32_t modes = p[consumed + used];
+            if (modes & 3) return ~0u;
+            b->flags |= modes << ZB_MODES_SHIFT;
+            b->seq_off = ip + consumed + used + 1;
+            bool defines = false;
+            for (int k = 0; k < 3; k++) {
+              const uint32_t m = (modes >> (6 - 2 * k)) & 3;
+              if (m == 0) def_seq[k] = kDefPredef;
+              else if (m != 3) { def_seq[k] = nb; defines = true; }
+              else if (def_seq[k] == kDefNone) return ~0u;
+              b->seq_def[k] = def_seq[k];
+            }
+            if (defines) b->tab_slot = needs->tabs++;
+            b->st_seq = 1;
+            needs->nseq += nseq;
+          }
+          needs->comp++;
+        }
+        ip += bsize;
+      }
+      nb++;
+      if (last) break;
+    }
+    if (checksum) {  // XXH64 content checksum: present but not verified (blake3 of the content is)
+      if (src_len - ip < 4) return ~0u;
+      ip += 4;
+    }
+  }
+  return nb;
+}
+
+// ---------------------------------------------------------------------------------------------------------- tables
+ZN_HD void table_params(int k, int* max_log, int* max_sym) {
+  *max_log = k == 1 ? 8 : 9;
+  *max_sym = k == 0 ? 35 : (k == 1 ? 31 : 52);
+}
+
+// value baseline and extra-bit count of symbol s of table kind k (0 LL, 1 OF, 2 ML); false = symbol not decodable here
+ZN_HD bool sym_value(int k, uint32_t s, uint32_t* base, uint32_t* extra) {
+  if (k == 0) { if (s > 35) return false; *base = zs::kLLBase[s]; *extra = zs::kLLBits[s]; }
+  else if (k == 1) { if (s > 30) return false; *base = 1u << s; *extra = s; }
+  else { if (s > 52) return false; *base = zs::kMLBase[s]; *extra = zs::kMLBits[s]; }
+  return true;
+}
+
+// Fat decoding table from normalized counts (same spreading as zs::fse_build).  `next` = scratch for nsym uint16.
+ZN_HD bool build_fat_table(FseD* t, int k, const int16_t* norm, int nsym, int log, uint16_t* next) {
+  const int size = 1 << log;
+  int high = size - 1;
+  for (int s = 0; s < nsym; s++) {
+    if (norm[s] == -1) { t[high--].x = (uint32_t)s; next[s] = 1; }
+    else next[s] = (uint16_t)norm[s];
+  }
+  const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+  int pos = 0;
+  for (int s = 0; s < nsym; s++)
+    for (int i = 0; i < norm[s]; i++) {
+      t[pos].x = (uint32_t)s;
+      do pos = (pos + step) & mask; while (pos > high);
+    }
+  for (int u = 0; u < size; u++) {
+    const uint32_t s = t[u].x;
+    const uint32_t ns = next[s]++;
+    const uint32_t nb = (uint32_t)(log - hibit32(ns));
+    uint32_t base, extra;
+    if (!sym_value(k, s, &base, &extra)) return false;
+    t[u].x = ((ns << nb) - (uint32_t)size) | (nb << 16) | (extra << 24);
+    t[u].y = base;
+  }
+  return true;
+}
+
+// Step 1 (one thread): parses the table descriptions of block b in order.  For mode-2 tables the normalized counts go
+// to norm[k][0..64), nsym[k], log[k]; mode-1 tables are written directly (one entry).  Sets *bits_off.  false = malformed.
+ZN_HD bool parse_table_descs(const uint8_t* src, const ZBlock* b, FseD* set, int16_t (*norm)[64], int* nsym, int* log,
+                             uint32_t* bits_off) {
+  const uint32_t modes = (b->flags >> ZB_MODES_SHIFT) & 0xFFu;
+  const uint8_t* q = src + b->seq_off;
+  const uint8_t* end = src + b->src_off + b->len;
+  const uint32_t offs[3] = {kTabOffLL, kTabOffOF, kTabOffML};
+  for (int k = 0; k < 3; k++) {
+    const uint32_t m = (modes >> (6 - 2 * k)) & 3;
+    int max_log, max_sym;
+    table_params(k, &max_log, &max_sym);
+    log[k] = -1;
+    if (m == 1) {
+      if (q >= end) return false;
+      const uint32_t sym = *q++;
+      if ((int)sym > max_sym) return false;
+      uint32_t base, extra;
+      if (!sym_value(k, sym, &base, &extra)) return false;
+      set[offs[k]].x = extra << 24;
+      set[offs[k]].y = base;
+      log[k] = 0;
+      nsym[k] = 0;  // nothing to build
+    } else if (m == 2) {
+      if (q >= end) return false;
+      const int used = zs::fse_read_ncount(q, (uint32_t)(end - q), max_log, max_sym, norm[k], &log[k], &nsym[k]);
+      if (used < 0) return false;
+      q += used;
+    }
+  }
+  if (q >= end) return false;  // the bit stream must hold at least its end-marker byte
+  *bits_off = (uint32_t)(q - src);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------- seq
+// Per-block table view used by the sequence decoder.
+struct SeqTabs {
+  const FseD* t[3];  // LL, OF, ML
+  uint32_t log[3];
+};
+
+// One thread decodes every sequence of block b into rec[0 .. nseq).  Fills matched / lit_used / rep_fin and returns
+// true, or false when anything is off (the blob then goes to the legacy decoder).
+ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const SeqTabs& tabs, SeqRec16* rec, uint32_t* matched,
+                            uint32_t* lit_used, uint32_t* rep_fin) {
+  const uint32_t nseq = b->nseq, lit_len = b->lit_regen;
+  const uint32_t end = b->src_off + b->len;
+  if (b->bits_off >= end) return false;
+  BackBits bb;
+  if (!bb.init(src + b->bits_off, end - b->bits_off)) return false;
+  bb.refill();
+  uint32_t sl = bb.read(tabs.log[0]), so = bb.read(tabs.log[1]), sm = bb.read(tabs.log[2]);
+  if (bb.bits_left < 0) return false;
+  uint32_t h0 = sym_make(0), h1 = sym_make(1), h2 = sym_make(2);
+  uint32_t lit_pos = 0, out_pos = 0;
+  const FseD* tl = tabs.t[0];
+  const FseD* to = tabs.t[1];
+  const FseD* tm = tabs.t[2];
+  for (uint32_t i = 0; i < nseq; i++) {
+    const FseD el = tl[sl], eo = to[so], em = tm[sm];
+    bb.refill();
+    const uint32_t ov = eo.y + bb.read(fd_extra(eo.x));
+    bb.refill();
+    const uint32_t ml = em.y + bb.read(fd_extra(em.x));
+    const uint32_t ll = el.y + bb.read(fd_extra(el.x));
+    if (i + 1 < nseq) {
+      bb.refill();
+      sl = fd_base(el.x) + bb.read(fd_nbits(el.x));
+      sm = fd_base(em.x) + bb.read(fd_nbits(em.x));
+      so = fd_base(eo.x) + bb.read(fd_nbits(eo.x));
+    }
+    if (bb.bits_left < 0) return false;
+    uint32_t offset;
+    if (ov > 3) {
+      offset = ov - 3;
+      h2 = h1; h1 = h0; h0 = offset;
+    } else {
+      const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+      if (idx == 0) offset = h0;
+      else {
+        if (idx == 3) {
+          if (is_sym(h0)) offset = sym_minus1(h0);
+          else { offset = h0 - 1; if (offset == 0) return false; }
+        } else offset = idx == 1 ? h1 : h2;
+        if (idx != 1) h2 = h1;
+        h1 = h0;
+        h0 = offset;
+      }
+    }
+    if (ll > lit_len - lit_pos) return false;
+    if (ll > kZstdBlockMax || ml > kZstdBlockMax + 3u || out_pos + ll + ml > kZstdBlockMax) return false;
+    rec[i] = rec_pack(out_pos, lit_pos, ll, ml, offset);
+    lit_pos += ll;
+    out_pos += ll + ml;
+  }
+  if (bb.bits_left != 0) return false;
+  *matched = out_pos;
+  *lit_used = lit_pos;
+  rep_fin[0] = h0; rep_fin[1] = h1; rep_fin[2] = h2;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------- lit
+// Huffman decoding table for tree description p[0..len) into h (entries sym | nbits << 8; 1 << max_bits of them).
+// Returns max_bits, or 0 when malformed.  Scratch lives on the caller's stack.
+ZN_HD uint32_t huf_build(uint16_t* h, const uint8_t* p, uint32_t len) {
+  uint8_t w[256];
+  if (len < 1) return 0;
+  const uint32_t hb = p[0];
+  int n = 0;
+  if (hb >= 128) {
+    n = (int)hb - 127;
+    const uint32_t bytes = (uint32_t)(n + 1) / 2;
+    if (1 + bytes > len) return 0;
+    for (int i = 0; i < n; i++) w[i] = (i & 1) ? (p[1 + i / 2] & 15) : (p[1 + i / 2] >> 4);
+  } else {
+    if (hb == 0 || hb + 1 > len) return 0;
+    int16_t norm[16];
+    int log, nsym;
+    const int hd = zs::fse_read_ncount(p + 1, hb, 6, 11, norm, &log, &nsym);
+    if (hd < 0 || (uint32_t)hd >= hb) return 0;
+    uint32_t tab[64];
+    uint16_t next[16];
+    {  // zs::fse_build on a 64-entry table
+      const int size = 1 << log;
+      int high = size - 1;
+      for (int s = 0; s < nsym; s++) {
+        if (norm[s] == -1) { tab[high--] = (uint32_t)s; next[s] = 1; }
+        else next[s] = (uint16_t)norm[s];
+      }
+      const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+      int pos = 0;
+      for (int s = 0; s < nsym; s++)
+        for (int i = 0; i < norm[s]; i++) {
+          tab[pos] = (uint32_t)s;
+          do pos = (pos + step) & mask; while (pos > high);
+        }
+      for (int u = 0; u < size; u++) {
+        const uint32_t s = tab[u];
+        const uint32_t ns = next[s]++;
+        const uint32_t nb = (uint32_t)(log - hibit32(ns));
+        tab[u] = zs::fse_pack(s, nb, (ns << nb) - (uint32_t)size);
+      }
+    }
+    BackBits b;
+    if (!b.init(p + 1 + hd, hb - (uint32_t)hd)) return 0;
+    b.refill();
+    uint32_t s1 = b.read((uint32_t)log), s2 = b.read((uint32_t)log);
+    if (b.bits_left < 0) return 0;
+    for (;;) {
+      if (n >= 254) return 0;
+      b.refill();
+      const uint32_t e1 = tab[s1];
+      w[n++] = (uint8_t)zs::fse_sym(e1);
+      s1 = zs::fse_base(e1) + b.read(zs::fse_nbits(e1));
+      if (b.bits_left < 0) { w[n++] = (uint8_t)zs::fse_sym(tab[s2]); break; }
+      if (n >= 254) return 0;
+      const uint32_t e2 = tab[s2];
+      w[n++] = (uint8_t)zs::fse_sym(e2);
+      s2 = zs::fse_base(e2) + b.read(zs::fse_nbits(e2));
+      if (b.bits_left < 0) { w[n++] = (uint8_t)zs::fse_sym(tab[s1]); break; }
+    }
+    if (n > 255) return 0;
+  }
+  uint32_t sum = 0;
+  for (int i = 0; i < n; i++) {
+    if (w[i] > 11) return 0;
+    if (w[i]) sum += 1u << (w[i] - 1);
+  }
+  if (sum == 0) return 0;
+  const int max_bits = hibit32(sum) + 1;
+  if (max_bits > 11) return 0;
+  const uint32_t left = (1u << max_bits) - sum;
+  if (left & (left - 1)) return 0;
+  w[n++] = (uint8_t)(hibit32(left) + 1);
+  uint32_t rank_start[13], count[13];
+  for (int i = 0; i < 13; i++) count[i] = 0;
+  for (int i = 0; i < n; i++) count[w[i]]++;
+  uint32_t pos = 0;
+  for (int wt = 1; wt <= max_bits; wt++) { rank_start[wt] = pos; pos += count[wt] << (wt - 1); }
+  if (pos != (1u << max_bits)) return 0;
+  for (int s = 0; s < n; s++) {
+    const uint32_t wt = w[s];
+    if (!wt) continue;
+    const uint32_t span = 1u << (wt - 1), start = rank_start[wt];
+    const uint16_t ent = (uint16_t)((uint32_t)s | ((uint32_t)(max_bits + 1 - wt) << 8));
+    for (uint32_t k = 0; k < span; k++) h[start + k] = ent;
+    rank_start[wt] = start + span;
+  }
+  return (uint32_t)max_bits;
+}
+
+// Stream k (of `streams`) of block b: source range and output range.  false = malformed.
+ZN_HD bool huf_stream_ranges(const uint8_t* src, const ZBlock* b, uint32_t k, uint32_t* s_off, uint32_t* s_len,
+                             uint32_t* o_off, uint32_t* o_len) {
+  const uint8_t* q = src + b->lit_off;
+  const uint32_t qlen = b->lit_clen, regen = b->lit_regen;
+  if (!(b->flags & ZB_STREAMS4)) {
+    *s_off = 0; *s_len = qlen; *o_off = 0; *o_len = regen;
+    return k == 0;
+  }
+  if (qlen < 6) return false;
+  const uint32_t s1 = ld16le(q), s2 = ld16le(q + 2), s3 = ld16le(q + 4);
+  if (6 + s1 + s2 + s3 > qlen) return false;
+  const uint32_t seg = (regen + 3) / 4;
+  if (seg * 3 > regen) return false;
+  const uint32_t so[4] = {6, 6 + s1, 6 + s1 + s2, 6 + s1 + s2 + s3};
+  const uint32_t sl[4] = {s1, s2, s3, qlen - (6 + s1 + s2 + s3)};
+  *s_off = so[k]; *s_len = sl[k];
+  *o_off = seg * k; *o_len = k < 3 ? seg : regen - 3 * seg;
+  return true;
+}
+
+// One Huffman stream of n symbols, decoded by the calling thread; `out` may have any alignment, full words are
+// stored as words (a lane-per-stream warp would otherwise issue 32 scattered byte stores per symbol).
+ZN_HD bool huf_decode_stream_w(const uint16_t* h, uint32_t mb, const uint8_t* p, uint32_t len, uint8_t* out, uint32_t n) {
+  BackBits b;
+  if (!b.init(p, len)) return false;
+  uint32_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(out + i) & 3)) {
+    b.refill();
+    const uint32_t e0 = h[b.peek(mb)];
+    b.skip(e0 >> 8);
+    out[i++] = (uint8_t)e0;
+  }
+  for (; i + 4 <= n; i += 4) {
+    b.refill();
+    const uint32_t e0 = h[b.peek(mb)];
+    b.skip(e0 >> 8);
+    const uint32_t e1 = h[b.peek(mb)];
+    b.skip(e1 >> 8);
+    b.refill();
+    const uint32_t e2 = h[b.peek(mb)];
+    b.skip(e2 >> 8);
+    const uint32_t e3 = h[b.peek(mb)];
+    b.skip(e3 >> 8);
+    *reinterpret_cast<uint32_t*>(out + i) = (e0 & 0xFFu) | ((e1 & 0xFFu) << 8) | ((e2 & 0xFFu) << 16) | (e3 << 24);
+  }
+  for (; i < n; i++) {
+    b.refill();
+    const uint32_t e0 = h[b.peek(mb)];
+    b.skip(e0 >> 8);
+    out[i] = (uint8_t)e0;
+  }
+  return b.bits_left == 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------- chain
+// One thread per blob: output offsets, true histories, frame sizes.  Returns false when the blob has to go to the
+// legacy decoder (any phase reported a problem, sizes do not add up).
+ZN_HD bool chain_blob(ZBlock* blocks, uint32_t n_blocks, uint32_t dst_cap) {
+  uint32_t pos = 0, r0 = 1, r1 = 4, r2 = 8, frame_start = 0;
+  uint64_t fcs = 0;
+  bool has_fcs = false;
+  for (uint32_t j = 0; j < n_blocks; j++) {
+    ZBlock* b = &blocks[j];
+    const uint32_t type = b->flags & ZB_TYPE_MASK;
+    if (b->flags & ZB_FIRST) {
+      r0 = 1; r1 = 4; r2 = 8;
+      frame_start = pos;
+      has_fcs = (b->flags & ZB_HAS_FCS) != 0;
+      fcs = (uint64_t)b->fcs_lo | ((uint64_t)b->fcs_hi << 32);
+    }
+    uint32_t dec;
+    if (type != 2) dec = b->len;
+    else {
+      if (b->st_seq != 0 || b->st_lit != 0) return false;
+      if (b->lit_used > b->lit_regen) return false;
+      dec = b->matched + (b->lit_regen - b->lit_used);
+      if (dec > kZstdBlockMax) return false;
+    }
+    if (dec > dst_cap - pos) return false;
+    b->out_base = pos;
+    b->rep_in[0] = r0; b->rep_in[1] = r1; b->rep_in[2] = r2;
+    b->frame_start = frame_start;
+    if (type == 2 && b->nseq) {
+      const uint32_t n0 = sym_resolve(b->rep_fin[0], r0, r1, r2), n1 = sym_resolve(b->rep_fin[1], r0, r1, r2),
+                     n2 = sym_resolve(b->rep_fin[2], r0, r1, r2);
+      if (!n0 || !n1 || !n2) return false;
+      r0 = n0; r1 = n1; r2 = n2;
+    }
+    pos += dec;
+    if ((b->flags & ZB_LAST) && has_fcs && (uint64_t)(pos - frame_start) != fcs) return false;
+  }
+  return pos == dst_cap;
+}
+
+// predefined table set in the fat format (kTabSet entries; LL log 6, OF log 5, ML log 6)
+inline void build_predef_set(FseD* set) {
+  uint16_t next[64];
+  build_fat_table(set + kTabOffLL, 0, zs::kLLDefault, 36, 6, next);
+  build_fat_table(set + kTabOffOF, 1, zs::kOFDefault, 29, 5, next);
+  build_fat_table(set + kTabOffML, 2, zs::kMLDefault, 53, 6, next);
+}
+
+#if !defined(__CUDA_ARCH__)
+}  // namespace zp
+}  // namespace zn
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+namespace zn {
+namespace zp {
+// ---- host emulation of the whole pipeline for ONE blob (serial), used by tests/host_emu.  Returns 0 when the pipeline
+// decoded the blob (bytes in out), 1 when it would hand the blob to the legacy decoder.
+inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uint32_t cap, const FseD* predef_set,
+                         uint64_t* stats /* nullable: [0] blocks [1] sequences [2] huffman literal bytes */) {
+  const uint32_t slot_cap = cap / 16384 + 8;  // level >= 16 frames split their 128 KiB blocks
+  std::vector<ZBlock> blocks(slot_cap);
+  WalkNeeds needs;
+  const uint32_t nb = walk_blob(src, src_len, slot_cap, blocks.data(), &needs);
+  if (nb == ~0u) return 1;
+  std::vector<SeqRec16> recs(needs.nseq + 1);
+  std::vector<uint8_t> lits((size_t)needs.lit16 * 16 + 16);
+  std::vector<FseD> tabs((size_t)(needs.tabs + 1) * kTabSet);
+  // tables
+  for (uint32_t j = 0; j < nb; j++) {
+    ZBlock* b = &blocks[j];
+    if ((b->flags & ZB_TYPE_MASK) != 2 || b->nseq == 0) continue;
+    FseD* set = b->tab_slot != kNoSlot ? tabs.data() + (size_t)b->tab_slot * kTabSet : nullptr;  // null: defines nothing
+    int16_t norm[3][64];
+    int nsym[3], log[3];
+    uint32_t bits_off;
+    if (!parse_table_descs(src, b, set, norm, nsym, log, &bits_off)) continue;
+    bool ok = true;
+    const uint32_t offs[3] = {kTabOffLL, kTabOffOF, kTabOffML};
+    uint32_t tlogs = 0;
+    for (int k = 0; k < 3; k++) {
+      if (log[k] >= 5) {  // FSE-described (mode 2); RLE tables (log 0) were written by the parser
+        uint16_t next[64];
+        ok = ok && build_fat_table(set + offs[k], k, norm[k], nsym[k], log[k], next);
+      }
+      if (log[k] >= 0) tlogs |= (uint32_t)log[k] << (8 * k);
+    }
+    if (!ok) continue;
+    b->tlogs = tlogs;
+    b->bits_off = bits_off;
+  }
+  // seq
+  for (uint32_t j = 0; j < nb; j++) {
+    ZBlock* b = &blocks[j];
+    if ((b->flags & ZB_TYPE_MASK) != 2 || b->nseq == 0) continue;
+    if (b->bits_off == ~0u) continue;
+    SeqTabs st;
+    bool ok = true;
+    const uint32_t offs[3] = {kTabOffLL, kTabOffOF, kTabOffML};
+    const uint32_t plog[3] = {6, 5, 6};
+    for (int k = 0; k < 3; k++) {
+      const uint32_t def = b->seq_def[k];
+      if (def == kDefPredef) { st.t[k] = predef_set + offs[k]; st.log[k] = plog[k]; }
+      else if (def == kDefNone) ok = false;
+      else {
+        const ZBlock* d = &blocks[def];
+        if (d->bits_off == ~0u || d->tab_slot == kNoSlot) ok = false;
+        else { st.t[k] = tabs.data() + (size_t)d->tab_slot * kTabSet + offs[k]; st.log[k] = (d->tlogs >> (8 * k)) & 0xFFu; }
+      }
+    }
+    if (!ok) continue;
+    if (decode_sequences(src, b, st, recs.data() + b->seq_base, &b->matched, &b->lit_used, b->rep_fin)) b->st_seq = 0;
+  }
+  // lit
+  for (uint32_t j = 0; j < nb; j++) {
+    ZBlock* b = &blocks[j];
+    const uint32_t lt = (b->flags >> ZB_LIT_SHIFT) & 3u;
+    if ((b->flags & ZB_TYPE_MASK) != 2 || lt < 2) continue;
+    const ZBlock* d = &blocks[b->huf_def];
+    uint16_t h[2048];
+    const uint32_t mb = huf_build(h, src + d->huf_desc, d->huf_dlen);
+    if (!mb) continue;
+    const uint32_t streams = (b->flags & ZB_STREAMS4) ? 4u : 1u;
+    for (uint32_t k = 0; k < streams; k++) {
+      uint32_t so, sl, oo, ol;
+      if (!huf_stream_ranges(src, b, k, &so, &sl, &oo, &ol)) continue;
+      if (huf_decode_stream_w(h, mb, src + b->lit_off + so, sl, lits.data() + (size_t)b->lit_base16 * 16 + oo, ol)) b->st_lit--;
+    }
+  }
+  if (getenv("ZP_DEBUG")) for (uint32_t j = 0; j < nb; j++) fprintf(stderr, "blk %u type %u nseq %u st_seq %u st_lit %u bits_off %u tab %u defs %x %x %x lt %u\n", j, blocks[j].flags & 3, blocks[j].nseq, blocks[j].st_seq, blocks[j].st_lit, blocks[j].bits_off, blocks[j].tab_slot, blocks[j].seq_def[0], blocks[j].seq_def[1], blocks[j].seq_def[2], (blocks[j].flags >> 4) & 3);
+  if (!chain_blob(blocks.data(), nb, cap)) return 1;
+  // exec (plain serial loops; the device kernel's group logic is checked on the GPU against the same oracle)
+  uint64_t nseq_total = 0, nlit = 0;
+  for (uint32_t j = 0; j < nb; j++) {
+    const ZBlock* b = &blocks[j];
+    const uint32_t type = b->flags & ZB_TYPE_MASK;
+    uint8_t* o = out + b->out_base;
+    if (type == 0) memcpy(o, src + b->src_off, b->len);
+    else if (type == 1) memset(o, src[b->src_off], b->len);
+    else {
+      const uint32_t lt = (b->flags >> ZB_LIT_SHIFT) & 3u;
+      const uint8_t* lit = lt == 0 ? src + b->lit_off : lits.data() + (size_t)b->lit_base16 * 16;
+      const int rle = lt == 1 ? (int)b->lit_off : -1;
+      if (lt >= 2) nlit += b->lit_regen;
+      nseq_total += b->nseq;
+      if (stats && getenv("ZP_STATS")) {  // development: dependence structure as the exec kernel sees it
+        const uint32_t GB = 16384, NT = 512;
+        uint32_t s0 = 0, gpos = 0;
+        while (s0 < b->nseq) {
+          uint32_t cnt = 0;
+          while (cnt < NT && s0 + cnt < b->nseq) {
+            const SeqRec16 r = recs[b->seq_base + s0 + cnt];
+            if (rec_out(r) + rec_ll(r) + rec_ml(r) - gpos > GB) break;
+            cnt++;
+          }
+          if (cnt == 0) { stats[4]++; const SeqRec16 r = recs[b->seq_base + s0]; gpos = rec_out(r) + rec_ll(r) + rec_ml(r); s0++; continue; }
+          stats[5]++;  // groups
+          for (uint32_t w = 0; w < cnt; w += 32) {
+            const uint32_t n = cnt - w < 32 ? cnt - w : 32;
+            uint32_t pend = 0; int32_t dst[32], send[32];
+            for (uint32_t l = 0; l < n; l++) {
+              const SeqRec16 r = recs[b->seq_base + s0 + w + l];
+              const uint32_t off = sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]);
+              dst[l] = (int32_t)(rec_out(r) + rec_ll(r));
+              const int32_t sp = dst[l] - (int32_t)off;
+              send[l] = off >= rec_ml(r) ? sp + (int32_t)rec_ml(r) : dst[l];
+              stats[10 + (rec_ml(r) > 64 ? 3 : rec_ml(r) > 32 ? 2 : rec_ml(r) > 16 ? 1 : 0)]++;
+              stats[14 + (rec_ll(r) > 64 ? 3 : rec_ll(r) > 32 ? 2 : rec_ll(r) > 16 ? 1 : 0)]++;
+              if (rec_ml(r) && send[l] > (int32_t)gpos) { pend |= 1u << l; stats[6]++; } else stats[7]++;
+            }
+            if (pend) stats[18]++;  // warp turns with work
+            {  // exact-dependence rounds for comparison
+              uint32_t pe = pend; int32_t srcp[32], mlv[32];
+              for (uint32_t l = 0; l < n; l++) { const SeqRec16 r = recs[b->seq_base + s0 + w + l]; mlv[l] = (int32_t)rec_ml(r); srcp[l] = dst[l] - (int32_t)sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]); }
+              while (pe) {
+                stats[9]++;
+                uint32_t ready = 0;
+                for (uint32_t l = 0; l < n; l++) if (pe >> l & 1) {
+                  bool ok = true;
+                  for (uint32_t j = 0; j < l; j++) if ((pe >> j & 1) && dst[j] < send[l] && dst[j] + mlv[j] > srcp[l]) ok = false;
+                  if (ok) ready |= 1u << l;
+                }
+                pe &= ~ready;
+              }
+            }
+            while (pend) {
+              stats[8]++;  // rounds
+              const uint32_t f = (uint32_t)__builtin_ctz(pend);
+              uint32_t ready = 0;
+              for (uint32_t l = f; l < n; l++) if ((pend >> l & 1) && (l == f || send[l] <= dst[f])) ready |= 1u << l;
+              pend &= ~ready;
+            }
+          }
+          const SeqRec16 rl = recs[b->seq_base + s0 + cnt - 1];
+          gpos = rec_out(rl) + rec_ll(rl) + rec_ml(rl);
+          s0 += cnt;
+        }
+      }
+      for (uint32_t i = 0; i < b->nseq; i++) {
+        const SeqRec16 r = recs[b->seq_base + i];
+        const uint32_t ll = rec_ll(r), ml = rec_ml(r), orl = rec_out(r), lr = rec_lit(r);
+        for (uint32_t k = 0; k < ll; k++) o[orl + k] = rle >= 0 ? (uint8_t)rle : lit[lr + k];
+        const uint32_t off = sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]);
+        const uint32_t d = b->out_base + orl + ll;
+        if (off == 0 || off > d - b->frame_start) return 1;
+        for (uint32_t k = 0; k < ml; k++) out[d + k] = out[d - off + k];
+      }
+      for (uint32_t k = b->lit_used; k < b->lit_regen; k++) o[b->matched + k - b->lit_used] = rle >= 0 ? (uint8_t)rle : lit[k];
+    }
+  }
+  if (stats) { stats[0] = nb; stats[1] = nseq_total; stats[2] = nlit; }
+  return 0;
+}
+
+#endif
+
+}  // namespace zp
+}  // namespace zn
