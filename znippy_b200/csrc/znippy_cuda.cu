@@ -18,11 +18,10 @@
 
 #include "../../include/znippy_cuda.h"
 #include "blake3_kernels.cuh"
-#include "compress_kernels.cuh"
+#include "host_api.h"
 #include "decode_kernels.cuh"
 #include "par_kernel.cuh"
 #include "fused_ws.cuh"
-#include "zpipe_kernels.cuh"
 
 using namespace zn;
 
@@ -184,14 +183,7 @@ extern "C" zn_ctx* zn_ctx_create(int device, size_t staging_bytes) {
   cudaFuncSetAttribute(k_decode<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kB3SmemPerWarp);
   cudaFuncSetAttribute(k_decode_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes);
   cudaFuncSetAttribute(par::k_decode_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(par::ParShared));
-  {
-    static zp::FseD zset[zp::kTabSet];
-    zp::build_predef_set(zset);
-    if (cudaMemcpyToSymbol(zp::g_zpredef, zset, sizeof zset) != cudaSuccess) { zn_ctx_destroy(c); return nullptr; }
-  }
-  cudaFuncSetAttribute(zp::k_zlit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zp::kLitSmem);
-  cudaFuncSetAttribute(zp::k_zexec<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(zp::ExecShared<512>));
-  cudaFuncSetAttribute(zp::k_zexec<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(zp::ExecShared<128>));
+  if (!zp::pipeline_init()) { zn_ctx_destroy(c); return nullptr; }
   compress_init_attrs();
   return c;
 }
@@ -483,15 +475,6 @@ static bool zgrow(T** ptr, size_t* have, size_t want, size_t bytes_per) {
   return true;
 }
 
-__global__ void k_zinit(zp::ZPools* pools, uint32_t seq_cap, uint32_t lit_cap16, uint32_t tab_cap, uint32_t comp_cap) {
-  zp::ZPools z;
-  z.seq_used = 0; z.seq_cap = seq_cap;
-  z.lit_used16 = 0; z.lit_cap16 = lit_cap16;
-  z.tab_used = 0; z.tab_cap = tab_cap;
-  z.comp_used = 0; z.comp_cap = comp_cap;
-  *pools = z;
-}
-
 // DC_PIPE rows: the device-wide pipeline, then the one-team decoder for whatever the pipeline handed back.
 static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cudaStream_t st, uint32_t* launches) {
   zn_ctx* c = p->ctx;
@@ -510,39 +493,27 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
   zp::ZArgs a;
   a.blobs = p->d_blobs; a.blobs_base = d_blobs; a.zb = p->d_zb; a.nzb = p->nzb; a.blocks = z.blocks; a.pools = z.pools;
   a.comp_list = z.comp_list; a.tabs = z.tabs; a.recs = z.recs; a.lits = z.lits;
-  const uint32_t sms = (uint32_t)c->sm_count, slots = (uint32_t)p->z_slots;
   // development: ZN_ZPROF=1 prints the device time of every pipeline kernel of this run on stderr (synchronises)
   const bool prof = getenv("ZN_ZPROF") != nullptr;
-  cudaEvent_t pe[9];
-  int npe = 0;
-  auto mark = [&]() { if (prof) { cudaEventCreate(&pe[npe]); cudaEventRecord(pe[npe], st); npe++; } };
-  mark();
-  k_zinit<<<1, 1, 0, st>>>(z.pools, (uint32_t)p->z_seqs, (uint32_t)p->z_lit16, (uint32_t)p->z_tabs, slots);
-  zp::k_zwalk<<<(p->nzb + 63) / 64, 64, 0, st>>>(a);
-  mark();
-  zp::k_ztables<<<std::min<uint32_t>((slots + zp::kTabWarps - 1) / zp::kTabWarps, sms * 8), zp::kTabWarps * 32, 0, st>>>(a);
-  mark();
-  zp::k_zseq<<<(slots + 63) / 64, 64, 0, st>>>(a);
-  mark();
-  zp::k_zlit<<<std::min<uint32_t>((slots + zp::kLitBlocks - 1) / zp::kLitBlocks, sms * 3), zp::kLitBlocks * 4, zp::kLitSmem, st>>>(a);
-  mark();
-  zp::k_zchain<<<(p->nzb + 63) / 64, 64, 0, st>>>(a);
-  mark();
+  cudaEvent_t pe[8];
+  if (prof) for (auto& e : pe) cudaEventCreate(&e);
   uint32_t* ctr = p->d_counter + DC_COUNT;  // [0] exec, [1] legacy pass
-  if (p->z_mean >= (256u << 10))
-    zp::k_zexec<512><<<std::min<uint32_t>(p->nzb, sms * 2), 512, sizeof(zp::ExecShared<512>), st>>>(a, d_out, p->d_produced, ctr);
-  else
-    zp::k_zexec<128><<<std::min<uint32_t>(p->nzb, sms * 6), 128, sizeof(zp::ExecShared<128>), st>>>(a, d_out, p->d_produced, ctr);
-  mark();
+  zp::PipelineLaunch L;
+  L.a = a;
+  L.slots = (uint32_t)p->z_slots; L.seq_cap = (uint32_t)p->z_seqs; L.lit_cap16 = (uint32_t)p->z_lit16; L.tab_cap = (uint32_t)p->z_tabs;
+  L.sm_count = (uint32_t)c->sm_count;
+  L.mean_bytes = p->z_mean;
+  L.d_out = d_out; L.produced = p->d_produced; L.exec_counter = ctr;
+  zp::pipeline_enqueue(L, st, prof ? pe : nullptr);
   // rows the pipeline handed back (ZBlob.state != 0): the one-team decoder, which also produces their status
   const uint32_t* list = p->d_list_dec + p->cls_off[DC_PIPE];
   const uint32_t grid = std::min<uint32_t>(p->nzb, c->dec_grid);
   k_decode<kDecodeThreads, 1, false><<<grid, kDecodeThreads, 0, st>>>(p->d_blobs, list, p->nzb, d_blobs, d_out, c->d_lit, p->d_status,
                                                                    p->d_produced, ctr + 1, nullptr, 1u, &p->d_zb[0].state,
                                                                    (uint32_t)(sizeof(zp::ZBlob) / 4));
-  mark();
   if (prof) {
-    cudaEventSynchronize(pe[npe - 1]);
+    cudaEventRecord(pe[7], st);
+    cudaEventSynchronize(pe[7]);
     static const char* names[] = {"walk", "tables", "seq", "lit", "chain", "exec", "legacy"};
     zp::ZPools hp;
     cudaMemcpy(&hp, z.pools, sizeof hp, cudaMemcpyDeviceToHost);
@@ -551,11 +522,11 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
     uint32_t handed = 0;
     for (auto& b : hz) handed += b.state != 0;
     fprintf(stderr, "zpipe: %u blobs (%u handed back), %u blocks, %u seqs, %u table sets, %u lit16 |", p->nzb, handed, hp.comp_used, hp.seq_used, hp.tab_used, hp.lit_used16);
-    for (int i = 0; i + 1 < npe; i++) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
+    for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
     fprintf(stderr, " ms\n");
-    for (int i = 0; i < npe; i++) cudaEventDestroy(pe[i]);
+    for (auto& e : pe) cudaEventDestroy(e);
   }
-  *launches += 8;
+  *launches += zp::kPipelineLaunches + 1;
   return ZN_OK;
 }
 

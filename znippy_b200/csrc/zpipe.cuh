@@ -116,6 +116,20 @@ struct ZPools {
 struct alignas(16) SeqRec16 {
   uint32_t w0, w1, w2, w3;
 };
+// everything the pipeline kernels share
+struct ZArgs {
+  const BlobDesc* blobs;
+  const uint8_t* blobs_base;
+  ZBlob* zb;
+  uint32_t nzb;
+  ZBlock* blocks;
+  ZPools* pools;
+  uint32_t* comp_list;
+  FseD* tabs;
+  SeqRec16* recs;
+  uint8_t* lits;
+};
+
 ZN_HD SeqRec16 rec_pack(uint32_t out_rel, uint32_t lit_rel, uint32_t ll, uint32_t ml, uint32_t off) {
   SeqRec16 r;
   r.w0 = off;
@@ -681,6 +695,7 @@ inline void build_predef_set(FseD* set) {
 }  // namespace zn
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 namespace zn {
@@ -820,6 +835,28 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
               uint32_t ready = 0;
               for (uint32_t l = f; l < n; l++) if ((pend >> l & 1) && (l == f || send[l] <= dst[f])) ready |= 1u << l;
               pend &= ~ready;
+            }
+          }
+          {  // compacted near list, turns of 32, watermark rounds
+            std::vector<int32_t> nd, ns;
+            for (uint32_t l = 0; l < cnt; l++) {
+              const SeqRec16 r = recs[b->seq_base + s0 + l];
+              const uint32_t off = sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]);
+              const int32_t d = (int32_t)(rec_out(r) + rec_ll(r)), sp = d - (int32_t)off;
+              const int32_t se = off >= rec_ml(r) ? sp + (int32_t)rec_ml(r) : d;
+              if (rec_ml(r) && !(off >= rec_ml(r) && se <= (int32_t)gpos)) { nd.push_back(d); ns.push_back(se); }
+            }
+            for (size_t w = 0; w < nd.size(); w += 32) {
+              const uint32_t n = (uint32_t)std::min<size_t>(32, nd.size() - w);
+              uint32_t pend = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1);
+              stats[19]++;
+              while (pend) {
+                stats[20]++;
+                const uint32_t f = (uint32_t)__builtin_ctz(pend);
+                uint32_t ready = 0;
+                for (uint32_t l = f; l < n; l++) if ((pend >> l & 1) && (l == f || ns[w + l] <= nd[w + f])) ready |= 1u << l;
+                pend &= ~ready;
+              }
             }
           }
           const SeqRec16 rl = recs[b->seq_base + s0 + cnt - 1];
