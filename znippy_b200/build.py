@@ -77,6 +77,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, unit), "-o", _obj(unit)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if os.environ.get("ZN_TRACE_BUILD"):  # development: phase counters in the pipeline's exec kernel
+            cmd.insert(1, "-DZP_TRACE")
         return unit, subprocess.run(cmd, capture_output=True, text=True)
 
     todo = [u for u in UNITS if force or _unit_stale(u)]

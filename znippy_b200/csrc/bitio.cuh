@@ -39,7 +39,9 @@ struct BackBits {
   const uint32_t* wbase;  // aligned word holding the first stream byte
   uint32_t lowmask;       // clears the bytes of word 0 that precede the stream
   int32_t widx;           // index of the word held in `pre` (descending); < 0 -> zeros
-  uint32_t pre;           // word widx, loaded one refill ahead so its memory latency is off the critical path
+  uint32_t pre2;          // word widx - 1, RAW, loaded two refills ahead
+  uint32_t pre;           // word widx, RAW (lowmask not applied yet), loaded one refill ahead: nothing touches it until the
+                          // next refill, so its memory latency stays off the critical path
   uint64_t win;           // unread bits, MSB-aligned
   int32_t navail;         // valid bits in win
   int32_t bits_left;      // unread bits in the stream; < 0 == over-read
@@ -49,6 +51,8 @@ struct BackBits {
     const uint32_t w = wbase[i];
     return i == 0 ? (w & lowmask) : w;
   }
+  ZN_HD uint32_t fetch_raw(int32_t i) const { return i < 0 ? 0u : wbase[i]; }
+  ZN_HD uint32_t pre_word() const { return widx == 0 ? (pre & lowmask) : pre; }  // the word in `pre`, masked at the time of use
   ZN_HD bool init(const uint8_t* p, uint32_t len) {
     if (len == 0) return false;
     const uint32_t last = p[len - 1];
@@ -65,7 +69,8 @@ struct BackBits {
     win = nvalid ? ((uint64_t)w << (64 - nvalid)) : 0;
     navail = nvalid;
     widx = t - 1;
-    pre = fetch(widx);
+    pre = fetch_raw(widx);
+    pre2 = fetch_raw(widx - 1);
     return true;
   }
 #if defined(__CUDA_ARCH__)
@@ -75,20 +80,24 @@ struct BackBits {
     if (navail <= 32) {
       uint32_t hi = (uint32_t)(win >> 32);
       const uint32_t n = (uint32_t)navail;
-      hi |= __funnelshift_rc(pre, 0u, n);                    // pre >> n          (0 when n == 32)
-      const uint32_t lo = __funnelshift_rc(0u, pre, n);      // pre << (32 - n)   (0 when n == 0)
+      const uint32_t p = pre_word();
+      hi |= __funnelshift_rc(p, 0u, n);                      // p >> n          (0 when n == 32)
+      const uint32_t lo = __funnelshift_rc(0u, p, n);        // p << (32 - n)   (0 when n == 0)
       win = ((uint64_t)hi << 32) | lo;
       navail += 32;
       widx--;
-      pre = fetch(widx);
+      pre = pre2;
+      pre2 = fetch_raw(widx - 1);
       if (navail <= 32) {  // the window was empty: take a second word
         const uint32_t n2 = (uint32_t)navail;
+        const uint32_t p2 = pre_word();
         uint32_t h2 = (uint32_t)(win >> 32);
-        h2 |= __funnelshift_rc(pre, 0u, n2);
-        win = ((uint64_t)h2 << 32) | __funnelshift_rc(0u, pre, n2);
+        h2 |= __funnelshift_rc(p2, 0u, n2);
+        win = ((uint64_t)h2 << 32) | __funnelshift_rc(0u, p2, n2);
         navail += 32;
         widx--;
-        pre = fetch(widx);
+        pre = pre2;
+        pre2 = fetch_raw(widx - 1);
       }
     }
   }
@@ -102,10 +111,11 @@ struct BackBits {
 #else
   ZN_HD void refill() {  // afterwards navail > 32, so any read of <= 32 bits is served from the window
     while (navail <= 32) {
-      win |= (uint64_t)pre << (32 - navail);
+      win |= (uint64_t)pre_word() << (32 - navail);
       navail += 32;
       widx--;
-      pre = fetch(widx);
+      pre = pre2;
+      pre2 = fetch_raw(widx - 1);
     }
   }
   ZN_HD uint32_t peek(uint32_t n) const { return n ? (uint32_t)(win >> (64 - n)) : 0u; }  // n <= 32

@@ -56,6 +56,7 @@ struct PipelineLaunch {
 // the first kernel and after walk / tables / seq / lit / chain / exec.
 void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks);
 constexpr uint32_t kPipelineLaunches = 7;
+void pipeline_trace_dump();  // development builds (ZN_TRACE_BUILD=1): prints and clears the exec kernel's phase counters
 }  // namespace zp
 
 }  // namespace zn

@@ -524,6 +524,7 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
     fprintf(stderr, "zpipe: %u blobs (%u handed back), %u blocks, %u seqs, %u table sets, %u lit16 |", p->nzb, handed, hp.comp_used, hp.seq_used, hp.tab_used, hp.lit_used16);
     for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
     fprintf(stderr, " ms\n");
+    zp::pipeline_trace_dump();
     for (auto& e : pe) cudaEventDestroy(e);
   }
   *launches += zp::kPipelineLaunches + 1;

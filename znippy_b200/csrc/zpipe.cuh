@@ -10,8 +10,8 @@
 //            literals / Huffman tree / sequence tables are DEFINED (own section, an earlier block for treeless and
 //            repeat modes, or the predefined distribution) — which removes the table dependence between blocks — and
 //            bump-allocates the blob's sequence records, literal bytes and table sets from batch-wide pools;
-//   tables   one warp per compressed block parses the three FSE table descriptions and builds "fat" decoding tables
-//            (next-state base, state bits, extra bits, value baseline in one 8-byte entry) in global memory;
+//   tables   one warp per compressed block parses the three FSE table descriptions and builds decoding tables whose
+//            4-byte entries hold next-state base, state bits, extra-bit count and symbol, in global memory;
 //   seq      ONE LANE PER BLOCK runs the three interleaved FSE state machines: 32 independent bit streams per warp,
 //            thousands per device.  Repeat offsets that reach back before the block are kept SYMBOLIC (history entry
 //            i minus k), so no block waits for its predecessor.  Output: one 16-byte record per sequence;
@@ -41,13 +41,15 @@ constexpr uint32_t kTabLL = 512, kTabOF = 256, kTabML = 512;      // entries per
 constexpr uint32_t kTabSet = kTabLL + kTabOF + kTabML;             // entries of one block's table set
 constexpr uint32_t kTabOffLL = 0, kTabOffOF = kTabLL, kTabOffML = kTabLL + kTabOF;
 
-// fat FSE decoding-table entry: x = next-state base | state bits << 16 | extra bits << 24, y = value baseline
-struct alignas(8) FseD {
-  uint32_t x, y;
-};
-ZN_HD uint32_t fd_base(uint32_t x) { return x & 0xFFFFu; }
-ZN_HD uint32_t fd_nbits(uint32_t x) { return (x >> 16) & 0xFFu; }
-ZN_HD uint32_t fd_extra(uint32_t x) { return x >> 24; }
+// FSE decoding-table entry, 4 bytes: next-state base (10 bits) | state bits << 10 (4) | extra bits << 14 (5) | symbol << 19
+// (6).  Everything the bit-position chain needs sits in the entry; the value baseline is looked up by symbol
+// (value_base()), off the critical path.  A block's three tables are 5 KiB: 32 streams fit one SM's shared memory.
+typedef uint32_t FseD;
+ZN_HD uint32_t fd_pack(uint32_t base, uint32_t nbits, uint32_t extra, uint32_t sym) { return base | (nbits << 10) | (extra << 14) | (sym << 19); }
+ZN_HD uint32_t fd_base(uint32_t e) { return e & 0x3FFu; }
+ZN_HD uint32_t fd_nbits(uint32_t e) { return (e >> 10) & 0xFu; }
+ZN_HD uint32_t fd_extra(uint32_t e) { return (e >> 14) & 0x1Fu; }
+ZN_HD uint32_t fd_sym(uint32_t e) { return e >> 19; }
 
 // block flags
 enum : uint32_t {
@@ -143,6 +145,13 @@ ZN_HD uint32_t rec_out(const SeqRec16& r) { return r.w1 & 0x3FFFFu; }
 ZN_HD uint32_t rec_lit(const SeqRec16& r) { return r.w2 & 0x3FFFFu; }
 ZN_HD uint32_t rec_ll(const SeqRec16& r) { return (r.w1 >> 18) | ((r.w3 & 0xFFu) << 14); }
 ZN_HD uint32_t rec_ml(const SeqRec16& r) { return (r.w2 >> 18) | ((r.w3 >> 8) << 14); }
+
+// records are written once and read once, much later: stream them past the L2-resident decoding tables
+#if defined(__CUDA_ARCH__)
+ZN_D void rec_store(SeqRec16* p, const SeqRec16& r) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(r.w0, r.w1, r.w2, r.w3)); }
+#else
+inline void rec_store(SeqRec16* p, const SeqRec16& r) { *p = r; }
+#endif
 
 ZN_HD bool is_sym(uint32_t v) { return (v & kSymBit) != 0; }
 ZN_HD uint32_t sym_make(uint32_t i) { return kSymBit | i; }
@@ -367,29 +376,28 @@ ZN_HD bool sym_value(int k, uint32_t s, uint32_t* base, uint32_t* extra) {
   return true;
 }
 
-// Fat decoding table from normalized counts (same spreading as zs::fse_build).  `next` = scratch for nsym uint16.
+// Decoding table from normalized counts (same spreading as zs::fse_build).  `next` = scratch for nsym uint16.
 ZN_HD bool build_fat_table(FseD* t, int k, const int16_t* norm, int nsym, int log, uint16_t* next) {
   const int size = 1 << log;
   int high = size - 1;
   for (int s = 0; s < nsym; s++) {
-    if (norm[s] == -1) { t[high--].x = (uint32_t)s; next[s] = 1; }
+    if (norm[s] == -1) { t[high--] = (uint32_t)s; next[s] = 1; }
     else next[s] = (uint16_t)norm[s];
   }
   const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
   int pos = 0;
   for (int s = 0; s < nsym; s++)
     for (int i = 0; i < norm[s]; i++) {
-      t[pos].x = (uint32_t)s;
+      t[pos] = (uint32_t)s;
       do pos = (pos + step) & mask; while (pos > high);
     }
   for (int u = 0; u < size; u++) {
-    const uint32_t s = t[u].x;
+    const uint32_t s = t[u];
     const uint32_t ns = next[s]++;
     const uint32_t nb = (uint32_t)(log - hibit32(ns));
     uint32_t base, extra;
     if (!sym_value(k, s, &base, &extra)) return false;
-    t[u].x = ((ns << nb) - (uint32_t)size) | (nb << 16) | (extra << 24);
-    t[u].y = base;
+    t[u] = fd_pack((ns << nb) - (uint32_t)size, nb, extra, s);
   }
   return true;
 }
@@ -413,8 +421,7 @@ ZN_HD bool parse_table_descs(const uint8_t* src, const ZBlock* b, FseD* set, int
       if ((int)sym > max_sym) return false;
       uint32_t base, extra;
       if (!sym_value(k, sym, &base, &extra)) return false;
-      set[offs[k]].x = extra << 24;
-      set[offs[k]].y = base;
+      set[offs[k]] = fd_pack(0, 0, extra, sym);
       log[k] = 0;
       nsym[k] = 0;  // nothing to build
     } else if (m == 2) {
@@ -430,43 +437,78 @@ ZN_HD bool parse_table_descs(const uint8_t* src, const ZBlock* b, FseD* set, int
 }
 
 // ------------------------------------------------------------------------------------------------------------- seq
-// Per-block table view used by the sequence decoder.
-struct SeqTabs {
-  const FseD* t[3];  // LL, OF, ML
-  uint32_t log[3];
+// Per-block table view used by the sequence decoder: Acc::ld(k, i) returns entry i of table k (0 LL, 1 OF, 2 ML) and
+// Acc::base(k, sym) the value baseline of a symbol — on the device both are shared-memory reads of the lane's own
+// table copy and of the baseline LUTs, on the host plain arrays.
+struct HostTabs {
+  const FseD* t[3];
+  ZN_HD uint32_t ld(int k, uint32_t i) const { return t[k][i]; }
+  ZN_HD uint32_t base(int k, uint32_t s) const { return k == 0 ? zs::kLLBase[s] : zs::kMLBase[s]; }
 };
+
+#if defined(__CUDA_ARCH__)
+ZN_D uint32_t shl_c(uint32_t w, uint32_t n) { return __funnelshift_lc(0u, w, n); }  // w << n, 0 for n >= 32
+ZN_D uint32_t shr_c(uint32_t w, uint32_t n) { return __funnelshift_rc(w, 0u, n); }  // w >> n, 0 for n >= 32
+#else
+inline uint32_t shl_c(uint32_t w, uint32_t n) { return n >= 32 ? 0u : w << n; }
+inline uint32_t shr_c(uint32_t w, uint32_t n) { return n >= 32 ? 0u : w >> n; }
+#endif
 
 // One thread decodes every sequence of block b into rec[0 .. nseq).  Fills matched / lit_used / rep_fin and returns
 // true, or false when anything is off (the blob then goes to the legacy decoder).
-ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const SeqTabs& tabs, SeqRec16* rec, uint32_t* matched,
-                            uint32_t* lit_used, uint32_t* rep_fin) {
+//
+// Bit reading: the three table entries of a sequence say how many bits each of its six fields takes before any bit is
+// read, so the common case (<= 32 bits in all) is ONE refill of the 64-bit window, six shift-pairs out of its top word
+// and one skip; longer sequences (huge offsets) take the field-by-field path.
+template <class Acc>
+ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const Acc& tabs, const uint32_t* logs, SeqRec16* rec,
+                            uint32_t* matched, uint32_t* lit_used, uint32_t* rep_fin) {
   const uint32_t nseq = b->nseq, lit_len = b->lit_regen;
   const uint32_t end = b->src_off + b->len;
   if (b->bits_off >= end) return false;
   BackBits bb;
   if (!bb.init(src + b->bits_off, end - b->bits_off)) return false;
   bb.refill();
-  uint32_t sl = bb.read(tabs.log[0]), so = bb.read(tabs.log[1]), sm = bb.read(tabs.log[2]);
+  uint32_t sl = bb.read(logs[0]), so = bb.read(logs[1]), sm = bb.read(logs[2]);
   if (bb.bits_left < 0) return false;
   uint32_t h0 = sym_make(0), h1 = sym_make(1), h2 = sym_make(2);
   uint32_t lit_pos = 0, out_pos = 0;
-  const FseD* tl = tabs.t[0];
-  const FseD* to = tabs.t[1];
-  const FseD* tm = tabs.t[2];
+  uint32_t bad = 0;  // sticky: no early exit from the lane-per-block loop (a diverged warp pays for both sides)
   for (uint32_t i = 0; i < nseq; i++) {
-    const FseD el = tl[sl], eo = to[so], em = tm[sm];
+    const uint32_t el = tabs.ld(0, sl), eo = tabs.ld(1, so), em = tabs.ld(2, sm);
+    const uint32_t ofx = fd_extra(eo), mlx = fd_extra(em), llx = fd_extra(el);
+    const bool lastq = i + 1 == nseq;
+    const uint32_t nl = lastq ? 0u : fd_nbits(el), nm = lastq ? 0u : fd_nbits(em), no = lastq ? 0u : fd_nbits(eo);
+    // the offset's extra bits (up to 31, ~20 for a far match) are read on their own; the other five fields (two length
+    // extras + three state updates, typically ~20 bits) come out of ONE 32-bit window
     bb.refill();
-    const uint32_t ov = eo.y + bb.read(fd_extra(eo.x));
+    const uint32_t ofv = bb.read(ofx);
     bb.refill();
-    const uint32_t ml = em.y + bb.read(fd_extra(em.x));
-    const uint32_t ll = el.y + bb.read(fd_extra(el.x));
-    if (i + 1 < nseq) {
+    const uint32_t a1 = mlx, a2 = a1 + llx, a3 = a2 + nl, a4 = a3 + nm, rest = a4 + no;
+    uint32_t mlv, llv, vl, vm, vo;
+    if (rest <= 32) {
+      const uint32_t w = (uint32_t)(bb.win >> 32);
+      mlv = shr_c(w, 32 - mlx);
+      llv = shr_c(shl_c(w, a1), 32 - llx);
+      vl = shr_c(shl_c(w, a2), 32 - nl);
+      vm = shr_c(shl_c(w, a3), 32 - nm);
+      vo = shr_c(shl_c(w, a4), 32 - no);
+      bb.skip(rest);
+    } else {
+      mlv = bb.read(mlx);
+      llv = bb.read(llx);
       bb.refill();
-      sl = fd_base(el.x) + bb.read(fd_nbits(el.x));
-      sm = fd_base(em.x) + bb.read(fd_nbits(em.x));
-      so = fd_base(eo.x) + bb.read(fd_nbits(eo.x));
+      vl = bb.read(nl);
+      vm = bb.read(nm);
+      vo = bb.read(no);
     }
-    if (bb.bits_left < 0) return false;
+    const uint32_t oc = fd_sym(eo);
+    const uint32_t ov = (1u << oc) + ofv;
+    const uint32_t ml = tabs.base(2, fd_sym(em)) + mlv;
+    const uint32_t ll = tabs.base(0, fd_sym(el)) + llv;
+    sl = fd_base(el) + vl;
+    sm = fd_base(em) + vm;
+    so = fd_base(eo) + vo;
     uint32_t offset;
     if (ov > 3) {
       offset = ov - 3;
@@ -477,19 +519,20 @@ ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const SeqTabs& 
       else {
         if (idx == 3) {
           if (is_sym(h0)) offset = sym_minus1(h0);
-          else { offset = h0 - 1; if (offset == 0) return false; }
+          else { offset = h0 - 1; bad |= offset == 0; }
         } else offset = idx == 1 ? h1 : h2;
         if (idx != 1) h2 = h1;
         h1 = h0;
         h0 = offset;
       }
     }
-    if (ll > lit_len - lit_pos) return false;
-    if (ll > kZstdBlockMax || ml > kZstdBlockMax + 3u || out_pos + ll + ml > kZstdBlockMax) return false;
-    rec[i] = rec_pack(out_pos, lit_pos, ll, ml, offset);
+    // (an over-read shows up as bits_left < 0 at the end: the reader returns zeros below the stream start, never faults)
+    bad |= (ll > lit_len - lit_pos) | (out_pos + ll + ml > kZstdBlockMax);
+    rec_store(rec + i, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll & 0x3FFFFu, ml & 0x3FFFFu, offset));
     lit_pos += ll;
     out_pos += ll + ml;
   }
+  if (bad) return false;
   if (bb.bits_left != 0) return false;
   *matched = out_pos;
   *lit_used = lit_pos;
@@ -740,22 +783,23 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
     ZBlock* b = &blocks[j];
     if ((b->flags & ZB_TYPE_MASK) != 2 || b->nseq == 0) continue;
     if (b->bits_off == ~0u) continue;
-    SeqTabs st;
+    HostTabs st;
+    uint32_t logs[3];
     bool ok = true;
     const uint32_t offs[3] = {kTabOffLL, kTabOffOF, kTabOffML};
     const uint32_t plog[3] = {6, 5, 6};
     for (int k = 0; k < 3; k++) {
       const uint32_t def = b->seq_def[k];
-      if (def == kDefPredef) { st.t[k] = predef_set + offs[k]; st.log[k] = plog[k]; }
+      if (def == kDefPredef) { st.t[k] = predef_set + offs[k]; logs[k] = plog[k]; }
       else if (def == kDefNone) ok = false;
       else {
         const ZBlock* d = &blocks[def];
         if (d->bits_off == ~0u || d->tab_slot == kNoSlot) ok = false;
-        else { st.t[k] = tabs.data() + (size_t)d->tab_slot * kTabSet + offs[k]; st.log[k] = (d->tlogs >> (8 * k)) & 0xFFu; }
+        else { st.t[k] = tabs.data() + (size_t)d->tab_slot * kTabSet + offs[k]; logs[k] = (d->tlogs >> (8 * k)) & 0xFFu; }
       }
     }
     if (!ok) continue;
-    if (decode_sequences(src, b, st, recs.data() + b->seq_base, &b->matched, &b->lit_used, b->rep_fin)) b->st_seq = 0;
+    if (decode_sequences(src, b, st, logs, recs.data() + b->seq_base, &b->matched, &b->lit_used, b->rep_fin)) b->st_seq = 0;
   }
   // lit
   for (uint32_t j = 0; j < nb; j++) {
@@ -789,6 +833,54 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
       const int rle = lt == 1 ? (int)b->lit_off : -1;
       if (lt >= 2) nlit += b->lit_regen;
       nseq_total += b->nseq;
+      if (stats && getenv("ZP_STATS")) {  // development: true dependence depth of the block's matches (sources inside the block)
+        std::vector<uint16_t> bd(kZstdBlockMax + 16, 0);
+        uint32_t maxd = 0;
+        for (uint32_t i = 0; i < b->nseq; i++) {
+          const SeqRec16 r = recs[b->seq_base + i];
+          const uint32_t off = sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]);
+          const int32_t d = (int32_t)(rec_out(r) + rec_ll(r)), sp = d - (int32_t)off, ml = (int32_t)rec_ml(r);
+          const int32_t se = (int32_t)off >= ml ? sp + ml : d;
+          uint32_t dep = 0;
+          for (int32_t p = sp < 0 ? 0 : sp; p < se; p++) dep = std::max<uint32_t>(dep, bd[p]);
+          dep += 1;
+          for (int32_t k = 0; k < ml; k++) bd[d + k] = (uint16_t)dep;
+          maxd = std::max(maxd, dep);
+        }
+        stats[26] += maxd;
+        // wavefront passes with groups of <= 2048 sequences / 32 KiB: depth counted inside each group only
+        {
+          const uint32_t GBW = 32768, GS = 2048;
+          uint32_t s0 = 0, gpos = 0;
+          while (s0 < b->nseq) {
+            uint32_t cnt = 0;
+            while (cnt < GS && s0 + cnt < b->nseq) {
+              const SeqRec16 r = recs[b->seq_base + s0 + cnt];
+              if (rec_out(r) + rec_ll(r) + rec_ml(r) - gpos > GBW) break;
+              cnt++;
+            }
+            if (cnt == 0) { const SeqRec16 r = recs[b->seq_base + s0]; gpos = rec_out(r) + rec_ll(r) + rec_ml(r); s0++; continue; }
+            std::fill(bd.begin(), bd.end(), 0);
+            uint32_t gd = 0;
+            for (uint32_t i = 0; i < cnt; i++) {
+              const SeqRec16 r = recs[b->seq_base + s0 + i];
+              const uint32_t off = sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]);
+              const int32_t d = (int32_t)(rec_out(r) + rec_ll(r)), sp = d - (int32_t)off, ml = (int32_t)rec_ml(r);
+              const int32_t se = (int32_t)off >= ml ? sp + ml : d;
+              uint32_t dep = 0;
+              for (int32_t p = sp < (int32_t)gpos ? (int32_t)gpos : sp; p < se; p++) dep = std::max<uint32_t>(dep, bd[p]);
+              const bool farm = (int32_t)off >= ml && se <= (int32_t)gpos;
+              if (!farm) dep += 1;
+              for (int32_t k = 0; k < ml; k++) bd[d + k] = (uint16_t)dep;
+              gd = std::max(gd, dep);
+            }
+            stats[27] += gd; stats[28]++;
+            const SeqRec16 rl = recs[b->seq_base + s0 + cnt - 1];
+            gpos = rec_out(rl) + rec_ll(rl) + rec_ml(rl);
+            s0 += cnt;
+          }
+        }
+      }
       if (stats && getenv("ZP_STATS")) {  // development: dependence structure as the exec kernel sees it
         const uint32_t GB = 16384, NT = 512;
         uint32_t s0 = 0, gpos = 0;
@@ -844,7 +936,11 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
               const uint32_t off = sym_resolve(rec_off(r), b->rep_in[0], b->rep_in[1], b->rep_in[2]);
               const int32_t d = (int32_t)(rec_out(r) + rec_ll(r)), sp = d - (int32_t)off;
               const int32_t se = off >= rec_ml(r) ? sp + (int32_t)rec_ml(r) : d;
-              if (rec_ml(r) && !(off >= rec_ml(r) && se <= (int32_t)gpos)) { nd.push_back(d); ns.push_back(se); }
+              if (rec_ml(r) && !(off >= rec_ml(r) && se <= (int32_t)gpos)) {
+                nd.push_back(d); ns.push_back(se);
+                stats[21 + (off < 4 ? 0 : off < 16 ? 1 : off < rec_ml(r) ? 2 : 3)]++;
+                if (off < 16) stats[25] += rec_ml(r);
+              }
             }
             for (size_t w = 0; w < nd.size(); w += 32) {
               const uint32_t n = (uint32_t)std::min<size_t>(32, nd.size() - w);

@@ -17,7 +17,16 @@
 namespace zn {
 namespace zp {
 
-__device__ FseD g_zpredef[kTabSet];  // predefined distributions in the fat format (filled by zn_ctx_create)
+__device__ FseD g_zpredef[kTabSet];  // decoding tables of the predefined distributions (filled by zn_ctx_create)
+
+// shared-memory accesses by 32-bit shared address (no generic-address arithmetic in the byte loops)
+ZN_D uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+ZN_D void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+ZN_D uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+ZN_D void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// table reads of the sequence decoder: not volatile (the lane's tables never change while it decodes), so the
+// compiler may schedule them early
+ZN_D uint32_t lds32_ro(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 constexpr uint32_t kTabWarps = 8;    // k_ztables: warps per CTA
 constexpr uint32_t kLitBlocks = 16;  // k_zlit: blocks per CTA (4 lanes each), one 4 KiB Huffman table per block
@@ -102,9 +111,33 @@ __global__ void __launch_bounds__(kTabWarps * 32) k_ztables(ZArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------------------------- seq
-__global__ void __launch_bounds__(64) k_zseq(ZArgs a) {
+// One lane per block.  The lane's three decoding tables (5 KiB of 4-byte entries) are copied into shared memory first:
+// with them in global memory the kernel was bound by DRAM latency (16 384 table sets = 168 MB of random 8-byte reads
+// thrashed the L2: 26 GB of DRAM reads, 15 ms); now the state chain runs at shared-memory latency.  kSeqLanes streams
+// per SM (one CTA, two warps) is what 227 KB of shared memory hold.
+constexpr uint32_t kSeqLanes = 44;
+constexpr uint32_t kSeqSmem = kSeqLanes * kTabSet * 4 + (36 + 53) * 4;
+
+struct SmemTabs {
+  uint32_t tab_s, lut_s;  // shared addresses: the lane's table set, the baseline LUTs (LL at 0, ML at 36)
+  ZN_D uint32_t ld(int k, uint32_t i) const { return lds32_ro(tab_s + 4u * ((k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML)) + i)); }
+  ZN_D uint32_t base(int k, uint32_t sym) const { return lds32_ro(lut_s + 4u * ((k == 0 ? 0u : 36u) + sym)); }
+};
+
+__global__ void __launch_bounds__(64, 1) k_zseq(ZArgs a) {
+  extern __shared__ __align__(16) uint8_t seq_smem[];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(seq_smem);
+  const uint32_t lut_s = smem_s + kSeqLanes * kTabSet * 4;
+  for (uint32_t i = tid; i < 36; i += 64) sts32(lut_s + 4 * i, zs::kLLBase[i]);
+  for (uint32_t i = tid; i < 53; i += 64) sts32(lut_s + 4 * (36 + i), zs::kMLBase[i]);
+  __syncthreads();
+  if (tid >= kSeqLanes) return;
+  SmemTabs st;
+  st.tab_s = smem_s + tid * kTabSet * 4;
+  st.lut_s = lut_s;
   const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
-  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n_comp; it += gridDim.x * blockDim.x) {
+  for (uint32_t it = blockIdx.x * kSeqLanes + tid; it < n_comp; it += gridDim.x * kSeqLanes) {
     const uint32_t slot = a.comp_list[it];
     if (slot == kNoSlot) continue;
     ZBlock* b = &a.blocks[slot];
@@ -112,27 +145,86 @@ __global__ void __launch_bounds__(64) k_zseq(ZArgs a) {
     const ZBlob z = a.zb[b->pad[0]];
     const BlobDesc d = a.blobs[z.blob];
     const uint8_t* src = a.blobs_base + d.src_off;
-    SeqTabs st;
+    uint32_t logs[3];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint32_t offs = k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML);
+      const uint32_t def = b->seq_def[k];
+      const FseD* t = g_zpredef + offs;
+      logs[k] = k == 1 ? 5u : 6u;
+      if (def == kDefNone) ok = false;
+      else if (def != kDefPredef) {
+        const ZBlock* db = &a.blocks[z.slot0 + def];
+        if (db->bits_off == ~0u || db->tab_slot == kNoSlot) ok = false;
+        else {
+          t = a.tabs + (size_t)db->tab_slot * kTabSet + offs;
+          logs[k] = (db->tlogs >> (8 * k)) & 0xFFu;
+        }
+      }
+      if (ok) {
+        const uint32_t n = 1u << logs[k], dst = st.tab_s + 4u * offs;
+        for (uint32_t i = 0; i < n; i++) sts32(dst + 4 * i, t[i]);
+      }
+    }
+    if (!ok) continue;
+    uint32_t matched, lit_used, rep[3];
+    if (decode_sequences(src, b, st, logs, a.recs + b->seq_base, &matched, &lit_used, rep)) {
+      b->matched = matched;
+      b->lit_used = lit_used;
+      b->rep_fin[0] = rep[0]; b->rep_fin[1] = rep[1]; b->rep_fin[2] = rep[2];
+      b->st_seq = 0;
+    }
+  }
+}
+
+// Variant with the tables left in global memory (4-byte entries: all table sets of a 2 GiB batch are 84 MB and stay
+// L2-resident when the record stores stream past them): every block of the batch is decoded at once, one lane each.
+struct GlobalTabs {
+  const FseD* t[3];
+  uint32_t lut_s;
+  ZN_D uint32_t ld(int k, uint32_t i) const { return __ldg(t[k] + i); }
+  ZN_D uint32_t base(int k, uint32_t sym) const { return lds32_ro(lut_s + 4u * ((k == 0 ? 0u : 36u) + sym)); }
+};
+
+__global__ void __launch_bounds__(32) k_zseq_g(ZArgs a) {
+  __shared__ uint32_t s_lut[36 + 53];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < 36; i += 32) s_lut[i] = zs::kLLBase[i];
+  for (uint32_t i = tid; i < 53; i += 32) s_lut[36 + i] = zs::kMLBase[i];
+  __syncwarp();
+  GlobalTabs st;
+  st.lut_s = (uint32_t)__cvta_generic_to_shared(s_lut);
+  const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
+  for (uint32_t it = blockIdx.x * 32 + tid; it < n_comp; it += gridDim.x * 32) {
+    const uint32_t slot = a.comp_list[it];
+    if (slot == kNoSlot) continue;
+    ZBlock* b = &a.blocks[slot];
+    if (b->nseq == 0 || b->bits_off == ~0u) continue;
+    const ZBlob z = a.zb[b->pad[0]];
+    const BlobDesc d = a.blobs[z.blob];
+    const uint8_t* src = a.blobs_base + d.src_off;
+    uint32_t logs[3];
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const uint32_t offs = k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML);
       const uint32_t def = b->seq_def[k];
       st.t[k] = g_zpredef + offs;
-      st.log[k] = k == 1 ? 5u : 6u;
+      logs[k] = k == 1 ? 5u : 6u;
       if (def == kDefNone) ok = false;
       else if (def != kDefPredef) {
         const ZBlock* db = &a.blocks[z.slot0 + def];
         if (db->bits_off == ~0u || db->tab_slot == kNoSlot) ok = false;
         else {
           st.t[k] = a.tabs + (size_t)db->tab_slot * kTabSet + offs;
-          st.log[k] = (db->tlogs >> (8 * k)) & 0xFFu;
+          logs[k] = (db->tlogs >> (8 * k)) & 0xFFu;
         }
       }
     }
     if (!ok) continue;
     uint32_t matched, lit_used, rep[3];
-    if (decode_sequences(src, b, st, a.recs + b->seq_base, &matched, &lit_used, rep)) {
+    if (decode_sequences(src, b, st, logs, a.recs + b->seq_base, &matched, &lit_used, rep)) {
       b->matched = matched;
       b->lit_used = lit_used;
       b->rep_fin[0] = rep[0]; b->rep_fin[1] = rep[1]; b->rep_fin[2] = rep[2];
@@ -197,72 +289,101 @@ __global__ void __launch_bounds__(64) k_zchain(ZArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------- exec
-// One CTA per blob, blocks in order.  A block's sequences are executed in GROUPS (the next <= NT-32 sequences whose
-// output spans <= kGroupBytes) through a ring buffer in shared memory that holds the last 32 KiB of the blob's output.
-// The only serial dependence of LZ77 execution — a match that reads bytes produced by matches just before it — is
-// isolated in ONE warp; everything else is prepared around it by the other warps:
+// One CTA per blob, blocks in order.  A block's sequences are executed in GROUPS: the next <= K * NT
+// sequences whose output spans <= kGroupBytes, assembled in a shared-memory buffer and flushed with one coalesced copy.
 //
-//   producers (warps 1..)  for group g: sequence records (prefetched a group ahead), the group's literals (staged with
-//                          coalesced loads), one lane per sequence: literal runs and every FAR match (source entirely
-//                          below the start of group g-1, i.e. already flushed: read from global memory) into the ring,
-//                          and a compacted list of the NEAR matches; then, once the executor is done with group g-1,
-//                          one coalesced flush of that group from the ring to global memory;
-//   executor (warp 0)      near matches of group g, 32 per turn, in rounds: every pending lane whose source ends below
-//                          the first pending lane's destination copies (those bytes are final), the rest wait a round.
-//                          Measured on python sources: 40 % of the matches are near, ~1 100 rounds per 128 KiB block.
+// LZ77 execution is only serial where a match reads bytes that an earlier match of the same neighbourhood produces.
+// Measured on python sources (zstd level 3): the TRUE dependence depth of a 128 KiB block is ~70 matches, while it
+// holds ~10 000 of them — so a group is executed as a WAVEFRONT by all warps at once:
 //
-// Producers and executor meet at hardware named barriers (bar.arrive / bar.sync: no polling, waiting warps cost no
-// issue slots): READY[g & 1] (group g prepared) and DONE[g & 1] (its near matches executed).  The executor works on
-// group g while the producers prepare g+1 and flush g-1; three groups (<= 24 KiB) are live in the 32 KiB ring.
-// A sequence longer than a group, raw / RLE blocks and a block's trailing literals are written straight to global
-// memory by the producer team after draining the pipeline.
-constexpr uint32_t kRing = 32768, kRingMask = kRing - 1;
-constexpr uint32_t kGroupBytes = 8192;
-constexpr uint32_t kLitWin = 8192;  // staged literal window
-constexpr uint32_t kLaneFar = 64;   // far matches up to this length are copied by their own lane (memory latency bound)
-constexpr uint32_t kLaneNear = 32;  // near matches up to this length likewise (two 16-byte chunks); longer: whole warp
-constexpr uint32_t kNearEnd = 0xFFFFFFFFu;
+//   setup   every thread owns K sequences (records prefetched a group ahead).  Literal runs come from the
+//           group's staged literals; FAR matches (source entirely before the group: final, read from global memory) are
+//           copied at once; every NEAR match leaves its parameters in shared memory and marks its destination bytes in a
+//           "pending" bitmap (one bit per byte).  Runs longer than 16 bytes become jobs that a whole warp copies;
+//   passes  the pending matches live in a compact list: one lane takes one match, looks at the pending bits of its source
+//           range, and either copies it (shared -> shared, 16 bytes per step) and clears its bits, or puts it on the
+//           next pass's list.  One barrier per pass; a pass executes (at least) one dependence level of the group,
+//           ~20 passes per group, and costs in proportion to the matches still pending;
+//   flush   one coalesced copy of the group to global memory.
+//
+// Everything is sized by instruction issue, not bytes: a lone lane that copies costs its warp as much as 32, so the
+// common cases are straight-line predicated code (<= 8 literal bytes, <= 16 match bytes) and the exceptions are
+// compacted into lists that are worked off densely.
+// A sequence longer than the buffer, raw / RLE blocks and a block's trailing literals are written straight to global
+// memory by the whole team.
+constexpr uint32_t kGroupBytes = 32768;
+constexpr uint32_t kLitLane = 8;     // literal runs up to this length: straight-line code in the owning lane
+constexpr uint32_t kMatchLane = 16;  // far matches up to this length likewise; longer runs become warp jobs
+constexpr uint32_t kLitWin = 16384;   // literal bytes of one group (staged in shared memory)
+constexpr uint32_t kNearLane = 64;   // ready near matches up to this length are copied by one lane, longer by a warp
 
-template <int NT>
+// development (build with ZN_TRACE_BUILD=1): cycle counters of the exec kernel's phases, summed over the grid
+#ifdef ZP_TRACE
+__device__ unsigned long long g_ztrace[32];
+#define ZT_DECL long long zt_t = clock64(); long long zt_acc[16] = {0}
+#define ZT(i) do { const long long n__ = clock64(); zt_acc[i] += n__ - zt_t; zt_t = n__; } while (0)
+#define ZT_CNT(i, v) zt_acc[i] += (v)
+#define ZT_FLUSH(base, n) do { for (int i__ = 0; i__ < (n); i__++) atomicAdd(&g_ztrace[(base) + i__], (unsigned long long)zt_acc[i__]); } while (0)
+#else
+#define ZT_DECL
+#define ZT(i)
+#define ZT_CNT(i, v)
+#define ZT_FLUSH(base, n)
+#endif
+
+
+template <int NT, int K>
 struct ExecShared {
-  alignas(16) uint8_t ring[kRing];
+  static constexpr uint32_t kSeqs = K * NT;
+  alignas(16) uint8_t buf[kGroupBytes + 16];
   alignas(16) uint8_t lits[kLitWin + 32];
-  uint32_t n_off[2][NT - 32], n_dst[2][NT - 32], n_ml[2][NT - 32];  // near lists of the two groups in flight
-  uint32_t gi_n[2], gi_lo[2];  // entries; lowest position still valid in the ring for that group's sources
+  uint32_t bm[kGroupBytes / 32 + 2];           // pending bytes of the group's near matches
+  uint32_t m_a[kSeqs], m_off[kSeqs];  // near matches: (destination - gpos) | (length - 1) << 15, distance
+  uint16_t jobs[kSeqs * 2];           // warp jobs of the setup: sequence (index in the group's thread layout) | kind << 15 (1 = literal run, 0 = far match)
+  uint16_t plist[2][kSeqs];           // pending near matches of this / the next pass (match indices, any order)
+  uint16_t longs[kSeqs];              // ready matches longer than kNearLane: a whole warp copies each at the start of the next pass
+  uint32_t n_pend[3], n_long[3], n_jobs;  // list lengths, rotating over three slots: pass q reads [q % 3], appends to [(q + 1) % 3], clears [(q + 2) % 3]
   uint32_t pat[kPatWords];
-  uint32_t wcnt[NT / 32], wnear[NT / 32];
-  SeqRec16 big;
-  uint32_t gend, lit_lo, lit_hi;
+  SeqRec16 first;                     // record of the group's first candidate sequence
+  uint32_t cnt, gend, lit_hi;
   uint32_t err, item;
 };
 
-ZN_D void bar_sync_n(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-ZN_D void bar_arrive_n(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-constexpr uint32_t kBarProd = 1, kBarReady = 2, kBarDone = 4;  // named barriers: 1, 2-3, 4-5
-
-// ring -> global: output bytes [lo, hi) of the blob
-ZN_D void ring_flush(const Team& t, uint8_t* out, const uint8_t* ring, uint32_t lo, uint32_t hi) {
-  if (hi <= lo) return;
-  const uint32_t r0 = lo & kRingMask, n = hi - lo;
-  if (r0 + n <= kRing) team_copy(t, out + lo, ring + r0, n);
-  else {
-    const uint32_t n0 = kRing - r0;
-    team_copy(t, out + lo, ring + r0, n0);
-    team_copy(t, out + lo + n0, ring, n - n0);
+// first word of the pending bitmap at or after bit p0 that has a pending bit in [p0, p1): returns its index and the
+// mask through *mask, or ~0u when the range is clear (p1 > p0)
+ZN_D uint32_t bm_first(uint32_t bm_s, uint32_t p0, uint32_t p1, uint32_t* mask) {
+  const uint32_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
+  const uint32_t m0 = 0xFFFFFFFFu << (p0 & 31), m1 = 0xFFFFFFFFu >> (31 - ((p1 - 1) & 31));
+  for (uint32_t w = w0; w <= w1; w++) {
+    const uint32_t m = (w == w0 ? m0 : 0xFFFFFFFFu) & (w == w1 ? m1 : 0xFFFFFFFFu);
+    if (lds32(bm_s + 4 * w) & m) { *mask = m; return w; }
   }
+  return ~0u;
+}
+template <bool SET>
+ZN_D void bm_mark(uint32_t* bm, uint32_t p0, uint32_t p1) {
+  const uint32_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
+  const uint32_t m0 = 0xFFFFFFFFu << (p0 & 31), m1 = 0xFFFFFFFFu >> (31 - ((p1 - 1) & 31));
+  if (w0 == w1) { if (SET) atomicOr(bm + w0, m0 & m1); else atomicAnd(bm + w0, ~(m0 & m1)); return; }
+  if (SET) atomicOr(bm + w0, m0); else atomicAnd(bm + w0, ~m0);
+  for (uint32_t w = w0 + 1; w < w1; w++) bm[w] = SET ? 0xFFFFFFFFu : 0u;  // whole words belong to this match alone
+  if (SET) atomicOr(bm + w1, m1); else atomicAnd(bm + w1, ~m1);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 6) k_zexec(ZArgs a, uint8_t* out_base, uint32_t* produced, uint32_t* work_counter) {
+template <int NT, int K>
+__global__ void __launch_bounds__(NT, 2) k_zexec(ZArgs a, uint8_t* out_base, uint32_t* produced, uint32_t* work_counter) {
   extern __shared__ __align__(16) uint8_t exec_smem[];
-  ExecShared<NT>* sh = reinterpret_cast<ExecShared<NT>*>(exec_smem);
-  constexpr uint32_t NP = NT - 32;  // producer threads
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  ExecShared<NT, K>* sh = reinterpret_cast<ExecShared<NT, K>*>(exec_smem);
+  const Team t{threadIdx.x, (uint32_t)NT};
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(sh->buf), lits_s = (uint32_t)__cvta_generic_to_shared(sh->lits),
+                 bm_s = (uint32_t)__cvta_generic_to_shared(sh->bm);
+  for (uint32_t i = tid; i < kGroupBytes / 32 + 2; i += NT) sh->bm[i] = 0;
   for (;;) {
     if (tid == 0) sh->item = atomicAdd(work_counter, 1u);
     __syncthreads();
     const uint32_t item = sh->item;
-    if (tid == 0) sh->err = 0;
+    if (tid == 0) { sh->err = 0; sh->cnt = 0; sh->gend = 0; sh->lit_hi = 0; sh->n_jobs = 0; sh->n_pend[0] = sh->n_pend[1] = sh->n_pend[2] = 0; sh->n_long[0] = sh->n_long[1] = sh->n_long[2] = 0; }
     __syncthreads();
     if (item >= a.nzb) break;
     const ZBlob z = a.zb[item];
@@ -270,268 +391,307 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 6) k_zexec(ZArgs a, uint8_
     const BlobDesc d = a.blobs[z.blob];
     const uint8_t* src = a.blobs_base + d.src_off;
     uint8_t* out = out_base + d.dst_off;
-    if (warp == 0) {
-      // ================================================================ executor: near matches, group after group
-      for (uint32_t g = 0;; g++) {
-        const uint32_t par = g & 1u;
-        bar_sync_n(kBarReady + par, NT);
-        const uint32_t n = sh->gi_n[par], vlo = sh->gi_lo[par];
-        if (n == kNearEnd) break;
-        for (uint32_t base = 0; base < n; base += 32) {
-          const uint32_t i = base + lane;
-          bool pending = i < n;
-          uint32_t off = 1, dst = 0, ml = 0;
-          if (pending) { off = sh->n_off[par][i]; dst = sh->n_dst[par][i]; ml = sh->n_ml[par][i]; }
-          const uint32_t srcp = dst - off;
-          const uint32_t src_end = off >= ml ? srcp + ml : dst;
-          for (;;) {
-            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pending);
-            if (!pm) break;
-            const uint32_t f = (uint32_t)__ffs((int)pm) - 1u;
-            const uint32_t dstf = __shfl_sync(0xFFFFFFFFu, dst, f);
-            const bool ready = pending && (lane == f || src_end <= dstf);
-            if (ready && ml <= kLaneNear) {
-              const uint32_t ro = dst & kRingMask, rs = srcp & kRingMask;
-              if (off >= 16 && srcp >= vlo && ro + ml <= kRing && rs + ml <= kRing) {  // 16 loads in flight, then 16 stores
-                const uint8_t* s = sh->ring + rs;
-                uint8_t* o = sh->ring + ro;
-                for (uint32_t c = 0; c < ml; c += 16) {
-                  uint8_t v[16];
+    bool bad = false;
+    ZT_DECL;
+    for (uint32_t j = 0; j < z.n_blocks && !bad; j++) {
+      const ZBlock* b = &a.blocks[z.slot0 + j];
+      const uint32_t flags = b->flags, type = flags & ZB_TYPE_MASK;
+      const uint32_t blk0 = b->out_base;
+      if (type == 0) { team_copy(t, out + blk0, src + b->src_off, b->len); __syncthreads(); continue; }
+      if (type == 1) { team_fill(t, out + blk0, src[b->src_off], b->len); __syncthreads(); continue; }
+      const uint32_t lt = (flags >> ZB_LIT_SHIFT) & 3u;
+      const uint8_t* lit = lt == 0 ? src + b->lit_off : a.lits + (size_t)b->lit_base16 * 16;
+      const int rle = lt == 1 ? (int)b->lit_off : -1;
+      const SeqRec16* seqs = a.recs + b->seq_base;
+      const uint32_t nseq = b->nseq, frame_start = b->frame_start;
+      const uint32_t r0 = b->rep_in[0], r1 = b->rep_in[1], r2 = b->rep_in[2];
+      uint32_t s0 = 0, gpos = blk0;  // gpos: blob-absolute output position where the next group starts
+      uint32_t lit_next = 0;         // literal position where the next group starts
+      SeqRec16 rn[K];                // prefetched records of sequences s0 + k * NT + tid
 #pragma unroll
-                  for (int k = 0; k < 16; k++) if (c + k < ml) v[k] = s[c + k];
+      for (int k = 0; k < K; k++) {
+        rn[k].w0 = rn[k].w1 = rn[k].w2 = rn[k].w3 = 0;
+        if (k * NT + tid < nseq) rn[k] = seqs[k * NT + tid];
+      }
+      while (s0 < nseq) {
+        ZT(0);
+        // ---- the group: the leading sequences that fit the buffer (end positions are monotonic, so "fits" is a prefix)
+        uint32_t inm = 0, my_gend = 0, my_lit_hi = 0;
+        SeqRec16 r[K];
 #pragma unroll
-                  for (int k = 0; k < 16; k++) if (c + k < ml) o[c + k] = v[k];
-                }
-              } else {  // short distance (bytes feed later bytes), ring wrap, or a source that starts below the ring
-                for (uint32_t k = 0; k < ml; k++) {
-                  const uint32_t p = srcp + k;
-                  sh->ring[(dst + k) & kRingMask] = p >= vlo ? sh->ring[p & kRingMask] : out[p];
-                }
-              }
-            }
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, ready && ml > kLaneNear);
-            while (m) {  // long match: byte k reads window[k mod off], which existed before the match began
-              const uint32_t sl = (uint32_t)__ffs((int)m) - 1u;
-              m &= m - 1u;
-              const uint32_t dd = __shfl_sync(0xFFFFFFFFu, dst, sl), oo = __shfl_sync(0xFFFFFFFFu, off, sl),
-                             l = __shfl_sync(0xFFFFFFFFu, ml, sl);
-              for (uint32_t k = lane; k < l; k += 32) {
-                const uint32_t p = dd - oo + (oo >= l ? k : k % oo);
-                sh->ring[(dd + k) & kRingMask] = p >= vlo ? sh->ring[p & kRingMask] : out[p];
-              }
-            }
-            pending = pending && !ready;
-            __syncwarp();
+        for (int k = 0; k < K; k++) {
+          r[k] = rn[k];
+          const bool have = s0 + k * NT + tid < nseq;
+          const uint32_t endp = blk0 + rec_out(r[k]) + rec_ll(r[k]) + rec_ml(r[k]);
+          if (have && endp - gpos <= kGroupBytes && rec_lit(r[k]) + rec_ll(r[k]) - lit_next <= kLitWin) {
+            inm |= 1u << k;
+            my_gend = endp;  // k ascending = sequence index ascending
+            my_lit_hi = rec_lit(r[k]) + rec_ll(r[k]);
           }
         }
-        __threadfence_block();
-        bar_arrive_n(kBarDone + par, NT);
-      }
-    } else {
-      // ================================================================ producers
-      const uint32_t pt = tid - 32, pw = warp - 1;
-      const Team t{pt, NP, kBarProd};
-      uint32_t g = 0;              // groups handed to the executor so far
-      bool pend = false;           // group g-1 is with the executor / not flushed yet
-      uint32_t pend_lo = 0, pend_hi = 0;
-      uint32_t ring_lo = 0;        // lowest output position whose bytes are valid in the ring for the NEXT group's near matches
-      bool bad = false;
-      // waits for the executor to finish the group in flight and flushes it: afterwards everything produced so far is
-      // in global memory and visible to the producer team
-      auto drain = [&]() {
-        if (pend) {
-          bar_sync_n(kBarDone + ((g - 1) & 1u), NT);
-          ring_flush(t, out, sh->ring, pend_lo, pend_hi);
-          pend = false;
+        {
+          const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(inm));
+          const uint32_t ge = __reduce_max_sync(0xFFFFFFFFu, my_gend), lh = __reduce_max_sync(0xFFFFFFFFu, my_lit_hi);
+          if (lane == 0 && c) { atomicAdd(&sh->cnt, c); atomicMax(&sh->gend, ge); atomicMax(&sh->lit_hi, lh); }
+          if (tid == 0) sh->first = r[0];
         }
-        bar_sync_n(kBarProd, NP);
-      };
-      for (uint32_t j = 0; j < z.n_blocks && !bad; j++) {
-        const ZBlock* b = &a.blocks[z.slot0 + j];
-        const uint32_t flags = b->flags, type = flags & ZB_TYPE_MASK;
-        const uint32_t blk0 = b->out_base;
-        if (type != 2) {
-          drain();
-          if (type == 0) team_copy(t, out + blk0, src + b->src_off, b->len);
-          else team_fill(t, out + blk0, src[b->src_off], b->len);
-          bar_sync_n(kBarProd, NP);
-          ring_lo = blk0 + b->len;
+        __syncthreads();
+        const uint32_t count = sh->cnt, gend = sh->gend, lit_hi = sh->lit_hi;
+        const SeqRec16 q = sh->first;
+        if (count == 0) {
+          // ---- a sequence longer than the buffer: alone, in global memory, by the whole team
+          const uint32_t qo = blk0 + rec_out(q), qll = rec_ll(q), qlr = rec_lit(q), qml = rec_ml(q);
+          if (qll) {
+            if (rle >= 0) team_fill(t, out + qo, (uint32_t)rle, qll);
+            else team_copy(t, out + qo, lit + qlr, qll);
+          }
+          const uint32_t o = sym_resolve(rec_off(q), r0, r1, r2);
+          const uint32_t da = qo + qll;
+          if (qml && (o == 0 || o > da - frame_start)) { bad = true; break; }
+          __syncthreads();
+          if (qml) team_match(t, out + da, o, qml, sh->pat, nullptr);
+          __syncthreads();
+          gpos = da + qml;
+          lit_next = qlr + qll;
+          s0 += 1;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            rn[k].w0 = rn[k].w1 = rn[k].w2 = rn[k].w3 = 0;
+            if (s0 + k * NT + tid < nseq) rn[k] = seqs[s0 + k * NT + tid];
+          }
           continue;
         }
-        const uint32_t lt = (flags >> ZB_LIT_SHIFT) & 3u;
-        const uint8_t* lit = lt == 0 ? src + b->lit_off : a.lits + (size_t)b->lit_base16 * 16;
-        const int rle = lt == 1 ? (int)b->lit_off : -1;
-        const SeqRec16* seqs = a.recs + b->seq_base;
-        const uint32_t nseq = b->nseq, frame_start = b->frame_start;
-        const uint32_t r0 = b->rep_in[0], r1 = b->rep_in[1], r2 = b->rep_in[2];
-        uint32_t s0 = 0, gpos = blk0;       // gpos: blob-absolute output position where the next group starts
-        uint32_t lw_lo = 0, lw_hi = 0;      // literal window staged in sh->lits: literals [lw_lo, lw_hi) of this block
-        SeqRec16 rn;                        // prefetched record of sequence s0 + pt
-        rn.w0 = rn.w1 = rn.w2 = rn.w3 = 0;
-        if (pt < nseq) rn = seqs[pt];
-        while (s0 < nseq) {
-          // ---- the group: leading sequences that fit
-          const bool have = s0 + pt < nseq;
-          const SeqRec16 r = rn;
-          const uint32_t orl = rec_out(r), ll = rec_ll(r), lr = rec_lit(r), ml = rec_ml(r);
-          const uint32_t endp = blk0 + orl + ll + ml;
-          const bool in = have && endp - gpos <= kGroupBytes;
-          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in);
-          if (lane == 0) sh->wcnt[pw] = bal == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~bal) - 1u;
-          if (pt == 0) sh->big = r;
-          bar_sync_n(kBarProd, NP);
-          uint32_t count = 0;
+        // prefetch the next group's records: their latency hides behind this group's passes
 #pragma unroll
-          for (int w = 0; w < (int)(NP / 32); w++) {
-            const uint32_t c = sh->wcnt[w];
-            if (count == (uint32_t)w * 32u) count += c;
-          }
-          if (count == 0) {
-            // ---- a sequence longer than a group: alone, in global memory, by the producer team
-            drain();
-            const SeqRec16 q = sh->big;
-            const uint32_t qo = blk0 + rec_out(q), qll = rec_ll(q), qlr = rec_lit(q), qml = rec_ml(q);
-            if (qll) {
-              if (rle >= 0) team_fill(t, out + qo, (uint32_t)rle, qll);
-              else team_copy(t, out + qo, lit + qlr, qll);
+        for (int k = 0; k < K; k++) {
+          rn[k].w0 = rn[k].w1 = rn[k].w2 = rn[k].w3 = 0;
+          if (s0 + count + k * NT + tid < nseq) rn[k] = seqs[s0 + count + k * NT + tid];
+        }
+        const uint32_t lit_lo = rec_lit(q);
+        if (rle < 0 && lit_hi > lit_lo) team_copy(t, sh->lits, lit + lit_lo, lit_hi - lit_lo);
+        __syncthreads();
+        if (tid == 0) { sh->cnt = 0; sh->gend = 0; sh->lit_hi = 0; }  // (used again only after more barriers)
+        ZT(1);
+        // ---- setup: literal runs, far matches, parameters + pending bits of the near matches
+        // far sources first into L1 (one touch per 32-byte sector), so that the K copy steps below do not each pay a trip to DRAM
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if ((inm >> k) & 1u) {
+            const uint32_t ml = rec_ml(r[k]), off = sym_resolve(r[k].w0, r0, r1, r2);
+            const uint32_t dabs = blk0 + rec_out(r[k]) + rec_ll(r[k]);
+            if (ml && off >= ml && off <= dabs && dabs - off + ml <= gpos) {
+              const uint8_t* s = out + (dabs - off);
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(s));
+              if (ml > 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(s + (ml <= kMatchLane ? ml : kMatchLane) - 1));
             }
-            const uint32_t off = sym_resolve(rec_off(q), r0, r1, r2);
-            const uint32_t dabs = qo + qll;
-            if (qml && (off == 0 || off > dabs - frame_start)) { bad = true; break; }
-            bar_sync_n(kBarProd, NP);
-            if (qml) team_match(t, out + dabs, off, qml, sh->pat, nullptr);
-            bar_sync_n(kBarProd, NP);
-            gpos = dabs + qml;
-            ring_lo = gpos;
-            s0 += 1;
-            rn.w0 = rn.w1 = rn.w2 = rn.w3 = 0;
-            if (s0 + pt < nseq) rn = seqs[s0 + pt];
-            continue;
           }
-          // prefetch the next group's records: their latency hides behind this group's work
-          rn.w0 = rn.w1 = rn.w2 = rn.w3 = 0;
-          if (s0 + count + pt < nseq) rn = seqs[s0 + count + pt];
-          if (pt == count - 1) { sh->gend = endp; sh->lit_hi = lr + ll; }
-          if (pt == 0) sh->lit_lo = lr;
-          bar_sync_n(kBarProd, NP);
-          const uint32_t gend = sh->gend, lit_lo = sh->lit_lo, lit_hi = sh->lit_hi;
-          if (rle < 0 && lit_hi > lit_lo && (lit_lo < lw_lo || lit_hi > lw_hi)) {  // (re)stage the literal window
-            lw_lo = lit_lo;
-            lw_hi = min(b->lit_regen, lit_lo + kLitWin);
-            bar_sync_n(kBarProd, NP);  // nobody still reads the old window
-            team_copy(t, sh->lits, lit + lw_lo, lw_hi - lw_lo);
-            bar_sync_n(kBarProd, NP);
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const bool mine = (inm >> k) & 1u;
+          const uint32_t orl = rec_out(r[k]), ll = mine ? rec_ll(r[k]) : 0u, lr = rec_lit(r[k]);
+          const uint32_t ml = mine ? rec_ml(r[k]) : 0u;
+          const uint32_t oabs = blk0 + orl, dabs = oabs + ll;
+          // literal run: <= kLitLane bytes straight-line, longer ones as a warp job
+          if (ll && ll <= kLitLane) {
+            const uint32_t o = buf_s + (oabs - gpos), ls = lits_s + (lr - lit_lo);
+            uint32_t v[kLitLane];
+#pragma unroll
+            for (int i = 0; i < (int)kLitLane; i++) v[i] = rle >= 0 ? (uint32_t)rle : ((uint32_t)i < ll ? lds8(ls + i) : 0u);
+#pragma unroll
+            for (int i = 0; i < (int)kLitLane; i++) if ((uint32_t)i < ll) sts8(o + i, v[i]);
           }
-          // ---- phase 1: literal runs and far matches into the ring; near matches into the list
-          const uint32_t par = g & 1u;
-          const bool mine = pt < count;
-          bool near_m = false, far = false;
-          uint32_t dabs = 0, sabs = 0, off = 1;
-          if (mine) {
-            const uint32_t oabs = blk0 + orl;
-            if (ll <= kLaneFar) {
-              if (rle >= 0) for (uint32_t i = 0; i < ll; i++) sh->ring[(oabs + i) & kRingMask] = (uint8_t)rle;
-              else { const uint8_t* ls = sh->lits + (lr - lw_lo); for (uint32_t i = 0; i < ll; i++) sh->ring[(oabs + i) & kRingMask] = ls[i]; }
-            }
-            if (ml) {
-              off = sym_resolve(r.w0, r0, r1, r2);
-              dabs = oabs + ll;
-              if (off == 0 || off > dabs - frame_start) sh->err = 1;
-              else {
-                sabs = dabs - off;
-                // far: the whole source lies below the ring's valid range (flushed, final) and the match does not feed itself
-                far = off >= ml && sabs + ml <= ring_lo;
-                near_m = !far;
+          bool job_lit = ll > kLitLane, job_far = false, near_m = false;
+          uint32_t off = 1;
+          if (ml) {
+            off = sym_resolve(r[k].w0, r0, r1, r2);
+            if (off == 0 || off > dabs - frame_start) sh->err = 1;
+            else {
+              // far: the whole source lies before the group (final, in global memory) and the match does not feed itself
+              const bool far = off >= ml && dabs - off + ml <= gpos;
+              near_m = !far;
+              job_far = far && ml > kMatchLane;
+              if (far && ml <= kMatchLane) {
+                const uint8_t* s = out + (dabs - off);
+                const uint32_t o = buf_s + (dabs - gpos);
+                uint32_t v[kMatchLane];
+#pragma unroll
+                for (int i = 0; i < (int)kMatchLane; i++) if ((uint32_t)i < ml) v[i] = s[i];
+#pragma unroll
+                for (int i = 0; i < (int)kMatchLane; i++) if ((uint32_t)i < ml) sts8(o + i, v[i]);
               }
             }
-          }
-          if (far && ml <= kLaneFar) {
-            const uint8_t* s = out + sabs;
-            const uint32_t ro = dabs & kRingMask;
-            if (ro + ml <= kRing) {
-              uint8_t* o = sh->ring + ro;
-              for (uint32_t c = 0; c < ml; c += 16) {
-                uint8_t v[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) if (c + i < ml) v[i] = s[c + i];
-#pragma unroll
-                for (int i = 0; i < 16; i++) if (c + i < ml) o[c + i] = v[i];
-              }
-            } else for (uint32_t i = 0; i < ml; i++) sh->ring[(dabs + i) & kRingMask] = s[i];
-          }
-          {  // long literal runs and long far matches: whole warp per copy
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, mine && ll > kLaneFar);
-            while (m) {
-              const uint32_t sl = (uint32_t)__ffs((int)m) - 1u;
-              m &= m - 1u;
-              const uint32_t dd = blk0 + __shfl_sync(0xFFFFFFFFu, orl, sl), lr2 = __shfl_sync(0xFFFFFFFFu, lr, sl) - lw_lo,
-                             l = __shfl_sync(0xFFFFFFFFu, ll, sl);
-              for (uint32_t k = lane; k < l; k += 32) sh->ring[(dd + k) & kRingMask] = rle >= 0 ? (uint8_t)rle : sh->lits[lr2 + k];
-            }
-            m = __ballot_sync(0xFFFFFFFFu, far && ml > kLaneFar);
-            while (m) {
-              const uint32_t sl = (uint32_t)__ffs((int)m) - 1u;
-              m &= m - 1u;
-              const uint32_t dd = __shfl_sync(0xFFFFFFFFu, dabs, sl), ss = __shfl_sync(0xFFFFFFFFu, sabs, sl),
-                             l = __shfl_sync(0xFFFFFFFFu, ml, sl);
-              for (uint32_t k = lane; k < l; k += 32) sh->ring[(dd + k) & kRingMask] = out[ss + k];
-            }
-          }
-          // near list, in sequence order
-          const uint32_t nb = __ballot_sync(0xFFFFFFFFu, near_m);
-          if (lane == 0) sh->wnear[pw] = (uint32_t)__popc(nb);
-          bar_sync_n(kBarProd, NP);
-          if (sh->err) { bad = true; break; }
-          uint32_t before = 0, total = 0;
-#pragma unroll
-          for (int w = 0; w < (int)(NP / 32); w++) {
-            const uint32_t c = sh->wnear[w];
-            if ((uint32_t)w < pw) before += c;
-            total += c;
           }
           if (near_m) {
-            const uint32_t slot = before + (uint32_t)__popc(nb & ((1u << lane) - 1u));
-            sh->n_off[par][slot] = off;
-            sh->n_dst[par][slot] = dabs;
-            sh->n_ml[par][slot] = ml;
+            const uint32_t idx = (uint32_t)k * NT + tid;
+            sh->m_a[idx] = (dabs - gpos) | ((ml - 1u) << 15); sh->m_off[idx] = off;
+            bm_mark<true>(sh->bm, dabs - gpos, dabs - gpos + ml);
           }
-          if (pt == 0) { sh->gi_n[par] = total; sh->gi_lo[par] = ring_lo; }
-          __threadfence_block();
-          bar_arrive_n(kBarReady + par, NT);
-          // ---- the previous group is done once the executor says so: flush it
-          if (pend) {
-            bar_sync_n(kBarDone + ((g - 1) & 1u), NT);
-            ring_flush(t, out, sh->ring, pend_lo, pend_hi);
+          {  // pending list of the first pass (order is irrelevant)
+            const uint32_t nb = __ballot_sync(0xFFFFFFFFu, near_m);
+            if (nb) {
+              uint32_t base = 0;
+              if (lane == 0) base = atomicAdd(&sh->n_pend[0], (uint32_t)__popc(nb));
+              base = __shfl_sync(0xFFFFFFFFu, base, 0);
+              if (near_m) sh->plist[0][base + __popc(nb & ((1u << lane) - 1u))] = (uint16_t)((uint32_t)k * NT + tid);
+            }
           }
-          bar_sync_n(kBarProd, NP);
-          // far sources of the next group may reach up to the start of THIS group's predecessor... which is what was
-          // just flushed: everything below gpos is now final in global memory except this group itself
-          ring_lo = gpos;
-          pend = true;
-          pend_lo = gpos;
-          pend_hi = gend;
-          gpos = gend;
-          s0 += count;
-          g++;
+          // jobs: long literal runs and long far matches
+          const uint32_t nj = (job_lit ? 1u : 0u) + (job_far ? 1u : 0u);
+          const uint32_t bj = __ballot_sync(0xFFFFFFFFu, nj != 0);
+          if (bj) {
+            uint32_t pre = nj;  // inclusive prefix sum of nj over the lanes
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pre, sft); if ((int)lane >= sft) pre += v; }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&sh->n_jobs, pre);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31);
+            uint32_t slot = base + pre - nj;
+            const uint32_t idx = (uint32_t)k * NT + tid;
+            if (job_lit) sh->jobs[slot++] = (uint16_t)(idx | 0x8000u);
+            if (job_far) sh->jobs[slot] = (uint16_t)idx;
+          }
         }
-        if (bad) break;
-        const uint32_t rest = b->lit_regen - b->lit_used;
-        if (rest) {
-          drain();
-          if (rle >= 0) team_fill(t, out + blk0 + b->matched, (uint32_t)rle, rest);
-          else team_copy(t, out + blk0 + b->matched, lit + b->lit_used, rest);
-          bar_sync_n(kBarProd, NP);
-          ring_lo = blk0 + b->matched + rest;
+        __syncthreads();
+        if (sh->err) { bad = true; break; }
+        {  // work off the jobs: one warp per job
+          const uint32_t nj = sh->n_jobs;
+          for (uint32_t i = warp; i < nj; i += NT / 32) {
+            const uint32_t jb = sh->jobs[i], idx = jb & 0x7FFFu;
+            const SeqRec16 rr = seqs[s0 + idx];  // idx = k * NT + tid of the owner = offset from s0 (broadcast load)
+            const uint32_t oabs = blk0 + rec_out(rr), ll = rec_ll(rr);
+            if (jb & 0x8000u) {
+              const uint32_t dd = buf_s + (oabs - gpos), l2 = lits_s + (rec_lit(rr) - lit_lo);
+              for (uint32_t x = lane; x < ll; x += 32) sts8(dd + x, rle >= 0 ? (uint32_t)rle : lds8(l2 + x));
+            } else {
+              const uint32_t dabs = oabs + ll, l = rec_ml(rr);
+              const uint8_t* s = out + (dabs - sym_resolve(rr.w0, r0, r1, r2));
+              const uint32_t dd = buf_s + (dabs - gpos);
+              for (uint32_t x = lane; x < l; x += 32) sts8(dd + x, s[x]);
+            }
+          }
         }
+        __syncthreads();
+        if (tid == 0) sh->n_jobs = 0;
+        ZT(2);
+        // ---- passes: one dependence level of the group per pass
+        for (uint32_t pass = 0;; pass++) {
+          ZT_CNT(8, tid == 0 ? 1 : 0);
+          const uint32_t par = pass & 1u, c0 = pass % 3u, c1 = (pass + 1u) % 3u, c2 = (pass + 2u) % 3u;
+          const uint32_t np = sh->n_pend[c0], nl = sh->n_long[c0];
+          if (np == 0 && nl == 0) break;
+          if (tid == 0) { sh->n_pend[c2] = 0; sh->n_long[c2] = 0; }  // read a pass ago, appended to a pass from now
+          if (pass > 4u * K * NT) { if (tid == 0) sh->err = 2; break; }  // cannot happen (every pass completes a match): never hang
+          ZT_CNT(10, tid == 0 ? np : 0);
+          // long matches that became ready in the previous pass: one warp each (byte x = window[x mod off])
+          for (uint32_t i = warp; i < nl; i += NT / 32) {
+            const uint32_t idx = sh->longs[i];
+            const uint32_t ma = sh->m_a[idx], oo = sh->m_off[idx];
+            const uint32_t drel = ma & 0x7FFFu, l = (ma >> 15) + 1u, da = gpos + drel;
+            // byte x = window[x mod off]; the phase advances by 32 mod off per step instead of a division per byte
+            uint32_t ph = oo >= l ? lane : lane % oo;
+            const uint32_t step = oo >= l ? 32u : 32u % oo;
+            for (uint32_t x = lane; x < l; x += 32) {
+              const uint32_t p = da - oo + ph;
+              sts8(buf_s + drel + x, p >= gpos ? lds8(buf_s + (p - gpos)) : (uint32_t)out[p]);
+              ph += step;
+              if (oo < l && ph >= oo) ph -= oo;
+            }
+            __syncwarp();
+            if (lane == 0) bm_mark<false>(sh->bm, drel, drel + l);
+          }
+          if (nl) __syncthreads();  // their bytes and cleared bits before anybody checks (uniform: nl is shared)
+          ZT(11);  // pass: counters + long matches
+          for (uint32_t base = warp * 32u; base < np; base += NT) {
+            const uint32_t i = base + lane;
+            const bool act = i < np;
+            uint32_t idx = 0, drel = 0, ml = 1, off = 1;
+            if (act) { idx = sh->plist[par][i]; const uint32_t ma = sh->m_a[idx]; drel = ma & 0x7FFFu; ml = (ma >> 15) + 1u; off = sh->m_off[idx]; }
+            const uint32_t dabs = gpos + drel, sabs = dabs - off;
+            // source bytes the match needs: the window before it, [sabs, min(sabs + ml, dabs)); bytes below gpos are final
+            const uint32_t send = off >= ml ? sabs + ml : dabs;
+            const uint32_t p0 = (sabs > gpos ? sabs : gpos) - gpos, p1 = send - gpos;
+            bool ready = act;
+            if (act && p1 > p0) { uint32_t m; ready = bm_first(bm_s, p0, p1, &m) == ~0u; }
+            const bool lane_copy = ready && ml <= kNearLane;
+            ZT(12);  // pass: list entry + readiness check
+            if (lane_copy) {
+              const uint32_t o = buf_s + drel;
+              if (off >= 16 && sabs >= gpos) {  // 16 loads in flight, then 16 stores
+                const uint32_t sa = buf_s + (sabs - gpos);
+                for (uint32_t c = 0; c < ml; c += 16) {
+                  uint32_t v[16];
+#pragma unroll
+                  for (int x = 0; x < 16; x++) if (c + x < ml) v[x] = lds8(sa + c + x);
+#pragma unroll
+                  for (int x = 0; x < 16; x++) if (c + x < ml) sts8(o + c + x, v[x]);
+                }
+              } else {  // short distance (bytes feed later bytes) or a source that starts before the group
+                for (uint32_t x = 0; x < ml; x++) {
+                  const uint32_t p = sabs + x;
+                  sts8(o + x, p >= gpos ? lds8(buf_s + (p - gpos)) : (uint32_t)out[p]);
+                }
+              }
+            }
+            // same-pass forwarding: the bytes are fenced before the bits are cleared, so a checker that sees clear bits
+            // later in this pass reads final bytes
+            ZT(13);  // pass: copy
+            // same-pass forwarding: the bytes are fenced before the bits are cleared, so a checker that sees clear bits
+            // later in this pass reads final bytes
+            if (__any_sync(0xFFFFFFFFu, lane_copy)) {
+              __threadfence_block();
+              if (lane_copy) bm_mark<false>(sh->bm, drel, drel + ml);
+            }
+            ZT(14);  // pass: clear bits
+            const bool is_long = ready && !lane_copy, again = act && !ready;
+            const uint32_t lb = __ballot_sync(0xFFFFFFFFu, is_long), ab = __ballot_sync(0xFFFFFFFFu, again);
+            if (lb) {
+              uint32_t b0 = 0;
+              if (lane == 0) b0 = atomicAdd(&sh->n_long[c1], (uint32_t)__popc(lb));
+              b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+              if (is_long) sh->longs[b0 + __popc(lb & ((1u << lane) - 1u))] = (uint16_t)idx;
+            }
+            if (ab) {
+              uint32_t b0 = 0;
+              if (lane == 0) b0 = atomicAdd(&sh->n_pend[c1], (uint32_t)__popc(ab));
+              b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+              if (again) sh->plist[par ^ 1u][b0 + __popc(ab & ((1u << lane) - 1u))] = (uint16_t)idx;
+            }
+            ZT(15);  // pass: appends
+          }
+          __syncthreads();
+          ZT(6);  // pass: barrier
+        }
+        __syncthreads();
+        if (tid == 0) { sh->n_pend[0] = sh->n_pend[1] = sh->n_pend[2] = 0; sh->n_long[0] = sh->n_long[1] = sh->n_long[2] = 0; }
+        ZT(3);
+        if (sh->err) { bad = true; break; }
+        // ---- flush
+        team_copy(t, out + gpos, sh->buf, gend - gpos);
+        __syncthreads();
+        ZT(4);
+        ZT_CNT(9, tid == 0 ? 1 : 0);
+        gpos = gend;
+        lit_next = lit_hi;
+        s0 += count;
       }
-      drain();
-      if (pt == 0) { sh->gi_n[g & 1u] = kNearEnd; sh->gi_lo[g & 1u] = 0; }
-      __threadfence_block();
-      bar_arrive_n(kBarReady + (g & 1u), NT);
-      if (pt == 0) {
-        if (bad) a.zb[item].state = 1;
-        else produced[z.blob] = (uint32_t)d.dst_cap;
+      if (bad) break;
+      const uint32_t rest = b->lit_regen - b->lit_used;
+      if (rest) {
+        if (rle >= 0) team_fill(t, out + blk0 + b->matched, (uint32_t)rle, rest);
+        else team_copy(t, out + blk0 + b->matched, lit + b->lit_used, rest);
       }
+      __syncthreads();
+    }
+    if (bad) {  // leave the shared state clean for the next blob
+      __syncthreads();
+      for (uint32_t i = tid; i < kGroupBytes / 32 + 2; i += NT) sh->bm[i] = 0;
+    }
+    if (tid == 0) {
+      if (bad) a.zb[item].state = 1;
+      else produced[z.blob] = (uint32_t)d.dst_cap;
+      ZT(5);
+      ZT_FLUSH(0, 16);
     }
   }
 }

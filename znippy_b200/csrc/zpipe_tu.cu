@@ -1,5 +1,7 @@
 // Translation unit of the device-wide zstd decode pipeline: kernels (zpipe_kernels.cuh) + their launcher.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "host_api.h"
 #include "zpipe_kernels.cuh"
@@ -20,10 +22,24 @@ bool pipeline_init() {
   static FseD zset[kTabSet];
   build_predef_set(zset);
   if (cudaMemcpyToSymbol(g_zpredef, zset, sizeof zset) != cudaSuccess) return false;
+  cudaFuncSetAttribute(k_zseq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqSmem);
   cudaFuncSetAttribute(k_zlit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLitSmem);
-  cudaFuncSetAttribute(k_zexec<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<512>));
-  cudaFuncSetAttribute(k_zexec<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<128>));
+  cudaFuncSetAttribute(k_zexec<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<512, 4>));
+  cudaFuncSetAttribute(k_zexec<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<256, 8>));
+  cudaFuncSetAttribute(k_zexec<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<128, 4>));
   return true;
+}
+
+void pipeline_trace_dump() {
+#ifdef ZP_TRACE
+  unsigned long long h[32];
+  cudaMemcpyFromSymbol(h, g_ztrace, sizeof h);
+  fprintf(stderr, "zexec trace (thread 0 cycles summed over CTAs): records+extent %llu stage %llu setup %llu passes-other %llu flush %llu rest %llu | passes %llu groups %llu pending-checks %llu\n",
+          h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10]);
+  fprintf(stderr, "  per pass: top+long %llu check %llu copy %llu fence+clear %llu append %llu barrier %llu\n", h[11], h[12], h[13], h[14], h[15], h[6]);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_ztrace, z, sizeof z);
+#endif
 }
 
 void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks) {
@@ -37,16 +53,21 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   mark();
   k_ztables<<<std::min<uint32_t>((slots + kTabWarps - 1) / kTabWarps, sms * 8), kTabWarps * 32, 0, st>>>(a);
   mark();
-  k_zseq<<<(slots + 63) / 64, 64, 0, st>>>(a);
+  if (getenv("ZN_SEQ_SMEM")) k_zseq<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeqSmem, st>>>(a);
+  else k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a);
   mark();
   k_zlit<<<std::min<uint32_t>((slots + kLitBlocks - 1) / kLitBlocks, sms * 3), kLitBlocks * 4, kLitSmem, st>>>(a);
   mark();
   k_zchain<<<(a.nzb + 63) / 64, 64, 0, st>>>(a);
   mark();
-  if (L.mean_bytes >= (256u << 10))
-    k_zexec<512><<<std::min<uint32_t>(a.nzb, sms * 2), 512, sizeof(ExecShared<512>), st>>>(a, L.d_out, L.produced, L.exec_counter);
+  const char* ev = getenv("ZN_EXEC");  // development: team shape of the exec kernel
+  const int shape = ev ? atoi(ev) : (L.mean_bytes >= (256u << 10) ? 256 : 128);
+  if (shape == 512)
+    k_zexec<512, 4><<<std::min<uint32_t>(a.nzb, sms * 2), 512, sizeof(ExecShared<512, 4>), st>>>(a, L.d_out, L.produced, L.exec_counter);
+  else if (shape == 256)
+    k_zexec<256, 8><<<std::min<uint32_t>(a.nzb, sms * 2), 256, sizeof(ExecShared<256, 8>), st>>>(a, L.d_out, L.produced, L.exec_counter);
   else
-    k_zexec<128><<<std::min<uint32_t>(a.nzb, sms * 6), 128, sizeof(ExecShared<128>), st>>>(a, L.d_out, L.produced, L.exec_counter);
+    k_zexec<128, 4><<<std::min<uint32_t>(a.nzb, sms * 2), 128, sizeof(ExecShared<128, 4>), st>>>(a, L.d_out, L.produced, L.exec_counter);
   mark();
 }
 
