@@ -102,6 +102,9 @@ int zn_hash_batch(zn_ctx* ctx, const uint8_t* base, const uint64_t* off, const u
  *   out_base       nullable         -> verify-only (decompress_archive with save_data=false)
  *   digest_out     nullable (n*32)
  *   status         required (n)
+ * Writes to out_base touch the declared ranges only, with one exception: when consecutive ranges are separated by
+ * alignment padding of fewer than 16 bytes each, the whole span returns in one copy and the padding bytes are
+ * unspecified.  Ranges further apart are copied row by row and the memory between them is left alone.
  */
 int zn_decode_verify_batch(zn_ctx* ctx, const uint8_t* blobs_base, const uint64_t* blob_off,
                            const uint64_t* blob_len, const uint8_t* compressed, const uint64_t* out_len,

@@ -15,12 +15,15 @@ def L():
     return N.lib()
 
 
-def _rows(n, seed=0, compressed_every=3):
+def _rows(n, seed=0, compressed_every=3, payload=77):
+    """Random index rows that are VALID for an archive with `payload` bytes of blobs (the reader rejects rows whose blob
+    lies outside the payload region or whose sizes reach 4 GiB)."""
     rng = np.random.default_rng(seed)
     rows = []
     for i in range(n):
+        bo = int(rng.integers(0, payload + 1))
         rows.append((f"dir{i % 7}/file_{i:05d}.txt" if i % 11 else "", i % 4, int(rng.integers(0, 1 << 40)), i % compressed_every != 0,
-                     int(rng.integers(0, 1 << 33)), int(rng.integers(0, 1 << 45)), int(rng.integers(0, 1 << 24)),
+                     int(rng.integers(0, 1 << 32)), bo, int(rng.integers(0, payload - bo + 1)),
                      bytes(rng.integers(0, 256, 32, dtype=np.uint8))))
     return rows
 
@@ -87,7 +90,7 @@ def test_native_reader_reads_pyarrow_archives(L, tmp_path):
 def test_pyarrow_reads_native_writer(L, tmp_path):
     from znippy_b200 import archive as A
     p = tmp_path / "w.znippy"
-    groups = [((0, ""), _rows(500, 5)), ((2, "pypi"), _rows(3, 6)), ((7, "x"), _rows(0, 7))]
+    groups = [((0, ""), _rows(500, 5, payload=1234)), ((2, "pypi"), _rows(3, 6, payload=1234)), ((7, "x"), _rows(0, 7))]
     fd = os.open(p, os.O_CREAT | os.O_RDWR, 0o644)
     os.pwrite(fd, b"Z" * 1234, 0)
     w = L.zn_index_writer_create(fd, 1234)
@@ -149,3 +152,60 @@ def test_native_reader_rejects_bad_archives(L, tmp_path):
     p.write_bytes(b"x" * 100 + b"ZNPYMIDX" + (10).to_bytes(8, "little"))   # garbage where the manifest should be
     assert not L.zn_index_open(str(p).encode(), err, 256)
     assert not L.zn_index_open(str(tmp_path / "missing").encode(), err, 256)
+
+
+def _write_archive(A, path, rows, payload=b"B" * 77, manifest_patch=None):
+    schema = A.INDEX_SCHEMA.with_metadata(A.config_metadata())
+    with open(path, "wb") as f:
+        f.write(payload)
+        sink = A.ArrowIpcSink(f, len(payload))
+        sink.push_subindex((0, ""), schema, [A.build_metadata_batch(rows, schema)])
+        sink.finish()
+
+
+def test_native_reader_rejects_hostile_index_rows(L, tmp_path):
+    """index columns are untrusted.  Rows whose blob lies outside the payload region, or whose sizes
+    reach 4 GiB (and could wrap the u64 sums of a batch), are refused when the index is opened."""
+    from znippy_b200 import archive as A
+    err = C.create_string_buffer(256)
+    ck = bytes(32)
+    p = tmp_path / "h.znippy"
+    good = ("a", 0, 0, True, 100, 10, 60, ck)
+    _write_archive(A, p, [good])
+    L.zn_index_close(_open(L, p))
+    for bad, what in [(("a", 0, 0, True, 100, 10, 68, ck), b"outside the payload"),          # 10 + 68 > 77
+                      (("a", 0, 0, True, 100, 78, 0, ck), b"outside the payload"),
+                      (("a", 0, 0, True, 100, (1 << 64) - 16, 32, ck), b"outside the payload"),  # offset + size wraps
+                      (("a", 0, 0, True, 1 << 63, 0, 10, ck), b"4 GiB"),
+                      (("a", 0, 0, True, 100, 0, (1 << 63) - 16, ck), b"4 GiB"),
+                      (("a", 0, 1 << 63, True, 100, 0, 10, ck), b"file offset")]:
+        _write_archive(A, p, [good, bad])
+        assert not L.zn_index_open(str(p).encode(), err, 256), bad
+        assert what in err.value, (bad, err.value)
+
+
+def test_native_reader_requires_exact_manifest_types(L, tmp_path):
+    """the hand-written Arrow IPC reader must not trust the schema — a manifest whose integer
+    columns have another width than index.rs declares would make get_uint read past the buffer."""
+    from znippy_b200 import archive as A
+    err = C.create_string_buffer(256)
+    p = tmp_path / "m.znippy"
+    _write_archive(A, p, [("a", 0, 0, True, 100, 10, 60, bytes(32))])
+    raw = bytearray(p.read_bytes())
+    moff = int.from_bytes(raw[-8:], "little")
+    man = pa.ipc.open_stream(pa.BufferReader(bytes(raw[moff:-16]))).read_all()
+    assert man.schema.field("index_offset").type == pa.uint64()
+    for col, typ in [("index_offset", pa.uint8()), ("row_count", pa.uint16()), ("pkg_type", pa.int64()), ("repo", pa.binary())]:
+        i = man.schema.get_field_index(col)
+        vals = man.column(col).to_pylist()
+        if typ == pa.uint8():
+            vals = [v & 0xFF for v in vals]
+        if typ == pa.binary():
+            vals = [v.encode() for v in vals]
+        t2 = man.set_column(i, pa.field(col, typ, False), pa.array(vals, typ))
+        sink = pa.BufferOutputStream()
+        with pa.ipc.new_stream(sink, t2.schema) as w:
+            w.write_table(t2)
+        blob = sink.getvalue().to_pybytes()
+        p.write_bytes(bytes(raw[:moff]) + blob + b"ZNPYMIDX" + moff.to_bytes(8, "little"))
+        assert not L.zn_index_open(str(p).encode(), err, 256), col

@@ -235,3 +235,26 @@ def test_read_worker_pipeline_and_file_windows(A, tmp_path, oracle, monkeypatch)
         f.write(bytes([b[0] ^ 0x40]))
     vr = A.decompress_archive(path, False, str(tmp_path))
     assert vr.corrupt_files == 1 and vr.verified_bytes == total - (8 << 20)
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_row_shards_never_truncate_each_others_files(A, tmp_path, oracle, native):
+    """shard_rows cuts on ROW boundaries, so a multi-chunk file can straddle two GPU shards.  Whatever the
+    order in which the shards run, no shard may truncate bytes another shard has written (the later shard used to
+    open the shared file with O_TRUNC).  A stale, longer file left from an earlier run is still cut to size."""
+    O = oracle
+    big = O.real_text(20 << 20).tobytes()  # 3 chunks
+    entries = [("a.txt", b"first file\n" * 100), ("d/big.txt", big), ("z.txt", b"last file\n" * 50)]
+    path, rep = _pack(A, tmp_path, entries)
+    t = A.read_znippy_index(path)
+    assert t.num_rows == 5
+    for cut in (2, 3):  # both cuts fall inside d/big.txt
+        out = tmp_path / f"x{cut}{int(native)}"
+        os.makedirs(out / "d")
+        (out / "d" / "big.txt").write_bytes(b"\xee" * (len(big) + 12345))  # stale leftover, longer than the file
+        # the LATER shard first: with O_TRUNC in the other one its chunks would be lost
+        v2 = A.decompress_archive(path, True, str(out), row_range=(cut, 5), native=native)
+        v1 = A.decompress_archive(path, True, str(out), row_range=(0, cut), native=native)
+        assert v1.corrupt_files == 0 and v2.corrupt_files == 0 and v1.chunks + v2.chunks == 5
+        for p, d in entries:
+            assert (out / p).read_bytes() == d, (cut, p)

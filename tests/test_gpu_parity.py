@@ -379,3 +379,29 @@ def test_fused_kernel_survives_corrupt_blobs(codec, oracle):
             assert st[victim] == 0  # the flip hit a bit that does not matter (e.g. the unverified frame checksum)
         else:
             assert st[victim] != 0, (trial, victim, pos)
+
+
+def test_caller_memory_between_output_ranges_is_left_alone(codec, oracle):
+    """the D2H copy used to return one span whenever the ranges were 'compact', overwriting caller
+    bytes that lie between two declared ranges with stale device memory.  Gaps of 16 bytes or more are never written;
+    alignment padding (< 16 bytes) is the only documented exception (include/znippy_cuda.h)."""
+    O = oracle
+    z = O.libzstd()
+    contents = [O.real_text(50_000 + 777 * i).tobytes() for i in range(6)]
+    blobs = [z.compress(c, 3) for c in contents]
+    buf, offs = _pack(blobs)
+    gaps = [0, 16, 100, 4000, 17, 64]
+    out_off, cur = [], 0
+    for c, g in zip(contents, gaps):
+        cur += g
+        out_off.append(cur)
+        cur += len(c)
+    out = np.full(cur + 64, 0x5A, np.uint8)
+    st, _ = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs], [1] * 6, [len(c) for c in contents],
+                                       b"".join(O.blake3(c) for c in contents), out, out_off)
+    assert not st.any()
+    keep = np.ones(out.size, bool)
+    for o, c in zip(out_off, contents):
+        assert out[o:o + len(c)].tobytes() == c
+        keep[o:o + len(c)] = False
+    assert (out[keep] == 0x5A).all()

@@ -269,12 +269,30 @@ def decompress_archive(index_path: str, save_data: bool, out_dir: str, ctx: Ctx 
     files, opened = None, {}
     if save_data:
         files = [None] * total_rows
+        # A file whose rows straddle this row range is also written by the neighbouring shard (another process / GPU):
+        # truncating it here could destroy chunks that shard has already written.  Such files are opened without
+        # O_TRUNC and sized to their full length from the index instead (idempotent, never cuts live data).
+        shared = set()
+        if lo < hi and lo > 0 and paths[lo - 1] == paths[lo]:
+            shared.add(paths[lo])
+        if lo < hi and hi < total_rows and paths[hi] == paths[hi - 1]:
+            shared.add(paths[hi - 1])
+        fo, us = cols[2], cols[4]
         for r in range(lo, hi):
             p = paths[r]
             if p not in opened:
                 full = os.path.join(out_dir, p)
                 os.makedirs(os.path.dirname(full) or ".", exist_ok=True)
-                opened[p] = os.open(full, os.O_CREAT | os.O_WRONLY | os.O_TRUNC, 0o644)
+                if p in shared:
+                    a = b = r
+                    while a > 0 and paths[a - 1] == p:
+                        a -= 1
+                    while b + 1 < total_rows and paths[b + 1] == p:
+                        b += 1
+                    opened[p] = os.open(full, os.O_CREAT | os.O_WRONLY, 0o644)
+                    os.ftruncate(opened[p], max(int(fo[k]) + int(us[k]) for k in range(a, b + 1)))
+                else:
+                    opened[p] = os.open(full, os.O_CREAT | os.O_WRONLY | os.O_TRUNC, 0o644)
             files[r] = opened[p]
     fd = os.open(index_path, os.O_RDONLY)
     try:

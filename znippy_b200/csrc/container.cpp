@@ -31,6 +31,7 @@
 #include "../../include/znippy_cuda.h"
 
 namespace {
+constexpr uint64_t kMaxRowBytes = 1ull << 32;  // blobs / slices of 4 GiB or more are unsupported (include/znippy_cuda.h)
 
 // ------------------------------------------------------------------------------------------------ flatbuffer reading
 struct Span {
@@ -234,13 +235,14 @@ void read_subindex(const Span& stream, IndexImpl* ix, bool first) {
   static const char* u64names[4] = {"blob_offset", "blob_size", "fdata_offset", "uncompressed_size"};
   int fi_u64[4], fi_path = find_field(fields, "relative_path"), fi_seq = find_field(fields, "chunk_seq"),
                  fi_comp = find_field(fields, "compressed"), fi_sum = find_field(fields, "checksum");
+  auto int_width_ok = [](const FieldInfo& f) { return f.type == T_INT && (f.bit_width == 8 || f.bit_width == 16 || f.bit_width == 32 || f.bit_width == 64); };
   for (int k = 0; k < 4; k++) {
     fi_u64[k] = find_field(fields, u64names[k]);
-    if (fi_u64[k] < 0 || fields[fi_u64[k]].type != T_INT) throw FbErr();
+    if (fi_u64[k] < 0 || !int_width_ok(fields[fi_u64[k]])) throw FbErr();
   }
   if (fi_path < 0 || fi_seq < 0 || fi_comp < 0 || fi_sum < 0) throw FbErr();
   if (fields[fi_path].type != T_UTF8 || fields[fi_comp].type != T_BOOL || fields[fi_sum].type != T_FSB ||
-      fields[fi_sum].byte_width != 32 || fields[fi_seq].type != T_INT)
+      fields[fi_sum].byte_width != 32 || !int_width_ok(fields[fi_seq]))
     throw FbErr();
   std::vector<Column> cols;
   while (next_message(stream, &pos, &m)) {
@@ -249,13 +251,13 @@ void read_subindex(const Span& stream, IndexImpl* ix, bool first) {
     for (int k = 0; k < 4; k++) {
       const Column& c = cols[fi_u64[k]];
       const int bits = fields[fi_u64[k]].bit_width;
-      if (c.data_len < n * (uint64_t)(bits / 8)) throw FbErr();
+      if (n > c.data_len / (uint64_t)(bits / 8)) throw FbErr();
       for (uint64_t i = 0; i < n; i++) ix->col[k].push_back(get_uint(c, bits, i));
     }
     {
       const Column& c = cols[fi_seq];
       const int bits = fields[fi_seq].bit_width;
-      if (c.data_len < n * (uint64_t)(bits / 8)) throw FbErr();
+      if (n > c.data_len / (uint64_t)(bits / 8)) throw FbErr();
       for (uint64_t i = 0; i < n; i++) ix->chunk_seq.push_back((uint32_t)get_uint(c, bits, i));
     }
     {
@@ -265,12 +267,12 @@ void read_subindex(const Span& stream, IndexImpl* ix, bool first) {
     }
     {
       const Column& c = cols[fi_sum];
-      if (c.data_len < n * 32) throw FbErr();
+      if (n > c.data_len / 32) throw FbErr();
       ix->checksums.insert(ix->checksums.end(), c.data, c.data + n * 32);
     }
     {
       const Column& c = cols[fi_path];
-      if (c.offsets_len < (n + 1) * 4) throw FbErr();
+      if (n >= c.offsets_len / 4) throw FbErr();
       for (uint64_t i = 0; i < n; i++) {
         int32_t a, b;
         memcpy(&a, c.offsets + 4 * i, 4);
@@ -293,10 +295,20 @@ void read_manifest(const Span& stream, IndexImpl* ix) {
   const int f_pkg = find_field(fields, "pkg_type"), f_repo = find_field(fields, "repo"), f_mod = find_field(fields, "module_name"),
             f_off = find_field(fields, "index_offset"), f_len = find_field(fields, "index_len"), f_rows = find_field(fields, "row_count");
   if (f_pkg < 0 || f_repo < 0 || f_mod < 0 || f_off < 0 || f_len < 0 || f_rows < 0) throw FbErr();
+  // exact types (index.rs manifest schema): Int8, Utf8, Utf8, UInt64 x3 — anything else is not this format
+  if (fields[f_pkg].type != T_INT || fields[f_pkg].bit_width != 8 || fields[f_repo].type != T_UTF8 || fields[f_mod].type != T_UTF8)
+    throw FbErr();
+  for (int f : {f_off, f_len, f_rows})
+    if (fields[f].type != T_INT || fields[f].bit_width != 64) throw FbErr();
   std::vector<Column> cols;
   while (next_message(stream, &pos, &m)) {
     if (m.header_type != 3) continue;
     const uint64_t n = parse_batch(m, fields, &cols);
+    if (n > cols[f_pkg].data_len) throw FbErr();
+    for (int f : {f_off, f_len, f_rows})
+      if (n > cols[f].data_len / 8) throw FbErr();
+    for (int f : {f_repo, f_mod})
+      if (n >= cols[f].offsets_len / 4) throw FbErr();
     auto str = [&](int f, uint64_t i) {
       const Column& c = cols[f];
       int32_t a, b;
@@ -583,6 +595,16 @@ extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) {
       first = false;
     }
     h->ix.path_off.insert(h->ix.path_off.begin(), 0);
+    // Index columns come from the file: every blob must lie inside the payload region (before the first sub-index)
+    // and both sizes stay below the 4 GiB the batch calls support, so that no later sum of them can wrap.
+    uint64_t payload_end = moff;
+    for (auto& g : h->ix.groups) payload_end = std::min(payload_end, g.index_offset);
+    for (uint64_t r = 0; r < h->ix.rows; r++) {
+      const uint64_t bo = h->ix.col[0][r], bs = h->ix.col[1][r], fo = h->ix.col[2][r], us = h->ix.col[3][r];
+      if (bs >= kMaxRowBytes || us >= kMaxRowBytes) throw std::string("index row " + std::to_string(r) + ": blob of 4 GiB or more");
+      if (bo > payload_end || bs > payload_end - bo) throw std::string("index row " + std::to_string(r) + ": blob outside the payload region");
+      if (fo > (1ull << 62)) throw std::string("index row " + std::to_string(r) + ": file offset out of range");
+    }
   } catch (const std::string& m) {
     set_err(err, errcap, m);
     delete h;
@@ -786,8 +808,22 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
           for (size_t p = 1; p < full.size(); p++)
             if (full[p] == '/') mkdir(full.substr(0, p).c_str(), 0755);
           const bool again = !created.insert(rel).second;
-          const int fd = open(full.c_str(), O_CREAT | O_WRONLY | (again ? 0 : O_TRUNC), 0644);
+          // A file whose rows straddle [row_lo, row_hi) is also written by the neighbouring shard (another process or
+          // GPU): truncating it here could destroy chunks that shard has already written.  It is opened without
+          // O_TRUNC and sized to its full length from the index instead (idempotent, never cuts live data).
+          auto same_path = [&](uint64_t r) {
+            return ix.path_off[r + 1] - ix.path_off[r] == rel.size() && memcmp(ix.paths.data() + ix.path_off[r], rel.data(), rel.size()) == 0;
+          };
+          const bool shared = (row_lo > 0 && same_path(row_lo - 1)) || (row_hi < ix.rows && same_path(row_hi));
+          const int fd = open(full.c_str(), O_CREAT | O_WRONLY | (again || shared ? 0 : O_TRUNC), 0644);
           if (fd < 0) { set_err(err, errcap, "failed to open output file " + full); rc = ZN_E_ARG; break; }
+          if (shared && !again) {
+            uint64_t a = w_hi, b = w_hi, size = 0;
+            while (a > 0 && same_path(a - 1)) a--;
+            while (b + 1 < ix.rows && same_path(b + 1)) b++;
+            for (uint64_t r = a; r <= b; r++) size = std::max(size, ix.col[2][r] + ix.col[3][r]);
+            if (ftruncate(fd, (off_t)size) != 0) { close(fd); set_err(err, errcap, "failed to size output file " + full); rc = ZN_E_ARG; break; }
+          }
           it = open_files.emplace(rel, fd).first;
         }
         fds[w_hi] = it->second;
@@ -1120,6 +1156,7 @@ extern "C" int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* 
     }
   }
   if (rows.empty()) return ZN_OK;
+  if (rows.size() > 0xFFFFFFF0ull) return ZN_E_ARG;  // row sizes were bounded by zn_index_open, so in_cur cannot wrap
   uint8_t* stage = (uint8_t*)zn_ctx_pinned_alloc(in_cur + 4096);
   if (!stage) return ZN_E_NOMEM;
   std::atomic<int> io_err{0};

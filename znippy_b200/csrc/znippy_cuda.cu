@@ -684,6 +684,7 @@ static int ensure(zn_ctx* c, uint8_t** buf, size_t* cap, size_t need) {
 // a Magazine slot) the device copy mirrors it and moves with ONE memcpy; otherwise ranges are packed 16-byte aligned.
 struct Layout {
   bool span = false;
+  bool exact = false;  // span only: no gap of 16 bytes or more between consecutive ranges
   uint64_t span_lo = 0, span_bytes = 0;  // host span [span_lo, span_lo + span_bytes)
   uint64_t total = 0;                    // device bytes
   std::vector<uint64_t> dev_off;
@@ -711,6 +712,17 @@ static Layout make_layout(const uint64_t* off, const uint64_t* len, uint32_t n) 
         if (off[ord[k]] < off[ord[k - 1]] + len[ord[k - 1]]) disjoint = false;
     }
     if (disjoint) {
+      // exact: the ranges tile the span up to alignment padding (< 16 bytes after a row) — the only gaps a D2H span
+      // copy may write over (include/znippy_cuda.h)
+      L.exact = true;
+      if (ascending) {
+        for (uint32_t k = 1; k < n && L.exact; k++) L.exact = off[k] - (off[k - 1] + len[k - 1]) < 16;
+      } else {
+        std::vector<uint32_t> ord(n);
+        std::iota(ord.begin(), ord.end(), 0u);
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return off[a] < off[b]; });
+        for (uint32_t k = 1; k < n && L.exact; k++) L.exact = off[ord[k]] - (off[ord[k - 1]] + len[ord[k - 1]]) < 16;
+      }
       L.span = true;
       L.span_lo = lo;
       L.span_bytes = hi - lo;
@@ -798,11 +810,11 @@ extern "C" int zn_decode_verify_batch(zn_ctx* c, const uint8_t* blobs_base, cons
   rc = zn_plan_run(p, c->d_in, c->d_out, nullptr);
   tp[4] = now();
   if (rc == ZN_OK && out_base) {
-    if (Lo.span) {
+    if (Lo.span && Lo.exact) {
       if (Lo.span_bytes)
         rc = cudaMemcpyAsync(out_base + Lo.span_lo, c->d_out, Lo.span_bytes, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess
                  ? ZN_OK : ZN_E_CUDA;
-    } else {
+    } else {  // caller memory between the declared ranges is never written: one copy per row
       for (uint32_t i = 0; i < n && rc == ZN_OK; i++)
         if (out_len[i] &&
             cudaMemcpyAsync(out_base + out_off[i], c->d_out + Lo.dev_off[i], out_len[i], cudaMemcpyDeviceToHost, c->stream) !=
@@ -914,6 +926,7 @@ extern "C" int zn_compress_batch(zn_ctx* c, const uint8_t* src_base, const uint6
 // staging slot by a few I/O threads, ONE zn_decode_verify_batch replaces the per-row decode + blake3 + compare, the
 // decoded bytes are pwritten at fdata_offset from the pinned output region, and status[] is folded into the
 // counters with the reference's rules (decompress.rs:140,156-184).
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -958,6 +971,20 @@ extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, ui
   if (row_hi > row_lo && (!blob_offset || !blob_size || !compressed || !uncompressed_size || !checksums)) return ZN_E_ARG;
   if (out_fd && !fdata_offset) return ZN_E_ARG;
   memset(stats, 0, sizeof *stats);
+  {
+    // The index columns are untrusted input (they come out of the archive): bound every row before any size is summed.
+    // Sizes below 4 GiB and fewer than 2^32 rows keep all u64 sums below exact; a blob must lie inside the archive file.
+    struct stat sb;
+    if (fstat(archive_fd, &sb) != 0) { c->err = "cannot stat the archive"; return ZN_E_ARG; }
+    const uint64_t flen = (uint64_t)sb.st_size;
+    const bool regular = S_ISREG(sb.st_mode);
+    if (row_hi - row_lo > 0xFFFFFFF0ull) { c->err = "row range too large"; return ZN_E_ARG; }
+    for (uint64_t r = row_lo; r < row_hi; r++) {
+      if (blob_size[r] >= (1ull << 32) || uncompressed_size[r] >= (1ull << 32)) { c->err = "index row with a blob of 4 GiB or more"; return ZN_E_ARG; }
+      if (regular && (blob_offset[r] > flen || blob_size[r] > flen - blob_offset[r])) { c->err = "index row points outside the archive file"; return ZN_E_ARG; }
+      if (out_fd && fdata_offset[r] > (1ull << 62)) { c->err = "index row with a file offset out of range"; return ZN_E_ARG; }
+    }
+  }
   if (batch_bytes < (64u << 20)) batch_bytes = 64u << 20;
   if (io_threads < 1) io_threads = 1;
   // Three stages — pread into pinned memory, GPU decode+verify, pwrite from pinned memory — over two sets of staging

@@ -311,10 +311,8 @@ __global__ void __launch_bounds__(64) k_zchain(ZArgs a) {
 // compacted into lists that are worked off densely.
 // A sequence longer than the buffer, raw / RLE blocks and a block's trailing literals are written straight to global
 // memory by the whole team.
-constexpr uint32_t kGroupBytes = 32768;
 constexpr uint32_t kLitLane = 8;     // literal runs up to this length: straight-line code in the owning lane
 constexpr uint32_t kMatchLane = 16;  // far matches up to this length likewise; longer runs become warp jobs
-constexpr uint32_t kLitWin = 16384;   // literal bytes of one group (staged in shared memory)
 constexpr uint32_t kNearLane = 64;   // ready near matches up to this length are copied by one lane, longer by a warp
 
 // development (build with ZN_TRACE_BUILD=1): cycle counters of the exec kernel's phases, summed over the grid
@@ -332,9 +330,11 @@ __device__ unsigned long long g_ztrace[32];
 #endif
 
 
-template <int NT, int K>
+template <int NT, int K, uint32_t GB>
 struct ExecShared {
   static constexpr uint32_t kSeqs = K * NT;
+  static constexpr uint32_t kGroupBytes = GB;                       // output bytes of one group (the buffer)
+  static constexpr uint32_t kLitWin = GB < 16384u ? GB : 16384u;    // literal bytes of one group (staged in shared memory)
   alignas(16) uint8_t buf[kGroupBytes + 16];
   alignas(16) uint8_t lits[kLitWin + 32];
   uint32_t bm[kGroupBytes / 32 + 2];           // pending bytes of the group's near matches
@@ -370,10 +370,12 @@ ZN_D void bm_mark(uint32_t* bm, uint32_t p0, uint32_t p1) {
   if (SET) atomicOr(bm + w1, m1); else atomicAnd(bm + w1, ~m1);
 }
 
-template <int NT, int K>
-__global__ void __launch_bounds__(NT, 2) k_zexec(ZArgs a, uint8_t* out_base, uint32_t* produced, uint32_t* work_counter) {
+template <int NT, int K, uint32_t GB, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_zexec(ZArgs a, uint8_t* out_base, uint32_t* produced, uint32_t* work_counter) {
   extern __shared__ __align__(16) uint8_t exec_smem[];
-  ExecShared<NT, K>* sh = reinterpret_cast<ExecShared<NT, K>*>(exec_smem);
+  using Sh = ExecShared<NT, K, GB>;
+  Sh* sh = reinterpret_cast<Sh*>(exec_smem);
+  constexpr uint32_t kGroupBytes = Sh::kGroupBytes, kLitWin = Sh::kLitWin;
   const Team t{threadIdx.x, (uint32_t)NT};
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(sh->buf), lits_s = (uint32_t)__cvta_generic_to_shared(sh->lits),

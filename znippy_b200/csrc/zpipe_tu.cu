@@ -24,9 +24,9 @@ bool pipeline_init() {
   if (cudaMemcpyToSymbol(g_zpredef, zset, sizeof zset) != cudaSuccess) return false;
   cudaFuncSetAttribute(k_zseq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqSmem);
   cudaFuncSetAttribute(k_zlit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLitSmem);
-  cudaFuncSetAttribute(k_zexec<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<512, 4>));
-  cudaFuncSetAttribute(k_zexec<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<256, 8>));
-  cudaFuncSetAttribute(k_zexec<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<128, 4>));
+  cudaFuncSetAttribute(k_zexec<512, 4, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<512, 4, 32768>));
+  cudaFuncSetAttribute(k_zexec<256, 8, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<256, 8, 32768>));
+  cudaFuncSetAttribute(k_zexec<128, 4, 16384, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<128, 4, 16384>));
   return true;
 }
 
@@ -51,23 +51,26 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   k_zinit<<<1, 1, 0, st>>>(a.pools, L.seq_cap, L.lit_cap16, L.tab_cap, slots);
   k_zwalk<<<(a.nzb + 63) / 64, 64, 0, st>>>(a);
   mark();
+  // (Running the literal kernel on a second stream beside tables + seq was measured and removed: 67.8 ms instead of
+  // 45.4 ms per step on real text — its 48 KB-per-CTA blocks crowd the sequence decoders off the SMs.)
+  const uint32_t lit_grid = std::min<uint32_t>((slots + kLitBlocks - 1) / kLitBlocks, sms * 3);
   k_ztables<<<std::min<uint32_t>((slots + kTabWarps - 1) / kTabWarps, sms * 8), kTabWarps * 32, 0, st>>>(a);
   mark();
   if (getenv("ZN_SEQ_SMEM")) k_zseq<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeqSmem, st>>>(a);
   else k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a);
   mark();
-  k_zlit<<<std::min<uint32_t>((slots + kLitBlocks - 1) / kLitBlocks, sms * 3), kLitBlocks * 4, kLitSmem, st>>>(a);
+  k_zlit<<<lit_grid, kLitBlocks * 4, kLitSmem, st>>>(a);
   mark();
   k_zchain<<<(a.nzb + 63) / 64, 64, 0, st>>>(a);
   mark();
   const char* ev = getenv("ZN_EXEC");  // development: team shape of the exec kernel
   const int shape = ev ? atoi(ev) : (L.mean_bytes >= (256u << 10) ? 256 : 128);
   if (shape == 512)
-    k_zexec<512, 4><<<std::min<uint32_t>(a.nzb, sms * 2), 512, sizeof(ExecShared<512, 4>), st>>>(a, L.d_out, L.produced, L.exec_counter);
+    k_zexec<512, 4, 32768, 2><<<std::min<uint32_t>(a.nzb, sms * 2), 512, sizeof(ExecShared<512, 4, 32768>), st>>>(a, L.d_out, L.produced, L.exec_counter);
   else if (shape == 256)
-    k_zexec<256, 8><<<std::min<uint32_t>(a.nzb, sms * 2), 256, sizeof(ExecShared<256, 8>), st>>>(a, L.d_out, L.produced, L.exec_counter);
+    k_zexec<256, 8, 32768, 2><<<std::min<uint32_t>(a.nzb, sms * 2), 256, sizeof(ExecShared<256, 8, 32768>), st>>>(a, L.d_out, L.produced, L.exec_counter);
   else
-    k_zexec<128, 4><<<std::min<uint32_t>(a.nzb, sms * 2), 128, sizeof(ExecShared<128, 4>), st>>>(a, L.d_out, L.produced, L.exec_counter);
+    k_zexec<128, 4, 16384, 4><<<std::min<uint32_t>(a.nzb, sms * 4), 128, sizeof(ExecShared<128, 4, 16384>), st>>>(a, L.d_out, L.produced, L.exec_counter);
   mark();
 }
 
