@@ -7,13 +7,21 @@ one batch: BASELINE configs[1], a single 2 GiB text-pattern file = 256 index row
 writer), plus its blake3 `checksum` column.
 
   value     device-resident: blobs and outputs already in HBM, zn_plan_run only          (GB/s of uncompressed bytes)
-  e2e       zn_decode_verify_batch with HOST buffers: H2D of the blobs and D2H of the decoded bytes inside the timing
-  roofline  dominant kernel, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
+  e2e       the verify call (`znippy verify`, decompress_archive(save_data=false)): zn_decode_verify_batch with HOST
+            buffers — H2D of blobs + expected digests, kernels, D2H of statuses + digests inside the timing
+  e2e_extract   the same call with save_data=true: additionally D2H of every decoded byte (PCIe-bound by construction)
+  roofline  dominant kernel, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json; `alu` inside
+            it is the second ceiling the survey asks for (the blake3 int-ALU pipe)
+  sustained the same step repeated for ~2 s with the clocks sampled (the K-step region can be 20 ms long)
+  compress  the write half of the metric: configs[3] through zn_compress_batch at the reference's level, ratio beside
+            libzstd's at the same level, every frame decoded again by stock libzstd
   cpu_baseline   the reference's CPU worker loop (oracle/cpu_pipeline.c restatement: libzstd + blake3, all host
                  threads) on a bounded sample of the same rows
 
-`--impl reference` times only that CPU loop.  N>1 (torchrun): rows shard by range, one process per GPU, no
-collective on the data path (weak scaling: every rank gets its own 2 GiB file).
+`--impl reference` times only that CPU loop, over the same rows and with the same `config` as our arm.  N>1
+(torchrun): rows shard by range, one process per GPU, no collective on the data path.  The default workload scales
+weakly (every rank gets its own 2 GiB file); `--workload multirepo` is BASELINE configs[4] — ONE 64 GiB archive whose
+index rows are cut into N ranges (archive.shard_rows), strong scaling, e2e through the archive file itself.
 """
 from __future__ import annotations
 
@@ -86,21 +94,33 @@ def build_text_corpus(total_bytes: int, level: int = 19, first_byte: int = 0):
     return blobs, lens, np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy()
 
 
-def lcg_random(n: int) -> np.ndarray:
-    """perf_bench.rs:86-92 exactly (val = val*6364136223846793005 + 1 from 12345; byte = val >> 33), vectorised with
-    the closed form x_k = a^k x_0 + c (a^k - 1)/(a - 1) in wrapping uint64 arithmetic."""
-    a, x = np.uint64(6364136223846793005), np.uint64(12345)
+_LCG_A = 6364136223846793005
+_LCG_TAB = {}
+
+
+def lcg_random(n: int, x0: int = 12345, c: int = 1) -> np.ndarray:
+    """perf_bench.rs:86-92 exactly (val = val*6364136223846793005 + c from x0; byte = val >> 33), vectorised with the
+    closed form x_k = a^k x_0 + c (a^k - 1)/(a - 1) in wrapping uint64 arithmetic.  c = 1442695040888963407 and
+    x0 = seed*0x9E3779B97F4A7C15 + 1 give repro_crate.rs:8-16 `incompressible(seed, len)`."""
+    a, x, cc = np.uint64(_LCG_A), np.uint64(x0 & (2**64 - 1)), np.uint64(c)
     out = np.empty(n, np.uint8)
     blk = 1 << 22
     with np.errstate(over="ignore"):
-        A = np.cumprod(np.full(blk, a, np.uint64))            # a^1 .. a^blk
-        S = np.concatenate([[np.uint64(1)], np.cumsum(A[:-1]) + np.uint64(1)])  # 1 + a + .. + a^(k-1), k = 1..blk
+        if "A" not in _LCG_TAB:
+            A = np.cumprod(np.full(blk, a, np.uint64))            # a^1 .. a^blk
+            _LCG_TAB["A"] = A
+            _LCG_TAB["S"] = np.concatenate([[np.uint64(1)], np.cumsum(A[:-1]) + np.uint64(1)])  # 1 + a + .. + a^(k-1)
+        A, S = _LCG_TAB["A"], _LCG_TAB["S"]
         for o in range(0, n, blk):
             m = min(blk, n - o)
-            xs = A[:m] * x + S[:m]
+            xs = A[:m] * x + S[:m] * cc
             out[o:o + m] = (xs >> np.uint64(33)).astype(np.uint8)
             x = xs[m - 1]
     return out
+
+
+def incompressible(seed: int, n: int) -> np.ndarray:  # repro_crate.rs:8-16
+    return lcg_random(n, (seed * 0x9E3779B97F4A7C15 + 1) & (2**64 - 1), 1442695040888963407)
 
 
 def build_rows(entries, level_for):
@@ -185,6 +205,111 @@ def build_workload(name: str, gib: float, rank: int):
         return blobs, lens, digs, np.ones(n, np.uint8), (
             f"{n} real-text files of 2-48 KB ({sum(lens) >> 20} MiB, python sources), one zstd level-3 frame per file")
     raise SystemExit(f"unknown workload {name}")
+
+
+def binary_slice(phase: int, n: int) -> np.ndarray:  # perf_bench.rs: byte[i] = i % 251
+    return ((np.arange(n, dtype=np.uint32) + np.uint32(phase)) % np.uint32(251)).astype(np.uint8)
+
+
+def build_multirepo(gib: float, n_groups: int = 16, want_paths: bool = False):
+    """BASELINE configs[4] / SURVEY §8(d) config 5: ONE archive of `gib` GiB holding n_groups (pkg_type, repo) groups, each a
+    deterministic mix of the README shapes — 40 % one text-pattern file, 20 % one binary-pattern file (8 MiB slices, zstd
+    L19), 20 % small 10 KiB text files (one row each), 10 % incompressible `random.bin` (zstd frames of raw blocks),
+    10 % `app.jar` stored as-is.  Content repeats (45 / 251 distinct slice phases, a pool of 32 incompressible slices)
+    so the 64 GiB never exist uncompressed on the host; every row still gets its own physical copy of its blob.
+    Returns rows in index order: (blobs, lens, digests, compressed, groups[(pkg_type, repo, row_lo, row_hi)], meta)
+    with meta = (paths | None, chunk_seq, fdata_offset)."""
+    z = _libzstd()
+    per_group = int(gib * (1 << 30)) // n_groups
+    cache = {}
+
+    def cached(kind, phase, n):
+        key = (kind, phase, n)
+        if key not in cache:
+            if kind == "text":
+                d = text_slice(phase, n)
+                cache[key] = (_zstd_compress(z, d, 19), _digest(d))
+            elif kind == "binary":
+                d = binary_slice(phase, n)
+                cache[key] = (_zstd_compress(z, d, 19), _digest(d))
+            elif kind == "rnd":      # compressed=true, but libzstd stores raw blocks
+                d = incompressible(phase, n)
+                cache[key] = (_zstd_compress(z, d, 1), _digest(d))
+            else:                     # "jar": stored as-is
+                d = incompressible(1000 + phase, n)
+                cache[key] = (d.tobytes(), _digest(d))
+        return cache[key]
+
+    blobs, lens, digs, comp, groups = [], [], [], [], []
+    paths, seqs, foffs = ([] if want_paths else None), [], []
+    pool = 32
+    rnd_i = 0
+
+    def add_file(path, kind, size, period, compressed):
+        nonlocal rnd_i
+        for k, o in enumerate(range(0, size, SLICE)):
+            n = min(SLICE, size - o)
+            if kind in ("text", "binary"):
+                b, d = cached(kind, o % period, n)
+            else:
+                b, d = cached(kind, rnd_i % pool if n == SLICE else pool + (rnd_i % 4), n)
+                rnd_i += 1
+            blobs.append(b); lens.append(n); digs.append(d); comp.append(compressed)
+            seqs.append(k); foffs.append(o)
+            if want_paths:
+                paths.append(path)
+
+    small_b, small_d = cached("text", 0, 10240)
+    for g in range(n_groups):
+        lo = len(blobs)
+        repo = f"repo{g:02d}"
+        add_file(f"{repo}/huge.txt", "text", per_group * 40 // 100, 45, 1)
+        add_file(f"{repo}/model.bin", "binary", per_group * 20 // 100, 251, 1)
+        n_small = per_group * 20 // 100 // 10240
+        blobs += [small_b] * n_small; lens += [10240] * n_small; digs += [small_d] * n_small; comp += [1] * n_small
+        seqs += [0] * n_small; foffs += [0] * n_small
+        if want_paths:
+            paths += [f"{repo}/files/file_{i:06d}.txt" for i in range(n_small)]
+        add_file(f"{repo}/random.bin", "rnd", per_group * 10 // 100, 0, 1)
+        add_file(f"{repo}/app.jar", "jar", per_group * 10 // 100, 0, 0)
+        groups.append((1 + g % 4, repo, lo, len(blobs)))
+    digs = np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy()
+    desc = (f"configs[4]: ONE {gib:g} GiB multi-repo archive, {n_groups} (pkg_type, repo) groups x [40 % text-pattern file, 20 % "
+            f"binary-pattern file (8 MiB slices, zstd L19), 20 % 10 KiB text files, 10 % incompressible zstd raw-block frames, "
+            f"10 % store-as-is], {len(blobs)} index rows sharded by row range over the GPUs (archive.shard_rows), decode/gather "
+            "+ blake3 + compare, output materialised in HBM")
+    return blobs, lens, digs, np.array(comp, np.uint8), groups, (paths, np.array(seqs, np.uint32), np.array(foffs, np.uint64)), desc
+
+
+def write_multirepo_archive(path: str, blobs, lens, digs, comp, groups, meta):
+    """The archive of build_multirepo as a real `.znippy` v0.7 file: blobs back to back, then sub-indexes / manifest /
+    footer through the library's own index writer (zn_index_writer_*)."""
+    from znippy_b200 import _native as N
+    from znippy_b200 import archive as A
+    L = N.lib()
+    paths, seqs, foffs = meta
+    buf, boff = pack(blobs, 1)
+    bs = np.array([len(b) for b in blobs], np.uint64)
+    fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o644)
+    try:
+        done = 0
+        mv = memoryview(buf)
+        while done < buf.size:
+            done += os.pwrite(fd, mv[done:done + (1 << 30)], done)
+        w = L.zn_index_writer_create(fd, int(buf.size))
+        for k, v in A.config_metadata().items():
+            assert L.zn_index_writer_metadata(w, k.encode(), v.encode()) == 0
+        us = np.array(lens, np.uint64)
+        for pt, repo, lo, hi in groups:
+            n = hi - lo
+            ps = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths[lo:hi]])
+            cols = [np.ascontiguousarray(a[lo:hi]) for a in (seqs, foffs, comp.astype(np.uint8), us, boff, bs)]
+            ck = np.ascontiguousarray(digs[lo:hi]).reshape(-1)
+            ptr = lambda a: C.c_void_p(a.ctypes.data)
+            assert L.zn_index_writer_push_group(w, pt, repo.encode(), n, ps, *[ptr(c) for c in cols], ptr(ck)) == 0
+        assert L.zn_index_writer_finish(w) == 0
+    finally:
+        os.close(fd)
 
 
 def pack(blobs, align=16):
@@ -300,10 +425,10 @@ def cpu_pipeline(blobs, lens, digs, min_seconds: float, passes_cap: int = 100000
     return done / dt / 1e9, threads, f"{n} rows ({int(us.sum()) >> 20} MiB) of the workload, {passes} passes, {dt:.1f} s", dt / passes
 
 
-def static_config(wl_desc: str, n_rows: int, out_bytes: int) -> dict:
+def static_config(wl_desc: str, n_rows: int, out_bytes: int, strong: bool = False) -> dict:
     """The part of the line both arms share verbatim (the driver compares it): what is processed, never how."""
-    return {"workload": wl_desc, "rows_per_gpu": n_rows,
-            "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"}
+    return {"workload": wl_desc, ("rows" if strong else "rows_per_gpu"): n_rows,
+            "l2": f"working set {out_bytes >> 20} MiB per step{' (all GPUs)' if strong else ''} > 126 MB L2, no flush needed"}
 
 
 def run_reference(args):
@@ -312,7 +437,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    blobs, lens, digs, comp, wl_desc = build_workload(args.workload, args.gib, 0)
+    strong = args.workload == "multirepo"
+    if strong:
+        blobs, lens, digs, comp, _, _, wl_desc = build_multirepo(args.gib)
+    else:
+        blobs, lens, digs, comp, wl_desc = build_workload(args.workload, args.gib, 0)
     n, out_bytes = len(blobs), int(sum(lens))
     stride = max(1, out_bytes // (4 << 30))  # bound a step to ~4 GiB of CPU work
     sb, sl, sd, sc = blobs[::stride], lens[::stride], digs[::stride], comp[::stride]
@@ -331,7 +460,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": round(1e3 * t_tot / args.steps, 3), "higher_is_better": True,
         "scaling": "strong" if args.workload == "multirepo" else "weak",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": static_config(wl_desc, n, out_bytes),
+        "config": static_config(wl_desc, n, out_bytes, strong),
         "note": "reference CPU worker loop (decompress.rs:105-192) restated in C over libzstd 1.5.5 + SIMD blake3, output "
                 "materialised in host memory; the Rust reference itself cannot be built in this image (no cargo, OpenZL "
                 "fetched at build time)",
@@ -340,6 +469,48 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- ours
+def compress_leg(ctx, codec, seconds_cap: float = 20.0):
+    """The write half of the metric (BASELINE: "compress GB/s + ratio"; configs[3]): zn_compress_batch — blake3 of the
+    source + one frame per 8 MiB slice — on the 500 MiB binary pattern at the reference's level (19,
+    common_config.rs:37), host buffers in pinned memory; every frame is decoded again by stock libzstd (standing in for
+    the reference decoder) and compared.  Ratio of libzstd at the same level on a 4-slice sample beside it."""
+    z = _libzstd()
+    z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    z.ZSTD_decompress.restype = C.c_size_t
+    total = 500 << 20
+    data = binary_slice(0, total)
+    offs = list(range(0, total, SLICE))
+    lens = [min(SLICE, total - o) for o in offs]
+    src = ctx.pinned()[:total]
+    src[:] = data
+    level = 19
+    codec.compress_batch(src, offs, lens, level, codec.CODEC_ZSTD, ctx)  # warm (allocations)
+    t0, reps, kms = time.perf_counter(), 0, 0.0
+    while reps < 5 and time.perf_counter() - t0 < seconds_cap:
+        blobs, dg, st = codec.compress_batch(src, offs, lens, level, codec.CODEC_ZSTD, ctx)
+        kms += ctx.last_compress_ms()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    kms /= reps
+    assert not st.any()
+    out_bytes = sum(len(b) for b in blobs)
+    buf = np.empty(SLICE, np.uint8)
+    for i, b in enumerate(blobs):  # round trip through the stock decoder, every frame
+        a = np.frombuffer(b, np.uint8)
+        r = z.ZSTD_decompress(buf.ctypes.data, SLICE, a.ctypes.data, a.size)
+        assert r == lens[i] and (buf[:r] == data[offs[i]:offs[i] + r]).all(), f"frame {i} does not round-trip through libzstd"
+    assert dg[0].tobytes() == _digest(data[:lens[0]])
+    ref_out = sum(len(_zstd_compress(z, np.ascontiguousarray(data[o:o + SLICE]), level)) for o in offs[:4])
+    ref_ratio = 4 * SLICE / ref_out
+    ratio = total / out_bytes
+    return {"workload": "configs[3]: 500 MiB binary pattern, 63 slices x 8 MiB, zstd frames + blake3 of the source",
+            "level": level, "value": round(total / kms / 1e6, 1), "unit": "GB/s (device, compress kernels)",
+            "e2e": round(total / dt / 1e9, 2), "e2e_unit": "GB/s (zn_compress_batch, pinned host buffers in and out)",
+            "ratio": round(ratio, 1), "ratio_libzstd_same_level": round(ref_ratio, 1),
+            "ratio_gap_pct": round(100.0 * (1.0 - ratio / ref_ratio), 1),
+            "roundtrip": f"all {len(blobs)} frames decoded by libzstd 1.5.5 to identical bytes", "reps": reps}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -354,9 +525,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from znippy_b200 import Ctx, Plan, codec
 
+    strong = args.workload == "multirepo"
     total = int(args.gib * (1 << 30))
-    # weak scaling: rank r holds rows [r*256, (r+1)*256) of an N x 2 GiB multi-file archive, no exchange
-    blobs, lens, digs, comp, wl_desc = build_workload(args.workload, args.gib, rank)
+    arch = None
+    if strong:
+        # strong scaling: ONE archive; its index rows are cut into `world` contiguous ranges balanced on uncompressed bytes
+        # (archive.shard_rows) and every GPU decodes + verifies its own range — no exchange, no collective
+        from znippy_b200.archive import shard_rows
+        blobs, lens, digs, comp, groups, meta, wl_desc = build_multirepo(args.gib, want_paths=(rank == 0))
+        rows_total, job_bytes = len(blobs), int(sum(lens))
+        lo, hi = shard_rows(np.array(lens, np.uint64), world)[rank]
+        arch = {"path": f"/dev/shm/znippy_bench_multirepo_{args.gib:g}.znippy", "lo": lo, "hi": hi}
+        if rank == 0:
+            write_multirepo_archive(arch["path"], blobs, lens, digs, comp, groups, meta)
+        blobs, lens, digs, comp = blobs[lo:hi], lens[lo:hi], digs[lo:hi], comp[lo:hi]
+    else:
+        # weak scaling: rank r holds rows [r*256, (r+1)*256) of an N x 2 GiB multi-file archive, no exchange
+        blobs, lens, digs, comp, wl_desc = build_workload(args.workload, args.gib, rank)
     n = len(blobs)
     in_buf, in_off = pack(blobs, 16)
     in_len = np.array([len(b) for b in blobs], np.uint64)
@@ -365,8 +550,10 @@ def run_ours(args):
     out_off = np.concatenate([[0], np.cumsum((out_len + np.uint64(15)) & ~np.uint64(15))])[:-1].astype(np.uint64)
     out_bytes = int(out_len.sum())
     out_span = int(out_off[-1] + out_len[-1]) if n else 0
+    if not strong:
+        rows_total, job_bytes = n, world * out_bytes
 
-    ctx = Ctx(local, staging_bytes=out_span + in_buf.size + (1 << 20))
+    ctx = Ctx(local, staging_bytes=(1 << 20) if strong else max(out_span + in_buf.size + (1 << 20), (501 << 20)))
     stream = torch.cuda.Stream()  # a real (non-default) stream: kernels and the timing events share it
     torch.cuda.set_stream(stream)
     d_in = torch.from_numpy(in_buf).cuda()
@@ -417,40 +604,84 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = plan.launches() * args.steps
 
-    # ---- end to end through the reference-facing call, HOST buffers in pinned memory (zn_ctx_pinned), every step:
+    # ---- sustained: the same step repeated for ~2 s, so that the clocks the GPU holds under a long run of this
+    # ALU-bound kernel are on record (the K-step region above can be as short as 20 ms)
+    sustained = None
+    if args.sustain > 0:
+        per = max(dev_ms / args.steps, 1e-3)
+        k = int(max(args.steps, min(20000, args.sustain * 1e3 / per)))
+        with Clocks(local) as clk2:
+            sync_all()
+            e0.record(stream)
+            for _ in range(k):
+                step()
+            e1.record(stream)
+            sync_all()
+            sus_ms = e0.elapsed_time(e1)
+        sustained = {"steps": k, "seconds": round(sus_ms / 1e3, 3), "ms_per_step": round(sus_ms / k, 4),
+                     "value_this_rank": round(out_bytes / (sus_ms / k * 1e-3) / 1e9, 2), "unit": "GB/s", "clocks": clk2.summary()}
+
+    # ---- end to end through the reference-facing call, HOST buffers, every step:
     #   verify  (the metric: `znippy verify` / decompress_archive(save_data=false), decompress.rs:135-184 without :186-189)
     #           H2D blobs + expected digests, kernels, D2H statuses + digests
     #   extract (save_data=true): additionally D2H of every decoded byte — PCIe-bound by construction
-    pinned = ctx.pinned()
-    h_in = pinned[: in_buf.size]
-    h_in[:] = in_buf
-    h_out = pinned[in_buf.size + 4096 - in_buf.size % 4096:][:out_span]
-    e2e_steps = max(3, min(args.steps, 20))
-    codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)  # warm (allocations)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        est, edg = codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    assert not est.any() and (edg == digs).all()
-    x_steps = 3
-    codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(x_steps):
-        est, _ = codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)
-    torch.cuda.synchronize()
-    x_s = (time.perf_counter() - t0) / x_steps
-    assert not est.any()
-    if args.workload == "text2g":  # spot-check returned bytes
-        assert bytes(h_out[:45]) == text_slice((rank * total) % len(PHRASE), 45).tobytes()
+    x_s = None
+    if strong:
+        # through the archive FILE (on /dev/shm): zn_archive_decompress over this rank's row range = index read, pread into
+        # pinned slots, H2D, kernels, D2H of statuses (+ decoded bytes and pwrite for extract)
+        from znippy_b200 import archive as A
+        sync_all()
+        A.decompress_archive(arch["path"], False, "/dev/null", ctx, row_range=(lo, min(hi, lo + 64)))  # warm (pinned slots)
+        e2e_steps = 1
+        sync_all()
+        t0 = time.perf_counter()
+        rep = A.decompress_archive(arch["path"], False, "/dev/null", ctx, row_range=(lo, hi))
+        e2e_s = time.perf_counter() - t0
+        assert rep.corrupt_files == 0 and rep.verified_bytes == out_bytes and rep.chunks == n, rep
+        e2e_api = ("zn_archive_decompress(save_data=false) over this GPU's row range of the ONE archive file (/dev/shm): index "
+                   "read, pread into pinned slots, H2D, kernels, D2H of statuses; host clock")
+        if args.extract:
+            out_dir = f"/dev/shm/znippy_bench_multirepo_out"
+            sync_all()
+            t0 = time.perf_counter()
+            rep = A.decompress_archive(arch["path"], True, out_dir, ctx, row_range=(lo, hi))
+            x_s = time.perf_counter() - t0
+            assert rep.corrupt_files == 0 and rep.total_bytes == out_bytes, rep
+            x_steps = 1
+    else:
+        pinned = ctx.pinned()
+        h_in = pinned[: in_buf.size]
+        h_in[:] = in_buf
+        h_out = pinned[in_buf.size + 4096 - in_buf.size % 4096:][:out_span]
+        e2e_steps = max(3, min(args.steps, 20))
+        codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)  # warm (allocations)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            est, edg = codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, None, None, ctx)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        assert not est.any() and (edg == digs).all()
+        e2e_api = ("zn_decode_verify_batch, verify-only (out_base=NULL): pinned host blobs + digests in, statuses + digests "
+                   "out, timed with the host clock around the calls")
+        x_steps = 3
+        codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(x_steps):
+            est, _ = codec.decode_verify_batch(h_in, in_off, in_len, comp, out_len, digs, h_out, out_off, ctx)
+        torch.cuda.synchronize()
+        x_s = (time.perf_counter() - t0) / x_steps
+        assert not est.any()
+        if args.workload == "text2g":  # spot-check returned bytes
+            assert bytes(h_out[:45]) == text_slice((rank * total) % len(PHRASE), 45).tobytes()
 
     # ---- reduce: max time over ranks
-    times = torch.tensor([dev_ms, e2e_s * 1e3, x_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s * 1e3, (x_s or 0.0) * 1e3, sustained["ms_per_step"] if sustained else 0.0],
+                         dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, x_ms = float(times[0]), float(times[1]), float(times[2])
+    dev_ms, e2e_ms, x_ms, sus_step_ms = (float(t) for t in times)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -458,14 +689,13 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     ms_per_step = dev_ms / args.steps
-    value = world * out_bytes / (ms_per_step * 1e-3) / 1e9
-    e2e_value = world * out_bytes / (e2e_ms * 1e-3) / 1e9
-    x_value = world * out_bytes / (x_ms * 1e-3) / 1e9
+    value = job_bytes / (ms_per_step * 1e-3) / 1e9
+    e2e_value = job_bytes / (e2e_ms * 1e-3) / 1e9
     blob_bytes = int(in_len.sum())
     # dominant kernel: the largest stage
     dec = comp.astype(bool)
     k_decode_bytes = int(in_len[dec].sum() + out_len[dec].sum())  # blob read + uncompressed written
-    k_hash_bytes = out_bytes + 32 * (out_bytes // 1024)  # content read + one 32 B chaining value per chunk written
+    k_hash_bytes = out_bytes + 32 * n  # content read + one 32 B digest per row (chaining values are scratch)
     kernels = {
         "k_decode": {"ms": round(float(stage_ms[1]), 4), "alg_bytes": k_decode_bytes,
                      "gbs": round(k_decode_bytes / (stage_ms[1] * 1e-3) / 1e9, 1) if stage_ms[1] > 0 else None},
@@ -474,44 +704,75 @@ def run_ours(args):
         "k_b3_tree": {"ms": round(float(stage_ms[3]), 4)}}
     dom = "k_b3_chunks" if stage_ms[2] >= stage_ms[1] else "k_decode"
     note = "blake3 is int-ALU bound (~10.5 int ops/byte), see DESIGN.md; hbm frac reported as asked"
+    hashed_ms = float(stage_ms[2])
     if plan.fused():
         # decode and hash are ONE kernel (fused_ws.cuh): algorithmic bytes of decode+verify per SURVEY §8(d) = blob read +
-        # content written + one 32 B chaining value per KiB; the hash's read of the fresh output is not algorithmic
-        fused_bytes = k_decode_bytes + 32 * (out_bytes // 1024)
+        # content written + 32 B digest per row; chaining values and the hash's read of the fresh output are not algorithmic
+        fused_bytes = k_decode_bytes + 32 * n
         kernels = {"k_decode_ws": {"ms": round(float(stage_ms[1]), 4), "alg_bytes": fused_bytes,
                                    "gbs": round(fused_bytes / (stage_ms[1] * 1e-3) / 1e9, 1)},
                    "k_b3_tree": {"ms": round(float(stage_ms[3]), 4)}}
         dom = "k_decode_ws"
+        hashed_ms = float(stage_ms[1])
         note = ("decode + blake3 chunk hashing fused in one warp-specialised kernel; its floor is the int-ALU pipe (the "
                 "standalone hash kernel needs 0.99 ms for this batch at 89 % ALU utilisation), not HBM; hbm frac reported as asked")
     achieved = kernels[dom]["gbs"]
+    # second ceiling (SURVEY §8d "additionally the int-ALU ceiling for blake3"): 448 ALU-pipe ops per 64-byte block on
+    # 64 ALU lanes per SM per clock at the SM clock measured during the timed region
+    sm_mhz = clocks.get("sm_mhz") or 1965
+    alu_peak = 148 * 64 * sm_mhz * 1e6 * 64 / 448 / 1e9
+    alu = {"kernel": "k_decode_ws" if plan.fused() else "k_b3_chunks", "bound": "int-alu", "unit": "GB/s of hashed content",
+           "achieved": round(out_bytes / (hashed_ms * 1e-3) / 1e9, 1) if hashed_ms > 0 else None,
+           "peak": round(alu_peak, 1), "peak_source": f"148 SM x 64 ALU lanes x {sm_mhz} MHz x 64 B / 448 ALU ops per block",
+           "frac": round(out_bytes / (hashed_ms * 1e-3) / 1e9 / alu_peak, 4) if hashed_ms > 0 else None}
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom) if args.workload == "text2g" else None,
                 "peak_source": peak_src,
-                "frac_of_nominal_8000": round(achieved / 8000.0, 4), "kernels": kernels, "note": note}
+                "frac_of_nominal_8000": round(achieved / 8000.0, 4), "kernels": kernels, "alu": alu, "note": note}
 
     cpu = None
     if not args.no_cpu:
         k = min(n, 64 if args.workload not in ("small100k", "realsmall") else 20000)
-        gbs, threads, desc, _ = cpu_pipeline(blobs[:k], lens[:k], digs[:k], args.cpu_seconds, comp=comp[:k])
+        pick = slice(0, k) if not strong else slice(0, n, max(1, n // 4096))  # multirepo: a stride sample keeps the mix
+        gbs, threads, desc, _ = cpu_pipeline(blobs[pick], lens[pick], digs[pick], args.cpu_seconds, comp=comp[pick])
         cpu = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": desc}
 
-    print(json.dumps({
+    compress = None
+    if args.compress and not strong:
+        compress = compress_leg(ctx, codec)
+
+    line = {
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": {"workload": wl_desc, "rows_per_gpu": n, "schedule": ("stages back to back on one stream" if args.groups <= 1 else
+        "config": static_config(wl_desc, rows_total if strong else n, job_bytes if strong else out_bytes, strong),
+        "detail": {"schedule": ("stages back to back on one stream" if args.groups <= 1 else
                                 f"{args.groups} row groups, decode(g+1) overlaps blake3(g) on 2 streams"),
                    "serial_ms_per_step": round(float(stage_ms[0]), 4), "serial_launches_per_step": serial_launches,
-                   "l2": f"working set {out_bytes >> 20} MiB per step > 126 MB L2, no flush needed"},
+                   "rows_this_rank": n, "distinct_blobs_this_rank": len({id(b) for b in blobs})},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": blob_bytes + 32 * n + 33 * n,
-                "d2h_bytes_per_step": 36 * n, "steps": e2e_steps, "ms_per_step": round(e2e_ms, 4),
-                "api": "zn_decode_verify_batch, verify-only (out_base=NULL): pinned host blobs + digests in, statuses + "
-                       "digests out, timed with the host clock around the calls",
-                "extract": {"value": round(x_value, 3), "unit": "GB/s", "d2h_bytes_per_step": out_bytes + 36 * n,
-                            "steps": x_steps, "note": "save_data=true: every decoded byte returns over PCIe"}},
-        "roofline": roofline, "cpu_baseline": cpu}))
+                "d2h_bytes_per_step": 36 * n, "steps": e2e_steps, "ms_per_step": round(e2e_ms, 4), "api": e2e_api},
+        "roofline": roofline, "cpu_baseline": cpu}
+    if x_s is not None:
+        line["e2e_extract"] = {"value": round(job_bytes / (x_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
+                               "h2d_bytes_per_step": blob_bytes + 32 * n + 33 * n, "d2h_bytes_per_step": out_bytes + 36 * n,
+                               "steps": x_steps, "ms_per_step": round(x_ms, 4),
+                               "note": "save_data=true: every decoded byte returns over PCIe" +
+                                       (" and is pwritten to /dev/shm" if strong else "")}
+    if sustained:
+        sustained["ms_per_step"] = round(sus_step_ms, 4)
+        sustained["value"] = round(job_bytes / (sus_step_ms * 1e-3) / 1e9, 2)
+        line["sustained"] = sustained
+    if compress:
+        line["compress"] = compress
+    print(json.dumps(line))
+    if strong and world >= 1:
+        try:
+            os.unlink(arch["path"])
+        except OSError:
+            pass
     if world > 1:
         dist.destroy_process_group()
 
@@ -522,13 +783,18 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed", "realtext", "realsmall"],
+    ap.add_argument("--workload", default="text2g", choices=["text2g", "small100k", "mixed", "realtext", "realsmall", "multirepo"],
                     help="text2g = BASELINE configs[1] (the metric's config); the others are secondary report lines")
     ap.add_argument("--gib", type=float, default=2.0, help="uncompressed GiB per GPU (2 = BASELINE configs[1])")
     ap.add_argument("--groups", type=int, default=1, help="row groups of the overlapped decode/hash schedule (1 = serial)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the extra sustained-clock run (0 = skip)")
+    ap.add_argument("--no-compress", dest="compress", action="store_false", help="skip the compress leg (configs[3])")
+    ap.add_argument("--extract", action="store_true", help="multirepo: also time save_data=true (writes the whole corpus to /dev/shm)")
     args = ap.parse_args()
+    if args.workload == "multirepo" and args.gib == 2.0:
+        args.gib = 64.0  # configs[4]
     if args.impl == "reference":
         run_reference(args)
     else:

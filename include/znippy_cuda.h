@@ -30,9 +30,10 @@
  * Blob wire formats accepted by the decoder (self-identifying by magic): Zstandard frames (RFC 8878, magic
  * 28 B5 2F FD; several concatenated frames and skippable frames allowed; no dictionaries) and LZ4 frames (magic
  * 04 22 4D 18, independent or linked blocks).  The optional XXH64 / XXH32 content and block checksums of those frames
- * are skipped, not verified: integrity on this path is the blake3 digest.  The OpenZL envelope the reference writes
- * around those payloads is NOT parsed (its layout is unpinned in this environment); such blobs get
- * ZN_S_UNSUPPORTED.
+ * are skipped, not verified: integrity on this path is the blake3 digest.  Envelopes around those payloads go through
+ * the envelope layer below (zn_envelope_parse): this library's own ZNB1 is built in; the OpenZL envelope the reference
+ * writes is NOT (its layout is unpinned in this environment) — until a parser for it is registered with
+ * zn_envelope_register such blobs get ZN_S_UNSUPPORTED.
  */
 #ifndef ZNIPPY_CUDA_H
 #define ZNIPPY_CUDA_H
@@ -68,7 +69,11 @@ enum {
 /* ---- codecs for zn_compress_batch ---- */
 enum {
   ZN_CODEC_ZSTD = 1, /* one Zstandard frame per slice */
-  ZN_CODEC_LZ4 = 2   /* one LZ4 frame (independent 64 KiB blocks, content size in header) per slice */
+  ZN_CODEC_LZ4 = 2,  /* one LZ4 frame (independent 64 KiB blocks, content size in header) per slice */
+  /* archive writer only, OR-ed into `codec`: every compressed row's blob is a ZNB1 envelope (see the envelope layer
+   * below) around the frame, or around the raw bytes when the frame did not shrink them (store-if-incompressible);
+   * the index metadata gets znippy_envelope = "ZNB1" and readers resolve such rows through zn_envelope_parse */
+  ZN_CODEC_ENVELOPE = 0x100
 };
 
 typedef struct zn_ctx zn_ctx;   /* one CUDA device + streams + scratch + pinned staging; not thread-safe */
@@ -96,7 +101,11 @@ int zn_hash_batch(zn_ctx* ctx, const uint8_t* base, const uint64_t* off, const u
 /*
  * For each blob i: if compressed[i], decode blobs_base[blob_off[i] .. +blob_len[i]) (capacity out_len[i]);
  * else the blob bytes are the content.  compressed[i] == 1: the codec is identified by the frame magic (Zstandard
- * or LZ4 frame); compressed[i] == 2: the blob is one raw LZ4 block (no header; both sizes come from the index).  Then BLAKE3 the content, compare with expect_digest[i] when given,
+ * or LZ4 frame); 2: the blob is one raw LZ4 block (no header; both sizes come from the index); 3: a Zstandard frame
+ * without its 4-byte magic (the 4 bytes in front of it must belong to the caller's buffer; only the device copy is
+ * touched); 4: enveloped — zn_envelope_parse decides per blob (ZNB1, bare frame, registered foreign parser; a RAW
+ * payload is treated like a store-as-is row, an envelope whose decoded size disagrees with out_len[i] gets
+ * ZN_S_SIZE_MISMATCH, an unknown one ZN_S_UNSUPPORTED).  Then BLAKE3 the content, compare with expect_digest[i] when given,
  * and copy the content to out_base[out_off[i] ..] when out_base is given.
  *   expect_digest  nullable (n*32)  -> no compare (extract_file semantics, archive.rs:144-168)
  *   out_base       nullable         -> verify-only (decompress_archive with save_data=false)
@@ -128,6 +137,33 @@ float zn_ctx_last_compress_ms(const zn_ctx* ctx);
 
 /* decoded size announced by the frame header. returns ZN_OK, 1 when the frame carries no size, <0 on error */
 int zn_frame_content_size(const uint8_t* blob, size_t len, uint64_t* size_out);
+
+/* ---- envelope layer (csrc/envelope.cpp): what the reference's zl_get_decompressed_size / zl_decompress pair does
+ * before any codec runs (znippy-common/src/codec.rs:67-78) — find the codec payload inside the blob and its decoded
+ * size.  Kernels never see an envelope; the host-buffer calls resolve rows flagged compressed == 4 through
+ * zn_envelope_parse and pass the payload range on.  Recognised: bare Zstandard / LZ4 frames (by magic); ZNB1, this
+ * library's own envelope: "ZNB1", one byte payload codec, LEB128 decoded size (< 4 GiB), payload; and whatever the one
+ * registered foreign parser accepts — the seam where a host that links OpenZL plugs in its frame-header reader (the
+ * OpenZL layout itself is unpinned here). ---- */
+enum { ZN_PAYLOAD_RAW = 0, ZN_PAYLOAD_ZSTD = 1, ZN_PAYLOAD_ZSTD_MAGICLESS = 2, ZN_PAYLOAD_LZ4_FRAME = 3, ZN_PAYLOAD_LZ4_BLOCK = 4 };
+enum { ZN_ENV_UNKNOWN = 0, ZN_ENV_BARE = 1, ZN_ENV_ZNB1 = 2, ZN_ENV_FOREIGN = 3 };
+#define ZN_ENVELOPE_ZNB1_MAX_HEADER 10
+typedef struct {
+  uint32_t kind;        /* ZN_ENV_* */
+  uint32_t codec;       /* ZN_PAYLOAD_* */
+  uint64_t payload_off; /* payload = blob[payload_off .. payload_off + payload_len) */
+  uint64_t payload_len;
+  uint64_t out_len;     /* decoded size the envelope announces; UINT64_MAX when it carries none */
+} zn_envelope;
+/* ZN_OK; 1 = not a recognised / well-formed envelope (the row gets ZN_S_UNSUPPORTED); < 0 bad arguments */
+int zn_envelope_parse(const uint8_t* blob, size_t len, zn_envelope* out);
+/* Writes the ZNB1 header for a payload of `codec` decoding to out_len bytes; returns its length (0 on bad arguments). */
+size_t zn_envelope_znb1_header(uint32_t codec, uint64_t out_len, uint8_t* hdr, size_t cap);
+/* Foreign envelope parser, consulted for blobs that are neither bare frames nor ZNB1 (NULL unregisters).  It fills
+ * codec / payload_off / payload_len / out_len and returns ZN_OK, or 1 to decline.  A ZN_PAYLOAD_ZSTD_MAGICLESS payload
+ * needs payload_off >= 4 (the decoder rebuilds the magic in front of it on the device copy). */
+typedef int (*zn_envelope_parser)(const uint8_t* blob, size_t len, zn_envelope* out);
+void zn_envelope_register(zn_envelope_parser fn);
 
 /* ---- native read worker: the loop shell of decompress_archive (znippy-common/src/decompress.rs:105-192) over rows
  * [row_lo, row_hi) of the merged index.  Per batch of rows: pread blobs into pinned staging (io_threads threads),
@@ -207,6 +243,12 @@ int zn_archive_writer_add(zn_archive_writer* w, const char* relative_path, const
                           int8_t pkg_type, const char* repo); /* data is consumed (copied into the slot) before returning */
 int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_report* report); /* also destroys w */
 const char* zn_archive_writer_error(const zn_archive_writer* w);
+/* The writer is a three-stage pipeline over three pinned slots (the Magazine, slotpool.rs:93-227): filling slot k+2,
+ * compressing slot k+1 on the GPU and pwriting slot k overlap; `ctx` belongs to the writer until finish().
+ * compress_dir (slot_packer.rs:329-609): walks input_dir (sorted), cuts every file into rounds placed in the slots and
+ * lets io_threads readers pread the bytes into place — the whole directory in one call. */
+int zn_archive_compress_dir(zn_ctx* ctx, const char* input_dir, const char* output_path, int no_skip, int level, int codec,
+                            size_t slot_bytes, int io_threads, zn_compression_report* report, char* err, size_t errcap);
 /* pinned host memory (cudaHostAlloc) for callers that stage their own buffers */
 void* zn_ctx_pinned_alloc(size_t bytes);
 void zn_ctx_pinned_free(void* p);

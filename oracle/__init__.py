@@ -455,3 +455,60 @@ def compress_slices(src: np.ndarray, src_off, src_len, level: int, n_threads: in
         raise RuntimeError("zn_ref_compress_slices failed")
     blobs = [dst[int(doff[i]): int(doff[i]) + int(dlen[i])].tobytes() for i in range(len(sl))]
     return blobs, dig
+
+
+# ---------------------------------------------------------------------------------------------- envelope layer
+# Restatement of the ZNB1 envelope of csrc/envelope.cpp (this build's own blob wrapper): "ZNB1", one byte
+# payload codec, LEB128 decoded size (< 4 GiB), payload.  The reference's counterpart is OpenZL's frame header
+# (codec.rs:67-78), whose layout is unpinned here — so this pins OUR format only.
+PAYLOAD_RAW, PAYLOAD_ZSTD, PAYLOAD_ZSTD_MAGICLESS, PAYLOAD_LZ4_FRAME, PAYLOAD_LZ4_BLOCK = range(5)
+
+
+def znb1_wrap(codec: int, out_len: int, payload: bytes) -> bytes:
+    v, leb = out_len, bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        leb.append(b | (0x80 if v else 0))
+        if not v:
+            break
+    return b"ZNB1" + bytes([codec]) + bytes(leb) + bytes(payload)
+
+
+def znb1_parse(blob: bytes):
+    """(codec, payload_off, payload_len, out_len) or None when malformed."""
+    if len(blob) < 6 or blob[:4] != b"ZNB1" or blob[4] > PAYLOAD_LZ4_BLOCK:
+        return None
+    v, p, shift = 0, 5, 0
+    while True:
+        if p >= len(blob) or shift > 28:
+            return None
+        b = blob[p]
+        p += 1
+        v |= (b & 0x7F) << shift
+        shift += 7
+        if not b & 0x80:
+            break
+    if v >= 1 << 32 or (blob[4] == PAYLOAD_RAW and len(blob) - p != v):
+        return None
+    return blob[4], p, len(blob) - p, v
+
+
+def envelope_decode(blob: bytes):
+    """Decoded content of one enveloped blob through the CPU decoders of this oracle (None when unsupported)."""
+    e = znb1_parse(blob)
+    if e is None:
+        return None
+    codec, off, n, out_len = e
+    payload = blob[off:off + n]
+    if codec == PAYLOAD_RAW:
+        return payload
+    if codec == PAYLOAD_ZSTD:
+        rc, out = zstd_decompress(payload, out_len)
+    elif codec == PAYLOAD_ZSTD_MAGICLESS:
+        rc, out = zstd_decompress(b"\x28\xb5\x2f\xfd" + payload, out_len)
+    elif codec == PAYLOAD_LZ4_FRAME:
+        rc, out = lz4_frame_decompress(payload, out_len)
+    else:
+        rc, out = lz4_block_decompress(payload, out_len)
+    return out if rc == 0 and len(out) == out_len else None

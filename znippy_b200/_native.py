@@ -13,6 +13,7 @@ from . import build as _build
 ZN_OK, ZN_E_ARG, ZN_E_CUDA, ZN_E_NOMEM, ZN_E_STATE = 0, -1, -2, -3, -4
 S_OK, S_DECODE_ERROR, S_DIGEST_MISMATCH, S_DST_TOO_SMALL, S_UNSUPPORTED, S_SIZE_MISMATCH = range(6)
 CODEC_ZSTD, CODEC_LZ4 = 1, 2
+CODEC_ENVELOPE = 0x100  # archive writer: wrap compressed rows in ZNB1 (include/znippy_cuda.h)
 
 EXPORTS = [
     "zn_abi_version", "zn_device_count", "zn_strerror", "zn_status_name", "zn_ctx_create", "zn_ctx_destroy",
@@ -25,7 +26,7 @@ EXPORTS = [
     "zn_index_writer_finish", "zn_archive_decompress", "zn_archive_writer_create", "zn_archive_writer_add",
     "zn_archive_writer_finish", "zn_archive_writer_error", "zn_ctx_pinned_alloc", "zn_ctx_pinned_free",
     "zn_archive_open", "zn_archive_close", "zn_archive_file_count", "zn_archive_file_name", "zn_archive_file_size",
-    "zn_archive_extract_files",
+    "zn_archive_extract_files", "zn_archive_compress_dir", "zn_envelope_parse", "zn_envelope_znb1_header", "zn_envelope_register",
 ]
 
 
@@ -138,6 +139,12 @@ def lib() -> C.CDLL:
     L.zn_ctx_pinned_alloc.restype = vp
     L.zn_ctx_pinned_free.argtypes = [vp]
     L.zn_ctx_pinned_free.restype = None
+    L.zn_archive_compress_dir.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, sz, C.c_int, vp, C.c_char_p, sz]
+    L.zn_envelope_parse.argtypes = [vp, sz, vp]
+    L.zn_envelope_znb1_header.argtypes = [u32, u64, vp, sz]
+    L.zn_envelope_znb1_header.restype = sz
+    L.zn_envelope_register.argtypes = [vp]
+    L.zn_envelope_register.restype = None
     L.zn_ctx_last_compress_ms.argtypes = [vp]
     L.zn_ctx_last_compress_ms.restype = C.c_float
     if L.zn_abi_version() != 1:

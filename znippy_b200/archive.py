@@ -183,8 +183,12 @@ def _columns(table: pa.Table):
     n = table.num_rows
     ck = (np.frombuffer(checks.buffers()[1], np.uint8, count=32 * n, offset=32 * checks.offset).reshape(n, 32)
           if n else np.zeros((0, 32), np.uint8))
+    comp = g("compressed", np.uint8)
+    md = table.schema.metadata or {}
+    if md.get(b"znippy_envelope") == b"ZNB1":  # compressed rows carry ZNB1 envelopes: resolved by zn_envelope_parse
+        comp = (comp * np.uint8(4)).astype(np.uint8)
     return (g("blob_offset", np.uint64), g("blob_size", np.uint64), g("fdata_offset", np.uint64),
-            g("compressed", np.uint8), g("uncompressed_size", np.uint64), ck)
+            comp, g("uncompressed_size", np.uint64), ck)
 
 
 def plan_row_batches(blob_size, uncompressed_size, lo: int, hi: int, budget: int):
@@ -421,8 +425,14 @@ class StreamCompressor:
     One `zn_compress_batch` (blake3 + frame per slice) per batch of rounds replaces the N barrel threads; skip
     rounds go through `zn_hash_batch` only (stream_packer.rs:222-227)."""
 
-    def __init__(self, output: str, no_skip: bool, level: int = 3, codec_id: int = codec.CODEC_ZSTD,
-                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20, native_index: bool = True, native: bool = True):
+    def __init__(self, output: str, no_skip: bool, level: int = 19, codec_id: int = codec.CODEC_ZSTD,
+                 ctx: Ctx | None = None, batch_bytes: int = 256 << 20, native_index: bool = True, native: bool = True,
+                 envelope: bool = False):
+        """level defaults to the reference's compression_level = 19 (common_config.rs:37).  envelope=True (native
+        writer only): blobs of compressed rows are ZNB1 envelopes, incompressible slices are stored raw inside them."""
+        if envelope and not native:
+            raise ValueError("the ZNB1 envelope is written by the native pipeline only")
+        self.envelope = envelope
         self.native_index = native_index
         self.native = native
         self._w = None
@@ -435,7 +445,7 @@ class StreamCompressor:
         if self._w is None:
             self._ctx = self.ctx or default_ctx()
             self._w = N.lib().zn_archive_writer_create(self._ctx.handle, self.output.encode(), int(self.no_skip), self.level,
-                                                       self.codec_id, self.batch_bytes)
+                                                       self.codec_id | (N.CODEC_ENVELOPE if self.envelope else 0), self.batch_bytes)
             if not self._w:
                 raise IOError(f"cannot create {self.output}")
         return self._w
@@ -584,3 +594,22 @@ class StreamCompressor:
 
 def compress_stream(output: str, no_skip: bool, **kw) -> StreamCompressor:
     return StreamCompressor(output, no_skip, **kw)
+
+
+def compress_dir(input_dir: str, output: str, no_skip: bool = False, level: int = 19, codec_id: int = codec.CODEC_ZSTD,
+                 ctx: Ctx | None = None, envelope: bool = False, io_threads: int = 8, slot_bytes: int = 256 << 20) -> CompressionReport:
+    """znippy-compress `compress_dir` (walk -> readers -> Magazine slots -> workers -> writer, slot_packer.rs:329-609) in
+    one native call: `zn_archive_compress_dir` walks the directory, places every round in a pinned slot, lets
+    `io_threads` readers pread the bytes into place, and runs the same three-stage slot pipeline as compress_stream."""
+    import ctypes as C
+
+    from . import _native as N
+    ctx = ctx or default_ctx()
+    out = os.path.splitext(output)[0] + ".znippy"
+    rep8 = (C.c_uint64 * 8)()
+    err = C.create_string_buffer(512)
+    rc = N.lib().zn_archive_compress_dir(ctx.handle, input_dir.encode(), out.encode(), int(no_skip), level,
+                                         codec_id | (N.CODEC_ENVELOPE if envelope else 0), slot_bytes, io_threads, C.byref(rep8), err, 512)
+    if rc != 0:
+        raise N.NativeError(f"zn_archive_compress_dir: {err.value.decode(errors='replace')}")
+    return CompressionReport(*[int(x) for x in rep8])

@@ -1,7 +1,7 @@
 """Builds libznippy_cuda.so (sm_100a) in-tree with nvcc.  `python -m znippy_b200.build [--force] [-v]`.
 
-The library is four translation units (C ABI + decode/hash kernels, compression kernels, the device-wide zstd decode
-pipeline, the native container); each is compiled to an object only when one of the files it includes changed, the
+The library is five translation units (C ABI + decode/hash kernels, compression kernels, the device-wide zstd decode
+pipeline, the native container, the envelope layer); each is compiled to an object only when one of the files it includes changed, the
 objects are compiled in parallel and linked into one shared library."""
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 SO = os.path.join(HERE, "libznippy_cuda.so")
-UNITS = ["znippy_cuda.cu", "compress_tu.cu", "zpipe_tu.cu", "container.cpp"]
+UNITS = ["znippy_cuda.cu", "compress_tu.cu", "zpipe_tu.cu", "container.cpp", "envelope.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 _INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
 

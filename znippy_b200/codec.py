@@ -8,8 +8,9 @@ Same names, argument meaning and error behaviour as `znippy-common/src/codec.rs`
                                                              stream_packer.rs:219, slot_packer.rs:553
 
 plus the batch-first forms the worker loops call (one call per batch of index rows instead of one per row).
-The wire format of a compressed blob is a standard Zstandard frame or LZ4 frame (not the OpenZL envelope — its layout
-is unpinned in this environment).  Everything computes on the GPU; there is no CPU fallback.
+The wire format of a compressed blob is a standard Zstandard frame or LZ4 frame, bare or inside this library's own ZNB1
+envelope; the envelope layer (`envelope_parse`, csrc/envelope.cpp) is also where a parser for the reference's OpenZL
+envelope plugs in (its layout is unpinned in this environment).  Everything computes on the GPU; there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -113,6 +114,40 @@ def frame_content_size(blob) -> int | None:
     return None if rc == 1 else int(v.value)
 
 
+# ----------------------------------------------------------------------------------------------- envelope layer
+PAYLOAD_RAW, PAYLOAD_ZSTD, PAYLOAD_ZSTD_MAGICLESS, PAYLOAD_LZ4_FRAME, PAYLOAD_LZ4_BLOCK = range(5)
+ENV_UNKNOWN, ENV_BARE, ENV_ZNB1, ENV_FOREIGN = range(4)
+COMPRESSED_ENVELOPED = 4  # compressed[] value: zn_envelope_parse decides per blob (include/znippy_cuda.h)
+
+
+class _Envelope(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("codec", C.c_uint32), ("payload_off", C.c_uint64), ("payload_len", C.c_uint64),
+                ("out_len", C.c_uint64)]
+
+
+def envelope_parse(blob):
+    """zn_envelope_parse: (kind, payload codec, payload_off, payload_len, out_len | None), or None when the blob is not a
+    recognised envelope (the batch calls give such a row S_UNSUPPORTED).  What OpenZL's frame-header read does in the
+    reference (codec.rs:69) happens here; kernels only ever see payload ranges."""
+    b = N.u8(blob)
+    e = _Envelope()
+    rc = N.lib().zn_envelope_parse(N.ptr(b) if b.size else None, b.size, C.byref(e))
+    if rc < 0:
+        raise ValueError("zn_envelope_parse: bad arguments")
+    if rc != 0:
+        return None
+    return e.kind, e.codec, int(e.payload_off), int(e.payload_len), None if e.out_len == 2**64 - 1 else int(e.out_len)
+
+
+def envelope_wrap(payload_codec: int, out_len: int, payload) -> bytes:
+    """One ZNB1 blob: "ZNB1", payload codec, LEB128 decoded size, payload."""
+    hdr = (C.c_uint8 * 10)()
+    n = N.lib().zn_envelope_znb1_header(payload_codec, out_len, hdr, 10)
+    if n == 0:
+        raise ValueError("zn_envelope_znb1_header: bad codec or size")
+    return bytes(hdr[:n]) + bytes(payload)
+
+
 # ----------------------------------------------------------------------------------------------- codec.rs mirror
 
 def blake3_hash(data, ctx: Ctx | None = None) -> bytes:
@@ -124,10 +159,11 @@ class CompressCtx:
     """codec.rs:8-55.  `level` follows the reference's meaning (higher = more effort); the GPU match finder has
     three effort settings (window geometries), so levels <= 2, 3..9 and >= 10 map onto them."""
 
-    def __init__(self, compression_level: int, codec: int = CODEC_ZSTD, ctx: Ctx | None = None):
+    def __init__(self, compression_level: int, codec: int = CODEC_ZSTD, ctx: Ctx | None = None, envelope: bool = False):
         self.level = int(compression_level)
         self.codec = codec
         self.ctx = ctx or default_ctx()
+        self.envelope = envelope  # wrap every frame in ZNB1; incompressible input is then stored RAW (size + 6..10 bytes)
 
     @classmethod
     def new(cls, compression_level: int) -> "CompressCtx":
@@ -138,6 +174,10 @@ class CompressCtx:
         blobs, _, st = compress_batch(b, [0], [b.size], self.level, self.codec, self.ctx)
         if st[0] != S_OK:
             raise CodecError(st[0], "compress")
+        if self.envelope:
+            if len(blobs[0]) >= b.size:
+                return envelope_wrap(PAYLOAD_RAW, b.size, b.tobytes())
+            return envelope_wrap(PAYLOAD_ZSTD if self.codec == CODEC_ZSTD else PAYLOAD_LZ4_FRAME, b.size, blobs[0])
         return blobs[0]
 
     def compress_into(self, data, out: bytearray) -> int:
@@ -148,12 +188,13 @@ class CompressCtx:
 
 def decompress_into(compressed, out: bytearray) -> int:
     """codec.rs:67-78: size from the frame header, grow `out`, decode, truncate to bytes written."""
-    size = frame_content_size(compressed)
-    if size is None:
+    env = envelope_parse(compressed)  # zl_get_decompressed_size: the size comes out of the frame / envelope header
+    if env is None or env[4] is None:
         raise CodecError(S_UNSUPPORTED, "getDecompressedSize")
+    size = env[4]
     b = N.u8(compressed)
     buf = np.zeros(max(size, 1), np.uint8)
-    st, _ = decode_verify_batch(b, [0], [b.size], [1], [size], None, buf, [0])
+    st, _ = decode_verify_batch(b, [0], [b.size], [COMPRESSED_ENVELOPED], [size], None, buf, [0])
     if st[0] != S_OK:
         raise CodecError(st[0], "decompress")
     out[:] = buf[:size].tobytes()

@@ -11,6 +11,7 @@
 // Message flatbuffer, 8-byte aligned body).  Only what this schema needs of Arrow is implemented: Schema and
 // RecordBatch messages; Utf8, Int/UInt 8-64, Bool, FixedSizeBinary columns; no dictionaries, no body compression.
 // Parity: pyarrow reads what this writes and this reads what pyarrow writes (tests/test_container_native.py).
+#include <dirent.h>
 #include <fcntl.h>
 #include <sys/resource.h>
 #include <sys/stat.h>
@@ -21,8 +22,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_set>
@@ -99,6 +103,7 @@ struct IndexImpl {
   std::vector<uint64_t> col[4];  // blob_offset, blob_size, fdata_offset, uncompressed_size
   std::vector<uint32_t> chunk_seq;
   std::vector<uint8_t> compressed;
+  std::vector<uint8_t> comp_eff;  // what the batch calls get: 4 (enveloped) instead of 1 when the archive declares an envelope
   std::vector<uint8_t> checksums;
   std::vector<uint64_t> path_off;  // rows + 1
   std::string paths;
@@ -597,6 +602,14 @@ extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) {
     h->ix.path_off.insert(h->ix.path_off.begin(), 0);
     // Index columns come from the file: every blob must lie inside the payload region (before the first sub-index)
     // and both sizes stay below the 4 GiB the batch calls support, so that no later sum of them can wrap.
+    h->ix.comp_eff = h->ix.compressed;
+    {
+      auto it = h->ix.metadata.find("znippy_envelope");
+      if (it != h->ix.metadata.end()) {
+        if (it->second != "ZNB1") throw std::string("archive declares an unknown blob envelope: " + it->second);
+        for (auto& c : h->ix.comp_eff) c = c ? 4 : 0;
+      }
+    }
     uint64_t payload_end = moff;
     for (auto& g : h->ix.groups) payload_end = std::min(payload_end, g.index_offset);
     for (uint64_t r = 0; r < h->ix.rows; r++) {
@@ -833,7 +846,7 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
     }
     if (rc == ZN_OK) {
       zn_verify_stats st;
-      rc = zn_decompress_rows(ctx, afd, w_lo, w_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.compressed.data(),
+      rc = zn_decompress_rows(ctx, afd, w_lo, w_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.comp_eff.data(),
                               ix.col[3].data(), ix.checksums.data(), save_data ? fds.data() : nullptr, batch_bytes, io_threads,
                               corrupt.data(), &st);
       if (rc != ZN_OK) set_err(err, errcap, zn_last_error(ctx));
@@ -906,91 +919,265 @@ struct EntryInfo {
 };
 }  // namespace
 
+// The Magazine (slotpool.rs:93-227) as a three-stage pipeline over `kSlots` pinned slots:
+//   fill     the caller (zn_archive_writer_add) or the directory readers (zn_archive_compress_dir) copy source bytes
+//            into the slot they hold; a full slot is published
+//   gpu      one thread: ONE zn_compress_batch per slot (blake3 + frame per slice, the barrel body
+//            stream_packer.rs:217-232 / slot_packer.rs:551-572) + one zn_hash_batch for its store-as-is rounds
+//   write    one thread (the reference's writer thread, stream_packer.rs:252-285): pwrite of the payloads at the running
+//            cursor, blob metas, report counters; then the slot is free again (Ejector::release_one)
+// so that filling slot k+2, compressing slot k+1 and writing slot k overlap.  The zn_ctx is used by the gpu thread
+// only, for as long as the writer lives.
+struct WSlot {
+  uint8_t* stage = nullptr;  // pinned: source slices
+  uint8_t* outb = nullptr;   // pinned: compressed frames
+  uint64_t outb_cap = 0, used = 0;
+  std::vector<Round> rounds;
+  std::vector<uint64_t> d_off, c_out;
+  std::vector<uint8_t> c_dig, s_dig;
+  std::atomic<uint32_t> pending{0};  // directory readers still copying into this slot
+};
+
 struct zn_archive_writer {
+  static constexpr int kSlots = 3;
   zn_ctx* ctx;
   int fd;
   bool no_skip;
   int level, codec;
-  uint64_t slot_bytes, stage_used = 0, out_cursor = 0;
-  uint8_t* stage = nullptr;  // pinned: source slices
-  uint8_t* outb = nullptr;   // pinned: compressed frames of one batch
-  uint64_t outb_cap = 0;
-  std::vector<Round> rounds;
+  bool envelope = false;  // ZN_CODEC_ENVELOPE: blobs of compressed rows are ZNB1 envelopes (store-if-incompressible)
+  uint64_t slot_bytes, out_cursor = 0;
+  WSlot slots[kSlots];
+  WSlot* cur = nullptr;  // the slot being filled
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<WSlot*> free_q, gpu_q, write_q;
+  bool closing = false;
+  int rc = ZN_OK;  // first failure of any stage (sticky)
+  std::thread gpu_thread, write_thread;
   std::vector<BlobMetaRow> metas;
   std::vector<EntryInfo> entries;
   zn_compression_report rep;
   std::string err;
 };
 
-static int writer_flush(zn_archive_writer* w) {
-  if (w->rounds.empty()) return ZN_OK;
-  const size_t n = w->rounds.size();
-  std::vector<uint64_t> c_off, c_len, s_off, s_len, d_off;
-  std::vector<size_t> c_idx, s_idx;
+namespace {
+void writer_fail(zn_archive_writer* w, int rc, const std::string& msg) {
+  std::lock_guard<std::mutex> g(w->mu);
+  if (w->rc == ZN_OK) { w->rc = rc; w->err = msg; }
+}
+
+// gpu stage of one slot
+int slot_compress(zn_archive_writer* w, WSlot* s) {
+  const size_t n = s->rounds.size();
+  std::vector<uint64_t> c_off, c_len, s_off, s_len;
+  s->d_off.clear();
   uint64_t dcur = 0;
   for (size_t i = 0; i < n; i++) {
-    const Round& r = w->rounds[i];
-    if (r.skip) { s_idx.push_back(i); s_off.push_back(r.stage_off); s_len.push_back(r.len); }
+    const Round& r = s->rounds[i];
+    if (r.skip) { s_off.push_back(r.stage_off); s_len.push_back(r.len); }
     else {
-      c_idx.push_back(i); c_off.push_back(r.stage_off); c_len.push_back(r.len);
-      d_off.push_back(dcur);
+      c_off.push_back(r.stage_off); c_len.push_back(r.len);
+      s->d_off.push_back(dcur);
       dcur += (zn_compress_bound(r.len, w->codec) + 15) & ~15ull;
     }
   }
-  d_off.push_back(dcur);
-  if (dcur > w->outb_cap) {
-    if (w->outb) zn_ctx_pinned_free(w->outb);
-    w->outb = (uint8_t*)zn_ctx_pinned_alloc(dcur + 4096);
-    w->outb_cap = w->outb ? dcur + 4096 : 0;
-    if (!w->outb) { w->err = "pinned output allocation failed"; return ZN_E_NOMEM; }
+  s->d_off.push_back(dcur);
+  if (dcur > s->outb_cap) {
+    if (s->outb) zn_ctx_pinned_free(s->outb);
+    s->outb = (uint8_t*)zn_ctx_pinned_alloc(dcur + 4096);
+    s->outb_cap = s->outb ? dcur + 4096 : 0;
+    if (!s->outb) { writer_fail(w, ZN_E_NOMEM, "pinned output allocation failed"); return ZN_E_NOMEM; }
   }
-  std::vector<uint64_t> c_out(c_idx.size());
-  std::vector<uint8_t> c_dig(c_idx.size() * 32), s_dig(s_idx.size() * 32);
-  std::vector<uint32_t> c_st(c_idx.size());
-  if (!c_idx.empty()) {
-    const int rc = zn_compress_batch(w->ctx, w->stage, c_off.data(), c_len.data(), (uint32_t)c_idx.size(), w->level, w->codec, w->outb,
-                                     d_off.data(), c_out.data(), c_dig.data(), c_st.data());
-    if (rc != ZN_OK) { w->err = zn_last_error(w->ctx); return rc; }
-    for (uint32_t s : c_st)
-      if (s != ZN_S_OK) { w->err = "compress failed for a slice"; return ZN_E_ARG; }  // `?` propagates, stream_packer.rs:230
+  s->c_out.assign(c_off.size(), 0);
+  s->c_dig.assign(c_off.size() * 32, 0);
+  s->s_dig.assign(s_off.size() * 32, 0);
+  std::vector<uint32_t> c_st(c_off.size());
+  if (!c_off.empty()) {
+    const int rc = zn_compress_batch(w->ctx, s->stage, c_off.data(), c_len.data(), (uint32_t)c_off.size(), w->level, w->codec, s->outb,
+                                     s->d_off.data(), s->c_out.data(), s->c_dig.data(), c_st.data());
+    if (rc != ZN_OK) { writer_fail(w, rc, zn_last_error(w->ctx)); return rc; }
+    for (uint32_t st : c_st)
+      if (st != ZN_S_OK) { writer_fail(w, ZN_E_ARG, "compress failed for a slice"); return ZN_E_ARG; }  // `?` propagates, stream_packer.rs:230
   }
-  if (!s_idx.empty()) {
-    const int rc = zn_hash_batch(w->ctx, w->stage, s_off.data(), s_len.data(), (uint32_t)s_idx.size(), s_dig.data());
-    if (rc != ZN_OK) { w->err = zn_last_error(w->ctx); return rc; }
+  if (!s_off.empty()) {
+    const int rc = zn_hash_batch(w->ctx, s->stage, s_off.data(), s_len.data(), (uint32_t)s_off.size(), s->s_dig.data());
+    if (rc != ZN_OK) { writer_fail(w, rc, zn_last_error(w->ctx)); return rc; }
   }
+  return ZN_OK;
+}
+
+// writer stage of one slot, in round order (stream_packer.rs:252-285)
+int slot_write(zn_archive_writer* w, WSlot* s) {
   size_t ci = 0, si = 0;
-  for (size_t i = 0; i < n; i++) {  // writer step, in round order
-    const Round& r = w->rounds[i];
+  // payloads of consecutive rounds are gathered into runs so that 100 000 small blobs are not 100 000 pwrite calls
+  std::vector<uint8_t> run;
+  uint64_t run_at = w->out_cursor;
+  auto flush_run = [&]() -> bool {
+    const bool ok = run.empty() || write_all(w->fd, run.data(), run.size(), run_at);
+    run.clear();
+    return ok;
+  };
+  for (size_t i = 0; i < s->rounds.size(); i++) {
+    const Round& r = s->rounds[i];
     BlobMetaRow m;
     m.file_index = r.file_index; m.chunk_seq = r.chunk_seq; m.fdata_offset = r.fdata_offset; m.usize = r.len;
     m.compressed = !r.skip; m.blob_offset = w->out_cursor;
     const uint8_t* payload;
-    if (r.skip) { payload = w->stage + r.stage_off; m.blob_size = r.len; memcpy(m.checksum, s_dig.data() + 32 * si, 32); si++; }
-    else { payload = w->outb + d_off[ci]; m.blob_size = c_out[ci]; memcpy(m.checksum, c_dig.data() + 32 * ci, 32); ci++; }
-    if (m.blob_size && !write_all(w->fd, payload, m.blob_size, w->out_cursor)) { w->err = "pwrite failed"; return ZN_E_ARG; }
-    w->out_cursor += m.blob_size;
+    uint8_t hdr[ZN_ENVELOPE_ZNB1_MAX_HEADER];
+    size_t hl = 0;
+    if (r.skip) { payload = s->stage + r.stage_off; m.blob_size = r.len; memcpy(m.checksum, s->s_dig.data() + 32 * si, 32); si++; }
+    else {
+      payload = s->outb + s->d_off[ci]; m.blob_size = s->c_out[ci]; memcpy(m.checksum, s->c_dig.data() + 32 * ci, 32); ci++;
+      if (w->envelope) {
+        // store-if-incompressible (deferred in the reference, TODO_NOW.md:37-38): a frame that did not shrink the slice
+        // is dropped for the raw bytes; the row stays `compressed` and the envelope says RAW
+        uint32_t pc = w->codec == ZN_CODEC_LZ4 ? ZN_PAYLOAD_LZ4_FRAME : ZN_PAYLOAD_ZSTD;
+        if (m.blob_size >= r.len) { pc = ZN_PAYLOAD_RAW; payload = s->stage + r.stage_off; m.blob_size = r.len; }
+        hl = zn_envelope_znb1_header(pc, r.len, hdr, sizeof hdr);
+      }
+    }
+    const uint64_t total = hl + m.blob_size;
+    if (total <= (256u << 10)) {
+      if (run.empty()) run_at = w->out_cursor;
+      run.insert(run.end(), hdr, hdr + hl);
+      run.insert(run.end(), payload, payload + m.blob_size);
+      if (run.size() >= (8u << 20) && !flush_run()) { writer_fail(w, ZN_E_ARG, "pwrite failed"); return ZN_E_ARG; }
+    } else {
+      if (!flush_run() || (hl && !write_all(w->fd, hdr, hl, w->out_cursor)) ||
+          !write_all(w->fd, payload, m.blob_size, w->out_cursor + hl)) { writer_fail(w, ZN_E_ARG, "pwrite failed"); return ZN_E_ARG; }
+    }
+    m.blob_size = total;
+    w->out_cursor += total;
     w->metas.push_back(m);
     w->rep.chunks++;
     w->rep.total_bytes_in += r.len;
-    w->rep.total_bytes_out += m.blob_size;
+    w->rep.total_bytes_out += total;
     if (r.skip) w->rep.uncompressed_bytes += r.len; else w->rep.compressed_bytes += r.len;
   }
-  w->rounds.clear();
-  w->stage_used = 0;
+  if (!flush_run()) { writer_fail(w, ZN_E_ARG, "pwrite failed"); return ZN_E_ARG; }
   return ZN_OK;
 }
+
+void gpu_loop(zn_archive_writer* w) {
+  for (;;) {
+    WSlot* s;
+    {
+      std::unique_lock<std::mutex> l(w->mu);
+      w->cv.wait(l, [&] { return !w->gpu_q.empty() || w->closing; });
+      if (w->gpu_q.empty()) break;
+      s = w->gpu_q.front();
+      w->gpu_q.pop_front();
+    }
+    while (s->pending.load(std::memory_order_acquire)) std::this_thread::yield();  // directory readers still copying
+    bool ok;
+    { std::lock_guard<std::mutex> g(w->mu); ok = w->rc == ZN_OK; }
+    if (ok) slot_compress(w, s);
+    {
+      std::lock_guard<std::mutex> g(w->mu);
+      w->write_q.push_back(s);
+    }
+    w->cv.notify_all();
+  }
+  {
+    std::lock_guard<std::mutex> g(w->mu);
+    w->write_q.push_back(nullptr);  // end marker
+  }
+  w->cv.notify_all();
+}
+
+void write_loop(zn_archive_writer* w) {
+  for (;;) {
+    WSlot* s;
+    {
+      std::unique_lock<std::mutex> l(w->mu);
+      w->cv.wait(l, [&] { return !w->write_q.empty(); });
+      s = w->write_q.front();
+      w->write_q.pop_front();
+    }
+    if (!s) break;
+    bool ok;
+    { std::lock_guard<std::mutex> g(w->mu); ok = w->rc == ZN_OK; }
+    if (ok) slot_write(w, s);
+    s->rounds.clear();
+    s->used = 0;
+    {
+      std::lock_guard<std::mutex> g(w->mu);
+      w->free_q.push_back(s);
+    }
+    w->cv.notify_all();
+  }
+}
+
+WSlot* writer_acquire(zn_archive_writer* w) {
+  std::unique_lock<std::mutex> l(w->mu);
+  w->cv.wait(l, [&] { return !w->free_q.empty(); });
+  WSlot* s = w->free_q.front();
+  w->free_q.pop_front();
+  return s;
+}
+
+void writer_publish(zn_archive_writer* w) {
+  if (!w->cur) return;
+  {
+    std::lock_guard<std::mutex> g(w->mu);
+    w->gpu_q.push_back(w->cur);
+  }
+  w->cur = nullptr;
+  w->cv.notify_all();
+}
+
+// Reserves room for one round in the current slot (publishing it first when full); returns where its bytes go.
+uint8_t* writer_reserve(zn_archive_writer* w, uint64_t file_index, uint32_t seq, uint64_t fdata_offset, uint64_t n, bool skip,
+                        WSlot** slot_out) {
+  if (w->cur && w->cur->used + n > w->slot_bytes) writer_publish(w);
+  if (!w->cur) w->cur = writer_acquire(w);
+  WSlot* s = w->cur;
+  Round r;
+  r.file_index = file_index; r.chunk_seq = seq; r.fdata_offset = fdata_offset; r.stage_off = s->used; r.len = n; r.skip = skip;
+  s->rounds.push_back(r);
+  uint8_t* dst = s->stage + s->used;
+  s->used += (n + 15) & ~15ull;
+  if (slot_out) *slot_out = s;
+  return dst;
+}
+
+uint64_t writer_new_entry(zn_archive_writer* w, const char* relative_path, int has_pkg_type, int8_t pkg_type, const char* repo, bool* skip) {
+  EntryInfo e;
+  e.path = relative_path;
+  e.repo = repo ? repo : "";
+  e.pkg_type = has_pkg_type ? pkg_type : 0;
+  e.skip = !w->no_skip && should_skip_compression(e.path);
+  *skip = e.skip;
+  w->entries.push_back(e);
+  w->rep.total_files++;
+  if (e.skip) w->rep.uncompressed_files++; else w->rep.compressed_files++;
+  return w->entries.size() - 1;
+}
+}  // namespace
 
 extern "C" zn_archive_writer* zn_archive_writer_create(zn_ctx* ctx, const char* output_path, int no_skip, int level, int codec,
                                                        size_t slot_bytes) {
   if (!ctx || !output_path) return nullptr;
+  const bool envelope = (codec & ZN_CODEC_ENVELOPE) != 0;
+  codec &= ~ZN_CODEC_ENVELOPE;
+  if (codec != ZN_CODEC_ZSTD && codec != ZN_CODEC_LZ4) return nullptr;
   if (slot_bytes < 2 * kSliceSize) slot_bytes = 2 * kSliceSize;
   const int fd = open(output_path, O_CREAT | O_RDWR | O_TRUNC, 0644);
   if (fd < 0) return nullptr;
   zn_archive_writer* w = new zn_archive_writer();
   w->ctx = ctx; w->fd = fd; w->no_skip = no_skip != 0; w->level = level; w->codec = codec; w->slot_bytes = slot_bytes;
+  w->envelope = envelope;
   memset(&w->rep, 0, sizeof w->rep);
-  w->stage = (uint8_t*)zn_ctx_pinned_alloc(slot_bytes + 4096);
-  if (!w->stage) { close(fd); delete w; return nullptr; }
+  for (auto& s : w->slots) {
+    s.stage = (uint8_t*)zn_ctx_pinned_alloc(slot_bytes + 4096);
+    if (!s.stage) {
+      for (auto& t : w->slots) if (t.stage) zn_ctx_pinned_free(t.stage);
+      close(fd); delete w; return nullptr;
+    }
+    w->free_q.push_back(&s);
+  }
+  w->gpu_thread = std::thread(gpu_loop, w);
+  w->write_thread = std::thread(write_loop, w);
   return w;
 }
 
@@ -999,36 +1186,31 @@ extern "C" const char* zn_archive_writer_error(const zn_archive_writer* w) { ret
 extern "C" int zn_archive_writer_add(zn_archive_writer* w, const char* relative_path, const uint8_t* data, uint64_t len,
                                      int has_pkg_type, int8_t pkg_type, const char* repo) {
   if (!w || !relative_path || (len && !data)) return ZN_E_ARG;
-  EntryInfo e;
-  e.path = relative_path;
-  e.repo = repo ? repo : "";
-  e.pkg_type = has_pkg_type ? pkg_type : 0;
-  e.skip = !w->no_skip && should_skip_compression(e.path);
-  const uint64_t fi = w->entries.size();
-  w->entries.push_back(e);
-  w->rep.total_files++;
-  if (e.skip) w->rep.uncompressed_files++; else w->rep.compressed_files++;
+  bool skip;
+  const uint64_t fi = writer_new_entry(w, relative_path, has_pkg_type, pkg_type, repo, &skip);
   uint64_t off = 0;
   uint32_t seq = 0;
   do {  // an empty entry still yields one zero-length round (stream_packer.rs:169-183)
     const uint64_t n = len - off < kSliceSize ? len - off : kSliceSize;
-    if (w->stage_used + n > w->slot_bytes) {
-      const int rc = writer_flush(w);
-      if (rc != ZN_OK) return rc;
-    }
-    Round r;
-    r.file_index = fi; r.chunk_seq = seq++; r.fdata_offset = off; r.stage_off = w->stage_used; r.len = n; r.skip = e.skip;
-    if (n) memcpy(w->stage + w->stage_used, data + off, n);
-    w->stage_used += (n + 15) & ~15ull;
-    w->rounds.push_back(r);
+    uint8_t* dst = writer_reserve(w, fi, seq++, off, n, skip, nullptr);
+    if (n) memcpy(dst, data + off, n);
     off += n;
   } while (off < len);
-  return ZN_OK;
+  std::lock_guard<std::mutex> g(w->mu);
+  return w->rc;
 }
 
 extern "C" int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_report* report) {
   if (!w) return ZN_E_ARG;
-  int rc = writer_flush(w);
+  writer_publish(w);
+  {
+    std::lock_guard<std::mutex> g(w->mu);
+    w->closing = true;
+  }
+  w->cv.notify_all();
+  w->gpu_thread.join();
+  w->write_thread.join();
+  int rc = w->rc;
   if (rc == ZN_OK) {
     std::stable_sort(w->metas.begin(), w->metas.end(), [](const BlobMetaRow& a, const BlobMetaRow& b) {
       return a.file_index != b.file_index ? a.file_index < b.file_index : a.chunk_seq < b.chunk_seq;
@@ -1048,6 +1230,7 @@ extern "C" int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_rep
       zn_index_writer_metadata(iw, "max_chunks", "128");
       zn_index_writer_metadata(iw, "compression_level", "19");
       zn_index_writer_metadata(iw, "zstd_output_buffer_size", "1048576");
+      if (w->envelope) zn_index_writer_metadata(iw, "znippy_envelope", "ZNB1");  // readers resolve compressed rows through zn_envelope_parse
     }
     for (auto& kv : groups) {
       const auto& rows = kv.second;
@@ -1072,9 +1255,125 @@ extern "C" int zn_archive_writer_finish(zn_archive_writer* w, zn_compression_rep
   }
   if (report) *report = w->rep;
   close(w->fd);
-  if (w->stage) zn_ctx_pinned_free(w->stage);
-  if (w->outb) zn_ctx_pinned_free(w->outb);
+  for (auto& s : w->slots) {
+    if (s.stage) zn_ctx_pinned_free(s.stage);
+    if (s.outb) zn_ctx_pinned_free(s.outb);
+  }
   delete w;
+  return rc;
+}
+
+// compress_dir (znippy-compress: walk -> readers -> Magazine -> workers -> writer, slot_packer.rs:329-609) natively:
+// the directory is walked once (sorted, so the archive is deterministic), every file is cut into rounds that are
+// ASSIGNED a place in a slot right away (sizes come from stat), and `io_threads` readers pread the file bytes into
+// those places in parallel; a slot goes to the GPU stage when its last reader is done.  No per-file call crosses the
+// language boundary.
+namespace {
+struct DirFile {
+  std::string rel, full;
+  uint64_t size;
+};
+void walk_dir(const std::string& root, const std::string& rel, std::vector<DirFile>* out) {
+  const std::string dir = rel.empty() ? root : root + "/" + rel;
+  DIR* d = opendir(dir.c_str());
+  if (!d) return;
+  std::vector<std::string> names;
+  while (dirent* e = readdir(d)) {
+    if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
+    names.push_back(e->d_name);
+  }
+  closedir(d);
+  std::sort(names.begin(), names.end());
+  for (auto& n : names) {
+    const std::string r = rel.empty() ? n : rel + "/" + n, full = root + "/" + r;
+    struct stat st;
+    if (lstat(full.c_str(), &st) != 0) continue;
+    if (S_ISDIR(st.st_mode)) walk_dir(root, r, out);
+    else if (S_ISREG(st.st_mode)) out->push_back({r, full, (uint64_t)st.st_size});
+  }
+}
+struct ReadJob {
+  const DirFile* f;
+  uint64_t off, len;
+  uint8_t* dst;
+  WSlot* slot;
+};
+}  // namespace
+
+extern "C" int zn_archive_compress_dir(zn_ctx* ctx, const char* input_dir, const char* output_path, int no_skip, int level, int codec,
+                                       size_t slot_bytes, int io_threads, zn_compression_report* report, char* err, size_t errcap) {
+  if (!ctx || !input_dir || !output_path) return ZN_E_ARG;
+  std::vector<DirFile> files;
+  walk_dir(input_dir, "", &files);
+  zn_archive_writer* w = zn_archive_writer_create(ctx, output_path, no_skip, level, codec, slot_bytes ? slot_bytes : (256u << 20));
+  if (!w) { set_err(err, errcap, "cannot create the output archive"); return ZN_E_ARG; }
+  if (io_threads < 1) io_threads = 1;
+  std::mutex jm;
+  std::condition_variable jcv;
+  std::deque<ReadJob> jobs;
+  bool jobs_done = false;
+  std::atomic<int> io_err{0};
+  std::vector<std::thread> readers;
+  for (int t = 0; t < io_threads; t++)
+    readers.emplace_back([&] {
+      int fd = -1;
+      const DirFile* open_for = nullptr;
+      for (;;) {
+        ReadJob j;
+        {
+          std::unique_lock<std::mutex> l(jm);
+          jcv.wait(l, [&] { return !jobs.empty() || jobs_done; });
+          if (jobs.empty()) break;
+          j = jobs.front();
+          jobs.pop_front();
+        }
+        if (j.len) {
+          if (open_for != j.f) {
+            if (fd >= 0) close(fd);
+            fd = open(j.f->full.c_str(), O_RDONLY);
+            open_for = j.f;
+          }
+          uint64_t done = 0;
+          while (fd >= 0 && done < j.len) {
+            const ssize_t r = pread(fd, j.dst + done, j.len - done, (off_t)(j.off + done));
+            if (r <= 0) break;
+            done += (uint64_t)r;
+          }
+          if (done < j.len) { io_err = 1; memset(j.dst + done, 0, j.len - done); }
+        }
+        j.slot->pending.fetch_sub(1, std::memory_order_release);
+      }
+      if (fd >= 0) close(fd);
+    });
+  for (const DirFile& f : files) {
+    bool skip;
+    const uint64_t fi = writer_new_entry(w, f.rel.c_str(), 0, 0, "", &skip);
+    uint64_t off = 0;
+    uint32_t seq = 0;
+    do {
+      const uint64_t n = f.size - off < kSliceSize ? f.size - off : kSliceSize;
+      WSlot* s;
+      uint8_t* dst = writer_reserve(w, fi, seq++, off, n, skip, &s);
+      s->pending.fetch_add(1, std::memory_order_relaxed);
+      {
+        std::lock_guard<std::mutex> g(jm);
+        jobs.push_back({&f, off, n, dst, s});
+      }
+      jcv.notify_one();
+      off += n;
+    } while (off < f.size);
+  }
+  {
+    std::lock_guard<std::mutex> g(jm);
+    jobs_done = true;
+  }
+  jcv.notify_all();
+  for (auto& t : readers) t.join();
+  if (io_err) writer_fail(w, ZN_E_ARG, "failed to read an input file");
+  std::string msg;
+  { std::lock_guard<std::mutex> g(w->mu); msg = w->err; }
+  const int rc = zn_archive_writer_finish(w, report);
+  if (rc != ZN_OK) set_err(err, errcap, msg.empty() ? "compress_dir failed" : msg);
   return rc;
 }
 
@@ -1149,7 +1448,7 @@ extern "C" int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* 
     uint64_t pos = out_off[k];
     for (uint64_t r : it->second.rows) {
       rows.push_back(r);
-      bo.push_back(in_cur); bl.push_back(I.col[1][r]); cf.push_back(I.compressed[r]); ol.push_back(I.col[3][r]); oo.push_back(pos);
+      bo.push_back(in_cur); bl.push_back(I.col[1][r]); cf.push_back(I.comp_eff[r]); ol.push_back(I.col[3][r]); oo.push_back(pos);
       owner.push_back(k);
       in_cur += (I.col[1][r] + 15) & ~15ull;
       pos += I.col[3][r];

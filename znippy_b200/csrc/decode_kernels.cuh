@@ -169,4 +169,14 @@ __global__ void __launch_bounds__(256) k_gather_raw(const BlobDesc* __restrict__
   }
 }
 
+
+// Rows whose payload is a Zstandard frame without its magic (envelope layer, compressed == 3): the four bytes in front of
+// the payload become the magic, so every decoder sees an ordinary frame.
+__global__ void __launch_bounds__(256) k_patch_magic(uint8_t* blobs_base, const uint64_t* __restrict__ off, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t* p = blobs_base + off[i];
+  p[0] = 0x28; p[1] = 0xB5; p[2] = 0x2F; p[3] = 0xFD;
+}
+
 }  // namespace zn
