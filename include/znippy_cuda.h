@@ -228,6 +228,11 @@ const char* zn_archive_file_name(const zn_archive* a, uint64_t i, uint64_t* size
 int zn_archive_file_size(const zn_archive* a, const char* path, uint64_t* size); /* 1 = present */
 int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* const* paths, uint32_t n, uint8_t* out_base,
                              const uint64_t* out_off, uint32_t* file_status);
+/* LRU of decoded slices for a serving process: with a non-zero budget, every slice extract_files decodes is
+ * kept in host memory (keyed by index row, evicted least-recently-used first) and later requests for it skip pread, H2D
+ * and the decode.  0 (the default) turns it off and drops what is cached.  stats: hits, misses, evictions, bytes, slices. */
+int zn_archive_set_cache(zn_archive* a, uint64_t budget_bytes);
+int zn_archive_cache_stats(zn_archive* a, uint64_t stats[5]);
 
 /* ---- native write pipeline: compress_stream (znippy-compress/src/stream_packer.rs:58-372).  Entries are cut into
  * <= 8 MiB rounds into a pinned slot; each full slot is one zn_compress_batch (+ zn_hash_batch for store-as-is rounds),

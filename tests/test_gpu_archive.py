@@ -258,3 +258,35 @@ def test_row_shards_never_truncate_each_others_files(A, tmp_path, oracle, native
         assert v1.corrupt_files == 0 and v2.corrupt_files == 0 and v1.chunks + v2.chunks == 5
         for p, d in entries:
             assert (out / p).read_bytes() == d, (cut, p)
+
+
+def test_extract_cache_is_lru_and_transparent(A, tmp_path, oracle):
+    """the LRU of decoded slices.  Same bytes with and without it; a repeated request is served from the
+    cache (no new kernel launches); the byte budget is respected and the least recently used slices go first."""
+    from znippy_b200 import codec
+    O = oracle
+    files = {f"pkg/f{i}.txt": O.real_text(300_000 + 1000 * i).tobytes() for i in range(6)}
+    files["pkg/big.bin"] = O.gen_binary(20 << 20).tobytes()  # 3 slices
+    path, _ = _pack(A, tmp_path, list(files.items()), level=3)
+    plain = A.ZnippyArchive.open(path)
+    ar = A.ZnippyArchive.open(path, cache_bytes=1_000_000)  # room for three of the ~300 KB files, not for an 8 MiB slice
+    names = [f"pkg/f{i}.txt" for i in range(6)]
+    assert ar.extract_files(names) == plain.extract_files(names) == [files[n] for n in names]
+    st = ar.cache_stats()
+    assert st["hits"] == 0 and st["misses"] == 6 and st["slices"] == 3 and st["evictions"] == 3 and st["bytes"] <= 1_000_000
+    ctx = codec.default_ctx()
+    before = ctx.launches()
+    assert ar.extract_files(names[3:]) == [files[n] for n in names[3:]]      # the three most recent: all hits
+    assert ctx.launches() == before and ar.cache_stats()["hits"] == 3
+    assert ar.extract_file(names[0]) == files[names[0]]                       # miss: evicts f3 (least recently used)
+    assert ar.extract_files([names[3], names[5]]) == [files[names[3]], files[names[5]]]
+    st = ar.cache_stats()
+    assert st["hits"] == 4 and st["misses"] == 8
+    assert ar.extract_file("pkg/big.bin") == files["pkg/big.bin"]            # slices larger than the budget are never cached
+    assert ar.cache_stats()["slices"] <= 3
+    ar.set_cache(64 << 20)
+    assert ar.extract_file("pkg/big.bin") == files["pkg/big.bin"] and ar.extract_file("pkg/big.bin") == files["pkg/big.bin"]
+    st2 = ar.cache_stats()
+    assert st2["hits"] == st["hits"] + 3 and st2["bytes"] >= 20 << 20
+    ar.set_cache(0)
+    assert ar.cache_stats()["slices"] == 0 and ar.extract_file(names[1]) == files[names[1]]

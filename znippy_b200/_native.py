@@ -26,7 +26,7 @@ EXPORTS = [
     "zn_index_writer_finish", "zn_archive_decompress", "zn_archive_writer_create", "zn_archive_writer_add",
     "zn_archive_writer_finish", "zn_archive_writer_error", "zn_ctx_pinned_alloc", "zn_ctx_pinned_free",
     "zn_archive_open", "zn_archive_close", "zn_archive_file_count", "zn_archive_file_name", "zn_archive_file_size",
-    "zn_archive_extract_files", "zn_archive_compress_dir", "zn_envelope_parse", "zn_envelope_znb1_header", "zn_envelope_register",
+    "zn_archive_extract_files", "zn_archive_set_cache", "zn_archive_cache_stats", "zn_archive_compress_dir", "zn_envelope_parse", "zn_envelope_znb1_header", "zn_envelope_register",
 ]
 
 
@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
     L.zn_ctx_pinned_alloc.restype = vp
     L.zn_ctx_pinned_free.argtypes = [vp]
     L.zn_ctx_pinned_free.restype = None
+    L.zn_archive_set_cache.argtypes = [vp, u64]
+    L.zn_archive_cache_stats.argtypes = [vp, vp]
     L.zn_archive_compress_dir.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, sz, C.c_int, vp, C.c_char_p, sz]
     L.zn_envelope_parse.argtypes = [vp, sz, vp]
     L.zn_envelope_znb1_header.argtypes = [u32, u64, vp, sz]

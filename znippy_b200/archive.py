@@ -331,8 +331,22 @@ class ZnippyArchive:
             raise IOError(f"cannot open {path}: {err.value.decode(errors='replace')}")
 
     @classmethod
-    def open(cls, path: str, ctx: Ctx | None = None) -> "ZnippyArchive":
-        return cls(path, ctx)
+    def open(cls, path: str, ctx: Ctx | None = None, cache_bytes: int = 0) -> "ZnippyArchive":
+        ar = cls(path, ctx)
+        if cache_bytes:
+            ar.set_cache(cache_bytes)
+        return ar
+
+    def set_cache(self, budget_bytes: int):
+        """LRU of decoded slices (zn_archive_set_cache): hot files are answered from host memory after their first decode."""
+        from . import _native as N
+        N.lib().zn_archive_set_cache(self._h, int(budget_bytes))
+
+    def cache_stats(self) -> dict:
+        from . import _native as N
+        st = np.zeros(5, np.uint64)
+        N.lib().zn_archive_cache_stats(self._h, N.ptr(st))
+        return dict(zip(("hits", "misses", "evictions", "bytes", "slices"), (int(x) for x in st)))
 
     def close(self):
         from . import _native as N

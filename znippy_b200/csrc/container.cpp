@@ -25,10 +25,12 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <list>
 #include <map>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -1390,6 +1392,14 @@ struct zn_archive {
   };
   std::map<std::string, FileEntry> files;
   std::vector<std::map<std::string, FileEntry>::const_iterator> order;  // first-seen order for listing
+  // LRU of decoded slices: an artifact server asks for the same hot files again and again; a slice that was
+  // decoded once is answered from host memory afterwards.  Keyed by index row, bounded by bytes, off until a budget is set.
+  struct Cache {
+    std::mutex mu;
+    uint64_t budget = 0, used = 0, hits = 0, misses = 0, evictions = 0;
+    std::list<std::pair<uint64_t, std::vector<uint8_t>>> lru;  // front = most recent
+    std::unordered_map<uint64_t, std::list<std::pair<uint64_t, std::vector<uint8_t>>>::iterator> at;
+  } cache;
 };
 
 extern "C" zn_archive* zn_archive_open(const char* path, char* err, size_t errcap) {
@@ -1432,6 +1442,25 @@ extern "C" int zn_archive_file_size(const zn_archive* a, const char* path, uint6
   return 1;
 }
 
+extern "C" int zn_archive_set_cache(zn_archive* a, uint64_t budget_bytes) {
+  if (!a) return ZN_E_ARG;
+  std::lock_guard<std::mutex> g(a->cache.mu);
+  a->cache.budget = budget_bytes;
+  while (a->cache.used > budget_bytes && !a->cache.lru.empty()) {
+    a->cache.used -= a->cache.lru.back().second.size();
+    a->cache.at.erase(a->cache.lru.back().first);
+    a->cache.lru.pop_back();
+    a->cache.evictions++;
+  }
+  return ZN_OK;
+}
+extern "C" int zn_archive_cache_stats(zn_archive* a, uint64_t stats[5]) {
+  if (!a || !stats) return ZN_E_ARG;
+  std::lock_guard<std::mutex> g(a->cache.mu);
+  stats[0] = a->cache.hits; stats[1] = a->cache.misses; stats[2] = a->cache.evictions; stats[3] = a->cache.used; stats[4] = a->cache.lru.size();
+  return ZN_OK;
+}
+
 // file_status[i]: 0 ok, 1 not in archive, 2 a chunk failed to decode (first failing chunk's per-blob status in the high half)
 extern "C" int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* const* paths, uint32_t n, uint8_t* out_base,
                                         const uint64_t* out_off, uint32_t* file_status) {
@@ -1441,12 +1470,25 @@ extern "C" int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* 
   std::vector<uint8_t> cf;
   std::vector<uint32_t> owner;
   uint64_t in_cur = 0;
+  zn_archive::Cache& K = a->cache;
   for (uint32_t k = 0; k < n; k++) {
     auto it = a->files.find(paths[k]);
     if (it == a->files.end()) { file_status[k] = 1; continue; }
     file_status[k] = 0;
     uint64_t pos = out_off[k];
     for (uint64_t r : it->second.rows) {
+      if (K.budget) {  // a cached slice is answered from host memory and never reaches the batch
+        std::lock_guard<std::mutex> g(K.mu);
+        auto c = K.at.find(r);
+        if (c != K.at.end()) {
+          K.lru.splice(K.lru.begin(), K.lru, c->second);
+          memcpy(out_base + pos, c->second->second.data(), c->second->second.size());
+          pos += I.col[3][r];
+          K.hits++;
+          continue;
+        }
+        K.misses++;
+      }
       rows.push_back(r);
       bo.push_back(in_cur); bl.push_back(I.col[1][r]); cf.push_back(I.comp_eff[r]); ol.push_back(I.col[3][r]); oo.push_back(pos);
       owner.push_back(k);
@@ -1488,6 +1530,21 @@ extern "C" int zn_archive_extract_files(zn_ctx* ctx, zn_archive* a, const char* 
     if (rc == ZN_OK)
       for (size_t i = 0; i < rows.size(); i++)
         if (st[i] != ZN_S_OK && file_status[owner[i]] == 0) file_status[owner[i]] = 2u | (st[i] << 16);
+    if (rc == ZN_OK && K.budget) {
+      std::lock_guard<std::mutex> g(K.mu);
+      for (size_t i = 0; i < rows.size(); i++) {
+        if (st[i] != ZN_S_OK || ol[i] > K.budget || K.at.count(rows[i])) continue;
+        while (K.used + ol[i] > K.budget && !K.lru.empty()) {  // evict from the cold end
+          K.used -= K.lru.back().second.size();
+          K.at.erase(K.lru.back().first);
+          K.lru.pop_back();
+          K.evictions++;
+        }
+        K.lru.emplace_front(rows[i], std::vector<uint8_t>(out_base + oo[i], out_base + oo[i] + ol[i]));
+        K.at[rows[i]] = K.lru.begin();
+        K.used += ol[i];
+      }
+    }
   }
   zn_ctx_pinned_free(stage);
   return rc;
