@@ -29,8 +29,9 @@
  *
  * Blob wire formats accepted by the decoder (self-identifying by magic): Zstandard frames (RFC 8878, magic
  * 28 B5 2F FD; several concatenated frames and skippable frames allowed; no dictionaries) and LZ4 frames (magic
- * 04 22 4D 18, independent or linked blocks).  The optional XXH64 / XXH32 content and block checksums of those frames
- * are skipped, not verified: integrity on this path is the blake3 digest.  Envelopes around those payloads go through
+ * 04 22 4D 18, independent or linked blocks).  A Zstandard frame's optional content checksum (XXH64) IS verified, as
+ * libzstd does: a mismatch is ZN_S_DECODE_ERROR.  The optional XXH32 content / block checksums of LZ4 frames are
+ * skipped, not verified: integrity on this path is the blake3 digest.  Envelopes around those payloads go through
  * the envelope layer below (zn_envelope_parse): this library's own ZNB1 is built in; the OpenZL envelope the reference
  * writes is NOT (its layout is unpinned in this environment) — until a parser for it is registered with
  * zn_envelope_register such blobs get ZN_S_UNSUPPORTED.

@@ -75,19 +75,24 @@ def test_frames_decode_with_reference_decoders(codec, oracle, codec_name):
 
 
 def test_ratio_against_reference_libraries(codec, oracle):
-    """Ratio gap vs the reference libraries, stated: pattern corpora within 10 % of libzstd level 19 / liblz4; real
-    text within 25 % of libzstd level 1 at every effort (Huffman literals with FSE-compressed or direct weights, FSE-described sequence tables, repeat
-    offsets, warp-wide lazy match selection in a 20-56 KiB window — DESIGN.md §4.3)."""
+    """North-star criterion: "ratio within a stated percentage of the reference AT THE SAME LEVEL".  The reference's codec
+    is OpenZL over zstd at `compression_level` (codec.rs:16-28); libzstd 1.5.5 at the same level stands in for it.  The
+    stated gaps (size of our frame over libzstd's, same level):
+        pattern corpora (README shapes)   <= 1 % at levels 1 and 3, <= 10 % at level 19
+        real text (python sources, 2 MB)  <= 12 % at level 1, <= 22 % at level 3, <= 55 % at level 19
+    The real-text gap GROWS with the level and that is the honest state of the compressor: its match finder is greedy /
+    warp-lazy inside a 20-62 KiB window per 128 KiB block, libzstd's level 3 searches a 2 MiB window
+    with hash chains and level 19 adds an optimal parser over 8 MiB.  Measured: 9.8 / 19.4 / 50.9 %."""
     O = oracle
     z, l = O.libzstd(), O.liblz4()
-    for name, d, ref_level, slack in [("text", O.gen_text(8 << 20), 19, 1.10), ("binary", O.gen_binary(8 << 20), 19, 1.10),
-                                      ("real", O.real_text(2_000_000), 1, 1.25)]:
-        ref = len(z.compress(d, ref_level))
+    gap = {"text": {1: 1.01, 3: 1.01, 19: 1.10}, "binary": {1: 1.01, 3: 1.01, 19: 1.10}, "real": {1: 1.12, 3: 1.22, 19: 1.55}}
+    for name, d in [("text", O.gen_text(8 << 20)), ("binary", O.gen_binary(8 << 20)), ("real", O.real_text(2_000_000))]:
         sizes = []
         for level in (1, 3, 19):  # the three efforts of the zstd match finder
+            ref = len(z.compress(d, level))  # the SAME level
             b = codec.CompressCtx(level).compress(d)
             assert z.decompress(b, len(d)) == d.tobytes()
-            assert len(b) <= ref * slack + 64, (name, level, len(b), ref)
+            assert len(b) <= ref * gap[name][level] + 16, (name, level, len(b), ref, round(len(b) / ref, 3))
             sizes.append(len(b))
         if name == "real":
             assert sizes[2] <= sizes[0], sizes  # more window, no worse

@@ -190,7 +190,7 @@ def test_status_rules(codec, oracle):
 
 def test_bitflip_fuzz_matches_oracle_verdict(codec, oracle):
     """Injected corruption: for every flipped frame the GPU agrees with the oracle on accept/reject, and on the bytes
-    when both accept (content checksums excepted: the GPU path does not verify XXH64, blake3 supersedes it)."""
+    when both accept."""
     O = oracle
     z = O.libzstd()
     data = O.real_text(60_000).tobytes()
@@ -405,3 +405,57 @@ def test_caller_memory_between_output_ranges_is_left_alone(codec, oracle):
         assert out[o:o + len(c)].tobytes() == c
         keep[o:o + len(c)] = False
     assert (out[keep] == 0x5A).all()
+
+
+def test_zstd_content_checksums_are_verified(codec, oracle):
+    """RFC 8878 §3.1.1 Content_Checksum (low 32 bits of XXH64 of the frame's content): libzstd — and so the reference's
+    decode — rejects a frame whose stored checksum is wrong; so does the GPU path (k_xxh64_verify).  Same accept/reject
+    verdict as the oracle and libzstd for every flipped bit of checksummed frames, tails of 0..31 bytes, a multi-frame
+    blob, and a frame the pipeline / pattern / small-blob classes decode."""
+    O = oracle
+    z = O.libzstd()
+    rnd = random.Random(9)
+    contents = [O.real_text(n).tobytes() for n in (0, 1, 5, 31, 32, 33, 63, 64, 1000, 65_537, 300_000, 3 << 20)]
+    contents += [O.gen_text(2 << 20).tobytes(), O.gen_binary(10_240).tobytes()]
+    blobs = [z.compress(c, 3, checksum=True) for c in contents]
+    contents.append(contents[8] + contents[9])            # two checksummed frames back to back
+    blobs.append(blobs[8] + blobs[9])
+    for c, b in zip(contents[:10], blobs[:10]):            # the oracle's XXH64 is what the frames carry
+        assert int.from_bytes(b[-4:], "little") == O.xxh64(c) & 0xFFFFFFFF
+    n = len(blobs)
+    buf, offs = _pack(blobs)
+    lens = [len(c) for c in contents]
+    ooff = np.concatenate([[0], np.cumsum([(x + 15) & ~15 for x in lens])])[:-1]
+    out = np.zeros(int(ooff[-1]) + lens[-1] + 16, np.uint8)
+    st, dg = codec.decode_verify_batch(buf, offs, [len(b) for b in blobs], [1] * n, lens, None, out, ooff)
+    assert not st.any()
+    for i, c in enumerate(contents):
+        assert out[ooff[i]:ooff[i] + len(c)].tobytes() == c and dg[i].tobytes() == O.blake3(c)
+    # a wrong stored checksum (any of its 32 bits) is a decode error; the neighbours are untouched
+    bad = list(blobs)
+    for i in range(n):
+        b = bytearray(blobs[i])
+        b[len(b) - 1 - rnd.randrange(4)] ^= 1 << rnd.randrange(8)
+        bad[i] = bytes(b)
+    bad[3] = blobs[3]
+    buf, offs = _pack(bad)
+    st, _ = codec.decode_verify_batch(buf, offs, [len(b) for b in bad], [1] * n, lens, None, out, ooff)
+    for i in range(n):
+        rc, _o = O.zstd_decompress(bad[i], lens[i])
+        assert (st[i] == 0) == (rc == 0), (i, st[i], rc)
+    assert st[3] == 0 and st[0] == codec.S_DECODE_ERROR and st[n - 1] == codec.S_DECODE_ERROR
+    # bit-flip fuzz over whole checksummed frames: verdict equality with the oracle, with no exception left
+    base = blobs[9]
+    fz = []
+    for _ in range(300):
+        c = bytearray(base)
+        c[rnd.randrange(len(c))] ^= 1 << rnd.randrange(8)
+        fz.append(bytes(c))
+    buf, offs = _pack(fz)
+    cap = lens[9]
+    o2 = np.zeros(len(fz) * (cap + 16), np.uint8)
+    st, _ = codec.decode_verify_batch(buf, offs, [len(b) for b in fz], [1] * len(fz), [cap] * len(fz), None, o2,
+                                      [i * (cap + 16) for i in range(len(fz))])
+    for i, b in enumerate(fz):
+        rc, o = O.zstd_decompress(b, cap)
+        assert (st[i] == 0) == (rc == 0 and len(o) == cap), (i, st[i], rc)

@@ -88,7 +88,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed on {unit}:\n" + r.stdout + r.stderr)
             if verbose:
                 print(r.stderr)
-    r = subprocess.run([nvcc, "-shared", "-o", SO, *[_obj(u) for u in UNITS]], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, *[_obj(u) for u in UNITS]],
+                       capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return SO

@@ -22,6 +22,7 @@
 #include "decode_kernels.cuh"
 #include "par_kernel.cuh"
 #include "fused_ws.cuh"
+#include "xxh_verify.cuh"
 
 using namespace zn;
 
@@ -33,6 +34,17 @@ struct zn_ctx {
   cudaStream_t stream2 = nullptr;  // hash stream of the overlapped schedule
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // pinned bump arena for the per-row arrays of a plan (descriptors, chunk prefix, work lists): built in place and uploaded
+  // by DMA — from pageable vectors the driver staged ~10 MB per 100 000 rows through its own bounce buffer first
+  uint8_t* plan_pin = nullptr;
+  size_t plan_pin_cap = 0, plan_pin_used = 0;
+  template <typename T>
+  T* arena(size_t count) {
+    plan_pin_used = (plan_pin_used + 63) & ~(size_t)63;
+    T* r = reinterpret_cast<T*>(plan_pin + plan_pin_used);
+    plan_pin_used += count * sizeof(T);
+    return r;
+  }
   uint8_t* d_lit = nullptr;  // Huffman literal scratch, one slot per decode CTA
   uint8_t* d_par = nullptr;  // scratch of the block-parallel decoder (sequence records + literals), allocated on first use
   uint32_t dec_grid = 0;
@@ -202,6 +214,7 @@ extern "C" void zn_ctx_destroy(zn_ctx* c) {
   if (c->d_out) cudaFree(c->d_out);
   c->cs.release();
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->plan_pin) cudaFreeHost(c->plan_pin);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
@@ -313,11 +326,30 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
   p->ctx = c;
   p->kind = kind;
   p->n = n;
-  std::vector<BlobDesc> descs(n);
-  std::vector<uint32_t> prefix(n + 1, 0), lsmall, llarge, pblob, pidx, cls[DC_COUNT];
-  std::vector<uint32_t> status0(n, 0);
+  {  // the arena is free again: the previous plan_build synchronised its uploads before returning
+    const size_t need = (size_t)n * (sizeof(BlobDesc) + 4 * 4) + 4096;
+    if (need > c->plan_pin_cap) {
+      if (c->plan_pin) cudaFreeHost(c->plan_pin);
+      c->plan_pin = nullptr;
+      c->plan_pin_cap = 0;
+      if (cudaHostAlloc((void**)&c->plan_pin, need + need / 4, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        delete p;
+        c->err = "pinned plan arena allocation failed";
+        return nullptr;
+      }
+      c->plan_pin_cap = need + need / 4;
+    }
+    c->plan_pin_used = 0;
+  }
+  BlobDesc* descs = c->arena<BlobDesc>(n);
+  uint32_t* prefix = c->arena<uint32_t>((size_t)n + 1);
+  uint32_t* status0 = c->arena<uint32_t>(n);
+  memset(status0, 0, (size_t)n * 4);
+  uint32_t* lsmall_a = c->arena<uint32_t>(n);  // rows whose tree fits one lane (the common case: filled in place)
+  uint32_t n_lsmall = 0;
+  std::vector<uint32_t> llarge, pblob, pidx, cls[DC_COUNT];
   std::vector<uint64_t> magic_off;
-  lsmall.reserve(n);
   const bool use_pipe = !env_off("ZN_PIPE"), use_fuse = !env_off("ZN_FUSE");
   uint64_t chunks = 0;
   bool any_status = false;
@@ -362,22 +394,24 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
       cls[k].push_back(i);
     } else if (gather_raw && kind == PLAN_DECODE_VERIFY && !skip)
       for (uint64_t o = 0, k = 0; o < d.dst_cap; o += kGatherPiece, k++) { pblob.push_back(i); pidx.push_back((uint32_t)k); }
-    (nc <= kTreeSmallMax ? lsmall : llarge).push_back(i);
+    if (nc <= kTreeSmallMax) lsmall_a[n_lsmall++] = i; else llarge.push_back(i);
   }
   prefix[n] = (uint32_t)chunks;
   p->total_chunks = (uint32_t)chunks;
   // class lists back to back, largest first inside a class (dynamic work counters)
-  std::vector<uint32_t> ldec;
+  uint32_t* ldec = c->arena<uint32_t>(n);
+  uint32_t n_ldec = 0;
   for (int k = 0; k < DC_COUNT; k++) {
     auto& L = cls[k];
     bool sorted_desc = true;
     for (size_t j = 1; j < L.size() && sorted_desc; j++) sorted_desc = descs[L[j]].dst_cap <= descs[L[j - 1]].dst_cap;
     if (!sorted_desc) std::stable_sort(L.begin(), L.end(), [&](uint32_t x, uint32_t y) { return descs[x].dst_cap > descs[y].dst_cap; });
-    p->cls_off[k] = (uint32_t)ldec.size();
-    ldec.insert(ldec.end(), L.begin(), L.end());
+    p->cls_off[k] = n_ldec;
+    if (!L.empty()) memcpy(ldec + n_ldec, L.data(), L.size() * 4);
+    n_ldec += (uint32_t)L.size();
   }
-  p->cls_off[DC_COUNT] = (uint32_t)ldec.size();
-  p->n_dec = (uint32_t)ldec.size();
+  p->cls_off[DC_COUNT] = n_ldec;
+  p->n_dec = n_ldec;
   // Large, highly compressible blobs go through the fused decode+hash kernel (fused_ws.cuh).  ZN_FUSE=0 keeps the two
   // kernels apart, ZN_FUSE=team selects the older fused kernel in which one team alternates between decoding and hashing.
   p->fused_hash = use_fuse && !cls[DC_BIGPAT].empty();
@@ -410,12 +444,12 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
     p->z_mean = zb.empty() ? 0 : bytes / zb.size();
     if (slots > lim) { delete p; c->err = "batch too large (zstd block slots)"; return nullptr; }
   }
-  p->n_small = (uint32_t)lsmall.size();
+  p->n_small = n_lsmall;
   p->n_large = (uint32_t)llarge.size();
   p->n_pieces = (uint32_t)pblob.size();
   p->n_magic = (uint32_t)magic_off.size();
-  bool ok = upload(c, &p->d_blobs, descs.data(), n) && upload(c, &p->d_chunk_prefix, prefix.data(), n + 1) &&
-            upload(c, &p->d_list_dec, ldec.data(), ldec.size()) && upload(c, &p->d_list_small, lsmall.data(), lsmall.size()) &&
+  bool ok = upload(c, &p->d_blobs, descs, n) && upload(c, &p->d_chunk_prefix, prefix, (size_t)n + 1) &&
+            upload(c, &p->d_list_dec, ldec, n_ldec) && upload(c, &p->d_list_small, lsmall_a, n_lsmall) &&
             upload(c, &p->d_list_large, llarge.data(), llarge.size()) &&
             upload(c, &p->d_piece_blob, pblob.data(), pblob.size()) && upload(c, &p->d_piece_idx, pidx.data(), pidx.size()) &&
             upload(c, &p->d_magic_off, magic_off.data(), magic_off.size()) &&
@@ -427,7 +461,7 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_counter, (const uint32_t*)nullptr, 16) &&
             upload(c, &p->d_wsq, (const uint32_t*)nullptr, p->fused_hash ? 4 + 2 * (size_t)p->ws_tiles : 0) &&
             upload(c, &p->d_zb, zb.data(), zb.size());
-  if (ok && any_status) ok = upload(c, &p->d_status0, status0.data(), n);
+  if (ok && any_status) ok = upload(c, &p->d_status0, status0, n);
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;  // host vectors go out of scope
   if (!ok) {
@@ -621,6 +655,11 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
                                                                      nullptr, 0u);
     launches++;
   }
+  if (p->n_dec && !env_off("ZN_XXH")) {  // Zstandard content checksums (rows without one cost an 8-byte read)
+    k_xxh64_verify<<<std::min<uint32_t>((p->n_dec + 31) / 32, (uint32_t)c->sm_count * 8u), 128, 0, st>>>(p->d_blobs, p->d_list_dec, p->n_dec,
+                                                                                                       d_blobs, d_out, p->d_status);
+    launches++;
+  }
   ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
   if (p->total_chunks && p->n_hashed != p->n) {
     const uint32_t tiles = (p->total_chunks + 31u) / 32u;
@@ -708,36 +747,39 @@ struct Layout {
 static Layout make_layout(const uint64_t* off, const uint64_t* len, uint32_t n) {
   Layout L;
   L.dev_off.resize(n);
-  uint64_t lo = ~0ull, hi = 0, sum = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    lo = std::min(lo, off[i]);
-    hi = std::max(hi, off[i] + len[i]);
-    sum += len[i];
-  }
   if (n == 0) return L;
+  // one pass: extent, total, and — for the common case of rows in ascending, non-overlapping order — whether any gap
+  // between consecutive ranges reaches 16 bytes
+  uint64_t lo = ~0ull, hi = 0, sum = 0, prev_end = 0, max_gap = 0;
+  bool ascending = true;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t o = off[i], e = o + len[i];
+    lo = std::min(lo, o);
+    hi = std::max(hi, e);
+    sum += len[i];
+    if (i) {
+      if (o < prev_end) ascending = false;
+      else max_gap = std::max(max_gap, o - prev_end);
+    }
+    prev_end = e;
+  }
   bool disjoint = true;
   if ((hi - lo) <= sum + sum / 4 + 4096) {
-    bool ascending = true;  // the common case (rows in blob order) needs no sort
-    for (uint32_t k = 1; k < n && ascending; k++) ascending = off[k] >= off[k - 1] + len[k - 1];
     if (!ascending) {
       std::vector<uint32_t> ord(n);
       std::iota(ord.begin(), ord.end(), 0u);
       std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return off[a] < off[b]; });
-      for (uint32_t k = 1; k < n && disjoint; k++)
-        if (off[ord[k]] < off[ord[k - 1]] + len[ord[k - 1]]) disjoint = false;
+      max_gap = 0;
+      for (uint32_t k = 1; k < n && disjoint; k++) {
+        const uint64_t pe = off[ord[k - 1]] + len[ord[k - 1]];
+        if (off[ord[k]] < pe) disjoint = false;
+        else max_gap = std::max(max_gap, off[ord[k]] - pe);
+      }
     }
     if (disjoint) {
       // exact: the ranges tile the span up to alignment padding (< 16 bytes after a row) — the only gaps a D2H span
       // copy may write over (include/znippy_cuda.h)
-      L.exact = true;
-      if (ascending) {
-        for (uint32_t k = 1; k < n && L.exact; k++) L.exact = off[k] - (off[k - 1] + len[k - 1]) < 16;
-      } else {
-        std::vector<uint32_t> ord(n);
-        std::iota(ord.begin(), ord.end(), 0u);
-        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return off[a] < off[b]; });
-        for (uint32_t k = 1; k < n && L.exact; k++) L.exact = off[ord[k]] - (off[ord[k - 1]] + len[ord[k - 1]]) < 16;
-      }
+      L.exact = max_gap < 16;
       L.span = true;
       L.span_lo = lo;
       L.span_bytes = hi - lo;

@@ -698,5 +698,390 @@ __global__ void __launch_bounds__(NT, MINB) k_zexec(ZArgs a, uint8_t* out_base, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------- exec, version 2
+// Same contract as k_zexec (one CTA per blob, blocks in order, groups of sequences assembled in shared memory), another
+// way of resolving the matches that read bytes of their own group: POINTER JUMPING over bytes instead of a wavefront
+// over matches.
+//
+//   setup   every output byte of the group is either KNOWN — a literal, or a match byte whose source lies before the group
+//           (final, in global memory): stored into the buffer at once — or it gets a PARENT: the group-relative position it
+//           copies from (par[], 16 bits per byte; a match with distance < length points every byte into the window before
+//           the match, so it adds one level, not length / distance levels);
+//   rounds  the first round scans par[] (8 entries per 16-byte load) and lists the bytes that are still unknown after it;
+//           later rounds walk that list densely, one lane per unknown byte, compacting it as they go.  An unknown byte
+//           looks at its parent: known -> copy the byte and become known; unknown -> adopt the parent's parent.  Chains halve every round, so a group whose
+//           dependence depth is ~20 matches is done in ~5 rounds of plain loads and stores: no pending lists, no bitmap,
+//           no atomics, no fences — one barrier per round.  "Known" must mean "known before this round's barrier": a byte
+//           resolved in round r is marked with r's parity (kFresh); a reader in a round of the same parity waits one round
+//           (the marker may be this round's), a reader of the other parity copies — so nobody ever reads a byte that was
+//           stored in the same round, and no marker ever needs a second visit;
+//   flush   one coalesced copy of the group to global memory, par[] reset to kKnown.
+// bytes per group (template parameter GB) <= 16384: parents are < 2^14, which leaves two flag bits in 16
+constexpr uint32_t kKnown = 0xFFFFu;  // par[] value of a byte whose value is in the buffer (since an earlier round)
+constexpr uint32_t kFresh = 0x8000u;  // | parity << 14: resolved in the round of that parity
+
+ZN_D uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+ZN_D void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+ZN_D uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+ZN_D void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+template <int NT, int K, uint32_t GB>
+struct Exec2Shared {
+  static_assert(GB <= 16384, "parents are 14-bit");
+  static constexpr uint32_t kSeqs = K * NT;
+  alignas(16) uint8_t buf[GB + 16];
+  alignas(16) uint16_t par[GB + 8];
+  alignas(16) uint8_t lits[GB + 32];
+  uint16_t jobs[kSeqs * 2];  // warp jobs of the setup: sequence (offset from the group's first) | kind << 15 (1 = literal run, 0 = match)
+  uint32_t n_jobs;
+  uint32_t lcnt[3];          // unknown bytes left after a round, rotating: round r appends to [(r + 1) % 3], clears [(r + 2) % 3]
+  uint32_t pat[kPatWords];
+  SeqRec16 first;
+  uint32_t cnt, gend, lit_hi;
+  uint32_t err, item;
+};
+
+template <int NT, int K, uint32_t GB, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_zexec2(ZArgs a, uint8_t* out_base, uint32_t* produced, uint32_t* work_counter) {
+  extern __shared__ __align__(16) uint8_t exec_smem[];
+  using Sh = Exec2Shared<NT, K, GB>;
+  Sh* sh = reinterpret_cast<Sh*>(exec_smem);
+  const Team t{threadIdx.x, (uint32_t)NT};
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(sh->buf), lits_s = (uint32_t)__cvta_generic_to_shared(sh->lits),
+                 par_s = (uint32_t)__cvta_generic_to_shared(sh->par);
+  const uint4 known4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  for (uint32_t i = tid * 8; i < GB + 8; i += NT * 8) sts128(par_s + 2 * i, known4);
+  for (;;) {
+    if (tid == 0) sh->item = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t item = sh->item;
+    if (tid == 0) { sh->err = 0; sh->cnt = 0; sh->gend = 0; sh->lit_hi = 0; sh->n_jobs = 0; }
+    __syncthreads();
+    if (item >= a.nzb) break;
+    const ZBlob z = a.zb[item];
+    if (z.state) continue;
+    const BlobDesc d = a.blobs[z.blob];
+    const uint8_t* src = a.blobs_base + d.src_off;
+    uint8_t* out = out_base + d.dst_off;
+    bool bad = false;
+    ZT_DECL;
+    for (uint32_t j = 0; j < z.n_blocks && !bad; j++) {
+      const ZBlock* b = &a.blocks[z.slot0 + j];
+      const uint32_t flags = b->flags, type = flags & ZB_TYPE_MASK;
+      const uint32_t blk0 = b->out_base;
+      if (type == 0) { team_copy(t, out + blk0, src + b->src_off, b->len); __syncthreads(); continue; }
+      if (type == 1) { team_fill(t, out + blk0, src[b->src_off], b->len); __syncthreads(); continue; }
+      const uint32_t lt = (flags >> ZB_LIT_SHIFT) & 3u;
+      const uint8_t* lit = lt == 0 ? src + b->lit_off : a.lits + (size_t)b->lit_base16 * 16;
+      const int rle = lt == 1 ? (int)b->lit_off : -1;
+      const SeqRec16* seqs = a.recs + b->seq_base;
+      const uint32_t nseq = b->nseq, frame_start = b->frame_start;
+      const uint32_t r0 = b->rep_in[0], r1 = b->rep_in[1], r2 = b->rep_in[2];
+      uint32_t s0 = 0, gpos = blk0;  // gpos: blob-absolute output position where the next group starts
+      uint32_t lit_next = 0;         // literal position where the next group starts
+      SeqRec16 rn[K];                // prefetched records of sequences s0 + k * NT + tid
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        rn[k].w0 = rn[k].w1 = rn[k].w2 = rn[k].w3 = 0;
+        if (k * NT + tid < nseq) rn[k] = seqs[k * NT + tid];
+      }
+      while (s0 < nseq) {
+        ZT(0);
+        // ---- the group: the leading sequences that fit the buffer (end positions are monotonic, so "fits" is a prefix)
+        uint32_t inm = 0, my_gend = 0, my_lit_hi = 0;
+        SeqRec16 r[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          r[k] = rn[k];
+          const bool have = s0 + k * NT + tid < nseq;
+          const uint32_t endp = blk0 + rec_out(r[k]) + rec_ll(r[k]) + rec_ml(r[k]);
+          if (have && endp - gpos <= GB && rec_lit(r[k]) + rec_ll(r[k]) - lit_next <= GB) {
+            inm |= 1u << k;
+            my_gend = endp;  // k ascending = sequence index ascending
+            my_lit_hi = rec_lit(r[k]) + rec_ll(r[k]);
+          }
+        }
+        {
+          const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(inm));
+          const uint32_t ge = __reduce_max_sync(0xFFFFFFFFu, my_gend), lh = __reduce_max_sync(0xFFFFFFFFu, my_lit_hi);
+          if (lane == 0 && c) { atomicAdd(&sh->cnt, c); atomicMax(&sh->gend, ge); atomicMax(&sh->lit_hi, lh); }
+          if (tid == 0) sh->first = r[0];
+        }
+        __syncthreads();
+        const uint32_t count = sh->cnt, gend = sh->gend, lit_hi = sh->lit_hi;
+        const SeqRec16 q = sh->first;
+        if (count == 0) {
+          // ---- a sequence longer than the buffer: alone, in global memory, by the whole team
+          const uint32_t qo = blk0 + rec_out(q), qll = rec_ll(q), qlr = rec_lit(q), qml = rec_ml(q);
+          if (qll) {
+            if (rle >= 0) team_fill(t, out + qo, (uint32_t)rle, qll);
+            else team_copy(t, out + qo, lit + qlr, qll);
+          }
+          const uint32_t o = sym_resolve(rec_off(q), r0, r1, r2);
+          const uint32_t da = qo + qll;
+          if (qml && (o == 0 || o > da - frame_start)) { bad = true; break; }
+          __syncthreads();
+          if (qml) team_match(t, out + da, o, qml, sh->pat, nullptr);
+          __syncthreads();
+          gpos = da + qml;
+          lit_next = qlr + qll;
+          s0 += 1;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            rn[k].w0 = rn[k].w1 = rn[k].w2 = rn[k].w3 = 0;
+            if (s0 + k * NT + tid < nseq) rn[k] = seqs[s0 + k * NT + tid];
+          }
+          continue;
+        }
+        // prefetch the next group's records: their latency hides behind this group's rounds
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          rn[k].w0 = rn[k].w1 = rn[k].w2 = rn[k].w3 = 0;
+          if (s0 + count + k * NT + tid < nseq) rn[k] = seqs[s0 + count + k * NT + tid];
+        }
+        ZT(1);
+        const uint32_t lit_lo = rec_lit(q);
+        if (rle < 0 && lit_hi > lit_lo) team_copy(t, sh->lits, lit + lit_lo, lit_hi - lit_lo);
+        // far sources into L1 while the literals arrive
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if ((inm >> k) & 1u) {
+            const uint32_t ml = rec_ml(r[k]), off = sym_resolve(r[k].w0, r0, r1, r2);
+            const uint32_t dabs = blk0 + rec_out(r[k]) + rec_ll(r[k]);
+            if (ml && off && off <= dabs && dabs - off < gpos) {
+              const uint8_t* sp = out + (dabs - off);
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+              if (ml > 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + (ml <= kMatchLane ? ml : kMatchLane) - 1));
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) { sh->cnt = 0; sh->gend = 0; sh->lit_hi = 0; }  // (used again only after more barriers)
+        ZT(2);
+        // ---- setup: known bytes into the buffer, parents for the rest
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const bool mine = (inm >> k) & 1u;
+          const uint32_t orl = rec_out(r[k]), ll = mine ? rec_ll(r[k]) : 0u, lr = rec_lit(r[k]);
+          const uint32_t ml = mine ? rec_ml(r[k]) : 0u;
+          const uint32_t oabs = blk0 + orl, dabs = oabs + ll;
+          if (ll && ll <= kLitLane) {
+            const uint32_t o = buf_s + (oabs - gpos), ls = lits_s + (lr - lit_lo);
+            uint32_t v[kLitLane];
+#pragma unroll
+            for (int i = 0; i < (int)kLitLane; i++) v[i] = rle >= 0 ? (uint32_t)rle : ((uint32_t)i < ll ? lds8(ls + i) : 0u);
+#pragma unroll
+            for (int i = 0; i < (int)kLitLane; i++) if ((uint32_t)i < ll) sts8(o + i, v[i]);
+          }
+          const bool job_lit = ll > kLitLane;
+          bool job_m = false;
+          if (ml) {
+            const uint32_t off = sym_resolve(r[k].w0, r0, r1, r2);
+            if (off == 0 || off > dabs - frame_start) sh->err = 1;
+            else if (ml > kMatchLane) job_m = true;
+            else {
+              const uint32_t drel = dabs - gpos;
+              const uint32_t sabs = dabs - off;
+              if (off >= ml && sabs + ml <= gpos) {  // wholly before the group: plain gather from global memory
+                const uint8_t* sp = out + sabs;
+                uint32_t v[kMatchLane];
+#pragma unroll
+                for (int i = 0; i < (int)kMatchLane; i++) if ((uint32_t)i < ml) v[i] = sp[i];
+#pragma unroll
+                for (int i = 0; i < (int)kMatchLane; i++) if ((uint32_t)i < ml) sts8(buf_s + drel + i, v[i]);
+              } else if (off >= ml && sabs >= gpos) {  // wholly inside the group: parents only
+                const uint32_t srel = sabs - gpos;
+#pragma unroll
+                for (int i = 0; i < (int)kMatchLane; i++) if ((uint32_t)i < ml) sts16(par_s + 2 * (drel + i), srel + i);
+              } else {  // straddles the group start and / or feeds itself: byte by byte, phase = i mod off
+                uint32_t ph = 0;
+#pragma unroll
+                for (int i = 0; i < (int)kMatchLane; i++) {
+                  if ((uint32_t)i < ml) {
+                    const uint32_t sp = sabs + ph;
+                    if (sp < gpos) sts8(buf_s + drel + i, (uint32_t)out[sp]);
+                    else sts16(par_s + 2 * (drel + i), sp - gpos);
+                    ph = ph + 1 == off ? 0u : ph + 1;
+                  }
+                }
+              }
+            }
+          }
+          // jobs: long literal runs and long matches, one warp each
+          const uint32_t nj = (job_lit ? 1u : 0u) + (job_m ? 1u : 0u);
+          const uint32_t bj = __ballot_sync(0xFFFFFFFFu, nj != 0);
+          if (bj) {
+            uint32_t pre = nj;  // inclusive prefix sum of nj over the lanes
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pre, sft); if ((int)lane >= sft) pre += v; }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&sh->n_jobs, pre);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31);
+            uint32_t slot = base + pre - nj;
+            const uint32_t idx = (uint32_t)k * NT + tid;
+            if (job_lit) sh->jobs[slot++] = (uint16_t)(idx | 0x8000u);
+            if (job_m) sh->jobs[slot] = (uint16_t)idx;
+          }
+        }
+        __syncthreads();
+        ZT(3);
+        if (sh->err) { bad = true; break; }
+        {
+          ZT_CNT(12, tid == 0 ? sh->n_jobs : 0);
+          const uint32_t nj = sh->n_jobs;
+          for (uint32_t i = warp; i < nj; i += NT / 32) {
+            const uint32_t jb = sh->jobs[i], idx = jb & 0x7FFFu;
+            const SeqRec16 rr = seqs[s0 + idx];  // idx = k * NT + tid of the owner = offset from s0 (broadcast load)
+            const uint32_t oabs = blk0 + rec_out(rr), ll = rec_ll(rr);
+            if (jb & 0x8000u) {
+              const uint32_t dd = buf_s + (oabs - gpos), l2 = lits_s + (rec_lit(rr) - lit_lo);
+              for (uint32_t x = lane; x < ll; x += 32) sts8(dd + x, rle >= 0 ? (uint32_t)rle : lds8(l2 + x));
+            } else {
+              const uint32_t dabs = oabs + ll, l = rec_ml(rr), oo = sym_resolve(rr.w0, r0, r1, r2);
+              const uint32_t drel = dabs - gpos, sabs = dabs - oo;
+              // byte x copies window[x mod oo]; the phase advances by 32 mod oo per step instead of a division per byte
+              uint32_t ph = oo >= l ? lane : lane % oo;
+              const uint32_t step = oo >= l ? 32u : 32u % oo;
+              for (uint32_t x = lane; x < l; x += 32) {
+                const uint32_t sp = sabs + ph;
+                if (sp < gpos) sts8(buf_s + drel + x, (uint32_t)out[sp]);
+                else sts16(par_s + 2 * (drel + x), sp - gpos);
+                ph += step;
+                if (oo < l && ph >= oo) ph -= oo;
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) { sh->n_jobs = 0; sh->lcnt[0] = sh->lcnt[1] = sh->lcnt[2] = 0; }
+        __syncthreads();
+        ZT(4);
+        // ---- rounds.  The first one SCANS par[] (8 entries per 16-byte load) and writes the bytes that are still unknown
+        // after it into a list; later rounds walk that list densely (one lane per unknown byte) and compact it as
+        // they go, so a late round that resolves three bytes costs three bytes' worth of work, not a pass over the group.
+        // The two lists alias the literal staging area (dead once the jobs are done); a group with more unknown bytes than
+        // a list holds is scanned again.
+        const uint32_t glen = gend - gpos;
+        constexpr uint32_t kListCap = GB / 4;
+        uint32_t nlist = ~0u;  // ~0u: scan round; else entries of list[round & 1]
+        for (uint32_t round = 0;; round++) {
+          const uint32_t cur = kFresh | ((round & 1u) << 14);
+          const uint32_t cw = (round + 1u) % 3u;  // counter appended to this round (cleared a round ago)
+          const uint32_t lst_r = lits_s + (round & 1u) * 2u * kListCap, lst_w = lits_s + ((round & 1u) ^ 1u) * 2u * kListCap;
+          if (tid == 0) sh->lcnt[(round + 2u) % 3u] = 0;
+          if (nlist == ~0u) {
+            for (uint32_t b0 = warp * 256u; b0 < glen; b0 += NT * 8) {
+              const uint32_t base = b0 + lane * 8u;
+              uint32_t km = 0;  // entries of this chunk that stay unknown
+              if (base < glen) {
+                const uint4 pv = lds128(par_s + 2 * base);
+                // bit 15 of an entry = its byte is in the buffer (kKnown, or kFresh of this or an earlier round)
+                if ((pv.x & pv.y & pv.z & pv.w & 0x80008000u) != 0x80008000u) {
+                  const uint32_t w4[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                  for (int e = 0; e < 8; e++) {
+                    const uint32_t me = (w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+                    if (me & 0x8000u) continue;
+                    const uint32_t i = base + e;
+                    const uint32_t pp = lds16(par_s + 2 * me);
+                    if (pp == kKnown || ((pp & 0x8000u) && pp != cur)) {  // the parent's byte was stored before this round's barrier
+                      sts8(buf_s + i, lds8(buf_s + me));
+                      sts16(par_s + 2 * i, cur);
+                    } else {
+                      // a parent resolved this very round (or carrying a stale marker of this parity): look again next
+                      // round; otherwise adopt the parent's parent
+                      if (!(pp & 0x8000u)) sts16(par_s + 2 * i, pp);
+                      km |= 1u << e;
+                    }
+                  }
+                }
+              }
+              const uint32_t c = (uint32_t)__popc(km);
+              if (__any_sync(0xFFFFFFFFu, c != 0)) {
+                uint32_t pre = c;  // inclusive prefix sum over the lanes
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, pre, sft); if ((int)lane >= sft) pre += v; }
+                uint32_t slot = 0;
+                if (lane == 31) slot = atomicAdd(&sh->lcnt[cw], pre);
+                slot = __shfl_sync(0xFFFFFFFFu, slot, 31) + pre - c;
+                while (km) {
+                  const uint32_t e = (uint32_t)__ffs(km) - 1u;
+                  km &= km - 1u;
+                  if (slot < kListCap) sts16(lst_w + 2 * slot, base + e);
+                  slot++;
+                }
+              }
+            }
+          } else {
+            for (uint32_t j0 = warp * 32u; j0 < nlist; j0 += NT) {
+              const uint32_t j = j0 + lane;
+              bool keep = false;
+              uint32_t i = 0;
+              if (j < nlist) {
+                i = lds16(lst_r + 2 * j);
+                const uint32_t me = lds16(par_s + 2 * i);
+                const uint32_t pp = lds16(par_s + 2 * me);
+                if (pp == kKnown || ((pp & 0x8000u) && pp != cur)) {
+                  sts8(buf_s + i, lds8(buf_s + me));
+                  sts16(par_s + 2 * i, cur);
+                } else {
+                  if (!(pp & 0x8000u)) sts16(par_s + 2 * i, pp);
+                  keep = true;
+                }
+              }
+              const uint32_t kb = __ballot_sync(0xFFFFFFFFu, keep);
+              if (kb) {
+                uint32_t b1 = 0;
+                if (lane == 0) b1 = atomicAdd(&sh->lcnt[cw], (uint32_t)__popc(kb));
+                b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+                if (keep) sts16(lst_w + 2 * (b1 + __popc(kb & ((1u << lane) - 1u))), i);
+              }
+            }
+          }
+          if (round > 96) { if (tid == 0) sh->err = 2; break; }  // cannot happen (chains halve every round): never hang
+          __syncthreads();
+          const uint32_t left = sh->lcnt[cw];
+          ZT_CNT(8, tid == 0 ? 1 : 0);
+          ZT_CNT(10, tid == 0 ? left : 0);
+          ZT_CNT(11, tid == 0 && nlist == ~0u ? 1 : 0);
+          if (left == 0) break;
+          nlist = left <= kListCap ? left : ~0u;
+        }
+        __syncthreads();
+        ZT(5);
+        if (sh->err) { bad = true; break; }
+        // ---- flush, and every parent back to "known" for the next group
+        team_copy(t, out + gpos, sh->buf, glen);
+        for (uint32_t i = tid * 8; i < glen + 8; i += NT * 8) sts128(par_s + 2 * i, known4);
+        __syncthreads();
+        ZT(6);
+        ZT_CNT(9, tid == 0 ? 1 : 0);
+        gpos = gend;
+        lit_next = lit_hi;
+        s0 += count;
+      }
+      if (bad) break;
+      const uint32_t rest = b->lit_regen - b->lit_used;
+      if (rest) {
+        if (rle >= 0) team_fill(t, out + blk0 + b->matched, (uint32_t)rle, rest);
+        else team_copy(t, out + blk0 + b->matched, lit + b->lit_used, rest);
+      }
+      __syncthreads();
+    }
+    if (bad) {  // leave the shared state clean for the next blob
+      __syncthreads();
+      for (uint32_t i = tid * 8; i < GB + 8; i += NT * 8) sts128(par_s + 2 * i, known4);
+    }
+    if (tid == 0) {
+      if (bad) a.zb[item].state = 1;
+      else produced[z.blob] = (uint32_t)d.dst_cap;
+      ZT(7);
+      ZT_FLUSH(0, 16);
+    }
+  }
+}
+
 }  // namespace zp
 }  // namespace zn

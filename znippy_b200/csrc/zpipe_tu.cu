@@ -27,6 +27,9 @@ bool pipeline_init() {
   cudaFuncSetAttribute(k_zexec<512, 4, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<512, 4, 32768>));
   cudaFuncSetAttribute(k_zexec<256, 8, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<256, 8, 32768>));
   cudaFuncSetAttribute(k_zexec<128, 4, 16384, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<128, 4, 16384>));
+#define ZN_A2(NT, K, GB, MINB) cudaFuncSetAttribute(k_zexec2<NT, K, GB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Exec2Shared<NT, K, GB>))
+  ZN_A2(256, 4, 16384, 2); ZN_A2(256, 4, 16384, 3); ZN_A2(512, 4, 16384, 2); ZN_A2(512, 2, 16384, 3); ZN_A2(1024, 2, 16384, 1); ZN_A2(1024, 2, 16384, 2); ZN_A2(128, 4, 8192, 6); ZN_A2(128, 4, 8192, 4);
+#undef ZN_A2
   return true;
 }
 
@@ -34,6 +37,13 @@ void pipeline_trace_dump() {
 #ifdef ZP_TRACE
   unsigned long long h[32];
   cudaMemcpyFromSymbol(h, g_ztrace, sizeof h);
+  if (!getenv("ZN_EXEC1")) {
+    fprintf(stderr, "zexec2 trace (thread 0 cycles summed over CTAs): other %llu formation %llu lits+prefetch %llu setup %llu jobs %llu rounds %llu flush %llu rest %llu | rounds %llu groups %llu unknown-after-round %llu scan-rounds %llu jobs %llu\n",
+            h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
+    unsigned long long z2[32] = {0};
+    cudaMemcpyToSymbol(g_ztrace, z2, sizeof z2);
+    return;
+  }
   fprintf(stderr, "zexec trace (thread 0 cycles summed over CTAs): records+extent %llu stage %llu setup %llu passes-other %llu flush %llu rest %llu | passes %llu groups %llu pending-checks %llu\n",
           h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10]);
   fprintf(stderr, "  per pass: top+long %llu check %llu copy %llu fence+clear %llu append %llu barrier %llu\n", h[11], h[12], h[13], h[14], h[15], h[6]);
@@ -63,6 +73,24 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   mark();
   k_zchain<<<(a.nzb + 63) / 64, 64, 0, st>>>(a);
   mark();
+  if (!getenv("ZN_EXEC1")) {  // pointer-jumping exec (ZN_EXEC1=1: the wavefront version)
+    const char* e2 = getenv("ZN_EXEC2");  // development: threads * 10 + CTAs per SM
+    const int shape2 = e2 ? atoi(e2) : (L.mean_bytes >= (256u << 10) ? 10242 : 5123);
+#define ZN_X2(NT, K, GB, MINB) k_zexec2<NT, K, GB, MINB><<<std::min<uint32_t>(a.nzb, sms * MINB), NT, sizeof(Exec2Shared<NT, K, GB>), st>>>(a, L.d_out, L.produced, L.exec_counter)
+    switch (shape2) {
+      case 2563: ZN_X2(256, 4, 16384, 3); break;
+      case 5122: ZN_X2(512, 4, 16384, 2); break;
+      case 5123: ZN_X2(512, 2, 16384, 3); break;
+      case 10241: ZN_X2(1024, 2, 16384, 1); break;
+      case 10242: ZN_X2(1024, 2, 16384, 2); break;
+      case 1286: ZN_X2(128, 4, 8192, 6); break;
+      case 1284: ZN_X2(128, 4, 8192, 4); break;
+      default: ZN_X2(256, 4, 16384, 2); break;
+    }
+#undef ZN_X2
+    mark();
+    return;
+  }
   const char* ev = getenv("ZN_EXEC");  // development: team shape of the exec kernel
   const int shape = ev ? atoi(ev) : (L.mean_bytes >= (256u << 10) ? 256 : 128);
   if (shape == 512)
