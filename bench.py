@@ -631,7 +631,9 @@ def run_ours(args):
         # pinned slots, H2D, kernels, D2H of statuses (+ decoded bytes and pwrite for extract)
         from znippy_b200 import archive as A
         sync_all()
-        A.decompress_archive(arch["path"], False, "/dev/null", ctx, row_range=(lo, min(hi, lo + 64)))  # warm (pinned slots)
+        # warm: the same call once, untimed — a serving process keeps its pinned slots for its lifetime (the reference keeps
+        # its Magazine, slotpool.rs:93-130); cudaHostAlloc of two 1 GiB slots would otherwise sit inside the timed call
+        A.decompress_archive(arch["path"], False, "/dev/null", ctx, row_range=(lo, hi))
         e2e_steps = 1
         sync_all()
         t0 = time.perf_counter()

@@ -290,3 +290,33 @@ def test_extract_cache_is_lru_and_transparent(A, tmp_path, oracle):
     assert st2["hits"] == st["hits"] + 3 and st2["bytes"] >= 20 << 20
     ar.set_cache(0)
     assert ar.cache_stats()["slices"] == 0 and ar.extract_file(names[1]) == files[names[1]]
+
+
+def test_row_shards_across_groups_parse_only_their_own_subindexes(A, tmp_path, oracle):
+    """configs[4] in small: an archive of several (pkg_type, repo) groups decoded as three row shards whose cuts fall inside
+    and between groups.  Each shard call opens only the sub-indexes it needs (archive rows -> local rows), yet files,
+    bytes and counters are those of the one-shot call."""
+    O = oracle
+    entries = []
+    for g in range(5):
+        for i in range(7):
+            entries.append(A.ArchiveEntry(f"g{g}/f{i}.txt", O.real_text(20_000 + 997 * (g * 7 + i)).tobytes(), pkg_type=1 + g % 3, repo=f"repo{g}"))
+        entries.append(A.ArchiveEntry(f"g{g}/big.bin", O.gen_binary((9 << 20) + g).tobytes(), pkg_type=1 + g % 3, repo=f"repo{g}"))
+    sc = A.compress_stream(str(tmp_path / "groups.znippy"), False, level=3)
+    for e in entries:
+        sc.sender().send(e)
+    rep = sc.finish()
+    assert len(A.read_znippy_manifest(sc.output)) == 5
+    n = A.read_znippy_index(sc.output).num_rows
+    assert n == rep.chunks == 5 * 9
+    whole = A.decompress_archive(sc.output, False, "/dev/null")
+    paths = A.read_znippy_index(sc.output).column("relative_path").to_pylist()
+    want = {e.relative_path: e.data for e in entries}
+    for cuts in ([0, 13, 31, n], [0, 9, 18, n], [0, 1, n - 1, n]):
+        out = tmp_path / ("x" + "_".join(map(str, cuts)))
+        reps = [A.decompress_archive(sc.output, True, str(out), row_range=(a, b)) for a, b in reversed(list(zip(cuts, cuts[1:])))]
+        assert sum(r.chunks for r in reps) == n and sum(r.verified_bytes for r in reps) == whole.verified_bytes
+        assert all(r.corrupt_files == 0 for r in reps)
+        assert sum(r.total_files for r in reps) >= len(set(paths))  # a straddling file is counted by both of its shards
+        for p, d in want.items():
+            assert (out / p).read_bytes() == d, (cuts, p)

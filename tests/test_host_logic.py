@@ -360,3 +360,52 @@ def test_two_rank_sharding_gloo():
     (r0, lo0, hi0, t0), (r1, lo1, hi1, t1) = res
     assert lo0 == 0 and hi0 == lo1 and hi1 == 507
     assert t0 == t1 == [507, 7 * (8 << 20) + 500 * 10240]
+
+
+def _multirepo_worker(rank, world, port, path, q):
+    """One rank of bench.py's configs[4] host logic on CPU: every rank derives the SAME index from the generator, takes its
+    own row range, and the per-shard counters add up on the host — no data-path collective."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    from znippy_b200 import _native as N
+    from znippy_b200 import archive as A
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    blobs, lens, digs, comp, groups, meta, _ = bench.build_multirepo(1 / 16, n_groups=4, want_paths=(rank == 0))
+    if rank == 0:
+        bench.write_multirepo_archive(path, blobs, lens, digs, comp, groups, meta)
+    dist.barrier()
+    L = N.lib()
+    err = C.create_string_buffer(256)
+    h = L.zn_index_open(path.encode(), err, 256)   # the native reader, as zn_archive_decompress uses it
+    assert h, err.value
+    n = L.zn_index_rows(h)
+    us = np.ctypeslib.as_array(L.zn_index_u64(h, 3), (n,)).copy()
+    bs = np.ctypeslib.as_array(L.zn_index_u64(h, 1), (n,)).copy()
+    ng = L.zn_index_groups(h)
+    L.zn_index_close(h)
+    assert n == len(blobs) and (us == np.array(lens, np.uint64)).all() and (bs == np.array([len(b) for b in blobs], np.uint64)).all()
+    lo, hi = A.shard_rows(us, world)[rank]
+    t = torch.tensor([hi - lo, int(us[lo:hi].sum()), int(bs[lo:hi].sum())], dtype=torch.int64)
+    dist.all_reduce(t)
+    q.put((rank, lo, hi, int(n), int(ng), t.tolist(), int(us.sum()), int(bs.sum())))
+    dist.destroy_process_group()
+
+
+def test_multirepo_archive_shards_over_two_ranks_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 337) % 1000
+    path = str(tmp_path / "mr.znippy")
+    ps = [ctx.Process(target=_multirepo_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=300) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    (_, lo0, hi0, n, ng, t0, us_sum, bs_sum), (_, lo1, hi1, n1, ng1, t1, _, _) = res
+    assert n == n1 and ng == ng1 == 4
+    assert lo0 == 0 and hi0 == lo1 and hi1 == n          # the two ranges tile the index
+    assert t0 == t1 == [n, us_sum, bs_sum]               # and their counters add up to the whole archive
+    assert abs((hi0 - lo0) - (hi1 - lo1)) < n            # (balanced on bytes, not rows)

@@ -29,6 +29,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
@@ -101,7 +102,9 @@ struct Column {  // one decoded column of one record batch (views into the file 
 };
 
 struct IndexImpl {
-  uint64_t rows = 0;
+  uint64_t rows = 0;        // rows held here (all of the archive's, or the groups a ranged open asked for)
+  uint64_t row_base = 0;    // archive row number of local row 0
+  uint64_t rows_total = 0;  // rows of the whole archive (manifest)
   std::vector<uint64_t> col[4];  // blob_offset, blob_size, fdata_offset, uncompressed_size
   std::vector<uint32_t> chunk_seq;
   std::vector<uint8_t> compressed;
@@ -231,7 +234,7 @@ uint64_t get_uint(const Column& c, int bits, uint64_t i) {
 }
 
 // Appends the rows of one sub-index stream to `ix` (columns looked up by NAME, as the reference does).
-void read_subindex(const Span& stream, IndexImpl* ix, bool first) {
+void read_subindex(const Span& stream, IndexImpl* ix, bool first, bool schema_only = false) {
   size_t pos = 0;
   Msg m;
   if (!next_message(stream, &pos, &m) || m.header_type != 1) throw FbErr();
@@ -239,6 +242,7 @@ void read_subindex(const Span& stream, IndexImpl* ix, bool first) {
   parse_schema(m, &fields, first ? &ix->metadata : nullptr);
   if (first)
     for (auto& f : fields) ix->field_names.push_back(f.name);
+  if (schema_only) return;
   static const char* u64names[4] = {"blob_offset", "blob_size", "fdata_offset", "uncompressed_size"};
   int fi_u64[4], fi_path = find_field(fields, "relative_path"), fi_seq = find_field(fields, "chunk_seq"),
                  fi_comp = find_field(fields, "compressed"), fi_sum = find_field(fields, "checksum");
@@ -576,7 +580,10 @@ struct zn_index {
   IndexImpl ix;
 };
 
-extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) {
+// Opens the index; only the sub-indexes that hold archive rows [want_lo, want_hi) are parsed (a GPU shard of a large
+// archive needs its own groups, not all of them: 1.3 M rows cost ~0.25 s to parse).  Local row r = archive row
+// row_base + r.  The first sub-index's schema is always read (metadata, field names).
+static zn_index* index_open_range(const char* path, uint64_t want_lo, uint64_t want_hi, char* err, size_t errcap) {
   const int fd = open(path, O_RDONLY);
   if (fd < 0) { set_err(err, errcap, "cannot open archive"); return nullptr; }
   zn_index* h = new zn_index();
@@ -595,12 +602,23 @@ extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) {
     read_manifest(Span{mbytes.data(), mbytes.size()}, &h->ix);
     bool first = true;
     std::vector<uint8_t> sub;
+    uint64_t g_lo = 0;
     for (auto& g : h->ix.groups) {
       if (g.index_offset > flen || g.index_len > flen - g.index_offset) throw std::string("sub-index outside file");
-      if (!read_range(fd, g.index_offset, g.index_len, &sub)) throw std::string("read error");
-      read_subindex(Span{sub.data(), sub.size()}, &h->ix, first);
+      const uint64_t g_hi = g_lo + g.row_count;
+      const bool wanted = g_hi > want_lo && g_lo < want_hi;
+      if (wanted || first) {
+        if (!read_range(fd, g.index_offset, g.index_len, &sub)) throw std::string("read error");
+        const uint64_t before = h->ix.rows;
+        read_subindex(Span{sub.data(), sub.size()}, &h->ix, first, !wanted);
+        if (wanted && h->ix.rows - before != g.row_count) throw std::string("sub-index row count differs from the manifest");
+      }
+      if (!wanted && h->ix.rows == 0) h->ix.row_base = g_hi;  // still in front of the first wanted group
       first = false;
+      g_lo = g_hi;
     }
+    h->ix.rows_total = g_lo;
+    if (h->ix.rows == 0) h->ix.row_base = std::min(want_lo, g_lo);
     h->ix.path_off.insert(h->ix.path_off.begin(), 0);
     // Index columns come from the file: every blob must lie inside the payload region (before the first sub-index)
     // and both sizes stay below the 4 GiB the batch calls support, so that no later sum of them can wrap.
@@ -636,6 +654,8 @@ extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) {
   close(fd);
   return h;
 }
+
+extern "C" zn_index* zn_index_open(const char* path, char* err, size_t errcap) { return index_open_range(path, 0, ~0ull, err, errcap); }
 
 extern "C" void zn_index_close(zn_index* h) { delete h; }
 extern "C" uint64_t zn_index_rows(const zn_index* h) { return h ? h->ix.rows : 0; }
@@ -781,14 +801,21 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
                                      size_t errcap) {
   if (!ctx || !index_path || !report) return ZN_E_ARG;
   memset(report, 0, sizeof *report);
-  zn_index* h = zn_index_open(index_path, err, errcap);
+  zn_index* h = index_open_range(index_path, row_lo, row_hi, err, errcap);  // this shard's groups only
   if (!h) return ZN_E_ARG;
   const IndexImpl& ix = h->ix;
+  // from here on rows are LOCAL to the parsed groups (a file's rows never leave its group, so every neighbour the
+  // shard logic below looks at is present)
+  if (row_hi > ix.rows_total) row_hi = ix.rows_total;
+  if (row_lo > row_hi) row_lo = row_hi;
+  row_lo = row_lo >= ix.row_base ? row_lo - ix.row_base : 0;
+  row_hi = row_hi >= ix.row_base ? row_hi - ix.row_base : 0;
   if (row_hi > ix.rows) row_hi = ix.rows;
   if (row_lo > row_hi) row_lo = row_hi;
-  std::unordered_set<std::string> uniq;
+  std::unordered_set<std::string_view> uniq;
+  uniq.reserve((size_t)(row_hi - row_lo) * 2);
   int rc = ZN_OK;
-  for (uint64_t r = row_lo; r < row_hi; r++) uniq.insert(std::string(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]));
+  for (uint64_t r = row_lo; r < row_hi; r++) uniq.insert(std::string_view(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]));
   // decompress.rs:74-101 keeps one fd per path for the whole run.  With 100 000 small files that needs a raised
   // RLIMIT_NOFILE, so here the row range is worked off in windows of at most `max_open` distinct paths (rows of a
   // file are adjacent in the index): same files, same bytes, any descriptor limit.
