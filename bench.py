@@ -386,10 +386,11 @@ class Clocks:
 
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full summary
-    of this same workload (profiles/r1_ncu_traffic.json); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
+    of this same workload (profiles/r2_ncu_traffic.json); None when no capture is committed."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p)).get(kernel)
     return None
 
 

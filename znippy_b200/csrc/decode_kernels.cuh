@@ -179,4 +179,15 @@ __global__ void __launch_bounds__(256) k_patch_magic(uint8_t* blobs_base, const 
   p[0] = 0x28; p[1] = 0xB5; p[2] = 0x2F; p[3] = 0xFD;
 }
 
+
+// Frames of a compress batch packed back to back for the way home (one warp per frame): n small device-to-host copies
+// cost ~3 us each, one copy of the packed bytes costs their size.
+__global__ void __launch_bounds__(256) k_pack_frames(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off,
+                                                     const uint64_t* __restrict__ len, const uint64_t* __restrict__ dst_off,
+                                                     uint32_t n, uint8_t* dst) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const Team t{threadIdx.x & 31u, 32u, 0u};
+  for (uint32_t i = warp; i < n; i += nwarps) team_copy(t, dst + dst_off[i], src + src_off[i], (uint32_t)len[i]);
+}
+
 }  // namespace zn
