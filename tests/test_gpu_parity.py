@@ -459,3 +459,30 @@ def test_zstd_content_checksums_are_verified(codec, oracle):
     for i, b in enumerate(fz):
         rc, o = O.zstd_decompress(b, cap)
         assert (st[i] == 0) == (rc == 0 and len(o) == cap), (i, st[i], rc)
+
+
+def test_fused_kernel_watchdog_ends_a_stalled_queue(codec, oracle, monkeypatch):
+    """the consumer-side watchdog of the fused decode+hash kernel (fused_ws.cuh) was never made to fire.  With
+    ZN_WS_TEST_STALL the host announces one tile more than the producers will ever publish; a hash warp then waits for an
+    entry that never comes, the spin limit (~3 s) trips, every other waiter sees the flag, the kernel ENDS, and the call
+    reports an error instead of results — the GPU is not left spinning, and the next call works."""
+    import time
+    from znippy_b200 import Ctx
+    O = oracle
+    z = O.libzstd()
+    data = O.gen_text(2 << 20).tobytes()
+    blob = z.compress(data, 19)
+    blobs = [blob] * 4
+    buf, offs = _pack(blobs)
+    ctx = Ctx(0)
+    args = (buf, offs, [len(b) for b in blobs], [1] * 4, [len(data)] * 4, O.blake3(data) * 4, None, None, ctx)
+    st, _ = codec.decode_verify_batch(*args)
+    assert not st.any()
+    monkeypatch.setenv("ZN_WS_TEST_STALL", "1")
+    t0 = time.time()
+    with pytest.raises(Exception, match="stalled"):
+        codec.decode_verify_batch(*args)
+    assert 1.0 < time.time() - t0 < 30.0
+    monkeypatch.delenv("ZN_WS_TEST_STALL")
+    st, dg = codec.decode_verify_batch(*args)
+    assert not st.any() and dg[0].tobytes() == O.blake3(data)

@@ -459,7 +459,7 @@ static zn_plan* plan_build(zn_ctx* c, int kind, uint32_t n, const uint64_t* src_
             upload(c, &p->d_digests, (const uint32_t*)nullptr, (size_t)n * 8) &&
             upload(c, &p->d_status, (const uint32_t*)nullptr, n) && upload(c, &p->d_produced, (const uint32_t*)nullptr, n) &&
             upload(c, &p->d_counter, (const uint32_t*)nullptr, 16) &&
-            upload(c, &p->d_wsq, (const uint32_t*)nullptr, p->fused_hash ? 4 + 2 * (size_t)p->ws_tiles : 0) &&
+            upload(c, &p->d_wsq, (const uint32_t*)nullptr, p->fused_hash ? 6 + 2 * (size_t)p->ws_tiles : 0) &&
             upload(c, &p->d_zb, zb.data(), zb.size());
   if (ok && any_status) ok = upload(c, &p->d_status0, status0, n);
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&p->ev[i]) == cudaSuccess;
@@ -616,9 +616,12 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
     const char* fm = getenv("ZN_FUSE");
     if (p->fused_hash && !(fm && !strcmp(fm, "team"))) {
       // warp-specialised fused kernel: one CTA per SM, two decode teams each; its tile queue starts empty
-      ZN_CUDA(c, cudaMemsetAsync(p->d_wsq, 0, 16 + 8 * (size_t)p->ws_tiles, st));
+      ZN_CUDA(c, cudaMemsetAsync(p->d_wsq, 0, 24 + 8 * (size_t)p->ws_tiles, st));
       p->ran_ws = true;
-      WsQueue q{p->d_wsq, reinterpret_cast<unsigned long long*>(p->d_wsq + 4), p->ws_tiles};
+      // tests (ZN_WS_TEST_STALL=1): announce one tile more than the producers will ever publish, so that a hash warp waits
+      // for an entry that never comes and the watchdog has to end the kernel
+      const uint32_t phantom = getenv("ZN_WS_TEST_STALL") ? 1u : 0u;
+      WsQueue q{p->d_wsq, reinterpret_cast<unsigned long long*>(p->d_wsq + 4), p->ws_tiles + phantom};
       uint32_t wgrid = (uint32_t)c->sm_count;  // every SM hashes, whether or not one of its teams gets a blob
       if (const char* gs = getenv("ZN_WS_GRID")) wgrid = std::max(1, std::min<int>((int)wgrid, atoi(gs)));
       k_decode_ws<<<wgrid, kWsThreads, kWsSmemBytes, st>>>(p->d_blobs, list, nd, d_blobs, d_out, c->d_lit, p->d_status,
