@@ -35,7 +35,18 @@ ZN_HD uint32_t ld_word_aligned(const uint8_t* a) {
 // 32-bit words; bytes below the stream start are masked to zero, so over-reads see zeros and are detected by
 // bits_left going negative (never by a fault).
 // ---------------------------------------------------------------------------------------------------------
+// ZN_BACKBITS_DEPTH (per translation unit; the struct's name carries it, so the two forms never meet): how many words the
+// reader keeps loaded ahead of the window.  2 in the device-wide pipeline's lane-per-block sequence decoder (one L2 round
+// trip must fit between two refills); 1 in the one-team decoders — their thread 0 shares an SM with the hash warps of the
+// fused kernel, where the extra register showed up as spills (k_decode_ws: 468 -> 496 B) and ~2 % of the metric.
+#ifndef ZN_BACKBITS_DEPTH
+#define ZN_BACKBITS_DEPTH 2
+#endif
+#define ZN_BB_CAT2(a, b) a##b
+#define ZN_BB_CAT(a, b) ZN_BB_CAT2(a, b)
+#define BackBits ZN_BB_CAT(BackBits_depth, ZN_BACKBITS_DEPTH)
 struct BackBits {
+  static constexpr int kDepth = ZN_BACKBITS_DEPTH;
   const uint32_t* wbase;  // aligned word holding the first stream byte
   uint32_t lowmask;       // clears the bytes of word 0 that precede the stream
   int32_t widx;           // index of the word held in `pre` (descending); < 0 -> zeros
@@ -52,6 +63,11 @@ struct BackBits {
     return i == 0 ? (w & lowmask) : w;
   }
   ZN_HD uint32_t fetch_raw(int32_t i) const { return i < 0 ? 0u : wbase[i]; }
+  // after widx moved down by one: the word for the next refill
+  ZN_HD void advance() {
+    if (kDepth > 1) { pre = pre2; pre2 = fetch_raw(widx - 1); }
+    else pre = fetch_raw(widx);
+  }
   ZN_HD uint32_t pre_word() const { return widx == 0 ? (pre & lowmask) : pre; }  // the word in `pre`, masked at the time of use
   ZN_HD bool init(const uint8_t* p, uint32_t len) {
     if (len == 0) return false;
@@ -70,7 +86,7 @@ struct BackBits {
     navail = nvalid;
     widx = t - 1;
     pre = fetch_raw(widx);
-    pre2 = fetch_raw(widx - 1);
+    pre2 = kDepth > 1 ? fetch_raw(widx - 1) : 0u;
     return true;
   }
 #if defined(__CUDA_ARCH__)
@@ -86,8 +102,7 @@ struct BackBits {
       win = ((uint64_t)hi << 32) | lo;
       navail += 32;
       widx--;
-      pre = pre2;
-      pre2 = fetch_raw(widx - 1);
+      advance();
       if (navail <= 32) {  // the window was empty: take a second word
         const uint32_t n2 = (uint32_t)navail;
         const uint32_t p2 = pre_word();
@@ -96,8 +111,7 @@ struct BackBits {
         win = ((uint64_t)h2 << 32) | __funnelshift_rc(0u, p2, n2);
         navail += 32;
         widx--;
-        pre = pre2;
-        pre2 = fetch_raw(widx - 1);
+        advance();
       }
     }
   }
@@ -114,8 +128,7 @@ struct BackBits {
       win |= (uint64_t)pre_word() << (32 - navail);
       navail += 32;
       widx--;
-      pre = pre2;
-      pre2 = fetch_raw(widx - 1);
+      advance();
     }
   }
   ZN_HD uint32_t peek(uint32_t n) const { return n ? (uint32_t)(win >> (64 - n)) : 0u; }  // n <= 32

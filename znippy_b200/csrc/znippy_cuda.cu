@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include <vector>
 
+#define ZN_BACKBITS_DEPTH 1  // one-team decoders: see bitio.cuh
 #include "../../include/znippy_cuda.h"
 #include "blake3_kernels.cuh"
 #include "host_api.h"

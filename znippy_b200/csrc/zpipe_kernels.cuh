@@ -183,17 +183,21 @@ __global__ void __launch_bounds__(64, 1) k_zseq(ZArgs a) {
 struct GlobalTabs {
   const FseD* t[3];
   uint32_t lut_s;
-  ZN_D uint32_t ld(int k, uint32_t i) const { return __ldg(t[k] + i); }
+  // .cg: the table sets of the lanes of one SM (3.5 warps x 32 lanes x 5 KiB) are several times its L1; left to allocate
+  // there they evict the lanes' bitstream lines, and the refill then waits for L2 as well (ZN_SEQ_LDG=1: the old form)
+  ZN_D uint32_t ld(int k, uint32_t i) const { return cg ? __ldcg(t[k] + i) : __ldg(t[k] + i); }
+  bool cg = true;
   ZN_D uint32_t base(int k, uint32_t sym) const { return lds32_ro(lut_s + 4u * ((k == 0 ? 0u : 36u) + sym)); }
 };
 
-__global__ void __launch_bounds__(32) k_zseq_g(ZArgs a) {
+__global__ void __launch_bounds__(32) k_zseq_g(ZArgs a, int cg) {
   __shared__ uint32_t s_lut[36 + 53];
   const uint32_t tid = threadIdx.x;
   for (uint32_t i = tid; i < 36; i += 32) s_lut[i] = zs::kLLBase[i];
   for (uint32_t i = tid; i < 53; i += 32) s_lut[36 + i] = zs::kMLBase[i];
   __syncwarp();
   GlobalTabs st;
+  st.cg = cg != 0;
   st.lut_s = (uint32_t)__cvta_generic_to_shared(s_lut);
   const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
   for (uint32_t it = blockIdx.x * 32 + tid; it < n_comp; it += gridDim.x * 32) {

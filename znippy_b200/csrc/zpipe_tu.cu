@@ -67,7 +67,7 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   k_ztables<<<std::min<uint32_t>((slots + kTabWarps - 1) / kTabWarps, sms * 8), kTabWarps * 32, 0, st>>>(a);
   mark();
   if (getenv("ZN_SEQ_SMEM")) k_zseq<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeqSmem, st>>>(a);
-  else k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a);
+  else k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a, getenv("ZN_SEQ_LDG") ? 0 : 1);
   mark();
   k_zlit<<<lit_grid, kLitBlocks * 4, kLitSmem, st>>>(a);
   mark();
