@@ -409,3 +409,21 @@ def test_multirepo_archive_shards_over_two_ranks_gloo(tmp_path):
     assert lo0 == 0 and hi0 == lo1 and hi1 == n          # the two ranges tile the index
     assert t0 == t1 == [n, us_sum, bs_sum]               # and their counters add up to the whole archive
     assert abs((hi0 - lo0) - (hi1 - lo1)) < n            # (balanced on bytes, not rows)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, the
+    same `config` our arm would print for the same flags, and no GPU anywhere near it."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gib", "0.0625", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "decode+blake3-verify GB/s (device)" and line["unit"] == "GB/s"
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 1 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "rows" in line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    blobs, lens, _digs, _comp, desc = bench.build_workload("text2g", 0.0625, 0)
+    assert line["config"] == bench.static_config(desc, len(blobs), int(sum(lens)))  # what run_ours prints for the same flags

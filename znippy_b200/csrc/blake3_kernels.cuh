@@ -9,6 +9,7 @@
 // 100 000 ten-chunk blobs, because lanes are assigned over the flat (blob, chunk) index space.
 #pragma once
 #include "blake3.cuh"
+#include "xxh_verify.cuh"
 
 namespace zn {
 
@@ -175,8 +176,11 @@ __global__ void __launch_bounds__(kB3Warps * 32) k_b3_chunks(const BlobDesc* __r
 
 // digest = cv words little-endian; compare with expect and fold into status (decode errors win).
 ZN_D void finish_blob(const BlobDesc& d, uint32_t blob, const uint32_t (&cv)[8], uint32_t* __restrict__ digests,
-                      const uint32_t* __restrict__ expect, uint32_t* __restrict__ status) {
+                      const uint32_t* __restrict__ expect, uint32_t* __restrict__ status, const uint8_t* blobs_base,
+                      const uint8_t* out_base) {
   b3::store_cv(digests + (uint64_t)blob * 8, cv);
+  // Zstandard content checksum (xxh_verify.cuh): a decoded row whose frame says XXH64 != content is a decode error
+  if (out_base && status[blob] == S_OK && xxh_row_bad(d, blobs_base, out_base)) status[blob] = S_DECODE_ERROR;
   if ((d.flags & F_HAS_EXPECT) && status[blob] == S_OK) {
     bool eq = true;
 #pragma unroll
@@ -190,7 +194,8 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
                                                        const uint32_t* __restrict__ list, uint32_t n_list,
                                                        uint32_t* cvs, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
-                                                       uint32_t* __restrict__ status, uint32_t one) {
+                                                       uint32_t* __restrict__ status, uint32_t one,
+                                                       const uint8_t* blobs_base, const uint8_t* out_base) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_list) return;
   const uint32_t blob = list[t];
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(128) k_b3_tree_small(const BlobDesc* __restric
     n = pairs + (n & 1);
   }
   b3::load_cv(base, o);
-  finish_blob(d, blob, o, digests, expect, status);
+  finish_blob(d, blob, o, digests, expect, status, blobs_base, out_base);
 }
 
 // K3c: large blobs: one CTA per blob, every level spread over the CTA.  Levels ping-pong between the blob's slots in
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(512) k_b3_tree_large(const BlobDesc* __restric
                                                        const uint32_t* __restrict__ list,
                                                        uint32_t* cvs, uint32_t* cvs2, uint32_t* __restrict__ digests,
                                                        const uint32_t* __restrict__ expect,
-                                                       uint32_t* __restrict__ status, uint32_t one) {
+                                                       uint32_t* __restrict__ status, uint32_t one,
+                                                       const uint8_t* blobs_base, const uint8_t* out_base) {
   const uint32_t blob = list[blockIdx.x];
   const BlobDesc d = blobs[blob];
   uint32_t* src = cvs + d.cv_base * 8;
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(512) k_b3_tree_large(const BlobDesc* __restric
   }
   if (threadIdx.x == 0) {
     b3::load_cv(src, o);
-    finish_blob(d, blob, o, digests, expect, status);
+    finish_blob(d, blob, o, digests, expect, status, blobs_base, out_base);
   }
 }
 

@@ -23,7 +23,6 @@
 #include "decode_kernels.cuh"
 #include "par_kernel.cuh"
 #include "fused_ws.cuh"
-#include "xxh_verify.cuh"
 
 using namespace zn;
 
@@ -659,11 +658,6 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
                                                                      nullptr, 0u);
     launches++;
   }
-  if (p->n_dec && !env_off("ZN_XXH")) {  // Zstandard content checksums (rows without one cost an 8-byte read)
-    k_xxh64_verify<<<std::min<uint32_t>((p->n_dec + 31) / 32, (uint32_t)c->sm_count * 8u), 128, 0, st>>>(p->d_blobs, p->d_list_dec, p->n_dec,
-                                                                                                       d_blobs, d_out, p->d_status);
-    launches++;
-  }
   ZN_CUDA(c, cudaEventRecord(p->ev[1], st));
   if (p->total_chunks && p->n_hashed != p->n) {
     const uint32_t tiles = (p->total_chunks + 31u) / 32u;
@@ -674,13 +668,16 @@ extern "C" int zn_plan_run(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, v
     launches++;
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[2], st));
+  // Zstandard content checksums are checked where a row's digest is compared (xxh_verify.cuh); ZN_XXH=0 turns that off
+  const uint8_t* xxh_out = p->n_dec && !env_off("ZN_XXH") ? d_out : nullptr;
   if (p->n_small) {
     k_b3_tree_small<<<(p->n_small + 127) / 128, 128, 0, st>>>(p->d_blobs, p->d_list_small, p->n_small, p->d_cvs, p->d_digests,
-                                                              p->d_expect, p->d_status, 1u);
+                                                              p->d_expect, p->d_status, 1u, d_blobs, xxh_out);
     launches++;
   }
   if (p->n_large) {
-    k_b3_tree_large<<<p->n_large, 512, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_cvs2, p->d_digests, p->d_expect, p->d_status, 1u);
+    k_b3_tree_large<<<p->n_large, 512, 0, st>>>(p->d_blobs, p->d_list_large, p->d_cvs, p->d_cvs2, p->d_digests, p->d_expect, p->d_status, 1u,
+                                                d_blobs, xxh_out);
     launches++;
   }
   ZN_CUDA(c, cudaEventRecord(p->ev[3], st));
