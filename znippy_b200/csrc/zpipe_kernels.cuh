@@ -730,9 +730,14 @@ ZN_D void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;"
 ZN_D uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 ZN_D void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 
-template <int NT, int K, uint32_t GB>
+template <int NT, int K, uint32_t GB, uint32_t LC>
 struct Exec2Shared {
   static_assert(GB <= 16384, "parents are 14-bit");
+  // LC = entries per list of unknown bytes.  GB / 4: the two lists alias the literal staging area (dead once the jobs are
+  // done); larger: they get their own array (a scan round costs ~17 k cycles, and with GB / 4 entries 70 % of the groups of
+  // python sources needed a second one)
+  static constexpr bool kOwnLists = LC > GB / 4;
+  alignas(16) uint16_t lists[kOwnLists ? 2 * LC : 8];
   static constexpr uint32_t kSeqs = K * NT;
   alignas(16) uint8_t buf[GB + 16];
   alignas(16) uint16_t par[GB + 8];
@@ -746,10 +751,10 @@ struct Exec2Shared {
   uint32_t err, item;
 };
 
-template <int NT, int K, uint32_t GB, int MINB>
+template <int NT, int K, uint32_t GB, int MINB, uint32_t LC = GB / 4>
 __global__ void __launch_bounds__(NT, MINB) k_zexec2(ZArgs a, uint8_t* out_base, uint32_t* produced, uint32_t* work_counter) {
   extern __shared__ __align__(16) uint8_t exec_smem[];
-  using Sh = Exec2Shared<NT, K, GB>;
+  using Sh = Exec2Shared<NT, K, GB, LC>;
   Sh* sh = reinterpret_cast<Sh*>(exec_smem);
   const Team t{threadIdx.x, (uint32_t)NT};
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -968,12 +973,13 @@ __global__ void __launch_bounds__(NT, MINB) k_zexec2(ZArgs a, uint8_t* out_base,
         // The two lists alias the literal staging area (dead once the jobs are done); a group with more unknown bytes than
         // a list holds is scanned again.
         const uint32_t glen = gend - gpos;
-        constexpr uint32_t kListCap = GB / 4;
+        constexpr uint32_t kListCap = LC;
+        const uint32_t lists_s = Sh::kOwnLists ? (uint32_t)__cvta_generic_to_shared(sh->lists) : lits_s;
         uint32_t nlist = ~0u;  // ~0u: scan round; else entries of list[round & 1]
         for (uint32_t round = 0;; round++) {
           const uint32_t cur = kFresh | ((round & 1u) << 14);
           const uint32_t cw = (round + 1u) % 3u;  // counter appended to this round (cleared a round ago)
-          const uint32_t lst_r = lits_s + (round & 1u) * 2u * kListCap, lst_w = lits_s + ((round & 1u) ^ 1u) * 2u * kListCap;
+          const uint32_t lst_r = lists_s + (round & 1u) * 2u * kListCap, lst_w = lists_s + ((round & 1u) ^ 1u) * 2u * kListCap;
           if (tid == 0) sh->lcnt[(round + 2u) % 3u] = 0;
           if (nlist == ~0u) {
             for (uint32_t b0 = warp * 256u; b0 < glen; b0 += NT * 8) {

@@ -27,9 +27,11 @@ bool pipeline_init() {
   cudaFuncSetAttribute(k_zexec<512, 4, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<512, 4, 32768>));
   cudaFuncSetAttribute(k_zexec<256, 8, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<256, 8, 32768>));
   cudaFuncSetAttribute(k_zexec<128, 4, 16384, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecShared<128, 4, 16384>));
-#define ZN_A2(NT, K, GB, MINB) cudaFuncSetAttribute(k_zexec2<NT, K, GB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Exec2Shared<NT, K, GB>))
-  ZN_A2(256, 4, 16384, 2); ZN_A2(256, 4, 16384, 3); ZN_A2(512, 4, 16384, 2); ZN_A2(512, 2, 16384, 3); ZN_A2(1024, 2, 16384, 1); ZN_A2(1024, 2, 16384, 2); ZN_A2(128, 4, 8192, 6); ZN_A2(128, 4, 8192, 4);
+#define ZN_A2(NT, K, GB, MINB) ZN_A2L(NT, K, GB, MINB, GB / 4)
+#define ZN_A2L(NT, K, GB, MINB, LC) cudaFuncSetAttribute(k_zexec2<NT, K, GB, MINB, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Exec2Shared<NT, K, GB, LC>))
+  ZN_A2(256, 4, 16384, 2); ZN_A2(256, 4, 16384, 3); ZN_A2(512, 4, 16384, 2); ZN_A2(512, 2, 16384, 3); ZN_A2(1024, 2, 16384, 1); ZN_A2(1024, 2, 16384, 2); ZN_A2L(1024, 2, 16384, 2, 8192); ZN_A2L(512, 4, 16384, 2, 8192); ZN_A2(128, 4, 8192, 6); ZN_A2(128, 4, 8192, 4);
 #undef ZN_A2
+#undef ZN_A2L
   return true;
 }
 
@@ -75,19 +77,23 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   mark();
   if (!getenv("ZN_EXEC1")) {  // pointer-jumping exec (ZN_EXEC1=1: the wavefront version)
     const char* e2 = getenv("ZN_EXEC2");  // development: threads * 10 + CTAs per SM
-    const int shape2 = e2 ? atoi(e2) : (L.mean_bytes >= (256u << 10) ? 10242 : 5123);
-#define ZN_X2(NT, K, GB, MINB) k_zexec2<NT, K, GB, MINB><<<std::min<uint32_t>(a.nzb, sms * MINB), NT, sizeof(Exec2Shared<NT, K, GB>), st>>>(a, L.d_out, L.produced, L.exec_counter)
+    const int shape2 = e2 ? atoi(e2) : (L.mean_bytes >= (256u << 10) ? 5124 : 5123);
+#define ZN_X2(NT, K, GB, MINB) ZN_X2L(NT, K, GB, MINB, GB / 4)
+#define ZN_X2L(NT, K, GB, MINB, LC) k_zexec2<NT, K, GB, MINB, LC><<<std::min<uint32_t>(a.nzb, sms * MINB), NT, sizeof(Exec2Shared<NT, K, GB, LC>), st>>>(a, L.d_out, L.produced, L.exec_counter)
     switch (shape2) {
       case 2563: ZN_X2(256, 4, 16384, 3); break;
       case 5122: ZN_X2(512, 4, 16384, 2); break;
       case 5123: ZN_X2(512, 2, 16384, 3); break;
       case 10241: ZN_X2(1024, 2, 16384, 1); break;
       case 10242: ZN_X2(1024, 2, 16384, 2); break;
+      case 10243: ZN_X2L(1024, 2, 16384, 2, 8192); break;
+      case 5124: ZN_X2L(512, 4, 16384, 2, 8192); break;
       case 1286: ZN_X2(128, 4, 8192, 6); break;
       case 1284: ZN_X2(128, 4, 8192, 4); break;
       default: ZN_X2(256, 4, 16384, 2); break;
     }
 #undef ZN_X2
+#undef ZN_X2L
     mark();
     return;
   }
