@@ -25,6 +25,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <list>
 #include <map>
 #include <mutex>
@@ -795,6 +796,12 @@ extern "C" int zn_index_writer_finish(zn_index_writer* w) {
 }
 
 // ================================================================================================ native decompress_archive
+extern "C" int zn_decompress_rows_ex(zn_ctx* c, int archive_fd, uint64_t row_lo, uint64_t row_hi, const uint64_t* blob_offset,
+                                     const uint64_t* blob_size, const uint64_t* fdata_offset, const uint8_t* compressed,
+                                     const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd,
+                                     size_t batch_bytes, int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats,
+                                     const char* out_root, const char* paths, const uint64_t* path_off);  // znippy_cuda.cu
+
 // decompress.rs:39-222 end to end: index -> (pre-create output files) -> zn_decompress_rows -> VerifyReport.
 extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int save_data, const char* out_dir, uint64_t row_lo,
                                      uint64_t row_hi, size_t batch_bytes, int io_threads, zn_verify_report* report, char* err,
@@ -837,47 +844,128 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
   if (save_data) fds.assign(ix.rows, -1);
   std::vector<uint64_t> corrupt(row_hi - row_lo + 1);
   std::unordered_set<std::string> created;  // a path met again in a later window is re-opened without truncation
+  std::unordered_set<std::string> made_dirs;  // directories known to exist (100 000 files in 100 directories: 100 mkdir walks)
+  const std::string root = out_dir ? out_dir : ".";
+  // helper threads for the per-file system calls of a window (open / ftruncate / close): 100 000 small files are 300 000 of
+  // them, and issued from one thread they took longer than decoding and writing the files did
+  auto for_each_parallel = [&](size_t n, const std::function<void(size_t)>& f) {
+    const int nt = n >= 64 ? std::max(1, std::min(io_threads, 16)) : 1;
+    if (nt == 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::atomic<size_t> cur{0};
+    std::vector<std::thread> ts;
+    for (int t = 0; t < nt; t++)
+      ts.emplace_back([&] { for (size_t i; (i = cur.fetch_add(1)) < n;) f(i); });
+    for (auto& t : ts) t.join();
+  };
+  struct OutFile {
+    std::string_view rel;
+    uint64_t first_row;
+    int fd = -1;
+    int err = 0;  // 1 open failed, 2 ftruncate failed
+  };
   for (uint64_t w_lo = row_lo; w_lo < row_hi && rc == ZN_OK;) {
-    std::map<std::string, int> open_files;
+    std::vector<OutFile> open_files;
     uint64_t w_hi = w_lo;
     if (save_data) {
-      for (; w_hi < row_hi && rc == ZN_OK; w_hi++) {
-        const std::string rel(ix.paths.data() + ix.path_off[w_hi], ix.path_off[w_hi + 1] - ix.path_off[w_hi]);
-        auto it = open_files.find(rel);
-        if (it == open_files.end()) {
-          if (open_files.size() >= max_open) break;
-          const std::string full = std::string(out_dir ? out_dir : ".") + "/" + rel;
-          for (size_t p = 1; p < full.size(); p++)
-            if (full[p] == '/') mkdir(full.substr(0, p).c_str(), 0755);
-          const bool again = !created.insert(rel).second;
-          // A file whose rows straddle [row_lo, row_hi) is also written by the neighbouring shard (another process or
-          // GPU): truncating it here could destroy chunks that shard has already written.  It is opened without
-          // O_TRUNC and sized to its full length from the index instead (idempotent, never cuts live data).
-          auto same_path = [&](uint64_t r) {
-            return ix.path_off[r + 1] - ix.path_off[r] == rel.size() && memcmp(ix.paths.data() + ix.path_off[r], rel.data(), rel.size()) == 0;
-          };
-          const bool shared = (row_lo > 0 && same_path(row_lo - 1)) || (row_hi < ix.rows && same_path(row_hi));
-          const int fd = open(full.c_str(), O_CREAT | O_WRONLY | (again || shared ? 0 : O_TRUNC), 0644);
-          if (fd < 0) { set_err(err, errcap, "failed to open output file " + full); rc = ZN_E_ARG; break; }
-          if (shared && !again) {
-            uint64_t a = w_hi, b = w_hi, size = 0;
-            while (a > 0 && same_path(a - 1)) a--;
-            while (b + 1 < ix.rows && same_path(b + 1)) b++;
-            for (uint64_t r = a; r <= b; r++) size = std::max(size, ix.col[2][r] + ix.col[3][r]);
-            if (ftruncate(fd, (off_t)size) != 0) { close(fd); set_err(err, errcap, "failed to size output file " + full); rc = ZN_E_ARG; break; }
-          }
-          it = open_files.emplace(rel, fd).first;
+      // 1. the window: rows up to max_open distinct paths (rows of a file are adjacent, so a path that differs from its
+      //    predecessor's is looked up, every other row reuses the previous answer)
+      std::unordered_map<std::string_view, uint32_t> at;
+      std::vector<uint32_t> row_file;
+      std::vector<std::string_view> lazy_dirs;  // paths of this window's one-row files (their directories must exist)
+      uint32_t prev = ~0u;
+      auto path_of = [&](uint64_t r) { return std::string_view(ix.paths.data() + ix.path_off[r], ix.path_off[r + 1] - ix.path_off[r]); };
+      for (; w_hi < row_hi; w_hi++) {
+        const std::string_view rel = path_of(w_hi);
+        // a file that is exactly this one row needs no descriptor here: the writer thread that holds the row opens, writes
+        // and closes it (zn_decompress_rows_ex); only multi-row files count against the descriptor window
+        if ((w_hi == 0 || path_of(w_hi - 1) != rel) && (w_hi + 1 >= ix.rows || path_of(w_hi + 1) != rel) && !created.count(std::string(rel))) {
+          lazy_dirs.push_back(rel);
+          row_file.push_back(~0u);
+          prev = ~0u;
+          continue;
         }
-        fds[w_hi] = it->second;
+        uint32_t fi;
+        if (prev != ~0u && open_files[prev].rel == rel) fi = prev;
+        else {
+          auto it = at.find(rel);
+          if (it != at.end()) fi = it->second;
+          else {
+            if (open_files.size() >= max_open) break;
+            fi = (uint32_t)open_files.size();
+            OutFile of;
+            of.rel = rel;
+            of.first_row = w_hi;
+            open_files.push_back(of);
+            at.emplace(rel, fi);
+          }
+        }
+        row_file.push_back(fi);
+        prev = fi;
       }
+      // 2. directories (serial: few; out_dir itself first), 3. open / size the files (parallel)
+      if (made_dirs.insert("").second) {
+        for (size_t p = 1; p <= root.size(); p++)
+          if (p == root.size() || root[p] == '/') mkdir(root.substr(0, p).c_str(), 0755);
+      }
+      auto ensure_dir = [&](std::string_view rel) {
+        const size_t slash = rel.find_last_of('/');
+        if (slash == std::string_view::npos) return;
+        const std::string dir(rel.substr(0, slash));
+        if (!made_dirs.insert(dir).second) return;
+        const std::string full = root + "/" + dir;
+        for (size_t p = root.size() + 1; p <= full.size(); p++)
+          if (p == full.size() || full[p] == '/') mkdir(full.substr(0, p).c_str(), 0755);
+      };
+      {
+        std::string_view last_dir;
+        for (const std::string_view rel : lazy_dirs) {  // consecutive files share their directory: one set lookup per change
+          const size_t slash = rel.find_last_of('/');
+          const std::string_view dir = slash == std::string_view::npos ? std::string_view() : rel.substr(0, slash);
+          if (dir == last_dir) continue;
+          last_dir = dir;
+          ensure_dir(rel);
+        }
+      }
+      for (const OutFile& of : open_files) ensure_dir(of.rel);
+      for_each_parallel(open_files.size(), [&](size_t k) {
+        OutFile& of = open_files[k];
+        const std::string rel(of.rel);
+        const std::string full = root + "/" + rel;
+        const bool again = created.count(rel) != 0;  // (read-only here; the set is updated after the parallel part)
+        // A file whose rows straddle [row_lo, row_hi) is also written by the neighbouring shard (another process or
+        // GPU): truncating it here could destroy chunks that shard has already written.  It is opened without
+        // O_TRUNC and sized to its full length from the index instead (idempotent, never cuts live data).
+        auto same_path = [&](uint64_t r) {
+          return ix.path_off[r + 1] - ix.path_off[r] == rel.size() && memcmp(ix.paths.data() + ix.path_off[r], rel.data(), rel.size()) == 0;
+        };
+        const bool shared = (row_lo > 0 && same_path(row_lo - 1)) || (row_hi < ix.rows && same_path(row_hi));
+        of.fd = open(full.c_str(), O_CREAT | O_WRONLY | (again || shared ? 0 : O_TRUNC), 0644);
+        if (of.fd < 0) { of.err = 1; return; }
+        if (shared && !again) {
+          uint64_t a = of.first_row, b = of.first_row, size = 0;
+          while (a > 0 && same_path(a - 1)) a--;
+          while (b + 1 < ix.rows && same_path(b + 1)) b++;
+          for (uint64_t r = a; r <= b; r++) size = std::max(size, ix.col[2][r] + ix.col[3][r]);
+          if (ftruncate(of.fd, (off_t)size) != 0) of.err = 2;
+        }
+      });
+      for (const OutFile& of : open_files) {
+        created.insert(std::string(of.rel));
+        if (of.err && rc == ZN_OK) {
+          set_err(err, errcap, std::string(of.err == 1 ? "failed to open output file " : "failed to size output file ") + root + "/" + std::string(of.rel));
+          rc = ZN_E_ARG;
+        }
+      }
+      for (uint64_t r = w_lo; r < w_hi; r++) fds[r] = row_file[r - w_lo] == ~0u ? -2 : open_files[row_file[r - w_lo]].fd;
+      for (const std::string_view rel : lazy_dirs) created.insert(std::string(rel));
     } else {
       w_hi = row_hi;
     }
     if (rc == ZN_OK) {
       zn_verify_stats st;
-      rc = zn_decompress_rows(ctx, afd, w_lo, w_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.comp_eff.data(),
-                              ix.col[3].data(), ix.checksums.data(), save_data ? fds.data() : nullptr, batch_bytes, io_threads,
-                              corrupt.data(), &st);
+      rc = zn_decompress_rows_ex(ctx, afd, w_lo, w_hi, ix.col[0].data(), ix.col[1].data(), ix.col[2].data(), ix.comp_eff.data(),
+                                 ix.col[3].data(), ix.checksums.data(), save_data ? fds.data() : nullptr, batch_bytes, io_threads,
+                                 corrupt.data(), &st, root.c_str(), ix.paths.data(), ix.path_off.data());
       if (rc != ZN_OK) set_err(err, errcap, zn_last_error(ctx));
       total.corrupt_rows += st.corrupt_rows;
       total.total_written_bytes += st.total_written_bytes;
@@ -885,7 +973,7 @@ extern "C" int zn_archive_decompress(zn_ctx* ctx, const char* index_path, int sa
       total.corrupt_bytes += st.corrupt_bytes;
       total.total_chunks += st.total_chunks;
     }
-    for (auto& kv : open_files) close(kv.second);
+    for_each_parallel(open_files.size(), [&](size_t k) { if (open_files[k].fd >= 0) close(open_files[k].fd); });
     w_lo = w_hi;
   }
   if (rc == ZN_OK) {

@@ -1047,6 +1047,7 @@ extern "C" int zn_compress_batch(zn_ctx* c, const uint8_t* src_base, const uint6
 // staging slot by a few I/O threads, ONE zn_decode_verify_batch replaces the per-row decode + blake3 + compare, the
 // decoded bytes are pwritten at fdata_offset from the pinned output region, and status[] is folded into the
 // counters with the reference's rules (decompress.rs:140,156-184).
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -1084,10 +1085,28 @@ void parallel_rows(uint32_t n, int threads, F f, uint32_t serial_below = 7) {
 }
 }  // namespace
 
+// Internal (container.cpp): zn_decompress_rows plus LAZY rows — out_fd[row] == -2 means "this row is its file": the writer
+// thread that holds the row opens out_root/path(row) (O_CREAT | O_TRUNC), writes, closes.  A corpus of 100 000 one-row
+// files then needs no descriptor window at all, and its open / close calls run on the io threads beside the pwrites.
+extern "C" int zn_decompress_rows_ex(zn_ctx* c, int archive_fd, uint64_t row_lo, uint64_t row_hi, const uint64_t* blob_offset,
+                                     const uint64_t* blob_size, const uint64_t* fdata_offset, const uint8_t* compressed,
+                                     const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd,
+                                     size_t batch_bytes, int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats,
+                                     const char* out_root, const char* paths, const uint64_t* path_off);
+
 extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, uint64_t row_hi, const uint64_t* blob_offset,
                                   const uint64_t* blob_size, const uint64_t* fdata_offset, const uint8_t* compressed,
                                   const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd,
                                   size_t batch_bytes, int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats) {
+  return zn_decompress_rows_ex(c, archive_fd, row_lo, row_hi, blob_offset, blob_size, fdata_offset, compressed, uncompressed_size,
+                               checksums, out_fd, batch_bytes, io_threads, corrupt_rows_out, stats, nullptr, nullptr, nullptr);
+}
+
+extern "C" int zn_decompress_rows_ex(zn_ctx* c, int archive_fd, uint64_t row_lo, uint64_t row_hi, const uint64_t* blob_offset,
+                                     const uint64_t* blob_size, const uint64_t* fdata_offset, const uint8_t* compressed,
+                                     const uint64_t* uncompressed_size, const uint8_t* checksums, const int* out_fd,
+                                     size_t batch_bytes, int io_threads, uint64_t* corrupt_rows_out, zn_verify_stats* stats,
+                                     const char* out_root, const char* paths, const uint64_t* path_off) {
   if (!c || !stats || row_hi < row_lo) return ZN_E_ARG;
   if (row_hi > row_lo && (!blob_offset || !blob_size || !compressed || !uncompressed_size || !checksums)) return ZN_E_ARG;
   if (out_fd && !fdata_offset) return ZN_E_ARG;
@@ -1200,16 +1219,28 @@ extern "C" int zn_decompress_rows(zn_ctx* c, int archive_fd, uint64_t row_lo, ui
     });
   };
   auto start_write = [&](Batch& B) {
-    B.writer = std::thread([&B, &io_err, out_fd, uncompressed_size, fdata_offset, io_threads]() {
+    B.writer = std::thread([&B, &io_err, out_fd, uncompressed_size, fdata_offset, io_threads, out_root, paths, path_off]() {
       parallel_rows(B.n, io_threads, [&](uint32_t i) {  // pwrite at fdata_offset (decompress.rs:186-189)
         const uint32_t s = B.status[i];
-        if ((s != ZN_S_OK && s != ZN_S_DIGEST_MISMATCH) || out_fd[B.a + i] < 0) return;
-        uint64_t done = 0, len = uncompressed_size[B.a + i];
-        while (done < len) {
-          const ssize_t r = pwrite(out_fd[B.a + i], B.pin_out.p + B.out_off[i] + done, len - done, (off_t)(fdata_offset[B.a + i] + done));
-          if (r <= 0) { io_err = 1; return; }
-          done += (uint64_t)r;
+        const bool ok = s == ZN_S_OK || s == ZN_S_DIGEST_MISMATCH;
+        int fd = out_fd[B.a + i];
+        const bool lazy = fd == -2 && out_root && paths && path_off;
+        if (lazy) {  // the file exists afterwards even when its only chunk failed to decode, as with the reference's up-front creation
+          std::string full(out_root);
+          full += '/';
+          full.append(paths + path_off[B.a + i], (size_t)(path_off[B.a + i + 1] - path_off[B.a + i]));
+          fd = open(full.c_str(), O_CREAT | O_WRONLY | O_TRUNC, 0644);
+          if (fd < 0) { io_err = 1; return; }
         }
+        if (ok && fd >= 0) {
+          uint64_t done = 0, len = uncompressed_size[B.a + i];
+          while (done < len) {
+            const ssize_t r = pwrite(fd, B.pin_out.p + B.out_off[i] + done, len - done, (off_t)(fdata_offset[B.a + i] + done));
+            if (r <= 0) { io_err = 1; break; }
+            done += (uint64_t)r;
+          }
+        }
+        if (lazy) close(fd);
       });
     });
   };
