@@ -209,3 +209,26 @@ def test_native_reader_requires_exact_manifest_types(L, tmp_path):
         blob = sink.getvalue().to_pybytes()
         p.write_bytes(bytes(raw[:moff]) + blob + b"ZNPYMIDX" + moff.to_bytes(8, "little"))
         assert not L.zn_index_open(str(p).encode(), err, 256), col
+
+
+def test_native_reader_rejects_unknown_envelope_declaration(L, tmp_path):
+    """An archive may declare a blob envelope in its index metadata (znippy_envelope); one this reader does not know is
+    refused at open instead of being decoded as bare frames."""
+    from znippy_b200 import archive as A
+    err = C.create_string_buffer(256)
+    p = tmp_path / "e.znippy"
+    for value, ok in (("ZNB1", True), ("OZL9", False)):
+        md = dict(A.config_metadata(), znippy_envelope=value)
+        schema = A.INDEX_SCHEMA.with_metadata(md)
+        with open(p, "wb") as f:
+            f.write(b"B" * 77)
+            sink = A.ArrowIpcSink(f, 77)
+            sink.push_subindex((0, ""), schema, [A.build_metadata_batch([("a", 0, 0, True, 100, 10, 60, bytes(32))], schema)])
+            sink.finish()
+        h = L.zn_index_open(str(p).encode(), err, 256)
+        assert bool(h) == ok, (value, err.value)
+        if h:
+            assert L.zn_index_metadata(h, b"znippy_envelope") == b"ZNB1"
+            L.zn_index_close(h)
+        else:
+            assert b"envelope" in err.value

@@ -486,3 +486,21 @@ def test_fused_kernel_watchdog_ends_a_stalled_queue(codec, oracle, monkeypatch):
     monkeypatch.delenv("ZN_WS_TEST_STALL")
     st, dg = codec.decode_verify_batch(*args)
     assert not st.any() and dg[0].tobytes() == O.blake3(data)
+
+
+def test_store_as_is_row_with_disagreeing_sizes_is_refused(codec, oracle):
+    """a store-as-is row whose blob_size differs from its uncompressed_size used to be gathered with
+    blob_size bytes into an output slot sized for uncompressed_size — an out-of-bounds device write into the neighbours.
+    Such a row now gets SIZE_MISMATCH, nothing of it is written, and its neighbours come out intact."""
+    O = oracle
+    a, b, c = O.real_text(50_000).tobytes(), O.gen_random(70_000).tobytes(), O.real_text(30_000).tobytes()
+    blobs = [a, b, c]
+    buf, offs = _pack(blobs)
+    out_len = [len(a), 1_000, len(c)]            # the middle row claims 1 000 bytes for a 70 000-byte blob
+    out_off = [0, 50_016, 51_024]
+    out = np.full(51_024 + 30_000 + 64, 0xCD, np.uint8)
+    st, dg = codec.decode_verify_batch(buf, offs, [len(x) for x in blobs], [0, 0, 0], out_len, None, out, out_off)
+    assert st.tolist() == [codec.S_OK, codec.S_SIZE_MISMATCH, codec.S_OK]
+    assert out[:50_000].tobytes() == a and out[51_024:51_024 + 30_000].tobytes() == c
+    assert (out[51_024 + 30_000:] == 0xCD).all()  # (the refused row's own 1 000-byte range is unspecified, nothing beyond the rows is touched)
+    assert dg[0].tobytes() == O.blake3(a) and dg[2].tobytes() == O.blake3(c)
