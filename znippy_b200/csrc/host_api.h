@@ -52,10 +52,10 @@ struct PipelineLaunch {
   uint32_t* produced;
   uint32_t* exec_counter;
 };
-// Enqueues init, walk, tables, seq, lit, chain, exec on `st` (7 launches).  `marks` (nullable): 7 events, recorded before
-// the first kernel and after walk / tables / seq / lit / chain / exec.
+// Enqueues init, walk, tables, seq phase 1, seq phase 2, lit, chain, exec on `st` (8 launches).  `marks` (nullable): 7
+// events, recorded before the first kernel and after walk / tables / seq (both phases) / lit / chain / exec.
 void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks);
-constexpr uint32_t kPipelineLaunches = 7;
+constexpr uint32_t kPipelineLaunches = 8;
 void pipeline_trace_dump();  // development builds (ZN_TRACE_BUILD=1): prints and clears the exec kernel's phase counters
 }  // namespace zp
 

@@ -443,6 +443,7 @@ ZN_HD bool parse_table_descs(const uint8_t* src, const ZBlock* b, FseD* set, int
 struct HostTabs {
   const FseD* t[3];
   ZN_HD uint32_t ld(int k, uint32_t i) const { return t[k][i]; }
+  ZN_HD uint32_t ld1(int k, uint32_t i) const;  // phase-1 view of the same entry (two-phase form below)
   ZN_HD uint32_t base(int k, uint32_t s) const { return k == 0 ? zs::kLLBase[s] : zs::kMLBase[s]; }
 };
 
@@ -538,6 +539,213 @@ ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const Acc& tabs
   *lit_used = lit_pos;
   rep_fin[0] = h0; rep_fin[1] = h1; rep_fin[2] = h2;
   return true;
+}
+
+// ----------------------------------------------------------------------------------------------- seq, two-phase form
+// decode_sequences() above keeps ~200 instructions per sequence on ONE lane's in-order chain: the only true serial
+// dependence of the sequence section is state -> table entry -> bit count -> next state, everything else (extra-bit
+// values, baselines, repeat offsets, positions, record packing) merely rides along and stalls the chain whenever one of
+// its own loads is late.  The two-phase form splits them:
+//   phase 1 (seq_phase1, lane per block)   the state chain alone: per sequence three table reads, one add, one 32-bit
+//            field out of the stream at a computed bit position, three state updates.  It leaves {bit cursor, three
+//            states} — 8 bytes — in the sequence's record slot;
+//   phase 2 (seq_run_sum / seq_scan / seq_run_emit, CTA per block, a thread per RUN of consecutive sequences)  with
+//            cursor and states known, every sequence decodes independently: values out of the stream, then positions and
+//            repeat-offset histories as a prefix scan over the runs (a run's effect on the history is a map "slot i
+//            minus k | fixed value" per entry, and such maps compose), then the final 16-byte records — bit-identical to
+//            what decode_sequences() writes (tests/host_emu compares the two on every block).
+
+// Random-access view of a backward bit stream: bit positions count from the aligned word that holds the first stream
+// byte; bits below the stream (and any word outside it) read as zero, so over-reads are harmless and show up as a
+// final cursor != bias.
+struct SeqBits {
+  const uint32_t* wbase;
+  uint32_t lowmask;
+  int32_t top;   // last aligned word holding stream bytes
+  int32_t bias;  // cursor when every bit has been read (bits of word 0 that precede the stream)
+  int32_t c0;    // cursor at the start: the end marker's position
+  ZN_HD bool init(const uint8_t* p, uint32_t len) {
+    if (len == 0) return false;
+    const uint32_t last = p[len - 1];
+    if (last == 0) return false;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), s_al = a & ~(uintptr_t)3;
+    wbase = reinterpret_cast<const uint32_t*>(s_al);
+    bias = (int32_t)(a & 3) * 8;
+    lowmask = 0xFFFFFFFFu << bias;
+    top = (int32_t)((((a + len - 1) & ~(uintptr_t)3) - s_al) >> 2);
+    c0 = bias + (int32_t)(len - 1) * 8 + hibit32(last);
+    return true;
+  }
+  ZN_HD uint32_t word(int32_t i) const {
+    if (i < 0 || i > top) return 0u;
+#if defined(__CUDA_ARCH__)
+    const uint32_t w = __ldg(wbase + i);  // the blobs are read-only for the whole batch
+#else
+    const uint32_t w = wbase[i];
+#endif
+    return i == 0 ? (w & lowmask) : w;
+  }
+  ZN_HD uint32_t bits32(int32_t lo) const {  // the 32 bits at positions lo .. lo + 31 (lo may be negative)
+    const int32_t wi = lo >> 5;
+    return funnel_r(word(wi), word(wi + 1), (uint32_t)lo & 31u);
+  }
+};
+ZN_HD uint32_t lowbits(uint32_t v, uint32_t n) { return v & ((1u << n) - 1u); }  // n <= 31
+
+// phase-1 view of a decoding-table entry: next-state base | state bits << 16 | (state bits + extra bits) << 24
+ZN_HD uint32_t p1_entry(FseD e) { return fd_base(e) | (fd_nbits(e) << 16) | ((fd_nbits(e) + fd_extra(e)) << 24); }
+ZN_HD uint32_t HostTabs::ld1(int k, uint32_t i) const { return p1_entry(t[k][i]); }
+constexpr uint32_t kSeq2Threads = 128;  // phase 2: runs per block (threads of k_zseq2)
+ZN_HD void p1_store(SeqRec16* r, uint32_t cursor, uint32_t states) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint2*>(r) = make_uint2(cursor, states);
+#else
+  r->w0 = cursor; r->w1 = states;
+#endif
+}
+
+// Phase 1.  Acc::ld1(k, state) returns the phase-1 entry of table k.  Leaves {cursor before the sequence, LL | OF << 9 |
+// ML << 18 states} in rec[i].w0 / w1.  false = the stream does not end exactly where the sequences do.
+template <class Acc>
+ZN_HD bool seq_phase1(const uint8_t* src, const ZBlock* b, const Acc& tabs, const uint32_t* logs, SeqRec16* rec) {
+  const uint32_t nseq = b->nseq;
+  const uint32_t end = b->src_off + b->len;
+  if (b->bits_off >= end) return false;
+  SeqBits sb;
+  if (!sb.init(src + b->bits_off, end - b->bits_off)) return false;
+  int32_t c = sb.c0;
+  c -= (int32_t)logs[0];
+  uint32_t sl = lowbits(sb.bits32(c), logs[0]);
+  c -= (int32_t)logs[1];
+  uint32_t so = lowbits(sb.bits32(c), logs[1]);
+  c -= (int32_t)logs[2];
+  uint32_t sm = lowbits(sb.bits32(c), logs[2]);
+  if (c < sb.bias) return false;
+  for (uint32_t i = 0; i + 1 < nseq; i++) {
+    const uint32_t el = tabs.ld1(0, sl), eo = tabs.ld1(1, so), em = tabs.ld1(2, sm);
+    p1_store(rec + i, (uint32_t)c, sl | (so << 9) | (sm << 18));
+    c -= (int32_t)((el >> 24) + (eo >> 24) + (em >> 24));
+    const uint32_t f = sb.bits32(c);  // from the bottom: OF state bits, ML state bits, LL state bits (read in the opposite order)
+    const uint32_t no = (eo >> 16) & 0xFFu, nm = (em >> 16) & 0xFFu, nl = (el >> 16) & 0xFFu;
+    so = (eo & 0xFFFFu) + lowbits(f, no);
+    sm = (em & 0xFFFFu) + lowbits(f >> no, nm);
+    sl = (el & 0xFFFFu) + lowbits(f >> (no + nm), nl);
+  }
+  const uint32_t el = tabs.ld1(0, sl), eo = tabs.ld1(1, so), em = tabs.ld1(2, sm);
+  p1_store(rec + (nseq - 1), (uint32_t)c, sl | (so << 9) | (sm << 18));
+  c -= (int32_t)((el >> 24) + (eo >> 24) + (em >> 24));  // the last sequence has no state update
+  c += (int32_t)(((el >> 16) & 0xFFu) + ((eo >> 16) & 0xFFu) + ((em >> 16) & 0xFFu));
+  return c == sb.bias;
+}
+
+// Positions and repeat-offset history: at the start of a run (after the scan) or a run's own effect (before it).
+struct RunSum {
+  uint32_t lit, out;    // literals consumed / bytes produced; sums saturate at kRunSat
+  uint32_t h0, h1, h2;  // history, possibly symbolic (relative to whatever precedes)
+};
+constexpr uint32_t kRunSat = 1u << 30;
+ZN_HD uint32_t sat_add(uint32_t a, uint32_t b) { const uint32_t s = a + b; return s < kRunSat ? s : kRunSat; }  // a, b <= 2^30
+
+// v as left by a run that starts with history (r0, r1, r2) — themselves symbolic or fixed; 0 = invalid, as in sym_resolve
+ZN_HD uint32_t sym_compose(uint32_t v, uint32_t r0, uint32_t r1, uint32_t r2) {
+  if (!is_sym(v)) return v;
+  const uint32_t i = v & 3u, k = (v >> 2) & 0x1FFFFFFFu;
+  const uint32_t base = i == 0 ? r0 : (i == 1 ? r1 : r2);
+  if (is_sym(base)) return base + (k << 2);
+  return base > k ? base - k : 0u;
+}
+
+// One sequence's effect on the history (RFC 8878 §3.1.1.5); returns its offset.  *zero is set when a fixed offset
+// reaches 0 (corrupt) — only meaningful when the history is relative to the block start.
+ZN_HD uint32_t rep_step(uint32_t ov, uint32_t ll, uint32_t& h0, uint32_t& h1, uint32_t& h2, uint32_t* zero) {
+  uint32_t offset;
+  if (ov > 3) {
+    offset = ov - 3;
+    h2 = h1; h1 = h0; h0 = offset;
+  } else {
+    const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+    if (idx == 0) offset = h0;
+    else {
+      if (idx == 3) {
+        if (is_sym(h0)) offset = sym_minus1(h0);
+        else { offset = h0 - 1; *zero |= offset == 0; }
+      } else offset = idx == 1 ? h1 : h2;
+      if (idx != 1) h2 = h1;
+      h1 = h0;
+      h0 = offset;
+    }
+  }
+  return offset;
+}
+
+// Phase 2, values of one sequence from its phase-1 slot.  Acc::ld(k, state) = FseD entry, Acc::base(k, sym) = baseline.
+template <class Acc>
+ZN_HD void seq_values(const SeqBits& sb, const Acc& tabs, const SeqRec16* slot, uint32_t* ll, uint32_t* ml, uint32_t* ov) {
+#if defined(__CUDA_ARCH__)
+  const uint2 p = *reinterpret_cast<const uint2*>(slot);
+  const uint32_t w0 = p.x, w1 = p.y;
+#else
+  const uint32_t w0 = slot->w0, w1 = slot->w1;
+#endif
+  const uint32_t el = tabs.ld(0, w1 & 511u), eo = tabs.ld(1, (w1 >> 9) & 511u), em = tabs.ld(2, w1 >> 18);
+  const uint32_t ofx = fd_extra(eo), mlx = fd_extra(em), llx = fd_extra(el);
+  const int32_t c1 = (int32_t)w0 - (int32_t)ofx;              // offset extra bits: [c1, c1 + ofx)
+  const int32_t c2 = c1 - (int32_t)(mlx + llx);                // then ML extras above LL extras: [c2, c2 + llx + mlx)
+  const uint32_t ofv = lowbits(sb.bits32(c1), ofx);
+  const uint32_t g = sb.bits32(c2);
+  *ov = (1u << fd_sym(eo)) + ofv;
+  *ml = tabs.base(2, fd_sym(em)) + lowbits(g >> llx, mlx);
+  *ll = tabs.base(0, fd_sym(el)) + lowbits(g, llx);
+}
+
+// Phase 2, first pass: what the sequences [i0, i1) of a block add to the positions and do to the history.
+template <class Acc>
+ZN_HD RunSum seq_run_sum(const SeqBits& sb, const Acc& tabs, const SeqRec16* rec, uint32_t i0, uint32_t i1) {
+  RunSum r;
+  r.lit = 0; r.out = 0; r.h0 = sym_make(0); r.h1 = sym_make(1); r.h2 = sym_make(2);
+  uint32_t zero = 0;
+  for (uint32_t i = i0; i < i1; i++) {
+    uint32_t ll, ml, ov;
+    seq_values(sb, tabs, rec + i, &ll, &ml, &ov);
+    rep_step(ov, ll, r.h0, r.h1, r.h2, &zero);
+    r.lit = sat_add(r.lit, ll);
+    r.out = sat_add(r.out, ll + ml);
+  }
+  return r;
+}
+
+// Exclusive scan over the runs of a block (one thread): runs[t] becomes the state at the start of run t; returns the
+// state after the last run.
+ZN_HD RunSum seq_scan(RunSum* runs, uint32_t n) {
+  RunSum acc;
+  acc.lit = 0; acc.out = 0; acc.h0 = sym_make(0); acc.h1 = sym_make(1); acc.h2 = sym_make(2);
+  for (uint32_t t = 0; t < n; t++) {
+    const RunSum r = runs[t];
+    runs[t] = acc;
+    const uint32_t n0 = sym_compose(r.h0, acc.h0, acc.h1, acc.h2), n1 = sym_compose(r.h1, acc.h0, acc.h1, acc.h2),
+                   n2 = sym_compose(r.h2, acc.h0, acc.h1, acc.h2);
+    acc.h0 = n0; acc.h1 = n1; acc.h2 = n2;
+    acc.lit = sat_add(acc.lit, r.lit);
+    acc.out = sat_add(acc.out, r.out);
+  }
+  return acc;
+}
+
+// Phase 2, second pass: final records of the sequences [i0, i1), given the state at i0.  Returns nonzero when a
+// sequence breaks a block limit (the same conditions decode_sequences() checks).
+template <class Acc>
+ZN_HD uint32_t seq_run_emit(const SeqBits& sb, const Acc& tabs, SeqRec16* rec, uint32_t i0, uint32_t i1, uint32_t lit_len, RunSum st) {
+  uint32_t bad = 0;
+  for (uint32_t i = i0; i < i1; i++) {
+    uint32_t ll, ml, ov;
+    seq_values(sb, tabs, rec + i, &ll, &ml, &ov);
+    const uint32_t offset = rep_step(ov, ll, st.h0, st.h1, st.h2, &bad);
+    bad |= (st.lit + ll > lit_len) | (st.out + ll + ml > kZstdBlockMax);
+    rec_store(rec + i, rec_pack(st.out & 0x3FFFFu, st.lit & 0x3FFFFu, ll & 0x3FFFFu, ml & 0x3FFFFu, offset));
+    st.lit = sat_add(st.lit, ll);
+    st.out = sat_add(st.out, ll + ml);
+  }
+  return bad;
 }
 
 // ------------------------------------------------------------------------------------------------------------- lit
@@ -799,7 +1007,39 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
       }
     }
     if (!ok) continue;
-    if (decode_sequences(src, b, st, logs, recs.data() + b->seq_base, &b->matched, &b->lit_used, b->rep_fin)) b->st_seq = 0;
+    // the one-pass form is the cross-check, the two-phase form (as k_zseq1 / k_zseq2 run it) is what the pipeline uses
+    std::vector<SeqRec16> ref(b->nseq);
+    uint32_t ref_matched = 0, ref_lit = 0, ref_rep[3] = {0, 0, 0};
+    const bool ok_ref = decode_sequences(src, b, st, logs, ref.data(), &ref_matched, &ref_lit, ref_rep);
+    SeqRec16* rec = recs.data() + b->seq_base;
+    bool ok2 = seq_phase1(src, b, st, logs, rec);
+    if (ok2) {
+      SeqBits sb;
+      sb.init(src + b->bits_off, b->src_off + b->len - b->bits_off);
+      RunSum runs[kSeq2Threads];
+      const uint32_t R = (b->nseq + kSeq2Threads - 1) / kSeq2Threads;
+      for (uint32_t t = 0; t < kSeq2Threads; t++) {
+        const uint32_t i0 = std::min(t * R, b->nseq), i1 = std::min(i0 + R, b->nseq);
+        runs[t] = seq_run_sum(sb, st, rec, i0, i1);
+      }
+      const RunSum tot = seq_scan(runs, kSeq2Threads);
+      uint32_t bad = 0;
+      for (uint32_t t = 0; t < kSeq2Threads; t++) {
+        const uint32_t i0 = std::min(t * R, b->nseq), i1 = std::min(i0 + R, b->nseq);
+        bad |= seq_run_emit(sb, st, rec, i0, i1, b->lit_regen, runs[t]);
+      }
+      ok2 = bad == 0;
+      if (ok2) {
+        b->matched = tot.out; b->lit_used = tot.lit;
+        b->rep_fin[0] = tot.h0; b->rep_fin[1] = tot.h1; b->rep_fin[2] = tot.h2;
+      }
+    }
+    if (ok2 != ok_ref) return 2;
+    if (ok2) {
+      if (memcmp(ref.data(), rec, (size_t)b->nseq * sizeof(SeqRec16)) != 0) return 2;
+      if (b->matched != ref_matched || b->lit_used != ref_lit || memcmp(b->rep_fin, ref_rep, sizeof ref_rep) != 0) return 2;
+      b->st_seq = 0;
+    }
   }
   // lit
   for (uint32_t j = 0; j < nb; j++) {

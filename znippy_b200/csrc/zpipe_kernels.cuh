@@ -237,6 +237,143 @@ __global__ void __launch_bounds__(32) k_zseq_g(ZArgs a, int cg) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------- seq, two-phase form
+// (zpipe.cuh, "seq, two-phase form").  Phase 1 is the state chain alone, one lane per block; phase 2 decodes the values
+// of every sequence independently, a thread per run of consecutive sequences, and writes the final records.
+
+// Where a block's three tables come from (own set, an earlier block's, predefined) and their logs; false = undefined.
+ZN_D bool seq_table_sources(const ZArgs& a, const ZBlock* b, const ZBlob& z, const FseD** t, uint32_t* logs) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const uint32_t offs = k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML);
+    const uint32_t def = b->seq_def[k];
+    t[k] = g_zpredef + offs;
+    logs[k] = k == 1 ? 5u : 6u;
+    if (def == kDefNone) ok = false;
+    else if (def != kDefPredef) {
+      const ZBlock* db = &a.blocks[z.slot0 + def];
+      if (db->bits_off == ~0u || db->tab_slot == kNoSlot) ok = false;
+      else {
+        t[k] = a.tabs + (size_t)db->tab_slot * kTabSet + offs;
+        logs[k] = (db->tlogs >> (8 * k)) & 0xFFu;
+      }
+    }
+  }
+  return ok;
+}
+
+// phase 1, tables in shared memory in the phase-1 entry format (converted while they are copied in)
+struct SmemTabs1 {
+  uint32_t tab_s;
+  ZN_D uint32_t ld1(int k, uint32_t i) const { return lds32_ro(tab_s + 4u * ((k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML)) + i)); }
+};
+constexpr uint32_t kSeq1Smem = kSeqLanes * kTabSet * 4;
+
+__global__ void __launch_bounds__(64, 1) k_zseq1(ZArgs a) {
+  extern __shared__ __align__(16) uint8_t seq_smem[];
+  const uint32_t tid = threadIdx.x;
+  if (tid >= kSeqLanes) return;
+  SmemTabs1 st;
+  st.tab_s = (uint32_t)__cvta_generic_to_shared(seq_smem) + tid * kTabSet * 4;
+  const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
+  for (uint32_t it = blockIdx.x * kSeqLanes + tid; it < n_comp; it += gridDim.x * kSeqLanes) {
+    const uint32_t slot = a.comp_list[it];
+    if (slot == kNoSlot) continue;
+    ZBlock* b = &a.blocks[slot];
+    if (b->nseq == 0 || b->bits_off == ~0u) continue;
+    const ZBlob z = a.zb[b->pad[0]];
+    const BlobDesc d = a.blobs[z.blob];
+    const FseD* t[3];
+    uint32_t logs[3];
+    if (!seq_table_sources(a, b, z, t, logs)) continue;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint32_t n = 1u << logs[k], dst = st.tab_s + 4u * (k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML));
+#pragma unroll 8
+      for (uint32_t i = 0; i < n; i++) sts32(dst + 4 * i, p1_entry(t[k][i]));
+    }
+    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.recs + b->seq_base)) b->st_seq = 2;
+  }
+}
+
+// phase 1 with the tables left in global memory (every block of the batch at once, one L2 round trip on the chain)
+struct GlobalTabs1 {
+  const FseD* t[3];
+  ZN_D uint32_t ld1(int k, uint32_t i) const { return p1_entry(__ldcg(t[k] + i)); }
+};
+
+__global__ void __launch_bounds__(32) k_zseq1_g(ZArgs a) {
+  const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
+  for (uint32_t it = blockIdx.x * 32 + threadIdx.x; it < n_comp; it += gridDim.x * 32) {
+    const uint32_t slot = a.comp_list[it];
+    if (slot == kNoSlot) continue;
+    ZBlock* b = &a.blocks[slot];
+    if (b->nseq == 0 || b->bits_off == ~0u) continue;
+    const ZBlob z = a.zb[b->pad[0]];
+    const BlobDesc d = a.blobs[z.blob];
+    GlobalTabs1 st;
+    uint32_t logs[3];
+    if (!seq_table_sources(a, b, z, st.t, logs)) continue;
+    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.recs + b->seq_base)) b->st_seq = 2;
+  }
+}
+
+// phase 2: one CTA per block, a thread per run of consecutive sequences
+struct GlobalTabs2 {
+  const FseD* t[3];
+  uint32_t lut_s;
+  ZN_D uint32_t ld(int k, uint32_t i) const { return __ldg(t[k] + i); }
+  ZN_D uint32_t base(int k, uint32_t sym) const { return lds32_ro(lut_s + 4u * ((k == 0 ? 0u : 36u) + sym)); }
+};
+
+__global__ void __launch_bounds__(kSeq2Threads) k_zseq2(ZArgs a) {
+  __shared__ uint32_t s_lut[36 + 53];
+  __shared__ RunSum s_run[kSeq2Threads];
+  __shared__ uint32_t s_bad;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < 36; i += kSeq2Threads) s_lut[i] = zs::kLLBase[i];
+  for (uint32_t i = tid; i < 53; i += kSeq2Threads) s_lut[36 + i] = zs::kMLBase[i];
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  GlobalTabs2 st;
+  st.lut_s = (uint32_t)__cvta_generic_to_shared(s_lut);
+  const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
+  for (uint32_t it = blockIdx.x; it < n_comp; it += gridDim.x) {
+    const uint32_t slot = a.comp_list[it];
+    if (slot == kNoSlot) continue;
+    ZBlock* b = &a.blocks[slot];
+    const uint32_t nseq = b->nseq;
+    if (nseq == 0 || b->st_seq != 2) continue;  // phase 1 did not get through: the blob goes to the legacy decoder
+    const ZBlob z = a.zb[b->pad[0]];
+    const BlobDesc d = a.blobs[z.blob];
+    const uint8_t* src = a.blobs_base + d.src_off;
+    uint32_t logs[3];
+    seq_table_sources(a, b, z, st.t, logs);
+    SeqBits sb;
+    sb.init(src + b->bits_off, b->src_off + b->len - b->bits_off);
+    SeqRec16* rec = a.recs + b->seq_base;
+    const uint32_t R = (nseq + kSeq2Threads - 1) / kSeq2Threads;
+    const uint32_t i0 = min(tid * R, nseq), i1 = min(i0 + R, nseq);
+    s_run[tid] = seq_run_sum(sb, st, rec, i0, i1);
+    __syncthreads();
+    if (tid == 0) {
+      const RunSum tot = seq_scan(s_run, kSeq2Threads);
+      b->matched = tot.out;
+      b->lit_used = tot.lit;
+      b->rep_fin[0] = tot.h0; b->rep_fin[1] = tot.h1; b->rep_fin[2] = tot.h2;
+    }
+    __syncthreads();
+    if (seq_run_emit(sb, st, rec, i0, i1, b->lit_regen, s_run[tid])) s_bad = 1;
+    __syncthreads();
+    if (tid == 0) {
+      if (!s_bad) b->st_seq = 0;
+      s_bad = 0;
+    }
+    __syncthreads();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------------- lit
 __global__ void __launch_bounds__(kLitBlocks * 4) k_zlit(ZArgs a) {
   extern __shared__ __align__(16) uint8_t lit_smem[];
