@@ -17,6 +17,17 @@ inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 inline int hibit32(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
 #endif
 
+// Non-blocking prefetch of the line that holds p.  A lane that walks its own bit stream has ONE dependent load in flight;
+// a sector it has not seen yet costs thousands of cycles (DRAM + address translation, every lane in another page), so the
+// lane-per-stream decoders ask for their bytes a few hundred bytes before they get there.
+#if defined(__CUDA_ARCH__)
+ZN_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+ZN_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+inline void prefetch_l1(const void*) {}
+inline void prefetch_l2(const void*) {}
+#endif
+
 ZN_HD uint32_t ld8(const uint8_t* p) { return *p; }
 ZN_HD uint32_t ld16le(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 ZN_HD uint32_t ld24le(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
@@ -65,7 +76,12 @@ struct BackBits {
   ZN_HD uint32_t fetch_raw(int32_t i) const { return i < 0 ? 0u : wbase[i]; }
   // after widx moved down by one: the word for the next refill
   ZN_HD void advance() {
-    if (kDepth > 1) { pre = pre2; pre2 = fetch_raw(widx - 1); }
+    if (kDepth > 1) {
+      pre = pre2; pre2 = fetch_raw(widx - 1);
+      const int32_t f1 = widx - 64, f2 = widx - 256;  // lane-per-stream decoders: 256 B / 1 KiB ahead (backward stream)
+      prefetch_l1(wbase + (f1 > 0 ? f1 : 0));
+      prefetch_l2(wbase + (f2 > 0 ? f2 : 0));
+    }
     else pre = fetch_raw(widx);
   }
   ZN_HD uint32_t pre_word() const { return widx == 0 ? (pre & lowmask) : pre; }  // the word in `pre`, masked at the time of use

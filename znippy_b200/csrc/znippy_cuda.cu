@@ -60,6 +60,7 @@ struct zn_ctx {
     zp::ZBlock* blocks = nullptr; uint32_t* comp_list = nullptr; size_t slots = 0;
     zp::FseD* tabs = nullptr; size_t tab_sets = 0;
     zp::SeqRec16* recs = nullptr; size_t seqs = 0;
+    zp::SeqP1* p1 = nullptr; size_t p1s = 0;
     uint8_t* lits = nullptr; size_t lit16 = 0;
     zp::ZPools* pools = nullptr;
   } zs;
@@ -208,7 +209,7 @@ extern "C" void zn_ctx_destroy(zn_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->d_lit) cudaFree(c->d_lit);
   if (c->d_par) cudaFree(c->d_par);
-  for (void* q : {(void*)c->zs.blocks, (void*)c->zs.comp_list, (void*)c->zs.tabs, (void*)c->zs.recs, (void*)c->zs.lits, (void*)c->zs.pools})
+  for (void* q : {(void*)c->zs.blocks, (void*)c->zs.comp_list, (void*)c->zs.tabs, (void*)c->zs.recs, (void*)c->zs.p1, (void*)c->zs.lits, (void*)c->zs.pools})
     if (q) cudaFree(q);
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
@@ -529,7 +530,7 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
     const size_t slots_before = z.slots;
     size_t dummy = slots_before;
     if (!zgrow(&z.blocks, &z.slots, p->z_slots, sizeof(zp::ZBlock)) || !zgrow(&z.comp_list, &dummy, p->z_slots, 4) ||
-        !zgrow(&z.tabs, &z.tab_sets, p->z_tabs, sizeof(zp::FseD) * zp::kTabSet) || !zgrow(&z.recs, &z.seqs, p->z_seqs, sizeof(zp::SeqRec16)) ||
+        !zgrow(&z.tabs, &z.tab_sets, p->z_tabs, sizeof(zp::FseD) * zp::kTabSet) || !zgrow(&z.recs, &z.seqs, p->z_seqs, sizeof(zp::SeqRec16)) || !zgrow(&z.p1, &z.p1s, p->z_seqs, sizeof(zp::SeqP1)) ||
         !zgrow(&z.lits, &z.lit16, p->z_lit16 + 4, 16)) {
       c->err = "zstd pipeline scratch allocation failed";
       return ZN_E_NOMEM;
@@ -537,10 +538,10 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
   }
   zp::ZArgs a;
   a.blobs = p->d_blobs; a.blobs_base = d_blobs; a.zb = p->d_zb; a.nzb = p->nzb; a.blocks = z.blocks; a.pools = z.pools;
-  a.comp_list = z.comp_list; a.tabs = z.tabs; a.recs = z.recs; a.lits = z.lits;
+  a.comp_list = z.comp_list; a.tabs = z.tabs; a.recs = z.recs; a.lits = z.lits; a.p1 = z.p1;
   // development: ZN_ZPROF=1 prints the device time of every pipeline kernel of this run on stderr (synchronises)
   const bool prof = getenv("ZN_ZPROF") != nullptr;
-  cudaEvent_t pe[8];
+  cudaEvent_t pe[9];
   if (prof) for (auto& e : pe) cudaEventCreate(&e);
   uint32_t* ctr = p->d_counter + DC_COUNT;  // [0] exec, [1] legacy pass
   zp::PipelineLaunch L;
@@ -568,6 +569,7 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
     for (auto& b : hz) handed += b.state != 0;
     fprintf(stderr, "zpipe: %u blobs (%u handed back), %u blocks, %u seqs, %u table sets, %u lit16 |", p->nzb, handed, hp.comp_used, hp.seq_used, hp.tab_used, hp.lit_used16);
     for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
+    if (getenv("ZN_ZPROF_SEQ1")) { float ms = 0; if (cudaEventElapsedTime(&ms, pe[2], pe[8]) == cudaSuccess) fprintf(stderr, " (seq phase 1 %.3f)", ms); else cudaGetLastError(); }
     fprintf(stderr, " ms\n");
     zp::pipeline_trace_dump();
     for (auto& e : pe) cudaEventDestroy(e);

@@ -114,6 +114,10 @@ struct ZPools {
   uint32_t comp_used, comp_cap;    // compressed blocks (work list of the tables / seq / lit phases)
 };
 
+// what phase 1 of the sequence stage leaves per sequence: bit cursor before it, LL | OF << 9 | ML << 18 states
+struct alignas(8) SeqP1 {
+  uint32_t cursor, states;
+};
 // 16-byte sequence record
 struct alignas(16) SeqRec16 {
   uint32_t w0, w1, w2, w3;
@@ -130,6 +134,7 @@ struct ZArgs {
   FseD* tabs;
   SeqRec16* recs;
   uint8_t* lits;
+  struct SeqP1* p1;  // phase-1 output of the sequence stage, one entry per record slot
 };
 
 ZN_HD SeqRec16 rec_pack(uint32_t out_rel, uint32_t lit_rel, uint32_t ll, uint32_t ml, uint32_t off) {
@@ -548,12 +553,14 @@ ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const Acc& tabs
 // its own loads is late.  The two-phase form splits them:
 //   phase 1 (seq_phase1, lane per block)   the state chain alone: per sequence three table reads, one add, one 32-bit
 //            field out of the stream at a computed bit position, three state updates.  It leaves {bit cursor, three
-//            states} — 8 bytes — in the sequence's record slot;
-//   phase 2 (seq_run_sum / seq_scan / seq_run_emit, CTA per block, a thread per RUN of consecutive sequences)  with
-//            cursor and states known, every sequence decodes independently: values out of the stream, then positions and
-//            repeat-offset histories as a prefix scan over the runs (a run's effect on the history is a map "slot i
-//            minus k | fixed value" per entry, and such maps compose), then the final 16-byte records — bit-identical to
-//            what decode_sequences() writes (tests/host_emu compares the two on every block).
+//            states} — 8 bytes, densely packed so that four sequences complete a 32-byte sector (a half-written sector
+//            costs a read-modify-write in ECC memory) — in the p1 pool;
+//   phase 2 (k_zseq2 on the device, seq_phase2_host here: a warp per block, a LANE PER SEQUENCE, 32 consecutive
+//            sequences per step)  with cursor and states known every sequence decodes independently and every access
+//            is coalesced: values out of the stream, then positions as a prefix sum and repeat-offset histories as a
+//            prefix scan — one sequence's effect on the history is a map "slot i minus k | fixed value" per entry, and
+//            such maps compose (sym_compose) — then the final 16-byte records, bit-identical to what decode_sequences()
+//            writes (tests/host_emu compares the two on every block).
 
 // Random-access view of a backward bit stream: bit positions count from the aligned word that holds the first stream
 // byte; bits below the stream (and any word outside it) read as zero, so over-reads are harmless and show up as a
@@ -585,6 +592,11 @@ struct SeqBits {
 #endif
     return i == 0 ? (w & lowmask) : w;
   }
+  ZN_HD void prefetch(int32_t c) const {  // the stream 256 B / 1 KiB below bit position c
+    const int32_t f1 = (c >> 5) - 64, f2 = (c >> 5) - 256;
+    prefetch_l1(wbase + (f1 > 0 ? f1 : 0));
+    prefetch_l2(wbase + (f2 > 0 ? f2 : 0));
+  }
   ZN_HD uint32_t bits32(int32_t lo) const {  // the 32 bits at positions lo .. lo + 31 (lo may be negative)
     const int32_t wi = lo >> 5;
     return funnel_r(word(wi), word(wi + 1), (uint32_t)lo & 31u);
@@ -595,19 +607,18 @@ ZN_HD uint32_t lowbits(uint32_t v, uint32_t n) { return v & ((1u << n) - 1u); } 
 // phase-1 view of a decoding-table entry: next-state base | state bits << 16 | (state bits + extra bits) << 24
 ZN_HD uint32_t p1_entry(FseD e) { return fd_base(e) | (fd_nbits(e) << 16) | ((fd_nbits(e) + fd_extra(e)) << 24); }
 ZN_HD uint32_t HostTabs::ld1(int k, uint32_t i) const { return p1_entry(t[k][i]); }
-constexpr uint32_t kSeq2Threads = 128;  // phase 2: runs per block (threads of k_zseq2)
-ZN_HD void p1_store(SeqRec16* r, uint32_t cursor, uint32_t states) {
+ZN_HD void p1_store(SeqP1* r, uint32_t cursor, uint32_t states) {
 #if defined(__CUDA_ARCH__)
   *reinterpret_cast<uint2*>(r) = make_uint2(cursor, states);
 #else
-  r->w0 = cursor; r->w1 = states;
+  r->cursor = cursor; r->states = states;
 #endif
 }
 
 // Phase 1.  Acc::ld1(k, state) returns the phase-1 entry of table k.  Leaves {cursor before the sequence, LL | OF << 9 |
-// ML << 18 states} in rec[i].w0 / w1.  false = the stream does not end exactly where the sequences do.
+// ML << 18 states} in rec[i].  false = the stream does not end exactly where the sequences do.
 template <class Acc>
-ZN_HD bool seq_phase1(const uint8_t* src, const ZBlock* b, const Acc& tabs, const uint32_t* logs, SeqRec16* rec) {
+ZN_HD bool seq_phase1(const uint8_t* src, const ZBlock* b, const Acc& tabs, const uint32_t* logs, SeqP1* rec) {
   const uint32_t nseq = b->nseq;
   const uint32_t end = b->src_off + b->len;
   if (b->bits_off >= end) return false;
@@ -624,6 +635,7 @@ ZN_HD bool seq_phase1(const uint8_t* src, const ZBlock* b, const Acc& tabs, cons
   for (uint32_t i = 0; i + 1 < nseq; i++) {
     const uint32_t el = tabs.ld1(0, sl), eo = tabs.ld1(1, so), em = tabs.ld1(2, sm);
     p1_store(rec + i, (uint32_t)c, sl | (so << 9) | (sm << 18));
+    sb.prefetch(c);
     c -= (int32_t)((el >> 24) + (eo >> 24) + (em >> 24));
     const uint32_t f = sb.bits32(c);  // from the bottom: OF state bits, ML state bits, LL state bits (read in the opposite order)
     const uint32_t no = (eo >> 16) & 0xFFu, nm = (em >> 16) & 0xFFu, nl = (el >> 16) & 0xFFu;
@@ -680,12 +692,12 @@ ZN_HD uint32_t rep_step(uint32_t ov, uint32_t ll, uint32_t& h0, uint32_t& h1, ui
 
 // Phase 2, values of one sequence from its phase-1 slot.  Acc::ld(k, state) = FseD entry, Acc::base(k, sym) = baseline.
 template <class Acc>
-ZN_HD void seq_values(const SeqBits& sb, const Acc& tabs, const SeqRec16* slot, uint32_t* ll, uint32_t* ml, uint32_t* ov) {
+ZN_HD void seq_values(const SeqBits& sb, const Acc& tabs, const SeqP1* slot, uint32_t* ll, uint32_t* ml, uint32_t* ov) {
 #if defined(__CUDA_ARCH__)
   const uint2 p = *reinterpret_cast<const uint2*>(slot);
   const uint32_t w0 = p.x, w1 = p.y;
 #else
-  const uint32_t w0 = slot->w0, w1 = slot->w1;
+  const uint32_t w0 = slot->cursor, w1 = slot->states;
 #endif
   const uint32_t el = tabs.ld(0, w1 & 511u), eo = tabs.ld(1, (w1 >> 9) & 511u), em = tabs.ld(2, w1 >> 18);
   const uint32_t ofx = fd_extra(eo), mlx = fd_extra(em), llx = fd_extra(el);
@@ -698,55 +710,53 @@ ZN_HD void seq_values(const SeqBits& sb, const Acc& tabs, const SeqRec16* slot, 
   *ll = tabs.base(0, fd_sym(el)) + lowbits(g, llx);
 }
 
-// Phase 2, first pass: what the sequences [i0, i1) of a block add to the positions and do to the history.
+#if !defined(__CUDA_ARCH__)
+// Phase 2 as k_zseq2 runs it, with the warp's 32 lanes as arrays: steps of 32 consecutive sequences; inclusive
+// Hillis-Steele scans over the lanes for the two sums and for the history maps; the state after a step is carried into
+// the next.  Returns false when a sequence breaks a block limit (the conditions decode_sequences() checks).
 template <class Acc>
-ZN_HD RunSum seq_run_sum(const SeqBits& sb, const Acc& tabs, const SeqRec16* rec, uint32_t i0, uint32_t i1) {
-  RunSum r;
-  r.lit = 0; r.out = 0; r.h0 = sym_make(0); r.h1 = sym_make(1); r.h2 = sym_make(2);
-  uint32_t zero = 0;
-  for (uint32_t i = i0; i < i1; i++) {
-    uint32_t ll, ml, ov;
-    seq_values(sb, tabs, rec + i, &ll, &ml, &ov);
-    rep_step(ov, ll, r.h0, r.h1, r.h2, &zero);
-    r.lit = sat_add(r.lit, ll);
-    r.out = sat_add(r.out, ll + ml);
-  }
-  return r;
-}
-
-// Exclusive scan over the runs of a block (one thread): runs[t] becomes the state at the start of run t; returns the
-// state after the last run.
-ZN_HD RunSum seq_scan(RunSum* runs, uint32_t n) {
-  RunSum acc;
-  acc.lit = 0; acc.out = 0; acc.h0 = sym_make(0); acc.h1 = sym_make(1); acc.h2 = sym_make(2);
-  for (uint32_t t = 0; t < n; t++) {
-    const RunSum r = runs[t];
-    runs[t] = acc;
-    const uint32_t n0 = sym_compose(r.h0, acc.h0, acc.h1, acc.h2), n1 = sym_compose(r.h1, acc.h0, acc.h1, acc.h2),
-                   n2 = sym_compose(r.h2, acc.h0, acc.h1, acc.h2);
-    acc.h0 = n0; acc.h1 = n1; acc.h2 = n2;
-    acc.lit = sat_add(acc.lit, r.lit);
-    acc.out = sat_add(acc.out, r.out);
-  }
-  return acc;
-}
-
-// Phase 2, second pass: final records of the sequences [i0, i1), given the state at i0.  Returns nonzero when a
-// sequence breaks a block limit (the same conditions decode_sequences() checks).
-template <class Acc>
-ZN_HD uint32_t seq_run_emit(const SeqBits& sb, const Acc& tabs, SeqRec16* rec, uint32_t i0, uint32_t i1, uint32_t lit_len, RunSum st) {
+inline bool seq_phase2_host(const SeqBits& sb, const Acc& tabs, const SeqP1* p1, SeqRec16* rec, uint32_t nseq, uint32_t lit_len, RunSum* fin) {
+  RunSum carry;
+  carry.lit = 0; carry.out = 0; carry.h0 = sym_make(0); carry.h1 = sym_make(1); carry.h2 = sym_make(2);
   uint32_t bad = 0;
-  for (uint32_t i = i0; i < i1; i++) {
-    uint32_t ll, ml, ov;
-    seq_values(sb, tabs, rec + i, &ll, &ml, &ov);
-    const uint32_t offset = rep_step(ov, ll, st.h0, st.h1, st.h2, &bad);
-    bad |= (st.lit + ll > lit_len) | (st.out + ll + ml > kZstdBlockMax);
-    rec_store(rec + i, rec_pack(st.out & 0x3FFFFu, st.lit & 0x3FFFFu, ll & 0x3FFFFu, ml & 0x3FFFFu, offset));
-    st.lit = sat_add(st.lit, ll);
-    st.out = sat_add(st.out, ll + ml);
+  for (uint32_t base = 0; base < nseq; base += 32) {
+    uint32_t ll[32], ml[32], offx[32], sl[32], so[32], m0[32], m1[32], m2[32];
+    for (uint32_t l = 0; l < 32; l++) {
+      ll[l] = ml[l] = 0; offx[l] = 0;
+      m0[l] = sym_make(0); m1[l] = sym_make(1); m2[l] = sym_make(2);
+      if (base + l < nseq) {
+        uint32_t ov, z = 0;
+        seq_values(sb, tabs, p1 + base + l, &ll[l], &ml[l], &ov);
+        offx[l] = rep_step(ov, ll[l], m0[l], m1[l], m2[l], &z);
+      }
+      sl[l] = ll[l]; so[l] = ll[l] + ml[l];
+    }
+    for (uint32_t d = 1; d < 32; d <<= 1)
+      for (uint32_t l = 31; l >= d; l--) {  // descending: lane l - d still holds the previous step's value
+        sl[l] += sl[l - d]; so[l] += so[l - d];
+        const uint32_t t0 = m0[l - d], t1 = m1[l - d], t2 = m2[l - d];
+        const uint32_t n0 = sym_compose(m0[l], t0, t1, t2), n1 = sym_compose(m1[l], t0, t1, t2), n2 = sym_compose(m2[l], t0, t1, t2);
+        m0[l] = n0; m1[l] = n1; m2[l] = n2;
+      }
+    for (uint32_t l = 0; l < 32 && base + l < nseq; l++) {
+      const uint32_t e0 = l ? m0[l - 1] : sym_make(0), e1 = l ? m1[l - 1] : sym_make(1), e2 = l ? m2[l - 1] : sym_make(2);
+      const uint32_t h0 = sym_compose(e0, carry.h0, carry.h1, carry.h2), h1 = sym_compose(e1, carry.h0, carry.h1, carry.h2),
+                     h2 = sym_compose(e2, carry.h0, carry.h1, carry.h2);
+      const uint32_t offset = sym_compose(offx[l], h0, h1, h2);
+      const uint32_t lit_pos = carry.lit + (sl[l] - ll[l]), out_pos = carry.out + (so[l] - ll[l] - ml[l]);
+      bad |= (offset == 0) | (lit_pos + ll[l] > lit_len) | (out_pos + ll[l] + ml[l] > kZstdBlockMax);
+      rec_store(rec + base + l, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll[l] & 0x3FFFFu, ml[l] & 0x3FFFFu, offset));
+    }
+    const uint32_t n0 = sym_compose(m0[31], carry.h0, carry.h1, carry.h2), n1 = sym_compose(m1[31], carry.h0, carry.h1, carry.h2),
+                   n2 = sym_compose(m2[31], carry.h0, carry.h1, carry.h2);
+    carry.h0 = n0; carry.h1 = n1; carry.h2 = n2;
+    carry.lit = sat_add(carry.lit, sl[31]);
+    carry.out = sat_add(carry.out, so[31]);
   }
-  return bad;
+  *fin = carry;
+  return bad == 0;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------------------- lit
 // Huffman decoding table for tree description p[0..len) into h (entries sym | nbits << 8; 1 << max_bits of them).
@@ -1012,23 +1022,13 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
     uint32_t ref_matched = 0, ref_lit = 0, ref_rep[3] = {0, 0, 0};
     const bool ok_ref = decode_sequences(src, b, st, logs, ref.data(), &ref_matched, &ref_lit, ref_rep);
     SeqRec16* rec = recs.data() + b->seq_base;
-    bool ok2 = seq_phase1(src, b, st, logs, rec);
+    std::vector<SeqP1> p1(b->nseq);
+    bool ok2 = seq_phase1(src, b, st, logs, p1.data());
     if (ok2) {
       SeqBits sb;
       sb.init(src + b->bits_off, b->src_off + b->len - b->bits_off);
-      RunSum runs[kSeq2Threads];
-      const uint32_t R = (b->nseq + kSeq2Threads - 1) / kSeq2Threads;
-      for (uint32_t t = 0; t < kSeq2Threads; t++) {
-        const uint32_t i0 = std::min(t * R, b->nseq), i1 = std::min(i0 + R, b->nseq);
-        runs[t] = seq_run_sum(sb, st, rec, i0, i1);
-      }
-      const RunSum tot = seq_scan(runs, kSeq2Threads);
-      uint32_t bad = 0;
-      for (uint32_t t = 0; t < kSeq2Threads; t++) {
-        const uint32_t i0 = std::min(t * R, b->nseq), i1 = std::min(i0 + R, b->nseq);
-        bad |= seq_run_emit(sb, st, rec, i0, i1, b->lit_regen, runs[t]);
-      }
-      ok2 = bad == 0;
+      RunSum tot;
+      ok2 = seq_phase2_host(sb, st, p1.data(), rec, b->nseq, b->lit_regen, &tot);
       if (ok2) {
         b->matched = tot.out; b->lit_used = tot.lit;
         b->rep_fin[0] = tot.h0; b->rep_fin[1] = tot.h1; b->rep_fin[2] = tot.h2;

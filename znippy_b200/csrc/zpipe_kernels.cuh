@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(64, 1) k_zseq1(ZArgs a) {
 #pragma unroll 8
       for (uint32_t i = 0; i < n; i++) sts32(dst + 4 * i, p1_entry(t[k][i]));
     }
-    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.recs + b->seq_base)) b->st_seq = 2;
+    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.p1 + b->seq_base)) b->st_seq = 2;
   }
 }
 
@@ -315,31 +315,31 @@ __global__ void __launch_bounds__(32) k_zseq1_g(ZArgs a) {
     GlobalTabs1 st;
     uint32_t logs[3];
     if (!seq_table_sources(a, b, z, st.t, logs)) continue;
-    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.recs + b->seq_base)) b->st_seq = 2;
+    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.p1 + b->seq_base)) b->st_seq = 2;
   }
 }
 
-// phase 2: one CTA per block, a thread per run of consecutive sequences
+// phase 2: one warp per block, a lane per sequence, 32 consecutive sequences per step (zpipe.cuh: seq_phase2_host is the
+// same arithmetic with the lanes as arrays)
 struct GlobalTabs2 {
   const FseD* t[3];
   uint32_t lut_s;
   ZN_D uint32_t ld(int k, uint32_t i) const { return __ldg(t[k] + i); }
   ZN_D uint32_t base(int k, uint32_t sym) const { return lds32_ro(lut_s + 4u * ((k == 0 ? 0u : 36u) + sym)); }
 };
+constexpr uint32_t kSeq2Warps = 4;
 
-__global__ void __launch_bounds__(kSeq2Threads) k_zseq2(ZArgs a) {
+__global__ void __launch_bounds__(kSeq2Warps * 32) k_zseq2(ZArgs a) {
   __shared__ uint32_t s_lut[36 + 53];
-  __shared__ RunSum s_run[kSeq2Threads];
-  __shared__ uint32_t s_bad;
-  const uint32_t tid = threadIdx.x;
-  for (uint32_t i = tid; i < 36; i += kSeq2Threads) s_lut[i] = zs::kLLBase[i];
-  for (uint32_t i = tid; i < 53; i += kSeq2Threads) s_lut[36 + i] = zs::kMLBase[i];
-  if (tid == 0) s_bad = 0;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  for (uint32_t i = tid; i < 36; i += kSeq2Warps * 32) s_lut[i] = zs::kLLBase[i];
+  for (uint32_t i = tid; i < 53; i += kSeq2Warps * 32) s_lut[36 + i] = zs::kMLBase[i];
   __syncthreads();
   GlobalTabs2 st;
   st.lut_s = (uint32_t)__cvta_generic_to_shared(s_lut);
   const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
-  for (uint32_t it = blockIdx.x; it < n_comp; it += gridDim.x) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  for (uint32_t it = blockIdx.x * kSeq2Warps + warp; it < n_comp; it += gridDim.x * kSeq2Warps) {
     const uint32_t slot = a.comp_list[it];
     if (slot == kNoSlot) continue;
     ZBlock* b = &a.blocks[slot];
@@ -353,24 +353,51 @@ __global__ void __launch_bounds__(kSeq2Threads) k_zseq2(ZArgs a) {
     SeqBits sb;
     sb.init(src + b->bits_off, b->src_off + b->len - b->bits_off);
     SeqRec16* rec = a.recs + b->seq_base;
-    const uint32_t R = (nseq + kSeq2Threads - 1) / kSeq2Threads;
-    const uint32_t i0 = min(tid * R, nseq), i1 = min(i0 + R, nseq);
-    s_run[tid] = seq_run_sum(sb, st, rec, i0, i1);
-    __syncthreads();
-    if (tid == 0) {
-      const RunSum tot = seq_scan(s_run, kSeq2Threads);
-      b->matched = tot.out;
-      b->lit_used = tot.lit;
-      b->rep_fin[0] = tot.h0; b->rep_fin[1] = tot.h1; b->rep_fin[2] = tot.h2;
+    const SeqP1* p1 = a.p1 + b->seq_base;
+    const uint32_t lit_len = b->lit_regen;
+    uint32_t c_lit = 0, c_out = 0, c0 = sym_make(0), c1 = sym_make(1), c2 = sym_make(2);  // state carried from step to step
+    uint32_t bad = 0;
+    for (uint32_t base = 0; base < nseq; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t ll = 0, ml = 0, offx = 0, m0 = sym_make(0), m1 = sym_make(1), m2 = sym_make(2);
+      if (i < nseq) {
+        uint32_t ov, zf = 0;
+        seq_values(sb, st, p1 + i, &ll, &ml, &ov);
+        offx = rep_step(ov, ll, m0, m1, m2, &zf);  // the sequence's own effect on an unknown history
+      }
+      uint32_t sl = ll, so = ll + ml;
+#pragma unroll
+      for (uint32_t dd = 1; dd < 32; dd <<= 1) {  // inclusive scans: the two sums, the history maps
+        const uint32_t tl = __shfl_up_sync(FULL, sl, dd), to = __shfl_up_sync(FULL, so, dd);
+        const uint32_t t0 = __shfl_up_sync(FULL, m0, dd), t1 = __shfl_up_sync(FULL, m1, dd), t2 = __shfl_up_sync(FULL, m2, dd);
+        if (lane >= dd) {
+          sl += tl; so += to;
+          const uint32_t n0 = sym_compose(m0, t0, t1, t2), n1 = sym_compose(m1, t0, t1, t2), n2 = sym_compose(m2, t0, t1, t2);
+          m0 = n0; m1 = n1; m2 = n2;
+        }
+      }
+      uint32_t e0 = __shfl_up_sync(FULL, m0, 1), e1 = __shfl_up_sync(FULL, m1, 1), e2 = __shfl_up_sync(FULL, m2, 1);
+      if (lane == 0) { e0 = sym_make(0); e1 = sym_make(1); e2 = sym_make(2); }
+      const uint32_t h0 = sym_compose(e0, c0, c1, c2), h1 = sym_compose(e1, c0, c1, c2), h2 = sym_compose(e2, c0, c1, c2);
+      if (i < nseq) {
+        const uint32_t offset = sym_compose(offx, h0, h1, h2);
+        const uint32_t lit_pos = c_lit + (sl - ll), out_pos = c_out + (so - ll - ml);
+        bad |= (offset == 0) | (lit_pos + ll > lit_len) | (out_pos + ll + ml > kZstdBlockMax);
+        rec_store(rec + i, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll & 0x3FFFFu, ml & 0x3FFFFu, offset));
+      }
+      const uint32_t T0 = __shfl_sync(FULL, m0, 31), T1 = __shfl_sync(FULL, m1, 31), T2 = __shfl_sync(FULL, m2, 31);
+      const uint32_t n0 = sym_compose(T0, c0, c1, c2), n1 = sym_compose(T1, c0, c1, c2), n2 = sym_compose(T2, c0, c1, c2);
+      c0 = n0; c1 = n1; c2 = n2;
+      c_lit = sat_add(c_lit, __shfl_sync(FULL, sl, 31));
+      c_out = sat_add(c_out, __shfl_sync(FULL, so, 31));
     }
-    __syncthreads();
-    if (seq_run_emit(sb, st, rec, i0, i1, b->lit_regen, s_run[tid])) s_bad = 1;
-    __syncthreads();
-    if (tid == 0) {
-      if (!s_bad) b->st_seq = 0;
-      s_bad = 0;
+    bad = __any_sync(FULL, bad != 0);
+    if (lane == 0 && !bad) {
+      b->matched = c_out;
+      b->lit_used = c_lit;
+      b->rep_fin[0] = c0; b->rep_fin[1] = c1; b->rep_fin[2] = c2;
+      b->st_seq = 0;
     }
-    __syncthreads();
   }
 }
 

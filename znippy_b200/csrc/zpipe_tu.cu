@@ -69,14 +69,15 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   const uint32_t lit_grid = std::min<uint32_t>((slots + kLitBlocks - 1) / kLitBlocks, sms * 3);
   k_ztables<<<std::min<uint32_t>((slots + kTabWarps - 1) / kTabWarps, sms * 8), kTabWarps * 32, 0, st>>>(a);
   mark();
-  static const int seq_mode = getenv("ZN_SEQ") ? atoi(getenv("ZN_SEQ")) : 2;  // development: 0 / 1 = the one-pass forms
+  static const int seq_mode = getenv("ZN_SEQ") ? atoi(getenv("ZN_SEQ")) : 0;  // 0 / 1: the one-pass forms; 2-4: two-phase (2 = table placement by batch shape)
   if (seq_mode == 1) k_zseq<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeqSmem, st>>>(a);
   else if (seq_mode == 0) k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a, getenv("ZN_SEQ_LDG") ? 0 : 1);
   else {  // two-phase form: the state chain per block, then every sequence on its own
     const bool smem_tabs = seq_mode == 2 ? L.mean_bytes >= (256u << 10) : seq_mode == 3;
     if (smem_tabs) k_zseq1<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeq1Smem, st>>>(a);
     else k_zseq1_g<<<(slots + 31) / 32, 32, 0, st>>>(a);
-    k_zseq2<<<std::min<uint32_t>(slots, sms * 16), kSeq2Threads, 0, st>>>(a);
+    if (marks && getenv("ZN_ZPROF_SEQ1")) { cudaEventRecord(marks[8], st); }  // development: end of phase 1
+    k_zseq2<<<std::min<uint32_t>((slots + kSeq2Warps - 1) / kSeq2Warps, sms * 16), kSeq2Warps * 32, 0, st>>>(a);
   }
   mark();
   k_zlit<<<lit_grid, kLitBlocks * 4, kLitSmem, st>>>(a);
