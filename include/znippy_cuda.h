@@ -286,6 +286,10 @@ int zn_plan_set_overlap(zn_plan* plan, int groups);
  *   [3] decoded size <= 64 KiB              -> one-warp teams
  *   [4] the rest                            -> 128-thread teams */
 int zn_plan_class_counts(const zn_plan* plan, uint32_t counts[5]);
+/* Rows of class [0] that the device-wide pipeline handed back to the one-team decoder in the last zn_plan_run (anything
+ * malformed or beyond the pipeline's budgets; the result is the same, only slower).  Synchronises with the run's
+ * stream.  A well-formed batch reports 0 — tests and bench.py check exactly that. */
+int zn_plan_pipeline_fallbacks(zn_plan* plan, uint32_t* rows);
 /* kernels launched by one zn_plan_run of this plan */
 uint32_t zn_plan_launches(const zn_plan* plan);
 /* 1 when the plan decodes and hashes in ONE kernel (batches of large, highly compressible blobs: decode warps feed

@@ -504,3 +504,44 @@ def test_store_as_is_row_with_disagreeing_sizes_is_refused(codec, oracle):
     assert out[:50_000].tobytes() == a and out[51_024:51_024 + 30_000].tobytes() == c
     assert (out[51_024 + 30_000:] == 0xCD).all()  # (the refused row's own 1 000-byte range is unspecified, nothing beyond the rows is touched)
     assert dg[0].tobytes() == O.blake3(a) and dg[2].tobytes() == O.blake3(c)
+
+
+def test_pipeline_keeps_well_formed_frames_at_every_alignment(codec, oracle):
+    """The device-wide pipeline hands a blob back to the one-team decoder only when something is off; a silent hand-back
+    of well-formed frames would keep every parity test green and cost the whole speed-up.  Entropy-coded frames of several
+    levels at all 16 byte alignments of the blob (the sequence stage stages its bit stream in 16-byte units and hands bit
+    positions from one kernel to the next): bytes and digests bit-exact, and zn_plan_pipeline_fallbacks reports 0."""
+    import torch
+    from znippy_b200 import Plan
+    O, z = oracle, oracle.libzstd()
+    rt = O.real_text(2_500_000)
+    contents, blobs = [], []
+    for k in range(16):
+        c = rt[k * 100_000: k * 100_000 + 300_000 + 4099 * k].tobytes()
+        contents.append(c)
+        blobs.append(z.compress(c, [1, 3, 7, 19][k % 4]))
+    offs, cur = [], 0
+    for k, b in enumerate(blobs):  # blob k starts at an address that is k modulo 16
+        cur = (cur + 15) // 16 * 16 + k
+        offs.append(cur)
+        cur += len(b)
+    buf = np.zeros(cur + 16, np.uint8)
+    for o, b in zip(offs, blobs):
+        buf[o:o + len(b)] = np.frombuffer(b, np.uint8)
+    out_len = np.array([len(c) for c in contents], np.uint64)
+    out_off = np.concatenate([[0], np.cumsum((out_len + np.uint64(15)) & ~np.uint64(15))])[:-1].astype(np.uint64)
+    digs = np.frombuffer(b"".join(O.blake3(c) for c in contents), np.uint8)
+    ctx = codec.default_ctx()
+    d_in = torch.from_numpy(buf).cuda()
+    d_out = torch.zeros(int(out_off[-1] + out_len[-1]) + 256, dtype=torch.uint8, device="cuda")
+    plan = Plan.decode_verify(ctx, offs, [len(b) for b in blobs], [1] * 16, out_off, out_len, digs)
+    assert plan.class_counts()[0] == 16
+    plan.run(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st, dg = plan.results()
+    assert st.tolist() == [0] * 16
+    assert plan.pipeline_fallbacks() == 0
+    out = d_out.cpu().numpy()
+    for i, c in enumerate(contents):
+        assert out[int(out_off[i]): int(out_off[i]) + len(c)].tobytes() == c, i
+        assert dg[i].tobytes() == O.blake3(c)

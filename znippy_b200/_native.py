@@ -19,7 +19,7 @@ EXPORTS = [
     "zn_abi_version", "zn_device_count", "zn_strerror", "zn_status_name", "zn_ctx_create", "zn_ctx_destroy",
     "zn_last_error", "zn_ctx_pinned", "zn_ctx_kernel_launches", "zn_hash_batch", "zn_decode_verify_batch",
     "zn_compress_batch", "zn_compress_bound", "zn_frame_content_size", "zn_plan_decode_verify", "zn_plan_hash",
-    "zn_plan_destroy", "zn_plan_run", "zn_plan_results", "zn_plan_launches", "zn_plan_fused", "zn_plan_last_ms", "zn_plan_set_overlap", "zn_plan_class_counts", "zn_ctx_last_compress_ms", "zn_decompress_rows",
+    "zn_plan_destroy", "zn_plan_run", "zn_plan_results", "zn_plan_launches", "zn_plan_fused", "zn_plan_last_ms", "zn_plan_set_overlap", "zn_plan_class_counts", "zn_plan_pipeline_fallbacks", "zn_ctx_last_compress_ms", "zn_decompress_rows",
     "zn_index_open", "zn_index_close", "zn_index_rows", "zn_index_u64", "zn_index_chunk_seq", "zn_index_compressed",
     "zn_index_checksums", "zn_index_path", "zn_index_groups", "zn_index_group", "zn_index_metadata", "zn_index_field_count",
     "zn_index_field_name", "zn_index_writer_create", "zn_index_writer_metadata", "zn_index_writer_push_group",
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.zn_plan_last_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     L.zn_plan_set_overlap.argtypes = [vp, C.c_int]
     L.zn_plan_class_counts.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.zn_plan_pipeline_fallbacks.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.zn_decompress_rows.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int, vp, vp]
     L.zn_index_open.argtypes = [C.c_char_p, C.c_char_p, sz]
     L.zn_index_open.restype = vp
@@ -265,6 +266,12 @@ class Plan:
         out = (C.c_uint32 * 5)()
         self.ctx.check(lib().zn_plan_class_counts(self._h, out), "zn_plan_class_counts")
         return list(out)
+
+    def pipeline_fallbacks(self) -> int:
+        """rows the device-wide pipeline handed back to the one-team decoder in the last run (zn_plan_pipeline_fallbacks)"""
+        n = C.c_uint32(0)
+        self.ctx.check(lib().zn_plan_pipeline_fallbacks(self._h, C.byref(n)), "zn_plan_pipeline_fallbacks")
+        return int(n.value)
 
     def set_overlap(self, groups: int):
         self.ctx.check(lib().zn_plan_set_overlap(self._h, groups), "zn_plan_set_overlap")

@@ -52,10 +52,10 @@ struct PipelineLaunch {
   uint32_t* produced;
   uint32_t* exec_counter;
 };
-// Enqueues init, walk, tables, seq phase 1, seq phase 2, lit, chain, exec on `st` (8 launches).  `marks` (nullable): 7
-// events, recorded before the first kernel and after walk / tables / seq (both phases) / lit / chain / exec.
-void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks);
-constexpr uint32_t kPipelineLaunches = 8;
+// Enqueues init, walk, tables, seq (one kernel, or phase 1 + phase 2 for batches of large blobs), lit, chain, exec on
+// `st` and returns the number of launches (7 or 8).  `marks` (nullable): 9 events; [0..6] are recorded before the first
+// kernel and after walk / tables / seq / lit / chain / exec, [8] after seq phase 1 when ZN_ZPROF_SEQ1 is set.
+uint32_t pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks);
 void pipeline_trace_dump();  // development builds (ZN_TRACE_BUILD=1): prints and clears the exec kernel's phase counters
 }  // namespace zp
 

@@ -495,6 +495,18 @@ extern "C" int zn_plan_class_counts(const zn_plan* p, uint32_t counts[5]) {
   return ZN_OK;
 }
 
+extern "C" int zn_plan_pipeline_fallbacks(zn_plan* p, uint32_t* rows) {
+  if (!p || !rows) return ZN_E_ARG;
+  *rows = 0;
+  if (!p->nzb || !p->ran) return ZN_OK;
+  cudaSetDevice(p->ctx->device);
+  if (cudaStreamSynchronize(p->last_stream) != cudaSuccess) { p->ctx->err = cudaGetErrorString(cudaGetLastError()); return ZN_E_CUDA; }
+  std::vector<zp::ZBlob> hz(p->nzb);
+  if (cudaMemcpy(hz.data(), p->d_zb, sizeof(zp::ZBlob) * p->nzb, cudaMemcpyDeviceToHost) != cudaSuccess) { p->ctx->err = cudaGetErrorString(cudaGetLastError()); return ZN_E_CUDA; }
+  for (auto& b : hz) *rows += b.state != 0;
+  return ZN_OK;
+}
+
 extern "C" void zn_plan_destroy(zn_plan* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
@@ -550,7 +562,7 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
   L.sm_count = (uint32_t)c->sm_count;
   L.mean_bytes = p->z_mean;
   L.d_out = d_out; L.produced = p->d_produced; L.exec_counter = ctr;
-  zp::pipeline_enqueue(L, st, prof ? pe : nullptr);
+  const uint32_t pipe_launches = zp::pipeline_enqueue(L, st, prof ? pe : nullptr);
   // rows the pipeline handed back (ZBlob.state != 0): the one-team decoder, which also produces their status
   const uint32_t* list = p->d_list_dec + p->cls_off[DC_PIPE];
   const uint32_t grid = std::min<uint32_t>(p->nzb, c->dec_grid);
@@ -574,7 +586,7 @@ static int run_pipeline(zn_plan* p, const uint8_t* d_blobs, uint8_t* d_out, cuda
     zp::pipeline_trace_dump();
     for (auto& e : pe) cudaEventDestroy(e);
   }
-  *launches += zp::kPipelineLaunches + 1;
+  *launches += pipe_launches + 1;
   return ZN_OK;
 }
 

@@ -28,6 +28,9 @@
 // checks them against the oracle on the CPU).
 #pragma once
 #include "zstd_tables.cuh"
+#if !defined(__CUDA_ARCH__)
+#include <cstring>
+#endif
 
 namespace zn {
 namespace zp {
@@ -448,7 +451,10 @@ ZN_HD bool parse_table_descs(const uint8_t* src, const ZBlock* b, FseD* set, int
 struct HostTabs {
   const FseD* t[3];
   ZN_HD uint32_t ld(int k, uint32_t i) const { return t[k][i]; }
-  ZN_HD uint32_t ld1(int k, uint32_t i) const;  // phase-1 view of the same entry (two-phase form below)
+  ZN_HD void ld1(int k, uint32_t i, uint32_t* nb, uint32_t* tot) const {  // phase-1 view of the same entry (two-phase form below)
+    const FseD e = t[k][i];
+    *nb = e & 0x3FFFu; *tot = fd_nbits(e) + fd_extra(e);
+  }
   ZN_HD uint32_t base(int k, uint32_t s) const { return k == 0 ? zs::kLLBase[s] : zs::kMLBase[s]; }
 };
 
@@ -555,8 +561,8 @@ ZN_HD bool decode_sequences(const uint8_t* src, const ZBlock* b, const Acc& tabs
 //            field out of the stream at a computed bit position, three state updates.  It leaves {bit cursor, three
 //            states} — 8 bytes, densely packed so that four sequences complete a 32-byte sector (a half-written sector
 //            costs a read-modify-write in ECC memory) — in the p1 pool;
-//   phase 2 (k_zseq2 on the device, seq_phase2_host here: a warp per block, a LANE PER SEQUENCE, 32 consecutive
-//            sequences per step)  with cursor and states known every sequence decodes independently and every access
+//   phase 2 (k_zseq2 on the device, seq_phase2_host here: a warp per block, 128 consecutive sequences per step, four
+//            per lane)  with cursor and states known every sequence decodes independently and every access
 //            is coalesced: values out of the stream, then positions as a prefix sum and repeat-offset histories as a
 //            prefix scan — one sequence's effect on the history is a map "slot i minus k | fixed value" per entry, and
 //            such maps compose (sym_compose) — then the final 16-byte records, bit-identical to what decode_sequences()
@@ -592,11 +598,8 @@ struct SeqBits {
 #endif
     return i == 0 ? (w & lowmask) : w;
   }
-  ZN_HD void prefetch(int32_t c) const {  // the stream 256 B / 1 KiB below bit position c
-    const int32_t f1 = (c >> 5) - 64, f2 = (c >> 5) - 256;
-    prefetch_l1(wbase + (f1 > 0 ? f1 : 0));
-    prefetch_l2(wbase + (f2 > 0 ? f2 : 0));
-  }
+  ZN_HD void advance(int32_t) {}  // (the device's phase-1 reader stages the stream ahead of the cursor here: RingBits)
+  ZN_HD uint32_t rel(int32_t c) const { return (uint32_t)c; }
   ZN_HD uint32_t bits32(int32_t lo) const {  // the 32 bits at positions lo .. lo + 31 (lo may be negative)
     const int32_t wi = lo >> 5;
     return funnel_r(word(wi), word(wi + 1), (uint32_t)lo & 31u);
@@ -604,9 +607,92 @@ struct SeqBits {
 };
 ZN_HD uint32_t lowbits(uint32_t v, uint32_t n) { return v & ((1u << n) - 1u); }  // n <= 31
 
-// phase-1 view of a decoding-table entry: next-state base | state bits << 16 | (state bits + extra bits) << 24
-ZN_HD uint32_t p1_entry(FseD e) { return fd_base(e) | (fd_nbits(e) << 16) | ((fd_nbits(e) + fd_extra(e)) << 24); }
-ZN_HD uint32_t HostTabs::ld1(int k, uint32_t i) const { return p1_entry(t[k][i]); }
+// Phase-1 view of the lane's bit stream (same interface as SeqBits): the stream is staged through a 64-word ring in
+// shared memory by asynchronous 16-byte copies issued 13 units (208 bytes, ~55 sequences) ahead of the cursor.  With the
+// words read straight from global memory a warp waits, at EVERY sequence, for whichever of its 32 lanes happens to touch
+// a new sector (each lane does so every ~9 sequences: 1 - 0.9^32 = 97 % of the steps see a miss); staged, the chain only
+// ever reads shared memory.  Bit positions count from the 16-byte unit that holds the first stream byte.  A unit that
+// holds a valid byte lies inside the allocation (allocations are 16-byte granular), like the aligned words elsewhere.
+#if defined(__CUDACC__)
+#define ZN_RING ZN_D
+#else
+#define ZN_RING inline
+#endif
+struct RingBits {
+#if defined(__CUDACC__)
+  uint32_t ring_s;       // shared address of the lane's ring (kRingBytes)
+#else
+  uint32_t ring_h[64];   // host emulation: the copies are synchronous
+#endif
+  const uint8_t* g16;    // unit 0
+  uint32_t lowmask;
+  int32_t first_w, top;  // first / last word holding stream bytes
+  int32_t bias, c0;
+  int32_t u_have;        // lowest unit asked for so far
+  // a lane's own copy groups complete in order, so "at most 12 pending" covers everything 13 or more units below the
+  // cursor whether the hardware counts groups per thread (PTX) or per warp (then ~12 of the warp's steps, still far
+  // more than a DRAM round trip)
+  static constexpr int32_t kAhead = 13;
+  static constexpr uint32_t kRingBytes = 256;
+#if defined(__CUDACC__)
+  ZN_D void fetch_unit(int32_t u) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + ((uint32_t)u & 15u) * 16u), "l"(__cvta_generic_to_global(g16 + (size_t)u * 16)) : "memory");
+  }
+  ZN_D void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  ZN_D void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  ZN_D void wait_12() { asm volatile("cp.async.wait_group 12;" ::: "memory"); }
+  ZN_D uint32_t ring_ld(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring_s + i * 4u)); return v; }
+#else
+  void fetch_unit(int32_t u) { memcpy(ring_h + ((uint32_t)u & 15u) * 4u, g16 + (size_t)u * 16, 16); }
+  void commit() {}
+  void wait_all() {}
+  void wait_12() {}
+  uint32_t ring_ld(uint32_t i) const { return ring_h[i]; }
+#endif
+  ZN_RING bool init(const uint8_t* p, uint32_t len) {
+    if (len == 0) return false;
+    const uint32_t last = p[len - 1];
+    if (last == 0) return false;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), s16 = a & ~(uintptr_t)15;
+    g16 = reinterpret_cast<const uint8_t*>(s16);
+    first_w = (int32_t)((a - s16) >> 2);
+    bias = (int32_t)(a - s16) * 8;
+    lowmask = 0xFFFFFFFFu << ((a & 3) * 8);
+    top = (int32_t)(((a + len - 1) - s16) >> 2);
+    c0 = bias + (int32_t)(len - 1) * 8 + hibit32(last);
+    const int32_t u_top = top >> 2;
+    u_have = u_top > kAhead + 1 ? u_top - (kAhead + 1) : 0;
+    for (int32_t u = u_top; u >= u_have; u--) fetch_unit(u);
+    commit();
+    wait_all();
+    return true;
+  }
+  ZN_RING uint32_t rel(int32_t c) const { return (uint32_t)(c - first_w * 32); }  // cursor as SeqBits (phase 2) counts it
+  // the cursor is about to be `lo`: ask for the unit kAhead below it, make sure everything at and above it has arrived
+  ZN_RING void advance(int32_t lo) {
+    if (u_have > 0 && (lo >> 7) < u_have + kAhead) {
+      u_have--;
+      fetch_unit(u_have);
+      commit();
+      if (u_have == 0) wait_all();  // nothing will be asked for any more: from here on every unit is in
+    }
+    wait_12();  // groups = units in descending order: all but the 12 lowest are in
+  }
+  ZN_RING uint32_t word(int32_t i) const {
+    if (i < first_w || i > top) return 0u;
+    const uint32_t w = ring_ld((uint32_t)i & 63u);
+    return i == first_w ? (w & lowmask) : w;
+  }
+  ZN_RING uint32_t bits32(int32_t lo) const {
+    const int32_t wi = lo >> 5;
+    return funnel_r(word(wi), word(wi + 1), (uint32_t)lo & 31u);
+  }
+};
+#undef ZN_RING
+
+// Phase-1 view of a decoding-table entry, Acc::ld1(k, state, &nb, &tot): nb = next-state base | state bits << 10 (the low
+// 14 bits of the FseD entry), tot = state bits + extra bits (what the sequence takes out of the stream for this table).
+// In shared memory that is 3 bytes per entry (u16 + u8), which is what lets two rounds of lanes cover a 2 GiB batch.
 ZN_HD void p1_store(SeqP1* r, uint32_t cursor, uint32_t states) {
 #if defined(__CUDA_ARCH__)
   *reinterpret_cast<uint2*>(r) = make_uint2(cursor, states);
@@ -615,14 +701,13 @@ ZN_HD void p1_store(SeqP1* r, uint32_t cursor, uint32_t states) {
 #endif
 }
 
-// Phase 1.  Acc::ld1(k, state) returns the phase-1 entry of table k.  Leaves {cursor before the sequence, LL | OF << 9 |
-// ML << 18 states} in rec[i].  false = the stream does not end exactly where the sequences do.
-template <class Acc>
-ZN_HD bool seq_phase1(const uint8_t* src, const ZBlock* b, const Acc& tabs, const uint32_t* logs, SeqP1* rec) {
+// Phase 1.  Leaves {cursor before the sequence, LL | OF << 9 | ML << 18 states} in rec[i].  false = the stream does not
+// end exactly where the sequences do.
+template <class Bits, class Acc>
+ZN_HD bool seq_phase1(Bits& sb, const uint8_t* src, const ZBlock* b, const Acc& tabs, const uint32_t* logs, SeqP1* rec) {
   const uint32_t nseq = b->nseq;
   const uint32_t end = b->src_off + b->len;
   if (b->bits_off >= end) return false;
-  SeqBits sb;
   if (!sb.init(src + b->bits_off, end - b->bits_off)) return false;
   int32_t c = sb.c0;
   c -= (int32_t)logs[0];
@@ -632,21 +717,22 @@ ZN_HD bool seq_phase1(const uint8_t* src, const ZBlock* b, const Acc& tabs, cons
   c -= (int32_t)logs[2];
   uint32_t sm = lowbits(sb.bits32(c), logs[2]);
   if (c < sb.bias) return false;
+  uint32_t el, eo, em, tl, to, tm;
   for (uint32_t i = 0; i + 1 < nseq; i++) {
-    const uint32_t el = tabs.ld1(0, sl), eo = tabs.ld1(1, so), em = tabs.ld1(2, sm);
-    p1_store(rec + i, (uint32_t)c, sl | (so << 9) | (sm << 18));
-    sb.prefetch(c);
-    c -= (int32_t)((el >> 24) + (eo >> 24) + (em >> 24));
+    tabs.ld1(0, sl, &el, &tl); tabs.ld1(1, so, &eo, &to); tabs.ld1(2, sm, &em, &tm);
+    p1_store(rec + i, sb.rel(c), sl | (so << 9) | (sm << 18));
+    c -= (int32_t)(tl + to + tm);
+    sb.advance(c);
     const uint32_t f = sb.bits32(c);  // from the bottom: OF state bits, ML state bits, LL state bits (read in the opposite order)
-    const uint32_t no = (eo >> 16) & 0xFFu, nm = (em >> 16) & 0xFFu, nl = (el >> 16) & 0xFFu;
-    so = (eo & 0xFFFFu) + lowbits(f, no);
-    sm = (em & 0xFFFFu) + lowbits(f >> no, nm);
-    sl = (el & 0xFFFFu) + lowbits(f >> (no + nm), nl);
+    const uint32_t no = eo >> 10, nm = em >> 10, nl = el >> 10;
+    so = (eo & 0x3FFu) + lowbits(f, no);
+    sm = (em & 0x3FFu) + lowbits(f >> no, nm);
+    sl = (el & 0x3FFu) + lowbits(f >> (no + nm), nl);
   }
-  const uint32_t el = tabs.ld1(0, sl), eo = tabs.ld1(1, so), em = tabs.ld1(2, sm);
-  p1_store(rec + (nseq - 1), (uint32_t)c, sl | (so << 9) | (sm << 18));
-  c -= (int32_t)((el >> 24) + (eo >> 24) + (em >> 24));  // the last sequence has no state update
-  c += (int32_t)(((el >> 16) & 0xFFu) + ((eo >> 16) & 0xFFu) + ((em >> 16) & 0xFFu));
+  tabs.ld1(0, sl, &el, &tl); tabs.ld1(1, so, &eo, &to); tabs.ld1(2, sm, &em, &tm);
+  p1_store(rec + (nseq - 1), sb.rel(c), sl | (so << 9) | (sm << 18));
+  c -= (int32_t)(tl + to + tm);  // the last sequence has no state update
+  c += (int32_t)((el >> 10) + (eo >> 10) + (em >> 10));
   return c == sb.bias;
 }
 
@@ -710,26 +796,36 @@ ZN_HD void seq_values(const SeqBits& sb, const Acc& tabs, const SeqP1* slot, uin
   *ll = tabs.base(0, fd_sym(el)) + lowbits(g, llx);
 }
 
+constexpr uint32_t kSeqPerLane = 4;  // phase 2: consecutive sequences per lane and step (one scan per 128 sequences)
+
 #if !defined(__CUDA_ARCH__)
-// Phase 2 as k_zseq2 runs it, with the warp's 32 lanes as arrays: steps of 32 consecutive sequences; inclusive
-// Hillis-Steele scans over the lanes for the two sums and for the history maps; the state after a step is carried into
-// the next.  Returns false when a sequence breaks a block limit (the conditions decode_sequences() checks).
+// Phase 2 as k_zseq2 runs it, with the warp's 32 lanes as arrays: steps of 32 x kSeqPerLane consecutive sequences; a
+// lane walks its own kSeqPerLane sequences serially (values, its own effect on the history, local positions), then
+// inclusive Hillis-Steele scans over the lanes give the two sums and the history maps; the state after a step is carried
+// into the next.  Returns false when a sequence breaks a block limit (the conditions decode_sequences() checks).
 template <class Acc>
 inline bool seq_phase2_host(const SeqBits& sb, const Acc& tabs, const SeqP1* p1, SeqRec16* rec, uint32_t nseq, uint32_t lit_len, RunSum* fin) {
   RunSum carry;
   carry.lit = 0; carry.out = 0; carry.h0 = sym_make(0); carry.h1 = sym_make(1); carry.h2 = sym_make(2);
   uint32_t bad = 0;
-  for (uint32_t base = 0; base < nseq; base += 32) {
-    uint32_t ll[32], ml[32], offx[32], sl[32], so[32], m0[32], m1[32], m2[32];
+  const uint32_t K = kSeqPerLane;
+  for (uint32_t base = 0; base < nseq; base += 32 * K) {
+    uint32_t ll[32][K], ml[32][K], offx[32][K], pl[32][K], po[32][K], sl[32], so[32], tl[32], to[32], m0[32], m1[32], m2[32];
     for (uint32_t l = 0; l < 32; l++) {
-      ll[l] = ml[l] = 0; offx[l] = 0;
       m0[l] = sym_make(0); m1[l] = sym_make(1); m2[l] = sym_make(2);
-      if (base + l < nseq) {
-        uint32_t ov, z = 0;
-        seq_values(sb, tabs, p1 + base + l, &ll[l], &ml[l], &ov);
-        offx[l] = rep_step(ov, ll[l], m0[l], m1[l], m2[l], &z);
+      sl[l] = so[l] = 0;
+      for (uint32_t j = 0; j < K; j++) {
+        const uint32_t i = base + l * K + j;
+        ll[l][j] = ml[l][j] = 0; offx[l][j] = 0;
+        if (i < nseq) {
+          uint32_t ov, z = 0;
+          seq_values(sb, tabs, p1 + i, &ll[l][j], &ml[l][j], &ov);
+          offx[l][j] = rep_step(ov, ll[l][j], m0[l], m1[l], m2[l], &z);
+        }
+        pl[l][j] = sl[l]; po[l][j] = so[l];
+        sl[l] += ll[l][j]; so[l] += ll[l][j] + ml[l][j];
       }
-      sl[l] = ll[l]; so[l] = ll[l] + ml[l];
+      tl[l] = sl[l]; to[l] = so[l];
     }
     for (uint32_t d = 1; d < 32; d <<= 1)
       for (uint32_t l = 31; l >= d; l--) {  // descending: lane l - d still holds the previous step's value
@@ -738,14 +834,17 @@ inline bool seq_phase2_host(const SeqBits& sb, const Acc& tabs, const SeqP1* p1,
         const uint32_t n0 = sym_compose(m0[l], t0, t1, t2), n1 = sym_compose(m1[l], t0, t1, t2), n2 = sym_compose(m2[l], t0, t1, t2);
         m0[l] = n0; m1[l] = n1; m2[l] = n2;
       }
-    for (uint32_t l = 0; l < 32 && base + l < nseq; l++) {
+    for (uint32_t l = 0; l < 32; l++) {
       const uint32_t e0 = l ? m0[l - 1] : sym_make(0), e1 = l ? m1[l - 1] : sym_make(1), e2 = l ? m2[l - 1] : sym_make(2);
-      const uint32_t h0 = sym_compose(e0, carry.h0, carry.h1, carry.h2), h1 = sym_compose(e1, carry.h0, carry.h1, carry.h2),
-                     h2 = sym_compose(e2, carry.h0, carry.h1, carry.h2);
-      const uint32_t offset = sym_compose(offx[l], h0, h1, h2);
-      const uint32_t lit_pos = carry.lit + (sl[l] - ll[l]), out_pos = carry.out + (so[l] - ll[l] - ml[l]);
-      bad |= (offset == 0) | (lit_pos + ll[l] > lit_len) | (out_pos + ll[l] + ml[l] > kZstdBlockMax);
-      rec_store(rec + base + l, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll[l] & 0x3FFFFu, ml[l] & 0x3FFFFu, offset));
+      const uint32_t lit_base = carry.lit + (sl[l] - tl[l]), out_base = carry.out + (so[l] - to[l]);
+      for (uint32_t j = 0; j < K; j++) {
+        const uint32_t i = base + l * K + j;
+        if (i >= nseq) break;
+        const uint32_t offset = sym_compose(sym_compose(offx[l][j], e0, e1, e2), carry.h0, carry.h1, carry.h2);
+        const uint32_t lit_pos = lit_base + pl[l][j], out_pos = out_base + po[l][j];
+        bad |= (offset == 0) | (lit_pos + ll[l][j] > lit_len) | (out_pos + ll[l][j] + ml[l][j] > kZstdBlockMax);
+        rec_store(rec + i, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll[l][j] & 0x3FFFFu, ml[l][j] & 0x3FFFFu, offset));
+      }
     }
     const uint32_t n0 = sym_compose(m0[31], carry.h0, carry.h1, carry.h2), n1 = sym_compose(m1[31], carry.h0, carry.h1, carry.h2),
                    n2 = sym_compose(m2[31], carry.h0, carry.h1, carry.h2);
@@ -1023,7 +1122,14 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
     const bool ok_ref = decode_sequences(src, b, st, logs, ref.data(), &ref_matched, &ref_lit, ref_rep);
     SeqRec16* rec = recs.data() + b->seq_base;
     std::vector<SeqP1> p1(b->nseq);
-    bool ok2 = seq_phase1(src, b, st, logs, p1.data());
+    SeqBits sb1;
+    bool ok2 = seq_phase1(sb1, src, b, st, logs, p1.data());
+    {  // the device's staged reader must see the same stream
+      std::vector<SeqP1> p1r(b->nseq);
+      RingBits rb;
+      if (seq_phase1(rb, src, b, st, logs, p1r.data()) != ok2) return 2;
+      if (ok2 && memcmp(p1r.data(), p1.data(), (size_t)b->nseq * sizeof(SeqP1)) != 0) return 2;
+    }
     if (ok2) {
       SeqBits sb;
       sb.init(src + b->bits_off, b->src_off + b->len - b->bits_off);

@@ -263,21 +263,32 @@ ZN_D bool seq_table_sources(const ZArgs& a, const ZBlock* b, const ZBlob& z, con
   return ok;
 }
 
-// phase 1, tables in shared memory in the phase-1 entry format (converted while they are copied in)
+// phase 1, tables in shared memory in the 3-byte phase-1 format (converted while they are copied in): per lane kTabSet
+// u16 {base | state bits << 10}, then kTabSet u8 {state bits + extra bits}
+ZN_D uint32_t lds16_ro(uint32_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+ZN_D uint32_t lds8_ro(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 struct SmemTabs1 {
   uint32_t tab_s;
-  ZN_D uint32_t ld1(int k, uint32_t i) const { return lds32_ro(tab_s + 4u * ((k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML)) + i)); }
+  ZN_D void ld1(int k, uint32_t i, uint32_t* nb, uint32_t* tot) const {
+    const uint32_t e = (k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML)) + i;
+    *nb = lds16_ro(tab_s + 2u * e);
+    *tot = lds8_ro(tab_s + 2u * kTabSet + e);
+  }
 };
-constexpr uint32_t kSeq1Smem = kSeqLanes * kTabSet * 4;
+constexpr uint32_t kSeq1Lanes = 56;
+constexpr uint32_t kSeq1Set = kTabSet * 3;  // bytes of one lane's tables
+constexpr uint32_t kSeq1Smem = kSeq1Lanes * (kSeq1Set + RingBits::kRingBytes);  // tables + one stream ring per lane
 
 __global__ void __launch_bounds__(64, 1) k_zseq1(ZArgs a) {
   extern __shared__ __align__(16) uint8_t seq_smem[];
   const uint32_t tid = threadIdx.x;
-  if (tid >= kSeqLanes) return;
+  if (tid >= kSeq1Lanes) return;
   SmemTabs1 st;
-  st.tab_s = (uint32_t)__cvta_generic_to_shared(seq_smem) + tid * kTabSet * 4;
+  st.tab_s = (uint32_t)__cvta_generic_to_shared(seq_smem) + tid * kSeq1Set;
+  RingBits sb;
+  sb.ring_s = (uint32_t)__cvta_generic_to_shared(seq_smem) + kSeq1Lanes * kSeq1Set + tid * RingBits::kRingBytes;
   const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
-  for (uint32_t it = blockIdx.x * kSeqLanes + tid; it < n_comp; it += gridDim.x * kSeqLanes) {
+  for (uint32_t it = blockIdx.x * kSeq1Lanes + tid; it < n_comp; it += gridDim.x * kSeq1Lanes) {
     const uint32_t slot = a.comp_list[it];
     if (slot == kNoSlot) continue;
     ZBlock* b = &a.blocks[slot];
@@ -289,21 +300,31 @@ __global__ void __launch_bounds__(64, 1) k_zseq1(ZArgs a) {
     if (!seq_table_sources(a, b, z, t, logs)) continue;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const uint32_t n = 1u << logs[k], dst = st.tab_s + 4u * (k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML));
+      const uint32_t n = 1u << logs[k], e0 = k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML);
 #pragma unroll 8
-      for (uint32_t i = 0; i < n; i++) sts32(dst + 4 * i, p1_entry(t[k][i]));
+      for (uint32_t i = 0; i < n; i++) {
+        const FseD e = t[k][i];
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(st.tab_s + 2u * (e0 + i)), "r"(e & 0x3FFFu) : "memory");
+        sts8(st.tab_s + 2u * kTabSet + e0 + i, fd_nbits(e) + fd_extra(e));
+      }
     }
-    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.p1 + b->seq_base)) b->st_seq = 2;
+    if (seq_phase1(sb, a.blobs_base + d.src_off, b, st, logs, a.p1 + b->seq_base)) b->st_seq = 2;
   }
 }
 
 // phase 1 with the tables left in global memory (every block of the batch at once, one L2 round trip on the chain)
 struct GlobalTabs1 {
   const FseD* t[3];
-  ZN_D uint32_t ld1(int k, uint32_t i) const { return p1_entry(__ldcg(t[k] + i)); }
+  ZN_D void ld1(int k, uint32_t i, uint32_t* nb, uint32_t* tot) const {
+    const FseD e = __ldcg(t[k] + i);
+    *nb = e & 0x3FFFu; *tot = fd_nbits(e) + fd_extra(e);
+  }
 };
 
 __global__ void __launch_bounds__(32) k_zseq1_g(ZArgs a) {
+  __shared__ __align__(16) uint8_t s_ring[32 * RingBits::kRingBytes];
+  RingBits sb;
+  sb.ring_s = (uint32_t)__cvta_generic_to_shared(s_ring) + threadIdx.x * RingBits::kRingBytes;
   const uint32_t n_comp = min(a.pools->comp_used, a.pools->comp_cap);
   for (uint32_t it = blockIdx.x * 32 + threadIdx.x; it < n_comp; it += gridDim.x * 32) {
     const uint32_t slot = a.comp_list[it];
@@ -315,12 +336,12 @@ __global__ void __launch_bounds__(32) k_zseq1_g(ZArgs a) {
     GlobalTabs1 st;
     uint32_t logs[3];
     if (!seq_table_sources(a, b, z, st.t, logs)) continue;
-    if (seq_phase1(a.blobs_base + d.src_off, b, st, logs, a.p1 + b->seq_base)) b->st_seq = 2;
+    if (seq_phase1(sb, a.blobs_base + d.src_off, b, st, logs, a.p1 + b->seq_base)) b->st_seq = 2;
   }
 }
 
-// phase 2: one warp per block, a lane per sequence, 32 consecutive sequences per step (zpipe.cuh: seq_phase2_host is the
-// same arithmetic with the lanes as arrays)
+// phase 2: one warp per block, 128 consecutive sequences per step, four per lane (zpipe.cuh: seq_phase2_host is the same
+// arithmetic with the lanes as arrays)
 struct GlobalTabs2 {
   const FseD* t[3];
   uint32_t lut_s;
@@ -357,17 +378,24 @@ __global__ void __launch_bounds__(kSeq2Warps * 32) k_zseq2(ZArgs a) {
     const uint32_t lit_len = b->lit_regen;
     uint32_t c_lit = 0, c_out = 0, c0 = sym_make(0), c1 = sym_make(1), c2 = sym_make(2);  // state carried from step to step
     uint32_t bad = 0;
-    for (uint32_t base = 0; base < nseq; base += 32) {
-      const uint32_t i = base + lane;
-      uint32_t ll = 0, ml = 0, offx = 0, m0 = sym_make(0), m1 = sym_make(1), m2 = sym_make(2);
-      if (i < nseq) {
-        uint32_t ov, zf = 0;
-        seq_values(sb, st, p1 + i, &ll, &ml, &ov);
-        offx = rep_step(ov, ll, m0, m1, m2, &zf);  // the sequence's own effect on an unknown history
-      }
-      uint32_t sl = ll, so = ll + ml;
+    for (uint32_t base = 0; base < nseq; base += 32 * kSeqPerLane) {
+      const uint32_t i0 = base + lane * kSeqPerLane;
+      uint32_t ll[kSeqPerLane], ml[kSeqPerLane], offx[kSeqPerLane], pl[kSeqPerLane], po[kSeqPerLane];
+      uint32_t m0 = sym_make(0), m1 = sym_make(1), m2 = sym_make(2), sl = 0, so = 0;
 #pragma unroll
-      for (uint32_t dd = 1; dd < 32; dd <<= 1) {  // inclusive scans: the two sums, the history maps
+      for (uint32_t j = 0; j < kSeqPerLane; j++) {  // the lane's own sequences: values, effect on an unknown history, local positions
+        ll[j] = 0; ml[j] = 0; offx[j] = 0;
+        if (i0 + j < nseq) {
+          uint32_t ov, zf = 0;
+          seq_values(sb, st, p1 + i0 + j, &ll[j], &ml[j], &ov);
+          offx[j] = rep_step(ov, ll[j], m0, m1, m2, &zf);
+        }
+        pl[j] = sl; po[j] = so;
+        sl += ll[j]; so += ll[j] + ml[j];
+      }
+      const uint32_t tot_l = sl, tot_o = so;
+#pragma unroll
+      for (uint32_t dd = 1; dd < 32; dd <<= 1) {  // inclusive scans over the lanes: the two sums, the history maps
         const uint32_t tl = __shfl_up_sync(FULL, sl, dd), to = __shfl_up_sync(FULL, so, dd);
         const uint32_t t0 = __shfl_up_sync(FULL, m0, dd), t1 = __shfl_up_sync(FULL, m1, dd), t2 = __shfl_up_sync(FULL, m2, dd);
         if (lane >= dd) {
@@ -378,13 +406,15 @@ __global__ void __launch_bounds__(kSeq2Warps * 32) k_zseq2(ZArgs a) {
       }
       uint32_t e0 = __shfl_up_sync(FULL, m0, 1), e1 = __shfl_up_sync(FULL, m1, 1), e2 = __shfl_up_sync(FULL, m2, 1);
       if (lane == 0) { e0 = sym_make(0); e1 = sym_make(1); e2 = sym_make(2); }
-      const uint32_t h0 = sym_compose(e0, c0, c1, c2), h1 = sym_compose(e1, c0, c1, c2), h2 = sym_compose(e2, c0, c1, c2);
-      if (i < nseq) {
-        const uint32_t offset = sym_compose(offx, h0, h1, h2);
-        const uint32_t lit_pos = c_lit + (sl - ll), out_pos = c_out + (so - ll - ml);
-        bad |= (offset == 0) | (lit_pos + ll > lit_len) | (out_pos + ll + ml > kZstdBlockMax);
-        rec_store(rec + i, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll & 0x3FFFFu, ml & 0x3FFFFu, offset));
-      }
+      const uint32_t lit_base = c_lit + (sl - tot_l), out_base = c_out + (so - tot_o);
+#pragma unroll
+      for (uint32_t j = 0; j < kSeqPerLane; j++)
+        if (i0 + j < nseq) {
+          const uint32_t offset = sym_compose(sym_compose(offx[j], e0, e1, e2), c0, c1, c2);
+          const uint32_t lit_pos = lit_base + pl[j], out_pos = out_base + po[j];
+          bad |= (offset == 0) | (lit_pos + ll[j] > lit_len) | (out_pos + ll[j] + ml[j] > kZstdBlockMax);
+          rec_store(rec + i0 + j, rec_pack(out_pos & 0x3FFFFu, lit_pos & 0x3FFFFu, ll[j] & 0x3FFFFu, ml[j] & 0x3FFFFu, offset));
+        }
       const uint32_t T0 = __shfl_sync(FULL, m0, 31), T1 = __shfl_sync(FULL, m1, 31), T2 = __shfl_sync(FULL, m2, 31);
       const uint32_t n0 = sym_compose(T0, c0, c1, c2), n1 = sym_compose(T1, c0, c1, c2), n2 = sym_compose(T2, c0, c1, c2);
       c0 = n0; c1 = n1; c2 = n2;

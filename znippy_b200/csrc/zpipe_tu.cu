@@ -55,7 +55,7 @@ void pipeline_trace_dump() {
 #endif
 }
 
-void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks) {
+uint32_t pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* marks) {
   const ZArgs& a = L.a;
   const uint32_t sms = L.sm_count, slots = L.slots;
   int m = 0;
@@ -69,15 +69,21 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   const uint32_t lit_grid = std::min<uint32_t>((slots + kLitBlocks - 1) / kLitBlocks, sms * 3);
   k_ztables<<<std::min<uint32_t>((slots + kTabWarps - 1) / kTabWarps, sms * 8), kTabWarps * 32, 0, st>>>(a);
   mark();
-  static const int seq_mode = getenv("ZN_SEQ") ? atoi(getenv("ZN_SEQ")) : 0;  // 0 / 1: the one-pass forms; 2-4: two-phase (2 = table placement by batch shape)
+  // Sequence stage.  Large blobs (blocks of ~10 000 sequences): the two-phase form with phase-1 tables in shared memory;
+  // small blobs (short chains, many more blocks than lanes that fit beside their tables): the one-pass form, every block
+  // at once.  Development: ZN_SEQ = 0 one-pass / 1 one-pass with shared-memory tables / 3 two-phase / 4 two-phase with
+  // phase-1 tables in global memory.
+  static const int seq_env = getenv("ZN_SEQ") ? atoi(getenv("ZN_SEQ")) : 2;
+  const int seq_mode = seq_env == 2 ? (L.mean_bytes >= (256u << 10) ? 3 : 0) : seq_env;
+  uint32_t n_launch = 7;
   if (seq_mode == 1) k_zseq<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeqSmem, st>>>(a);
   else if (seq_mode == 0) k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a, getenv("ZN_SEQ_LDG") ? 0 : 1);
-  else {  // two-phase form: the state chain per block, then every sequence on its own
-    const bool smem_tabs = seq_mode == 2 ? L.mean_bytes >= (256u << 10) : seq_mode == 3;
-    if (smem_tabs) k_zseq1<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeq1Smem, st>>>(a);
+  else {
+    if (seq_mode == 3) k_zseq1<<<std::min<uint32_t>((slots + kSeq1Lanes - 1) / kSeq1Lanes, sms), 64, kSeq1Smem, st>>>(a);
     else k_zseq1_g<<<(slots + 31) / 32, 32, 0, st>>>(a);
     if (marks && getenv("ZN_ZPROF_SEQ1")) { cudaEventRecord(marks[8], st); }  // development: end of phase 1
     k_zseq2<<<std::min<uint32_t>((slots + kSeq2Warps - 1) / kSeq2Warps, sms * 16), kSeq2Warps * 32, 0, st>>>(a);
+    n_launch = 8;
   }
   mark();
   k_zlit<<<lit_grid, kLitBlocks * 4, kLitSmem, st>>>(a);
@@ -104,7 +110,7 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
 #undef ZN_X2
 #undef ZN_X2L
     mark();
-    return;
+    return n_launch;
   }
   const char* ev = getenv("ZN_EXEC");  // development: team shape of the exec kernel
   const int shape = ev ? atoi(ev) : (L.mean_bytes >= (256u << 10) ? 256 : 128);
@@ -115,6 +121,7 @@ void pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t* mar
   else
     k_zexec<128, 4, 16384, 4><<<std::min<uint32_t>(a.nzb, sms * 4), 128, sizeof(ExecShared<128, 4, 16384>), st>>>(a, L.d_out, L.produced, L.exec_counter);
   mark();
+  return n_launch;
 }
 
 }  // namespace zp
