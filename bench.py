@@ -577,6 +577,8 @@ def run_ours(args):
     st, dg = plan.results()
     assert not st.any(), f"warm-up produced non-OK statuses: {np.unique(st)}"
     assert (dg == digs).all()
+    # rows the zstd pipeline handed back to the one-team decoder (same bytes, much slower): 0 on every workload here
+    pipeline_fallbacks = plan.pipeline_fallbacks() if args.warmup > 0 else None
 
     # ---- device-resident timing: K steps between events on the launching stream
     stage_ms = np.zeros(4)
@@ -754,7 +756,7 @@ def run_ours(args):
                                 f"{args.groups} row groups, decode(g+1) overlaps blake3(g) on 2 streams"),
                    "serial_ms_per_step": round(float(stage_ms[0]), 4), "serial_launches_per_step": serial_launches,
                    "rows_this_rank": n, "distinct_blobs_this_rank": len({id(b) for b in blobs})},
-        "clocks": clocks, "gpu_launches": launches,
+        "clocks": clocks, "gpu_launches": launches, "pipeline_fallbacks": pipeline_fallbacks,
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": blob_bytes + 32 * n + 33 * n,
                 "d2h_bytes_per_step": 36 * n, "steps": e2e_steps, "ms_per_step": round(e2e_ms, 4), "api": e2e_api},
         "roofline": roofline, "cpu_baseline": cpu}

@@ -69,12 +69,14 @@ uint32_t pipeline_enqueue(const PipelineLaunch& L, cudaStream_t st, cudaEvent_t*
   const uint32_t lit_grid = std::min<uint32_t>((slots + kLitBlocks - 1) / kLitBlocks, sms * 3);
   k_ztables<<<std::min<uint32_t>((slots + kTabWarps - 1) / kTabWarps, sms * 8), kTabWarps * 32, 0, st>>>(a);
   mark();
-  // Sequence stage.  Large blobs (blocks of ~10 000 sequences): the two-phase form with phase-1 tables in shared memory;
-  // small blobs (short chains, many more blocks than lanes that fit beside their tables): the one-pass form, every block
-  // at once.  Development: ZN_SEQ = 0 one-pass / 1 one-pass with shared-memory tables / 3 two-phase / 4 two-phase with
-  // phase-1 tables in global memory.
+  // Sequence stage.  The two-phase form runs its state chains ~7x faster per sequence but only kSeq1Lanes blocks per SM at
+  // a time; the one-pass form has every block of the batch in flight at once.  So: two-phase when the blocks are long
+  // (large blobs: ~10 000 sequences each) or when there are no more of them than two rounds of lanes; one-pass for
+  // batches of very many small blobs (40 000 files of 2-48 KB: 4.2 ms against 6.3).  Development: ZN_SEQ = 0 one-pass /
+  // 1 one-pass with shared-memory tables / 3 two-phase / 4 two-phase with phase-1 tables in global memory.
   static const int seq_env = getenv("ZN_SEQ") ? atoi(getenv("ZN_SEQ")) : 2;
-  const int seq_mode = seq_env == 2 ? (L.mean_bytes >= (256u << 10) ? 3 : 0) : seq_env;
+  const uint64_t est_blocks = L.mean_bytes * a.nzb / kZstdBlockMax + a.nzb;
+  const int seq_mode = seq_env == 2 ? ((L.mean_bytes >= (256u << 10) || est_blocks <= 2ull * sms * kSeq1Lanes) ? 3 : 0) : seq_env;
   uint32_t n_launch = 7;
   if (seq_mode == 1) k_zseq<<<std::min<uint32_t>((slots + kSeqLanes - 1) / kSeqLanes, sms), 64, kSeqSmem, st>>>(a);
   else if (seq_mode == 0) k_zseq_g<<<(slots + 31) / 32, 32, 0, st>>>(a, getenv("ZN_SEQ_LDG") ? 0 : 1);
