@@ -72,3 +72,16 @@ extern "C" int zn_hostemu_decode_pipe(const uint8_t* src, uint32_t src_len, uint
   free(in);
   return rc;
 }
+
+// the same with the blob at any of 16 alignments (the sequence stage stages its bit stream in 16-byte units)
+extern "C" int zn_hostemu_decode_pipe_at(const uint8_t* src, uint32_t src_len, uint32_t misalign, uint8_t* out, uint32_t cap, uint64_t* stats) {
+  static zn::zp::FseD predef[zn::zp::kTabSet];
+  static bool init = false;
+  if (!init) { zn::zp::build_predef_set(predef); init = true; }
+  uint8_t* in = (uint8_t*)calloc(1, (size_t)src_len + 64);
+  uint8_t* base = (uint8_t*)(((uintptr_t)in + 31) & ~(uintptr_t)15) + (misalign & 15);
+  memcpy(base, src, src_len);
+  const int rc = zn::zp::host_pipeline(base, src_len, out, cap, predef, stats);
+  free(in);
+  return rc;
+}

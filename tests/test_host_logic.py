@@ -72,15 +72,20 @@ def emu():
     L.zn_hostemu_decode_par.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.zn_hostemu_decode_lz4_block.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.zn_hostemu_decode_pipe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.zn_hostemu_decode_pipe_at.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
 
     class E:
         @staticmethod
-        def decode_pipe(blob, cap):
-            """0 = decoded by the device-wide pipeline logic, 1 = handed to the legacy decoder"""
+        def decode_pipe(blob, cap, mis=None):
+            """0 = decoded by the device-wide pipeline logic, 1 = handed to the legacy decoder, 2 = the two-phase sequence
+            stage (or its staged bit reader) disagrees with the one-pass form; mis: blob address modulo 16"""
             a = np.frombuffer(blob, np.uint8)
             out = np.zeros(max(cap, 1) + 64, np.uint8)
             stats = np.zeros(4, np.uint64)
-            rc = L.zn_hostemu_decode_pipe(a.ctypes.data, a.size, out.ctypes.data, cap, stats.ctypes.data)
+            if mis is None:
+                rc = L.zn_hostemu_decode_pipe(a.ctypes.data, a.size, out.ctypes.data, cap, stats.ctypes.data)
+            else:
+                rc = L.zn_hostemu_decode_pipe_at(a.ctypes.data, a.size, mis, out.ctypes.data, cap, stats.ctypes.data)
             return rc, out[:cap].tobytes(), stats
 
         @staticmethod
@@ -235,6 +240,10 @@ def test_hostemu_device_wide_pipeline(emu, oracle):
         assert rc == 0 and out == d.tobytes(), (lvl, len(d))
         nseq += int(stats[1])
     assert nseq > 100_000
+    for mis in range(16):  # bit cursors travel from phase 1 (16-byte units) to phase 2 (aligned words): every alignment
+        for d, lvl in ((rt[:200_000 + 977 * mis], 3), (O.gen_text(100_000), 19), (rt[:3000], 1)):
+            rc, out, _ = emu.decode_pipe(z.compress(d, lvl), len(d), mis)
+            assert rc == 0 and out == d.tobytes(), (mis, lvl, len(d))
     b = z.compress(rt[:50000], 3, checksum=True) + b"\x50\x2a\x4d\x18\x03\x00\x00\x00abc" + z.compress(rt[50000:90000], 19)
     rc, out, _ = emu.decode_pipe(b, 90000)
     assert rc == 0 and out == rt[:90000].tobytes()
