@@ -545,3 +545,42 @@ def test_pipeline_keeps_well_formed_frames_at_every_alignment(codec, oracle):
     for i, c in enumerate(contents):
         assert out[int(out_off[i]): int(out_off[i]) + len(c)].tobytes() == c, i
         assert dg[i].tobytes() == O.blake3(c)
+
+
+def test_entropy_coded_slices_at_baseline_size(codec, oracle):
+    """The realistic shape of the metric: 8 MiB slices (stream_packer.rs:31) of real text, entropy-coded (Huffman literals,
+    FSE tables, repeat offsets) at a fast level and at the reference's 19, decoded by the device-wide pipeline with the
+    two-phase sequence stage (mean decoded size >= 256 KiB).  Size-independent property at full slice size: every digest
+    equals the oracle's blake3 of the content, every byte equals the content, no slice is handed back."""
+    import torch
+    from znippy_b200 import Plan
+    O, z = oracle, oracle.libzstd()
+    rt = O.real_text((8 << 20) + 24 * 4099)
+    contents = [rt[k * 4099: k * 4099 + (8 << 20)] for k in range(24)]  # 24 distinct slices (shifted windows of the corpus)
+    blobs = [z.compress(c, 19 if k == 7 else (1 if k % 3 == 0 else 3)) for k, c in enumerate(contents)]
+    offs, cur = [], 0
+    for k, b in enumerate(blobs):
+        cur = (cur + 15) // 16 * 16 + (5 * k) % 16
+        offs.append(cur)
+        cur += len(b)
+    buf = np.zeros(cur + 16, np.uint8)
+    for o, b in zip(offs, blobs):
+        buf[o:o + len(b)] = np.frombuffer(b, np.uint8)
+    out_len = np.array([c.size for c in contents], np.uint64)
+    out_off = (np.arange(24, dtype=np.uint64) * np.uint64(8 << 20))
+    digs = np.frombuffer(b"".join(O.blake3(c.tobytes()) for c in contents), np.uint8)
+    ctx = codec.default_ctx()
+    d_in = torch.from_numpy(buf).cuda()
+    d_out = torch.zeros(24 * (8 << 20) + 256, dtype=torch.uint8, device="cuda")
+    plan = Plan.decode_verify(ctx, offs, [len(b) for b in blobs], [1] * 24, out_off, out_len, digs)
+    assert plan.class_counts()[0] == 24
+    for _ in range(2):  # a second run reuses the pipeline's pools
+        plan.run(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st, dg = plan.results()
+    assert st.tolist() == [0] * 24
+    assert plan.pipeline_fallbacks() == 0
+    assert (dg.reshape(-1) == digs).all()
+    out = d_out.cpu().numpy()
+    for k, c in enumerate(contents):
+        assert (out[k * (8 << 20): (k + 1) * (8 << 20)] == c).all(), k
