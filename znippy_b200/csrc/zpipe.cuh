@@ -410,6 +410,65 @@ ZN_HD bool build_fat_table(FseD* t, int k, const int16_t* norm, int nsym, int lo
   return true;
 }
 
+// ---- the same table, position by position (what lets a whole warp build it: k_ztables).  FSE spreads the occurrences of
+// the symbols over the table by walking pos = (pos + step) & mask from 0 and skipping the positions above `high` (those
+// hold the symbols of probability "less than one", one each, from the top down).  step is odd, so the unfiltered walk
+// visits position p at time t(p) = p * step^-1 mod size; the filtered walk reaches it after t(p) minus the number of
+// skipped positions visited earlier.  That rank j says which occurrence lands on p, and the inclusive prefix sums of
+// the counts say whose occurrence it is.  The state's number within its symbol (what FSE calls `next`) is then the
+// count of lower positions holding the same symbol.
+ZN_HD uint32_t fat_step_inv(uint32_t size) {  // inverse of the spread step modulo size (a power of two, >= 32)
+  const uint32_t step = (size >> 1) + (size >> 3) + 3;
+  uint32_t x = step;  // correct to 3 bits for any odd number; every Newton step doubles that
+  x *= 2u - step * x;
+  x *= 2u - step * x;
+  x *= 2u - step * x;
+  return x & (size - 1);
+}
+// symbol at position p.  cum[s] = inclusive prefix sum of the positive counts (0xFFFF from nsym up to 63), lowsym[i] = the
+// i-th symbol of count -1
+ZN_HD uint32_t fat_symbol_at(uint32_t p, uint32_t size, uint32_t n_low, uint32_t inv, const uint16_t* cum, const uint16_t* lowsym) {
+  const uint32_t mask = size - 1;
+  if (p + n_low >= size) return lowsym[size - 1 - p];  // above `high` (n_low may be the whole table)
+  const uint32_t t = (p * inv) & mask;
+  uint32_t skipped = 0;
+  for (uint32_t i = 0; i < n_low; i++) skipped += (((size - 1 - i) * inv) & mask) < t ? 1u : 0u;
+  const uint32_t j = t - skipped;
+  uint32_t s = 0;  // smallest s with cum[s] > j
+#pragma unroll
+  for (uint32_t w = 32; w; w >>= 1)
+    if (cum[s + w - 1] <= j) s += w;
+  return s;
+}
+ZN_HD bool fat_entry(int k, uint32_t sym, uint32_t ns, int log, FseD* e) {
+  const uint32_t nb = (uint32_t)(log - hibit32(ns));
+  uint32_t base, extra;
+  if (!sym_value(k, sym, &base, &extra)) return false;
+  *e = fd_pack((ns << nb) - (1u << log), nb, extra, sym);
+  return true;
+}
+#if !defined(__CUDA_ARCH__)
+// host mirror of the warp's build (k_ztables): same helpers, positions in ascending order
+inline bool build_fat_table_by_position(FseD* t, int k, const int16_t* norm, int nsym, int log) {
+  const uint32_t size = 1u << log, inv = fat_step_inv(size);
+  uint16_t cum[64], lowsym[64], run[64];
+  uint32_t acc = 0, n_low = 0;
+  for (int s = 0; s < 64; s++) {
+    run[s] = 0;
+    if (s < nsym && norm[s] > 0) acc += (uint32_t)norm[s];
+    if (s < nsym && norm[s] == -1) lowsym[n_low++] = (uint16_t)s;
+    cum[s] = s < nsym ? (uint16_t)acc : (uint16_t)0xFFFF;
+  }
+  for (uint32_t p = 0; p < size; p++) {
+    const uint32_t sym = fat_symbol_at(p, size, n_low, inv, cum, lowsym);
+    if (sym >= (uint32_t)nsym) return false;
+    const uint32_t ns = (norm[sym] == -1 ? 1u : (uint32_t)norm[sym]) + run[sym]++;
+    if (!fat_entry(k, sym, ns, log, &t[p])) return false;
+  }
+  return true;
+}
+#endif
+
 // Step 1 (one thread): parses the table descriptions of block b in order.  For mode-2 tables the normalized counts go
 // to norm[k][0..64), nsym[k], log[k]; mode-1 tables are written directly (one entry).  Sets *bits_off.  false = malformed.
 ZN_HD bool parse_table_descs(const uint8_t* src, const ZBlock* b, FseD* set, int16_t (*norm)[64], int* nsym, int* log,
@@ -1088,6 +1147,10 @@ inline int host_pipeline(const uint8_t* src, uint32_t src_len, uint8_t* out, uin
       if (log[k] >= 5) {  // FSE-described (mode 2); RLE tables (log 0) were written by the parser
         uint16_t next[64];
         ok = ok && build_fat_table(set + offs[k], k, norm[k], nsym[k], log[k], next);
+        if (ok) {  // the warp-parallel construction (k_ztables) must give the same table
+          FseD alt[512];
+          if (!build_fat_table_by_position(alt, k, norm[k], nsym[k], log[k]) || memcmp(alt, set + offs[k], sizeof(FseD) << log[k]) != 0) return 2;
+        }
       }
       if (log[k] >= 0) tlogs |= (uint32_t)log[k] << (8 * k);
     }

@@ -72,9 +72,58 @@ __global__ void __launch_bounds__(64) k_zwalk(ZArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------------------------- tables
+// One table built by the whole warp, position by position (zpipe.cuh: fat_symbol_at; build_fat_table_by_position is the
+// host mirror).  cum / lowsym / run: 64 uint16 each of shared memory.  Lane l takes positions l, l + 32, ...: the symbol
+// at a position comes out of the closed form, its number within the symbol is a running count per symbol that the
+// warp advances 32 positions at a time (match.any groups the lanes that hold the same symbol).
+ZN_D bool build_fat_table_warp(FseD* t, int k, const int16_t* norm, int nsym, int log, uint16_t* cum, uint16_t* lowsym, uint16_t* run,
+                               uint32_t lane) {
+  const uint32_t size = 1u << log, inv = fat_step_inv(size), FULL = 0xFFFFFFFFu, lt = (1u << lane) - 1u;
+  uint32_t acc = 0, n_low = 0;
+#pragma unroll
+  for (uint32_t sb = 0; sb < 64; sb += 32) {
+    const uint32_t s = sb + lane;
+    const int c = (int)s < nsym ? (int)norm[s] : 0;
+    uint32_t v = c > 0 ? (uint32_t)c : 0u;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(FULL, v, d);
+      if (lane >= d) v += n;
+    }
+    cum[s] = (int)s < nsym ? (uint16_t)(acc + v) : (uint16_t)0xFFFF;
+    run[s] = 0;
+    const uint32_t lowb = __ballot_sync(FULL, c == -1);
+    if (c == -1) lowsym[n_low + __popc(lowb & lt)] = (uint16_t)s;
+    acc += __shfl_sync(FULL, v, 31);
+    n_low += __popc(lowb);
+  }
+  __syncwarp();
+  bool ok = true;
+  for (uint32_t p0 = 0; p0 < size; p0 += 32) {
+    const uint32_t p = p0 + lane;
+    const uint32_t sym = fat_symbol_at(p, size, n_low, inv, cum, lowsym);
+    const bool valid = sym < (uint32_t)nsym;
+    const uint32_t key = valid ? sym : 63u;
+    const uint32_t peers = __match_any_sync(FULL, key);
+    const uint32_t rank = (uint32_t)run[key] + __popc(peers & lt);
+    __syncwarp();
+    if ((peers & lt) == 0) run[key] = (uint16_t)(run[key] + __popc(peers));  // the group's lowest lane
+    __syncwarp();
+    FseD e = 0;
+    bool good = valid;
+    if (valid) {
+      const int cs = (int)norm[sym];
+      good = fat_entry(k, sym, (cs == -1 ? 1u : (uint32_t)cs) + rank, log, &e);
+    }
+    if (good) t[p] = e;
+    ok = ok && good;
+  }
+  return __all_sync(FULL, ok);
+}
+
 __global__ void __launch_bounds__(kTabWarps * 32) k_ztables(ZArgs a) {
   __shared__ int16_t s_norm[kTabWarps][3][64];
-  __shared__ uint16_t s_next[kTabWarps][3][64];
+  __shared__ uint16_t s_aux[kTabWarps][3][64];  // cum / lowsym / run of the table being built
   __shared__ int s_nsym[kTabWarps][3], s_log[kTabWarps][3];
   __shared__ uint32_t s_bits[kTabWarps], s_ok[kTabWarps];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -94,11 +143,16 @@ __global__ void __launch_bounds__(kTabWarps * 32) k_ztables(ZArgs a) {
     }
     __syncwarp();
     bool ok = s_ok[warp] != 0;
-    if (ok && lane < 3 && s_log[warp][lane] >= 5) {
-      const uint32_t offs = lane == 0 ? kTabOffLL : (lane == 1 ? kTabOffOF : kTabOffML);
-      ok = build_fat_table(set + offs, (int)lane, s_norm[warp][lane], s_nsym[warp][lane], s_log[warp][lane], s_next[warp][lane]);
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (s_log[warp][k] < 5) continue;  // predefined, RLE (written by the parser) or repeated: nothing to build
+        const uint32_t offs = k == 0 ? kTabOffLL : (k == 1 ? kTabOffOF : kTabOffML);
+        ok = build_fat_table_warp(set + offs, k, s_norm[warp][k], s_nsym[warp][k], s_log[warp][k], s_aux[warp][0], s_aux[warp][1],
+                                  s_aux[warp][2], lane) && ok;
+        __syncwarp();
+      }
     }
-    ok = __all_sync(0xFFFFFFFFu, ok);
     if (lane == 0 && ok) {
       uint32_t tl = 0;
       for (int k = 0; k < 3; k++)
