@@ -85,3 +85,45 @@ extern "C" int zn_hostemu_decode_pipe_at(const uint8_t* src, uint32_t src_len, u
   free(in);
   return rc;
 }
+
+// FSE decoding tables: the position-by-position construction the warps of k_ztables run (zpipe.cuh: fat_symbol_at) against
+// the serial spread-and-number construction, on `n` random normalized distributions (log 5..9, with "less than one"
+// symbols and zero counts).  Returns the number of disagreements; *lows = how many -1 symbols were exercised.
+extern "C" int zn_hostemu_check_tables(uint32_t seed, uint32_t n, uint64_t* lows) {
+  using namespace zn::zp;
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x >> 16); };
+  int bad = 0;
+  *lows = 0;
+  for (uint32_t it = 0; it < n; it++) {
+    const int k = (int)(rnd() % 3);
+    int max_log, max_sym;
+    table_params(k, &max_log, &max_sym);
+    const int log = 5 + (int)(rnd() % (uint32_t)(max_log - 4)), size = 1 << log;
+    const int nsym = 1 + (int)(rnd() % (uint32_t)(max_sym + 1));
+    int16_t norm[64] = {0};
+    int remaining = size;
+    for (int s = 0; s < nsym && remaining > 0; s++) {
+      const uint32_t r = rnd() % 8;
+      if (r == 0) continue;
+      if (r <= 2) { norm[s] = -1; remaining -= 1; continue; }
+      int c = 1 + (int)(rnd() % (uint32_t)(remaining / 2 + 1));
+      if (c > remaining) c = remaining;
+      norm[s] = (int16_t)c;
+      remaining -= c;
+    }
+    if (remaining > 0) {  // the rest goes to one symbol (a -1 symbol weighs 1 already)
+      const int s = (int)(rnd() % (uint32_t)nsym);
+      norm[s] = (int16_t)((norm[s] < 0 ? 1 : norm[s]) + remaining);
+    }
+    int sum = 0;
+    for (int s = 0; s < nsym; s++) { sum += norm[s] < 0 ? 1 : norm[s]; *lows += norm[s] == -1; }
+    if (sum != size) continue;
+    FseD a[512], b[512];
+    uint16_t next[64];
+    const bool oka = build_fat_table(a, k, norm, nsym, log, next);
+    const bool okb = build_fat_table_by_position(b, k, norm, nsym, log);
+    if (oka != okb || (oka && memcmp(a, b, sizeof(FseD) * (size_t)size) != 0)) bad++;
+  }
+  return bad;
+}

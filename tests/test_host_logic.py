@@ -73,8 +73,11 @@ def emu():
     L.zn_hostemu_decode_lz4_block.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.zn_hostemu_decode_pipe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     L.zn_hostemu_decode_pipe_at.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.zn_hostemu_check_tables.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
 
     class E:
+        lib = L
+
         @staticmethod
         def decode_pipe(blob, cap, mis=None):
             """0 = decoded by the device-wide pipeline logic, 1 = handed to the legacy decoder, 2 = the two-phase sequence
@@ -263,6 +266,15 @@ def test_hostemu_device_wide_pipeline(emu, oracle):
         else:
             handed += 1
     assert handed > 50
+
+
+def test_hostemu_fse_tables_built_by_position(emu):
+    """k_ztables builds a decoding table position by position (closed form of FSE's spread walk, per-symbol running counts);
+    the host mirror of that construction equals the serial one on random normalized distributions of every table kind and
+    log, with many "less than one" symbols."""
+    lows = C.c_uint64(0)
+    assert emu.lib.zn_hostemu_check_tables(11, 60_000, C.byref(lows)) == 0
+    assert lows.value > 100_000
 
 
 def _skew256(n, seed=5):
