@@ -10,10 +10,14 @@
 //            literals / Huffman tree / sequence tables are DEFINED (own section, an earlier block for treeless and
 //            repeat modes, or the predefined distribution) — which removes the table dependence between blocks — and
 //            bump-allocates the blob's sequence records, literal bytes and table sets from batch-wide pools;
-//   tables   one warp per compressed block parses the three FSE table descriptions and builds decoding tables whose
-//            4-byte entries hold next-state base, state bits, extra-bit count and symbol, in global memory;
-//   seq      ONE LANE PER BLOCK runs the three interleaved FSE state machines: 32 independent bit streams per warp,
-//            thousands per device.  Repeat offsets that reach back before the block are kept SYMBOLIC (history entry
+//   tables   one warp per compressed block: lane 0 parses the three FSE table descriptions, then all lanes build each
+//            decoding table position by position (closed form of FSE's spread walk); 4-byte entries hold next-state
+//            base, state bits, extra-bit count and symbol, in global memory;
+//   seq      the three interleaved FSE state machines of every block.  Large blobs: in two phases — ONE LANE PER BLOCK
+//            runs the state chain alone (tables and bit stream staged in shared memory) and leaves {bit cursor, states}
+//            per sequence; then a warp per block decodes the values of 128 sequences per step and gets positions and
+//            repeat-offset histories from prefix scans.  Many small blobs: one pass, ONE LANE PER BLOCK, every block of
+//            the batch in flight.  Repeat offsets that reach back before the block are kept SYMBOLIC (history entry
 //            i minus k), so no block waits for its predecessor.  Output: one 16-byte record per sequence;
 //   lit      ONE LANE PER HUFFMAN STREAM (4 per block), the block's decoding table in shared memory;
 //   chain    one thread per blob: block output offsets (prefix sum of the regenerated sizes), true repeat-offset

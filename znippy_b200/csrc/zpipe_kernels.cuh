@@ -2,8 +2,10 @@
 // codec::decompress_into, znippy-common/src/codec.rs:67-78, for every row of a batch at once).
 //
 //   k_zwalk    thread per blob      block table + pool allocation
-//   k_ztables  warp per block       FSE table descriptions -> fat decoding tables (lanes 0-2 build LL / OF / ML)
-//   k_zseq     LANE per block       three interleaved FSE state machines, 16-byte sequence records
+//   k_ztables  warp per block       FSE table descriptions -> fat decoding tables (all lanes, position by position)
+//   k_zseq1    LANE per block       sequence stage, phase 1: the FSE state chain alone (tables + bit stream in shared memory)
+//   k_zseq2    warp per block       sequence stage, phase 2: values, positions, repeat offsets (prefix scans), 16-byte records
+//   k_zseq_g   LANE per block       the one-pass sequence stage (batches of many small blobs); k_zseq / k_zseq1_g: measured variants
 //   k_zlit     LANE per stream      Huffman literals, decoding table in shared memory, word stores
 //   k_zchain   thread per blob      output offsets, repeat-offset histories, size checks
 //   k_zexec    CTA per blob         sequence execution in shared memory, group by group
